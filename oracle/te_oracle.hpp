@@ -1,0 +1,377 @@
+// =====================================================================================
+// oracle/te_oracle.hpp  --  TEST INFRASTRUCTURE ONLY.  NOT PART OF THE PRODUCT.
+//
+// CPU restatement (C++17, Eigen-free, yaml-cpp-free) of the hot path of
+// graiola/target_estimation: KalmanFilter predict/update, the four target models,
+// TargetManager, the target_manager_c C-ABI semantics, IntersectionSolver and the
+// RosTargetManager tick/expiry rule.  Only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference leg may build, link, import or run it.
+// The product (target_estimation_b200/) never includes or links anything from here.
+//
+// PARITY UNPINNED: the reference holds no golden vectors / known-answer tests for this
+// path (its only KF test asserts statistical convergence at 0.01/0.05 tolerance,
+// test/target_manager_test.cpp:179-189,223-233,268-281,321-340) and it cannot be compiled
+// here (Eigen 3, yaml-cpp, gtest, ROS absent; no network).  This oracle is pinned only
+// (a) against those four convergence tests re-run verbatim with the libstdc++ RNG stream,
+// (b) against tests/golden/ anchors produced by an independent numpy restatement.
+//
+// Every function cites the reference file:line it follows (paths relative to
+// /root/reference).  Arithmetic is evaluated in the reference's order, without FMA
+// contraction (built with -ffp-contract=off), with Eigen's documented evaluation
+// semantics restated where the reference relies on them.
+// =====================================================================================
+#pragma once
+#include <cassert>
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace oracle {
+
+// -------------------------------------------------------------------------------------
+// Minimal dense matrix: column-major like Eigen::MatrixXd.
+// -------------------------------------------------------------------------------------
+struct Mat {
+  int r = 0, c = 0;
+  std::vector<double> d;
+  Mat() {}
+  Mat(int r_, int c_) : r(r_), c(c_), d((size_t)r_ * c_, 0.0) {}
+  double& operator()(int i, int j) { return d[(size_t)i + (size_t)r * j]; }
+  double operator()(int i, int j) const { return d[(size_t)i + (size_t)r * j]; }
+  int rows() const { return r; }
+  int cols() const { return c; }
+  static Mat Identity(int n) {
+    Mat m(n, n);
+    for (int i = 0; i < n; ++i) m(i, i) = 1.0;
+    return m;
+  }
+  // Eigen::Map<MatrixXd>(v.data(), s, s): column-major view of a flat list
+  // (src/target_manager.cpp:24-25) -- M(i,j) = v[i + s*j].
+  static Mat MapColMajor(const double* v, int s) {
+    Mat m(s, s);
+    std::memcpy(m.d.data(), v, sizeof(double) * (size_t)s * s);
+    return m;
+  }
+};
+typedef std::vector<double> Vec;
+
+Mat mul(const Mat& A, const Mat& B);           // increasing-k accumulation, materialised
+Mat transpose(const Mat& A);
+Mat add(const Mat& A, const Mat& B);
+Mat sub(const Mat& A, const Mat& B);
+Vec mulv(const Mat& A, const Vec& x);
+Mat inversePartialPivLU(const Mat& M);          // (Eigen) MatrixXd::inverse() for dynamic sizes
+
+// -------------------------------------------------------------------------------------
+// geometry.hpp restatement (only what the hot path uses)
+// -------------------------------------------------------------------------------------
+struct Quat { double x = 0, y = 0, z = 0, w = 1; };   // Eigen coeff order [x y z w]
+struct Mat3 { double m[3][3]; };
+
+double constrainAngle(double x);                         // geometry.hpp:31-36
+double angleConv(double a);                              // geometry.hpp:43-45
+double angleDiff(double a, double b);                    // geometry.hpp:53-58
+void unwrap3(const double prev[3], const double nw[3], double out[3]);  // geometry.hpp:70-76
+double wrapMax(double x, double max);                    // geometry.hpp:79-83
+double wrapMinMax(double x, double min, double max);     // geometry.hpp:85-88
+void quatNormalize(Quat& q);                             // (Eigen) QuaternionBase::normalize
+void quatToRpy(const Quat& q, double rpy[3]);            // geometry.hpp:154-176
+void rpyToQuat(const double rpy[3], Quat& q);            // geometry.hpp:178-189
+void rotToRpy(const Mat3& R, double rpy[3]);             // geometry.hpp:191-196
+Mat3 quatToRotationMatrix(const Quat& q);                // (Eigen) toRotationMatrix
+Quat rotationMatrixToQuat(const Mat3& R);                // (Eigen) Quaternion(Matrix3)
+void rpyToEarBase(const double rpy[3], Mat3& E);         // geometry.hpp:333-351
+void rpyToEarBaseInv(const double rpy[3], Mat3& E);      // geometry.hpp:359-374
+Mat3 EarBaseInvJacobianRpy(const double rpy[3], const double omega[3], double dt);   // :394-410
+Mat3 EarBaseInvJacobianOmega(const double rpy[3], double dt);                        // :412-426
+void Qtran(double dt, const double omega[3], double Q[4][4]);                        // :493-504
+void pose7dToPose6d(const double p7[7], double p6[6]);   // geometry.hpp:619-628
+Quat quatMul(const Quat& a, const Quat& b);              // (Eigen) Hamilton product
+Quat quatInverse(const Quat& q);                         // (Eigen) conjugate / squaredNorm
+double computeQuaternionErrorAngle(const Quat& q_des, const Quat& q);  // geometry.hpp:630-657
+double toSec(uint32_t sec, uint32_t nsec);               // utils.hpp:59-62
+
+// -------------------------------------------------------------------------------------
+// kalman.hpp / kalman.cpp restatement
+// -------------------------------------------------------------------------------------
+class KalmanFilterInterface {
+ public:
+  virtual ~KalmanFilterInterface() {}
+  void init(const Vec& x0);            // src/kalman.cpp:16-21
+  virtual void update(const Vec& y);   // src/kalman.cpp:30-42
+  virtual void update();               // src/kalman.cpp:44-54
+  Vec& getState() { return x_hat_; }
+  Mat& getQ() { return Q_; }
+  Mat& getR() { return R_; }
+  Mat& getP() { return P_; }
+  Mat& getP0() { return P0_; }
+
+ protected:
+  virtual void predict() = 0;
+  virtual void estimate(const Vec& y) = 0;
+  Mat A_, C_, Q_, R_, P_, K_, P0_, I_;
+  int m_ = 0, n_ = 0;
+  bool initialized_ = false;
+  Vec x_hat_, x_hat_new_;
+};
+
+class LinearKalmanFilter : public KalmanFilterInterface {
+ public:
+  LinearKalmanFilter(const Mat& A, const Mat& C, const Mat& Q, const Mat& R, const Mat& P);  // :62-82
+  using KalmanFilterInterface::update;
+  virtual void updateA(const Mat& A);                    // src/kalman.cpp:97-101
+  virtual void updateA(const Vec& y, const Mat& A);      // src/kalman.cpp:103-107
+ protected:
+  void predict() override;                               // src/kalman.cpp:84-88
+  void estimate(const Vec& y) override;                  // src/kalman.cpp:90-95
+};
+
+class ExtendedKalmanFilter : public LinearKalmanFilter {
+ public:
+  typedef std::function<Vec(const Vec&)> fn_t;
+  ExtendedKalmanFilter(fn_t f, fn_t h, const Mat& A, const Mat& C, const Mat& Q, const Mat& R, const Mat& P);
+  void updateF(fn_t f, const Mat& A);                    // src/kalman.cpp:142-146
+  void updateF(const Vec& y, fn_t f, const Mat& A);      // src/kalman.cpp:148-152
+ protected:
+  void predict() override;                               // src/kalman.cpp:129-133
+  void estimate(const Vec& y) override;                  // src/kalman.cpp:135-140
+  fn_t f_, h_;
+};
+
+// -------------------------------------------------------------------------------------
+// target_interface.hpp + types/*.hpp restatement
+// -------------------------------------------------------------------------------------
+enum target_t { ANGULAR_RATES = 0, ANGULAR_VELOCITIES, UNIFORM_ACCELERATION, UNIFORM_VELOCITY };
+
+class TargetInterface {
+ public:
+  typedef std::shared_ptr<TargetInterface> Ptr;
+  TargetInterface(unsigned id, const Mat& P0, double t0);            // src/target_interface.cpp:18-41
+  virtual ~TargetInterface() {}
+  virtual void addMeasurement(double dt, const double meas[7]) = 0;
+  virtual void update(double dt) = 0;
+  virtual void getEstimatedPoseAt(double t1, double out[7]);          // src/target_interface.cpp:123-128
+  virtual void getEstimatedTwistAt(double t1, double out[6]);         // :130-134
+  virtual void getEstimatedAccelerationAt(double t1, double out[6]);  // :136-140
+  double getPeriodEstimate();                                         // :80-87
+  double getTime() { return t_; }
+  void getEstimatedPose(double out[7]);                               // :100-104 (isometryToPose7d)
+  void getEstimatedTwist(double out[6]) { std::memcpy(out, twist_, sizeof(twist_)); }
+  void getEstimatedAcceleration(double out[6]) { std::memcpy(out, acceleration_, sizeof(acceleration_)); }
+  void getMeasuredPose(double out[7]) { std::memcpy(out, measured_pose_, sizeof(measured_pose_)); }
+  void getPoseInternal(double out[6]) { std::memcpy(out, pose_internal_, sizeof(pose_internal_)); }
+  unsigned getID() const { return (unsigned)id_; }
+  unsigned getN() const { return n_; }
+  unsigned getM() const { return m_; }
+  KalmanFilterInterface* getEstimator() const { return estimator_.get(); }
+  long long getNumberMeasurements() const { return n_meas_; }
+  const double* prevRpy() const { return meas_rpy_internal_; }
+
+ protected:
+  virtual void updateTargetState() = 0;
+  void updateMeasurement(const double meas[7]);   // src/target_interface.cpp:142-146
+  void updateTime(double dt);                     // src/target_interface.cpp:148-152
+  unsigned n_ = 0, m_ = 0;
+  int id_ = -1;
+  double t_ = 0;
+  double trans_[3] = {0, 0, 0};   // T_.translation()
+  Mat3 rot_;                      // T_.linear()
+  double twist_[6], acceleration_[6], pose_internal_[6], measured_pose_[7];
+  Mat P_;
+  Vec x_;
+  std::shared_ptr<KalmanFilterInterface> estimator_;
+  long long n_meas_ = 0;
+  std::mutex data_lock_;
+  Mat C_, A_;
+  // H3: meas_rpy_internal_ is uninitialised in the reference
+  // (types/angular_rates.hpp:110, types/angular_velocities.hpp:127); defined as 0 here.
+  double meas_rpy_internal_[3] = {0, 0, 0};
+};
+
+class TargetUniformVelocity : public TargetInterface {
+ public:
+  TargetUniformVelocity(unsigned id, double dt0, double t0, const Mat& Q, const Mat& R, const Mat& P0,
+                        const double p0[7], const double v0[6], const double a0[6]);
+  void addMeasurement(double dt, const double meas[7]) override;
+  void update(double dt) override;
+  void getEstimatedPoseAt(double t1, double out[7]) override;
+  void getEstimatedTwistAt(double t1, double out[6]) override;
+ private:
+  void updateTargetState() override;
+  void updateA(double dt);
+};
+
+class TargetUniformAcceleration : public TargetInterface {
+ public:
+  TargetUniformAcceleration(unsigned id, double dt0, double t0, const Mat& Q, const Mat& R, const Mat& P0,
+                            const double p0[7], const double v0[6], const double a0[6]);
+  void addMeasurement(double dt, const double meas[7]) override;
+  void update(double dt) override;
+  void getEstimatedPoseAt(double t1, double out[7]) override;
+  void getEstimatedTwistAt(double t1, double out[6]) override;
+ private:
+  void updateTargetState() override;
+  void updateA(double dt);
+};
+
+class TargetAngularRates : public TargetInterface {
+ public:
+  TargetAngularRates(unsigned id, double dt0, double t0, const Mat& Q, const Mat& R, const Mat& P0,
+                     const double p0[7], const double v0[6], const double a0[6]);
+  void addMeasurement(double dt, const double meas[7]) override;
+  void update(double dt) override;
+  void getEstimatedPoseAt(double t1, double out[7]) override;
+  void getEstimatedTwistAt(double t1, double out[6]) override;
+ private:
+  void updateTargetState() override;
+  void updateA(double dt);
+};
+
+class TargetAngularVelocities : public TargetInterface {
+ public:
+  TargetAngularVelocities(unsigned id, double dt0, double t0, const Mat& Q, const Mat& R, const Mat& P0,
+                          const double p0[7], const double v0[6], const double a0[6]);
+  void addMeasurement(double dt, const double meas[7]) override;
+  void update(double dt) override;
+  void getEstimatedPoseAt(double t1, double out[7]) override;
+ private:
+  void updateTargetState() override;
+  void updateA(double dt, const double rpy[3], const double omega[3]);
+  Vec f(const Vec& x, double dt);
+  Vec h(const Vec& x);
+};
+
+// -------------------------------------------------------------------------------------
+// target_manager.hpp / .cpp restatement
+// -------------------------------------------------------------------------------------
+bool loadYamlFile(const std::string& file, Mat& Q, Mat& R, Mat& P, target_t& type, double* frequency = nullptr);
+bool selectTargetType(const std::string& s, target_t& type);   // src/target_manager.cpp:52-65
+
+class TargetManager {
+ public:
+  typedef std::shared_ptr<TargetManager> Ptr;
+  TargetManager() {}
+  explicit TargetManager(const std::string& file);   // throws const char* like the reference (:112-118)
+  virtual ~TargetManager() {}
+  void init(unsigned id, double dt0, double t0, const double p0[7], const double v0[6] = nullptr, const double a0[6] = nullptr);
+  void init(target_t type, unsigned id, double dt0, double t0, const Mat& Q, const Mat& R, const Mat& P0,
+            const double p0[7], const double v0[6] = nullptr, const double a0[6] = nullptr);
+  void init(const std::string& file, unsigned id, double dt0, double t0, const double p0[7],
+            const double v0[6] = nullptr, const double a0[6] = nullptr);
+  bool update(unsigned id, double dt, const double meas[7]);   // src/target_manager.cpp:190-202
+  bool update(unsigned id, double dt);                         // :204-218
+  virtual void update(double dt);                              // :220-225
+  bool erase(unsigned id);                                     // :227-241
+  TargetInterface::Ptr getTarget(unsigned id);                 // :243-250
+  bool getTargetPose(unsigned id, double pose[7]);
+  bool getTargetTwist(unsigned id, double twist[6]);
+  bool getTargetAcceleration(unsigned id, double acc[6]);
+  long long getNumberMeasurements(unsigned id);
+  std::vector<unsigned> getAvailableTargets();
+  bool quiet = true;   // suppress the reference's stdout chatter (printInfo etc.)
+ protected:
+  std::map<unsigned, TargetInterface::Ptr> targets_;
+  std::mutex target_lock_;
+  Mat default_Q_, default_R_, default_P_;
+  target_t default_type_ = UNIFORM_VELOCITY;
+  bool default_values_loaded_ = false;
+};
+
+// -------------------------------------------------------------------------------------
+// utils.hpp filters
+// -------------------------------------------------------------------------------------
+class AvgFilter {   // utils.hpp:181-204
+ public:
+  explicit AvgFilter(unsigned n) : n_(n), avg_(0.0) {}
+  double update(double v) { avg_ = (avg_ * (n_ - 1) + v) / n_; return avg_; }
+ private:
+  unsigned n_;
+  double avg_;
+};
+
+class MovingAvgFilter {   // utils.hpp:206-265
+ public:
+  explicit MovingAvgFilter(unsigned n) : sum_(0.0), variance_(0.0), window_(n, 0.0), window_idx_(0), filter_complete_(false) {}
+  double update(double value);
+  double getVariance() const { return variance_; }
+ private:
+  double sum_, variance_;
+  std::vector<double> window_;
+  unsigned window_idx_;
+  bool filter_complete_;
+};
+
+std::vector<std::string> splitString(const std::string& s, const std::string& delimiter = "_");  // utils.hpp:273-294
+bool getId(const std::string& s, unsigned& id);                                                   // utils.hpp:302-313
+
+// -------------------------------------------------------------------------------------
+// intersection_solver.hpp / .cpp restatement (+ Eigen PolynomialSolver restated)
+// -------------------------------------------------------------------------------------
+// roots of c[0] + c[1] t + ... + c[deg] t^deg, c[deg] != 0  ((Eigen) PolynomialSolver::compute)
+std::vector<std::complex<double>> polynomialRoots(const std::vector<double>& coeffs);
+double lowestRealRoot(const std::vector<double>& coeffs);   // src/intersection_solver.cpp:4-17
+
+class IntersectionSolver {
+ public:
+  IntersectionSolver(TargetManager::Ptr tm, unsigned filters_length = 250);   // :19-40
+  double getIntersectionTimeWithSphere(unsigned id, double t1, const double origin[3], double radius);   // :42-89
+  bool getIntersectionPoseWithSphere(unsigned id, double t1, double pos_th, double ang_th,
+                                     const double origin[3], double radius, double pose[7]);              // :91-124
+ private:
+  TargetManager::Ptr target_manager_;
+  std::unique_ptr<MovingAvgFilter> pos_error_filter_, ang_error_filter_;
+  double intersection_pose_prev_[7];
+};
+
+// -------------------------------------------------------------------------------------
+// target_manager_ros.hpp / .cpp tick semantics restated without ROS types
+// -------------------------------------------------------------------------------------
+struct StampedPose {
+  uint32_t sec = 0, nsec = 0;
+  double pose[7] = {0, 0, 0, 0, 0, 0, 0};   // geometry_msgs default-constructs to zeros
+};
+
+class Measurement {   // target_manager_ros.hpp:74-134
+ public:
+  Measurement() : last_meas_time_(0.0), new_meas_(true) {}
+  bool read(StampedPose& tr) const {
+    if (new_meas_) { tr = tr_; return true; }
+    return false;
+  }
+  void update(const StampedPose& tr);
+  double getTime() const { return last_meas_time_; }
+ private:
+  double last_meas_time_;
+  bool new_meas_;
+  StampedPose tr_;
+};
+
+struct TfRecord { std::string child_frame_id; StampedPose tr; };
+
+class TickTargetManager : public TargetManager {   // RosTargetManager, target_manager_ros.cpp:6-92
+ public:
+  TickTargetManager(target_t type, const Mat& Q, const Mat& R, const Mat& P);
+  void measurementCallBack(const std::vector<TfRecord>& msg);   // :26-39
+  // ros::Time::now() is passed in as (sec,nsec); erased ids of this tick are appended to *erased
+  void tick(double dt, uint32_t now_sec, uint32_t now_nsec, std::vector<unsigned>* erased = nullptr);   // :41-92
+  void setTargetTokenName(const std::string& s) { token_name_ = s; }
+  void setExpirationTime(double t) { assert(t >= 0.0); expiration_time_ = t; }
+  double time() const { return t_; }
+  size_t mailboxCount() const { return measurements_.size(); }
+ private:
+  target_t type_;
+  Mat Q_, P_, R_;
+  std::string token_name_;
+  double t_;
+  std::map<unsigned, Measurement> measurements_;
+  double expiration_time_;
+};
+
+}  // namespace oracle
