@@ -1,0 +1,122 @@
+/* include/te_pool.h -- thin extern "C" CUDA layer under the TargetManager host surface.
+ *
+ * The reference keeps one heap object per target (std::map<unsigned, shared_ptr<TargetInterface>>,
+ * /root/reference/include/target_estimation/target_manager.hpp:36, each owning ~13 Eigen
+ * matrices, include/target_estimation/kalman.hpp:107-127).  This layer replaces that storage
+ * with one device-resident pool per model type: tiles of 32 targets laid out
+ * [tile][field][lane] in HBM, slots kept in ascending-id order (std::map iteration order),
+ * stepped by the sm_100a kernels in target_estimation_b200/csrc.  Nothing in this header
+ * exists in the reference; the reference-facing ABI is include/target_manager_c.h.
+ *
+ * All functions return >= 0 on success and a negative value on error (te_last_error()).
+ * "host" pointers are ordinary host memory; "dev" pointers are CUDA device memory of the
+ * pool's device.  There is no CPU fallback: without a CUDA device every entry point fails.
+ */
+#ifndef TE_POOL_H
+#define TE_POOL_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct te_pool te_pool;
+typedef struct te_isolver te_isolver;
+
+/* target_t of the reference (target_manager.hpp:38) */
+enum { TE_ANGULAR_RATES = 0, TE_ANGULAR_VELOCITIES = 1, TE_UNIFORM_ACCELERATION = 2, TE_UNIFORM_VELOCITY = 3 };
+/* per-target action of one tick */
+enum { TE_ACT_NONE = 0,      /* target untouched this tick                                      */
+       TE_ACT_PREDICT = 1,   /* TargetManager::update(id,dt)       (src/target_manager.cpp:204-218) */
+       TE_ACT_UPDATE = 2 };  /* TargetManager::update(id,dt,meas)  (src/target_manager.cpp:190-202) */
+
+const char* te_last_error(void);
+int te_device_count(void);
+int te_model_dims(int model, int* n, int* m);           /* state / measurement dims, asserts of src/types/*.cpp */
+size_t te_model_bytes_per_step(int model);                /* SURVEY.md 8(d) algorithmic bytes per target-step */
+
+/* ---- pool lifecycle ---------------------------------------------------------------- */
+te_pool* te_pool_create(int model, int device, void* cuda_stream /* cudaStream_t or NULL = own stream */);
+void te_pool_destroy(te_pool* p);
+int te_pool_set_stream(te_pool* p, void* cuda_stream);
+int te_pool_sync(te_pool* p);
+int te_pool_set_variant(te_pool* p, int variant);         /* kernel shape (warps x stages); tuning knob */
+int te_pool_reserve(te_pool* p, size_t n_targets);
+long long te_pool_size(te_pool* p);
+size_t te_pool_device_bytes(te_pool* p);
+
+/* Model class = (Q, R, P0) triple, row-major, interned by content.  The reference lets every
+ * target carry its own matrices (TargetManager::init(type,id,dt0,t0,Q,R,P0,...),
+ * src/target_manager.cpp:144-146).  Returns the class id. */
+int te_pool_register_class(te_pool* p, const double* Q, const double* R, const double* P0);
+int te_pool_class_count(te_pool* p);
+int te_pool_get_class(te_pool* p, int cls, double* Q, double* R, double* P0);
+
+/* ---- add / erase (stable stream compaction; ids stay ascending) ----------------------- */
+/* TargetManager::init for a batch: ids already present are skipped ("already exists",
+ * src/target_manager.cpp:177-178).  cls NULL = class 0; t0 NULL = 0; v0/a0 NULL = 0;
+ * p0_scale NULL = 1 (P = p0_scale * P0[cls]).  Host pointers.  Returns #targets added. */
+long long te_pool_add_batch(te_pool* p, long long n, const uint32_t* ids, const uint16_t* cls, const double* t0,
+                            const double* p0 /*[n][7]*/, const double* v0 /*[n][6]*/, const double* a0 /*[n][6]*/,
+                            const double* p0_scale);
+/* TargetManager::erase for a batch (src/target_manager.cpp:227-241).  Returns #erased. */
+long long te_pool_erase_batch(te_pool* p, long long n, const uint32_t* ids);
+/* ascending ids (getAvailableTargets, src/target_manager.cpp:126-133); returns pool size */
+long long te_pool_ids(te_pool* p, uint32_t* out, long long cap);
+int te_pool_contains(te_pool* p, uint32_t id);
+
+/* ---- stepping (the hot path) -------------------------------------------------------- */
+/* One tick over every slot, slot order = ascending id.  dev_meas: [size][meas_stride] doubles
+ * (meas_stride 7 = reference pose [x y z qx qy qz qw]; 3 = xyz only, UV/UA pools only);
+ * dev_action: [size] bytes of TE_ACT_* or NULL = default_action for all.  Device pointers. */
+int te_pool_step_dense(te_pool* p, double dt, const double* dev_meas, int meas_stride, const uint8_t* dev_action,
+                       int default_action);
+/* Same with HOST buffers: host->device copies are part of the call. */
+int te_pool_step_dense_host(te_pool* p, double dt, const double* meas, int meas_stride, const uint8_t* action,
+                            int default_action);
+/* Sparse tick by id (host buffers): op k applies action[k] with dt[k] (dt_scalar if dt NULL) and
+ * meas[k][7] to ids[k]; unknown ids are skipped.  An id may appear once per call.  Returns #applied. */
+long long te_pool_step_ids(te_pool* p, long long n, const uint32_t* ids, const double* dt, double dt_scalar,
+                           const double* meas /*[n][7]*/, const uint8_t* action /*NULL = UPDATE*/);
+/* TargetManager::update(dt): predict every target (src/target_manager.cpp:220-225). */
+int te_pool_predict_all(te_pool* p, double dt);
+
+/* ---- read-back (every getter is a device sync point) --------------------------------- */
+/* ids NULL = all targets in ascending-id order (n must equal pool size).  Any output may be NULL.
+ * P is row-major [n][N*N]; measured_pose is the last measurement applied through an id/host API. */
+int te_pool_read_state(te_pool* p, long long n, const uint32_t* ids, double* x, double* P, double* t, long long* n_meas,
+                       double* prev_rpy /*[n][3]*/, double* measured_pose /*[n][7]*/);
+/* getEstimatedPose/Twist/Acceleration([t1]) (src/types/*.cpp, src/target_interface.cpp:89-140).
+ * t1 NULL = current values; otherwise t1[k] per query.  found[k] = 1 if the id exists. */
+int te_pool_read_estimates(te_pool* p, long long n, const uint32_t* ids, const double* t1, double* pose7, double* twist6,
+                           double* acc6, double* pose6_internal, uint8_t* found);
+/* Estimate records of every slot into DEVICE memory: [size][13] = pose7 | twist6 (all-gather payload). */
+int te_pool_estimates_dev(te_pool* p, double* dev_out);
+/* raw device views for callers that keep their own buffers (bench, all-gather) */
+const uint32_t* te_pool_dev_ids(te_pool* p);
+
+/* ---- expiry (RosTargetManager::update, src/target_manager_ros.cpp:67-72) ---------------- */
+/* Record per-target last measurement stamps (toSec(sec,nsec), utils.hpp:59-62) for ids. */
+int te_pool_set_stamps(te_pool* p, long long n, const uint32_t* ids, const uint32_t* sec, const uint32_t* nsec);
+/* Erase every target with last_meas_time > 0 && (now - last_meas_time) >= timeout, evaluated on
+ * the device in non-contracted FP64 (bit-exact with the reference compare).  erased_out receives the
+ * ascending erased ids (up to cap).  Returns #erased. */
+long long te_pool_expire(te_pool* p, uint32_t now_sec, uint32_t now_nsec, double timeout, uint32_t* erased_out,
+                         long long cap);
+
+/* ---- batched IntersectionSolver (src/intersection_solver.cpp) ---------------------------- */
+/* n_streams independent solver states (each = one reference IntersectionSolver object: two moving
+ * average filters of filters_length samples + previous intersection pose). */
+te_isolver* te_isolver_create(te_pool* p, long long n_streams, unsigned filters_length);
+void te_isolver_destroy(te_isolver* s);
+/* query k: target ids[k] through solver stream stream[k] (NULL = k).  Each stream may appear at most
+ * once per call.  delta_t[k] = getIntersectionTimeWithSphere (-1 = none); pose7/converged as
+ * getIntersectionPoseWithSphere (pass pose7 NULL to only compute delta_t without touching filters). */
+int te_isolver_query(te_isolver* s, long long n, const uint32_t* ids, const int32_t* stream, const double* t1,
+                     const double* origin /*[n][3]*/, const double* radius, const double* pos_th, const double* ang_th,
+                     double* delta_t, double* pose7, uint8_t* converged);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TE_POOL_H */

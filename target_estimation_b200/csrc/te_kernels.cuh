@@ -1,0 +1,631 @@
+// te_kernels.cuh -- sm_100a kernels of the device-resident target pool.
+//   kf_step_kernel     : the hot path (one tick of predict [+ update] for every staged tile)
+//   init/rebuild/...   : add / erase by stable stream compaction, read-back gathers
+//   isolver_kernel     : batched IntersectionSolver
+#pragma once
+#include "te_device.cuh"
+
+namespace te {
+
+// -------------------------------------------------------------------------------------
+// kf_step_kernel: persistent, one CTA per SM, WARPS warps per CTA, each warp owns STAGES
+// shared-memory stages.  A stage holds one pool tile (32 targets x NF fields, contiguous
+// in HBM) plus the tile's 32 x meas_stride measurement block, both fetched with one-
+// dimensional TMA bulk copies (cp.async.bulk, completion on an mbarrier) and written back
+// with a bulk store, so the state streams HBM -> smem -> registers -> smem -> HBM exactly
+// once per tick without occupying registers while in flight.
+// Algorithmic traffic per target-step: SURVEY.md 8(d) (UA: 1496 B).
+// -------------------------------------------------------------------------------------
+struct StepArgs {
+  double* tiles;            // [n_tiles][NF][32]
+  int n_slots;
+  int n_tiles;
+  const int* tile_list;     // sparse mode: tiles to process (device), else nullptr
+  const int* d_nwork;       // sparse mode: number of entries in tile_list (device)
+  double dt;
+  const double* dt_slot;    // per-slot dt (sparse mode) or nullptr
+  const double* meas;       // [n_slots][meas_stride] slot-order AoS, or nullptr
+  int meas_stride;
+  int meas_tma;             // 1: full tiles fetch their measurement block by TMA
+  uint8_t* action;          // [n_slots] TE_ACT_* or nullptr
+  int default_action;
+  int clear_action;         // sparse mode: reset action[] and tile flags after use
+  uint8_t* tile_flag;       // sparse mode tile flags (cleared with the actions)
+  const uint16_t* cls;      // [n_slots] model class
+  const double* Qtab;       // [n_classes][N*N] row-major
+  const double* Rtab;       // [n_classes][M*M]
+};
+
+constexpr int MEAS_DOUBLES = 7 * TILE;   // measurement block of a stage (max stride 7)
+
+template <int TYPE> __host__ __device__ constexpr int stage_doubles() { return Layout<TYPE>::TILE_DOUBLES + MEAS_DOUBLES; }
+template <int TYPE> __host__ __device__ constexpr size_t step_smem_bytes(int warps, int stages) {
+  return 1024 + (size_t)warps * stages * stage_doubles<TYPE>() * 8;
+}
+
+template <int TYPE, int WARPS, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32, 1) kf_step_kernel(const StepArgs a) {
+  using MT = Model<TYPE>;
+  using LY = Layout<TYPE>;
+  constexpr int STAGE_DOUBLES = stage_doubles<TYPE>();
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  double* stage0 = reinterpret_cast<double*>(smem_raw + 1024);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* mybar = bars + warp * STAGES;
+  double* mystage = stage0 + (size_t)warp * STAGES * STAGE_DOUBLES;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&mybar[s], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+
+  const int n_work = a.d_nwork ? *a.d_nwork : a.n_tiles;
+  const int gw = blockIdx.x * WARPS + warp, GW = gridDim.x * WARPS;
+  const int n_my = (n_work > gw) ? (n_work - gw + GW - 1) / GW : 0;
+
+  auto tile_of = [&](int it) -> int {
+    const int w = gw + it * GW;
+    return a.tile_list ? a.tile_list[w] : w;
+  };
+  auto use_meas_tma = [&](int tile) -> bool { return a.meas_tma && (tile * TILE + TILE <= a.n_slots); };
+  // lane 0: fetch tile `it` into its stage
+  auto issue = [&](int it) {
+    const int tile = tile_of(it);
+    const int s = it % STAGES;
+    double* st = mystage + (size_t)s * STAGE_DOUBLES;
+    const bool mt = use_meas_tma(tile);
+    const uint32_t mbytes = mt ? (uint32_t)a.meas_stride * TILE * 8u : 0u;
+    mbar_expect_tx(&mybar[s], (uint32_t)LY::TILE_BYTES + mbytes);
+    bulk_g2s(st, a.tiles + (size_t)tile * LY::TILE_DOUBLES, LY::TILE_BYTES, &mybar[s]);
+    if (mt) bulk_g2s(st + LY::TILE_DOUBLES, a.meas + (size_t)tile * TILE * a.meas_stride, mbytes, &mybar[s]);
+  };
+
+  if (lane == 0) {
+    for (int pre = 0; pre < STAGES - 1 && pre < n_my; ++pre) issue(pre);
+  }
+
+  for (int it = 0; it < n_my; ++it) {
+    const int s = it % STAGES;
+    const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
+    const int tile = tile_of(it);
+    const int slot = tile * TILE + lane;
+    const bool valid = slot < a.n_slots;
+
+    // per-lane control words: issued before waiting on the tile so their latency overlaps
+    int act = ACT_NONE;
+    double dt = a.dt;
+    int cls = 0;
+    if (valid) {
+      act = a.action ? (int)a.action[slot] : a.default_action;
+      if (a.dt_slot) dt = a.dt_slot[slot];
+      cls = (int)a.cls[slot];
+    }
+    const bool mt = use_meas_tma(tile);
+    double meas[7];
+    if (!mt && act == ACT_UPDATE) {
+      const double* mp = a.meas + (size_t)slot * a.meas_stride;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) meas[k] = __ldg(mp + k);
+      if (MT::M == 6) {
+#pragma unroll
+        for (int k = 3; k < 7; ++k) meas[k] = __ldg(mp + k);
+      }
+    }
+
+    // refill the stage freed by the previous iteration's store (its smem must have been read)
+    if (lane == 0 && it + STAGES - 1 < n_my) {
+      bulk_wait_read<0>();
+      issue(it + STAGES - 1);
+    }
+
+    double* st = mystage + (size_t)s * STAGE_DOUBLES;
+    mbar_wait(&mybar[s], parity);
+
+    const unsigned any = __ballot_sync(0xffffffffu, act != ACT_NONE);
+    if (any) {
+      if (mt && act == ACT_UPDATE) {
+        const double* mp = st + LY::TILE_DOUBLES + lane * a.meas_stride;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) meas[k] = mp[k];
+        if (MT::M == 6) {
+#pragma unroll
+          for (int k = 3; k < 7; ++k) meas[k] = mp[k];
+        }
+      }
+      if (act != ACT_NONE) {
+        step_lane<TYPE>(st, lane, act, dt, meas, a.Qtab + (size_t)cls * MT::N * MT::N, a.Rtab + (size_t)cls * MT::M * MT::M);
+        if (a.clear_action) a.action[slot] = 0;
+      }
+      fence_proxy_async();   // generic-proxy writes of the stage -> visible to the bulk store
+      __syncwarp();
+      if (lane == 0) {
+        bulk_s2g(a.tiles + (size_t)tile * LY::TILE_DOUBLES, st, LY::TILE_BYTES);
+        bulk_commit();
+        if (a.clear_action) a.tile_flag[tile] = 0;
+      }
+    } else {
+      __syncwarp();
+    }
+  }
+  if (lane == 0) bulk_wait<0>();
+}
+
+// -------------------------------------------------------------------------------------
+// pool maintenance kernels
+// -------------------------------------------------------------------------------------
+__device__ __forceinline__ int lower_bound_u32(const uint32_t* __restrict__ a, int n, uint32_t key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// ids -> slots (-1 if absent)
+__global__ void lookup_slots_kernel(const uint32_t* __restrict__ ids_sorted, int n_slots, const uint32_t* __restrict__ q,
+                                    long long n, int* __restrict__ slots) {
+  long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int s = lower_bound_u32(ids_sorted, n_slots, q[k]);
+  slots[k] = (s < n_slots && ids_sorted[s] == q[k]) ? s : -1;
+}
+
+// initial state of one new target (constructors of src/types/*.cpp + KalmanFilterInterface::init,
+// src/kalman.cpp:16-21): x0 from (p0,v0,a0), P = scale*P0[cls], t = t0, n_meas = 0, prev_rpy = 0 (H3).
+struct AddData {
+  const uint32_t* ids;
+  const uint16_t* cls;
+  const double* t0;
+  const double* p0;      // [n][7]
+  const double* v0;      // [n][6] or nullptr
+  const double* a0;      // [n][6] or nullptr
+  const double* scale;   // [n] or nullptr
+};
+
+struct ColdArrays {
+  uint32_t* ids;
+  uint16_t* cls;
+  double* last_meas;   // last measurement stamp [s], 0 = never (Measurement::last_meas_time_)
+  double* meas;        // [slot][7] last measurement (TargetInterface::measured_pose_)
+};
+
+template <int TYPE>
+__device__ __forceinline__ void init_slot(double* tiles, const ColdArrays& cold, int slot, const AddData& ad, long long k,
+                                          const double* __restrict__ P0tab) {
+  using MT = Model<TYPE>;
+  using LY = Layout<TYPE>;
+  constexpr int N = MT::N;
+  double* rec = tiles + (size_t)(slot / TILE) * LY::TILE_DOUBLES + (slot % TILE);
+  const double* p0 = ad.p0 + 7 * k;
+  double x[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) x[i] = 0.0;
+  if (TYPE == UNIFORM_VELOCITY || TYPE == UNIFORM_ACCELERATION) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      x[i] = p0[i];
+      x[3 + i] = ad.v0 ? ad.v0[6 * k + i] : 0.0;
+      if (TYPE == UNIFORM_ACCELERATION) x[6 + i] = ad.a0 ? ad.a0[6 * k + i] : 0.0;
+    }
+  } else {
+    // pose7dToPose6d (geometry.hpp:619-628)
+    Quat q{p0[3], p0[4], p0[5], p0[6]};
+    quat_normalize(q);
+    double rpy[3];
+    quat_to_rpy(q, rpy);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { x[i] = p0[i]; x[3 + i] = rpy[i]; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      x[6 + i] = ad.v0 ? ad.v0[6 * k + i] : 0.0;
+      if (TYPE == ANGULAR_RATES) x[12 + i] = ad.a0 ? ad.a0[6 * k + i] : 0.0;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) rec[(LY::F_X + i) * TILE] = x[i];
+  const int c = ad.cls ? (int)ad.cls[k] : 0;
+  const double sc = ad.scale ? ad.scale[k] : 1.0;
+  const double* P0 = P0tab + (size_t)c * N * N;
+  for (int e = 0; e < N * N; ++e) rec[(LY::F_P + e) * TILE] = ad.scale ? sc * P0[e] : P0[e];
+  rec[LY::F_T * TILE] = ad.t0 ? ad.t0[k] : 0.0;
+  reinterpret_cast<long long*>(rec)[LY::F_NMEAS * TILE] = 0;
+  for (int e = 0; e < MT::NPREV; ++e) rec[(LY::F_PREV + e) * TILE] = 0.0;
+  cold.ids[slot] = ad.ids[k];
+  cold.cls[slot] = (uint16_t)c;
+  cold.last_meas[slot] = 0.0;
+  // initPose(measured_pose_) (src/target_interface.cpp:25)
+  for (int e = 0; e < 7; ++e) cold.meas[(size_t)slot * 7 + e] = (e == 6) ? 1.0 : 0.0;
+}
+
+// append path: new targets occupy slots [base, base+n)
+template <int TYPE>
+__global__ void init_append_kernel(double* tiles, ColdArrays cold, int base, AddData ad, long long n, const double* P0tab) {
+  long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  init_slot<TYPE>(tiles, cold, base + (int)k, ad, k, P0tab);
+}
+
+// alive[s] = 1 for all, then 0 for listed slots
+__global__ void fill_i32_kernel(int* a, int n, int v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+__global__ void clear_listed_kernel(int* alive, const int* slots, long long n) {
+  long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k < n && slots[k] >= 0) alive[slots[k]] = 0;
+}
+
+// merge ranks: surviving old slot s -> dest = pos[s] + #(new ids < id[s])
+__global__ void map_existing_kernel(int n_old, const int* __restrict__ alive, const int* __restrict__ pos,
+                                    const uint32_t* __restrict__ old_ids, const uint32_t* __restrict__ add_ids, int n_add,
+                                    int* __restrict__ srcmap) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_old || !alive[s]) return;
+  int d = pos[s] + (n_add ? lower_bound_u32(add_ids, n_add, old_ids[s]) : 0);
+  srcmap[d] = s;
+}
+// new id k -> dest = k + #(surviving old ids < new id)
+__global__ void map_new_kernel(int n_add, const uint32_t* __restrict__ add_ids, const uint32_t* __restrict__ old_ids, int n_old,
+                               const int* __restrict__ pos, int total_alive, int* __restrict__ srcmap) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_add) return;
+  int e = lower_bound_u32(old_ids, n_old, add_ids[k]);
+  int before = (e < n_old) ? pos[e] : total_alive;
+  srcmap[k + before] = -1 - k;
+}
+
+// stable gather of every field of every surviving target into the other buffer + init of new ones
+template <int TYPE>
+__global__ void rebuild_kernel(int n_new, const int* __restrict__ srcmap, const double* __restrict__ old_tiles, ColdArrays old_cold,
+                               double* __restrict__ new_tiles, ColdArrays new_cold, AddData ad, const double* P0tab) {
+  using LY = Layout<TYPE>;
+  int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n_new) return;
+  int s = srcmap[d];
+  if (s >= 0) {
+    const double* src = old_tiles + (size_t)(s / TILE) * LY::TILE_DOUBLES + (s % TILE);
+    double* dst = new_tiles + (size_t)(d / TILE) * LY::TILE_DOUBLES + (d % TILE);
+#pragma unroll 8
+    for (int f = 0; f < LY::NF; ++f) dst[f * TILE] = src[f * TILE];
+    new_cold.ids[d] = old_cold.ids[s];
+    new_cold.cls[d] = old_cold.cls[s];
+    new_cold.last_meas[d] = old_cold.last_meas[s];
+#pragma unroll
+    for (int e = 0; e < 7; ++e) new_cold.meas[(size_t)d * 7 + e] = old_cold.meas[(size_t)s * 7 + e];
+  } else {
+    init_slot<TYPE>(new_tiles, new_cold, d, ad, (long long)(-1 - s), P0tab);
+  }
+}
+
+// sparse tick: op k -> per-slot action / dt / measurement; tiles touched for the first time are
+// appended to tile_list (counters[0] = #tiles, counters[1] = #ops applied).  One op per id per call.
+__global__ void scatter_ops_kernel(const uint32_t* __restrict__ ids_sorted, int n_slots, long long n, const uint32_t* __restrict__ q,
+                                   const double* __restrict__ dt, double dt_scalar, const double* __restrict__ meas,
+                                   const uint8_t* __restrict__ action, uint8_t* act_slot, double* dt_slot, double* meas_slot,
+                                   uint8_t* tile_flag, int* tile_list, int* counters) {
+  long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int a = action ? (int)action[k] : ACT_UPDATE;
+  if (a == ACT_NONE) return;
+  int s = lower_bound_u32(ids_sorted, n_slots, q[k]);
+  if (s >= n_slots || ids_sorted[s] != q[k]) return;
+  act_slot[s] = (uint8_t)a;
+  dt_slot[s] = dt ? dt[k] : dt_scalar;
+  if (a == ACT_UPDATE) {
+#pragma unroll
+    for (int e = 0; e < 7; ++e) meas_slot[(size_t)s * 7 + e] = meas[(size_t)k * 7 + e];
+  }
+  // byte flags packed four to a word: claim the tile with an atomicOr on its byte
+  const int tile = s / TILE;
+  unsigned* w = reinterpret_cast<unsigned*>(tile_flag) + (tile >> 2);
+  const unsigned bit = 1u << ((tile & 3) * 8);
+  const unsigned old = atomicOr(w, bit);
+  if (!(old & bit)) tile_list[atomicAdd(&counters[0], 1)] = tile;
+  atomicAdd(&counters[1], 1);
+}
+
+// measured_pose_ refresh of a masked dense host tick (src/target_interface.cpp:142-146)
+__global__ void copy_meas_masked_kernel(double* __restrict__ dst, const double* __restrict__ src, const uint8_t* __restrict__ action, int n) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n || action[s] != ACT_UPDATE) return;
+#pragma unroll
+  for (int e = 0; e < 7; ++e) dst[(size_t)s * 7 + e] = src[(size_t)s * 7 + e];
+}
+// initPose (utils.hpp:64-72): [0 0 0 | 0 0 0 1]
+__global__ void init_pose_kernel(double* pose, long long n) {
+  long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  for (int e = 0; e < 7; ++e) pose[k * 7 + e] = (e == 6) ? 1.0 : 0.0;
+}
+
+// dense host-API tick: remember the applied measurement as measured_pose_ (stride 7 only)
+__global__ void fill_dt_kernel(double* dt_slot, int n, double v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dt_slot[i] = v;
+}
+
+// read-back gathers -------------------------------------------------------------------
+template <int TYPE>
+__global__ void gather_state_kernel(const double* __restrict__ tiles, const ColdArrays cold, const int* __restrict__ slots, long long n,
+                                    double* x, double* P, double* t, long long* n_meas, double* prev, double* mpose) {
+  using MT = Model<TYPE>;
+  using LY = Layout<TYPE>;
+  long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int s = slots ? slots[k] : (int)k;
+  if (s < 0) return;
+  const double* rec = tiles + (size_t)(s / TILE) * LY::TILE_DOUBLES + (s % TILE);
+  if (x) for (int i = 0; i < MT::N; ++i) x[k * MT::N + i] = rec[(LY::F_X + i) * TILE];
+  if (P) for (int e = 0; e < MT::N * MT::N; ++e) P[k * MT::N * MT::N + e] = rec[(LY::F_P + e) * TILE];
+  if (t) t[k] = rec[LY::F_T * TILE];
+  if (n_meas) n_meas[k] = reinterpret_cast<const long long*>(rec)[LY::F_NMEAS * TILE];
+  if (prev) for (int e = 0; e < 3; ++e) prev[k * 3 + e] = (MT::NPREV ? rec[(LY::F_PREV + (MT::NPREV ? e : 0)) * TILE] : 0.0);
+  if (mpose) for (int e = 0; e < 7; ++e) mpose[k * 7 + e] = cold.meas[(size_t)s * 7 + e];
+}
+
+template <int TYPE>
+__global__ void gather_estimates_kernel(const double* __restrict__ tiles, const int* __restrict__ slots, long long n,
+                                        const double* __restrict__ t1, double* pose, double* twist, double* acc, double* pose6,
+                                        uint8_t* found, int rec13) {
+  using MT = Model<TYPE>;
+  using LY = Layout<TYPE>;
+  long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int s = slots ? slots[k] : (int)k;
+  if (found) found[k] = (s >= 0);
+  if (s < 0) return;
+  const double* rec = tiles + (size_t)(s / TILE) * LY::TILE_DOUBLES + (s % TILE);
+  double x[MT::N];
+#pragma unroll
+  for (int i = 0; i < MT::N; ++i) x[i] = rec[(LY::F_X + i) * TILE];
+  const double t = rec[LY::F_T * TILE];
+  double po[7], tw[6], ac[6], p6[6];
+  derive_outputs<TYPE>(x, t, t1 != nullptr, t1 ? t1[k] : 0.0, po, tw, ac, p6);
+  if (rec13) {   // [n][13] = pose7 | twist6
+    for (int e = 0; e < 7; ++e) pose[k * 13 + e] = po[e];
+    for (int e = 0; e < 6; ++e) pose[k * 13 + 7 + e] = tw[e];
+    return;
+  }
+  if (pose) for (int e = 0; e < 7; ++e) pose[k * 7 + e] = po[e];
+  if (twist) for (int e = 0; e < 6; ++e) twist[k * 6 + e] = tw[e];
+  if (acc) for (int e = 0; e < 6; ++e) acc[k * 6 + e] = ac[e];
+  if (pose6) for (int e = 0; e < 6; ++e) pose6[k * 6 + e] = p6[e];
+}
+
+// expiry ---------------------------------------------------------------------------------
+// toSec (utils.hpp:59-62) with explicit round-to-nearest mul/add: never contracted to FMA (H5)
+__device__ __forceinline__ double to_sec_rn(uint32_t sec, uint32_t nsec) {
+  return __dadd_rn(__uint2double_rn(sec), __dmul_rn(1e-9, __uint2double_rn(nsec)));
+}
+__global__ void set_stamps_kernel(const uint32_t* __restrict__ ids_sorted, int n_slots, long long n, const uint32_t* __restrict__ q,
+                                  const uint32_t* __restrict__ sec, const uint32_t* __restrict__ nsec, double* last_meas) {
+  long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int s = lower_bound_u32(ids_sorted, n_slots, q[k]);
+  if (s >= n_slots || ids_sorted[s] != q[k]) return;
+  last_meas[s] = to_sec_rn(sec[k], nsec[k]);
+}
+// alive[s] = !(last > 0.0 && (now - last) >= timeout)   (src/target_manager_ros.cpp:67)
+__global__ void expire_flags_kernel(const double* __restrict__ last_meas, int n_slots, double now, double timeout, int* alive) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  const double last = last_meas[s];
+  const bool expired = (last > 0.0) && (__dsub_rn(now, last) >= timeout);
+  alive[s] = expired ? 0 : 1;
+}
+__global__ void collect_erased_kernel(const int* __restrict__ alive, const int* __restrict__ pos, const uint32_t* __restrict__ ids,
+                                      int n_slots, uint32_t* erased) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots || alive[s]) return;
+  erased[s - pos[s]] = ids[s];
+}
+
+// -------------------------------------------------------------------------------------
+// Batched IntersectionSolver (src/intersection_solver.cpp:42-124).
+// Roots of the quartic: Aberth-Ehrlich simultaneous iteration in complex FP64 (the reference
+// uses Eigen's companion-matrix QR; both are backward stable -- they differ only for
+// near-multiple roots), then the reference's selection rule: smallest real part
+// among roots with |imag| < 1e-10, -1 if none / leading coefficient 0 / negative.
+// -------------------------------------------------------------------------------------
+struct Cplx { double re, im; };
+__device__ __forceinline__ Cplx cadd(Cplx a, Cplx b) { return {a.re + b.re, a.im + b.im}; }
+__device__ __forceinline__ Cplx csub(Cplx a, Cplx b) { return {a.re - b.re, a.im - b.im}; }
+__device__ __forceinline__ Cplx cmul(Cplx a, Cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__device__ __forceinline__ Cplx cdiv(Cplx a, Cplx b) {
+  // Smith's algorithm
+  if (fabs(b.re) >= fabs(b.im)) {
+    double r = b.im / b.re, d = b.re + b.im * r;
+    return {(a.re + a.im * r) / d, (a.im - a.re * r) / d};
+  }
+  double r = b.re / b.im, d = b.re * r + b.im;
+  return {(a.re * r + a.im) / d, (a.im * r - a.re) / d};
+}
+__device__ __forceinline__ double cabs2(Cplx a) { return a.re * a.re + a.im * a.im; }
+
+__device__ __forceinline__ void horner4(const double c[5], Cplx z, Cplx& p, Cplx& dp) {
+  p = {c[4], 0.0};
+  dp = {0.0, 0.0};
+#pragma unroll
+  for (int i = 3; i >= 0; --i) {
+    dp = cadd(cmul(dp, z), p);
+    p = cadd(cmul(p, z), Cplx{c[i], 0.0});
+  }
+}
+// (Eigen) poly_eval: Horner for |x| <= 1, reversed Horner otherwise
+__device__ __forceinline__ double poly_abs4(const double c[5], Cplx x) {
+  if (cabs2(x) <= 1.0) {
+    Cplx v{c[4], 0.0};
+#pragma unroll
+    for (int i = 3; i >= 0; --i) v = cadd(cmul(v, x), Cplx{c[i], 0.0});
+    return sqrt(cabs2(v));
+  }
+  Cplx inv = cdiv(Cplx{1.0, 0.0}, x);
+  Cplx v{c[0], 0.0};
+#pragma unroll
+  for (int i = 1; i <= 4; ++i) v = cadd(cmul(v, inv), Cplx{c[i], 0.0});
+  Cplx x2 = cmul(x, x), x4 = cmul(x2, x2);
+  return sqrt(cabs2(cmul(x4, v)));
+}
+
+__device__ inline double lowest_real_root4(const double c[5]) {
+  if (!(fabs(c[4]) > 0.0)) return -1.0;
+  // monic coefficients for the root bound / starting circle
+  const double b3 = c[3] / c[4], b2 = c[2] / c[4], b1 = c[1] / c[4], b0 = c[0] / c[4];
+  // Fujiwara bound
+  double rad = fabs(b3);
+  rad = fmax(rad, sqrt(fabs(b2)));
+  rad = fmax(rad, cbrt(fabs(b1)));
+  rad = fmax(rad, sqrt(sqrt(fabs(b0) * 0.5)));
+  rad = 2.0 * rad;
+  if (!(rad > 0.0)) rad = 1.0;
+  const double ctr = -b3 * 0.25;
+  Cplx z[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double sn, cs;
+    sincos(0.7 + 1.5707963267948966 * k, &sn, &cs);
+    z[k] = {ctr + 0.5 * rad * cs, 0.5 * rad * sn};
+  }
+  for (int iter = 0; iter < 200; ++iter) {
+    double worst = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      Cplx p, dp;
+      horner4(c, z[k], p, dp);
+      if (p.re == 0.0 && p.im == 0.0) continue;
+      if (dp.re == 0.0 && dp.im == 0.0) { z[k].re += 1e-3 * rad; z[k].im += 1e-3 * rad; worst = 1.0; continue; }
+      Cplx w = cdiv(p, dp);
+      Cplx ssum{0.0, 0.0};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j == k) continue;
+        Cplx d = csub(z[k], z[j]);
+        if (d.re == 0.0 && d.im == 0.0) d = {1e-300, 1e-300};
+        ssum = cadd(ssum, cdiv(Cplx{1.0, 0.0}, d));
+      }
+      Cplx den = csub(Cplx{1.0, 0.0}, cmul(w, ssum));
+      Cplx dz = (den.re == 0.0 && den.im == 0.0) ? w : cdiv(w, den);
+      z[k] = csub(z[k], dz);
+      const double rel = sqrt(cabs2(dz)) / fmax(sqrt(cabs2(z[k])), 1e-300);
+      worst = fmax(worst, rel);
+    }
+    if (worst < 4e-16) break;
+  }
+  // (Eigen 3.4) clean imaginary noise of real roots
+  const double coarse_prec = 4096.0 * 2.220446049250313e-16;   // 4^(5+1) * eps
+  bool found = false;
+  double best = 0.0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (fabs(z[k].im) <= fabs(z[k].re) * coarse_prec) {
+      Cplx r{z[k].re, 0.0};
+      if (poly_abs4(c, r) <= poly_abs4(c, z[k])) z[k] = r;
+    }
+    if (fabs(z[k].im) < 1e-10) {
+      if (!found) { found = true; best = z[k].re; }
+      else if (z[k].re < best) best = z[k].re;
+    }
+  }
+  if (!found) return -1.0;
+  return best;
+}
+
+struct IsolverState {
+  long long n_streams;
+  unsigned L;            // filters_length
+  double* prev_pose;     // [n_streams][7]
+  double* pos_win;       // [L][n_streams]
+  double* ang_win;       // [L][n_streams]
+  double* pos_sum;       // [n_streams]
+  double* ang_sum;
+  unsigned* idx;         // [n_streams] window_idx_
+  uint8_t* complete;     // [n_streams] filter_complete_
+};
+
+// MovingAvgFilter::update (utils.hpp:222-251) without the variance by-product (never read by
+// IntersectionSolver).  Returns the filtered value.
+__device__ __forceinline__ double mavg_update(double* win, double* sum, unsigned idx, unsigned L, bool complete_after,
+                                              long long stream, long long n_streams, double value) {
+  double s = *sum;
+  double* w = win + (size_t)idx * n_streams + stream;
+  s -= *w;
+  s += value;
+  *w = value;
+  *sum = s;
+  unsigned num = complete_after ? L : idx + 1;
+  return s / num;
+}
+
+template <int TYPE>
+__global__ void isolver_kernel(const double* __restrict__ tiles, const int* __restrict__ slots, const int* __restrict__ stream, long long n,
+                               const double* __restrict__ t1, const double* __restrict__ origin, const double* __restrict__ radius,
+                               const double* __restrict__ pos_th, const double* __restrict__ ang_th, IsolverState st, double* delta_out,
+                               double* pose_out, uint8_t* conv_out) {
+  using MT = Model<TYPE>;
+  using LY = Layout<TYPE>;
+  long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int s = slots[k];
+  double delta = -1.0;
+  double pose[7] = {0, 0, 0, 0, 0, 0, 1};   // initPose(intersection_pose) (:99)
+  bool converged = false;
+  if (s >= 0) {   // target exists (:44)
+    const double* rec = tiles + (size_t)(s / TILE) * LY::TILE_DOUBLES + (s % TILE);
+    double x[MT::N];
+#pragma unroll
+    for (int i = 0; i < MT::N; ++i) x[i] = rec[(LY::F_X + i) * TILE];
+    const double t = rec[LY::F_T * TILE];
+    double po[7], tw[6], ac[6];
+    derive_outputs<TYPE>(x, t, true, t1[k], po, tw, ac, nullptr);
+    const double px = po[0] - origin[3 * k + 0], py = po[1] - origin[3 * k + 1], pz = po[2] - origin[3 * k + 2];
+    const double vx = tw[0], vy = tw[1], vz = tw[2];
+    const double ax = ac[0], ay = ac[1], az = ac[2];
+    const double Rr = radius[k];
+    double c[5];   // :66-70
+    c[4] = 0.25 * (ax * ax + ay * ay + az * az);
+    c[3] = vx * ax + vy * ay + vz * az;
+    c[2] = vx * vx + vy * vy + vz * vz + px * ax + py * ay + pz * az;
+    c[1] = 2 * (px * vx + py * vy + pz * vz);
+    c[0] = px * px + py * py + pz * pz - Rr * Rr;
+    delta = lowest_real_root4(c);
+    if (delta < 0) delta = -1.0;
+    if (pose_out && delta > -1.0) {   // :102-121
+      derive_outputs<TYPE>(x, t, true, delta + t1[k], pose, nullptr, nullptr, nullptr);
+      const long long sidx = stream ? stream[k] : k;
+      double* prev = st.prev_pose + sidx * 7;
+      const double dx = pose[0] - prev[0], dy = pose[1] - prev[1], dz = pose[2] - prev[2];
+      const double pos_error = sqrt(dx * dx + dy * dy + dz * dz);
+      Quat q1{pose[3], pose[4], pose[5], pose[6]}, q2{prev[3], prev[4], prev[5], prev[6]};
+      quat_normalize(q1);
+      quat_normalize(q2);
+      // computeQuaternionErrorAngle (geometry.hpp:630-657): q1 * q2^-1, normalise, 2 acos(w)
+      const double n2 = q2.x * q2.x + q2.y * q2.y + q2.z * q2.z + q2.w * q2.w;
+      Quat qi{-q2.x / n2, -q2.y / n2, -q2.z / n2, q2.w / n2};
+      Quat qe = quat_mul(q1, qi);
+      quat_normalize(qe);
+      const double ang_error = fabs(wrap_min_max(2 * acos(qe.w), -TE_PI, TE_PI));
+      const unsigned idx = st.idx[sidx];
+      bool complete = st.complete[sidx] != 0;
+      if (!complete && idx == st.L - 1) complete = true;
+      const double pf = mavg_update(st.pos_win, st.pos_sum + sidx, idx, st.L, complete, sidx, st.n_streams, pos_error);
+      const double af = mavg_update(st.ang_win, st.ang_sum + sidx, idx, st.L, complete, sidx, st.n_streams, ang_error);
+      st.idx[sidx] = (idx + 1) % st.L;
+      st.complete[sidx] = complete ? 1 : 0;
+#pragma unroll
+      for (int e = 0; e < 7; ++e) prev[e] = pose[e];
+      if (pf <= pos_th[k] && af <= ang_th[k]) converged = true;
+    }
+  }
+  if (delta_out) delta_out[k] = delta;
+  if (pose_out) {
+#pragma unroll
+    for (int e = 0; e < 7; ++e) pose_out[k * 7 + e] = pose[e];
+  }
+  if (conv_out) conv_out[k] = converged ? 1 : 0;
+}
+
+}  // namespace te

@@ -1,0 +1,1017 @@
+// te_pool.cu -- host side of the thin extern "C" CUDA layer declared in include/te_pool.h.
+//
+// One te_pool = the targets of one model type on one device, stored as tiles of 32 targets
+// ([tile][field][lane], te_device.cuh Layout) in ascending-id slot order -- the iteration order of
+// the reference's std::map<unsigned, TargetInterface::Ptr> (include/target_estimation/
+// target_manager.hpp:36).  Add / erase rebuild the pool by a stable gather into the second buffer
+// (stream compaction; ids stay sorted); the append fast path (all new ids larger than every
+// existing id) writes in place.  There is no CPU fallback: every entry point needs a CUDA device.
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/te_pool.h"
+#include "te_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+#define CK(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e__ = (call);                                                                          \
+    if (e__ != cudaSuccess)                                                                            \
+      throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+
+inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+// grow-only device scratch, bump-allocated per call
+struct Arena {
+  std::vector<void*> chunks;
+  std::vector<size_t> caps;
+  size_t off = 0, want = 0;
+  void reset() {
+    if (chunks.size() > 1 || (chunks.size() == 1 && want > caps[0])) {
+      for (void* c : chunks) cudaFree(c);
+      chunks.clear();
+      caps.clear();
+    }
+    if (chunks.empty() && want) {
+      void* p = nullptr;
+      size_t cap = want + want / 2;
+      CK(cudaMalloc(&p, cap));
+      chunks.push_back(p);
+      caps.push_back(cap);
+    }
+    off = 0;
+    want = 0;
+  }
+  void* get(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    want += bytes;
+    if (!chunks.empty() && chunks.size() == 1 && off + bytes <= caps[0]) {
+      void* p = (char*)chunks[0] + off;
+      off += bytes;
+      return p;
+    }
+    void* p = nullptr;
+    CK(cudaMalloc(&p, bytes ? bytes : 256));
+    chunks.push_back(p);
+    caps.push_back(bytes);
+    return p;
+  }
+  template <class T> T* get_n(size_t n) { return (T*)get(n * sizeof(T)); }
+  void destroy() {
+    for (void* c : chunks) cudaFree(c);
+    chunks.clear();
+    caps.clear();
+  }
+};
+
+struct Buf {   // one generation of the pool's per-slot storage
+  double* tiles = nullptr;
+  te::ColdArrays cold{nullptr, nullptr, nullptr, nullptr};
+  size_t cap = 0;   // slots (multiple of 32)
+};
+
+}  // namespace
+
+struct te_pool {
+  int model = 0, device = 0;
+  int N = 0, M = 0, NF = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int n_sm = 148;
+  int variant = 0;
+  long long n = 0;   // live targets
+  Buf buf[2];
+  int cur = 0;
+  // per-slot work arrays (capacity wcap slots)
+  size_t wcap = 0;
+  uint8_t* action = nullptr;
+  double* dt_slot = nullptr;
+  uint8_t* tile_flag = nullptr;
+  int* tile_list = nullptr;
+  int* alive = nullptr;
+  int* pos = nullptr;
+  int* srcmap = nullptr;
+  int* d_counters = nullptr;   // [0] = n_work, [1] = applied
+  void* cub_tmp = nullptr;
+  size_t cub_bytes = 0;
+  // model classes
+  std::vector<std::vector<double>> hQ, hR, hP0;
+  double *dQ = nullptr, *dR = nullptr, *dP0 = nullptr;
+  int cls_cap = 0;
+  // host mirror of the sorted ids (lazy)
+  std::vector<uint32_t> h_ids;
+  bool h_ids_valid = true;
+  Arena arena;
+};
+
+struct te_isolver {
+  te_pool* pool = nullptr;
+  te::IsolverState st{};
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = 0;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) CK(cudaSetDevice(dev));
+  }
+  ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+size_t tile_doubles(const te_pool* p) { return (size_t)p->NF * te::TILE; }
+
+void free_buf(Buf& b) {
+  cudaFree(b.tiles);
+  cudaFree(b.cold.ids);
+  cudaFree(b.cold.cls);
+  cudaFree(b.cold.last_meas);
+  cudaFree(b.cold.meas);
+  b = Buf();
+}
+
+void alloc_buf(te_pool* p, Buf& b, size_t slots) {
+  slots = (slots + te::TILE - 1) / te::TILE * te::TILE;
+  if (slots == 0) slots = te::TILE;
+  CK(cudaMalloc(&b.tiles, slots / te::TILE * tile_doubles(p) * sizeof(double)));
+  CK(cudaMalloc(&b.cold.ids, slots * sizeof(uint32_t)));
+  CK(cudaMalloc(&b.cold.cls, slots * sizeof(uint16_t)));
+  CK(cudaMalloc(&b.cold.last_meas, slots * sizeof(double)));
+  CK(cudaMalloc(&b.cold.meas, slots * 7 * sizeof(double)));
+  b.cap = slots;
+  // pad lanes of the last tile are streamed by the step kernel: keep them finite
+  CK(cudaMemsetAsync(b.tiles, 0, slots / te::TILE * tile_doubles(p) * sizeof(double), p->stream));
+  CK(cudaMemsetAsync(b.cold.meas, 0, slots * 7 * sizeof(double), p->stream));
+  CK(cudaMemsetAsync(b.cold.last_meas, 0, slots * sizeof(double), p->stream));
+}
+
+// make sure the per-slot work arrays cover `slots`
+void ensure_work(te_pool* p, size_t slots) {
+  slots = (slots + te::TILE - 1) / te::TILE * te::TILE;
+  if (slots <= p->wcap) return;
+  size_t cap = std::max(slots, p->wcap + p->wcap / 2);
+  cap = (cap + te::TILE - 1) / te::TILE * te::TILE;
+  CK(cudaStreamSynchronize(p->stream));
+  cudaFree(p->action); cudaFree(p->dt_slot); cudaFree(p->tile_flag); cudaFree(p->tile_list);
+  cudaFree(p->alive); cudaFree(p->pos); cudaFree(p->srcmap);
+  CK(cudaMalloc(&p->action, cap));
+  CK(cudaMalloc(&p->dt_slot, cap * sizeof(double)));
+  CK(cudaMalloc(&p->tile_flag, cap / te::TILE + 4));
+  CK(cudaMalloc(&p->tile_list, cap / te::TILE * sizeof(int)));
+  CK(cudaMalloc(&p->alive, cap * sizeof(int)));
+  CK(cudaMalloc(&p->pos, cap * sizeof(int)));
+  CK(cudaMalloc(&p->srcmap, cap * sizeof(int)));
+  CK(cudaMemsetAsync(p->action, 0, cap, p->stream));
+  CK(cudaMemsetAsync(p->tile_flag, 0, cap / te::TILE + 4, p->stream));
+  p->wcap = cap;
+  size_t need = 0;
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, need, p->alive, p->pos, (int)cap, p->stream));
+  if (need > p->cub_bytes) {
+    cudaFree(p->cub_tmp);
+    CK(cudaMalloc(&p->cub_tmp, need));
+    p->cub_bytes = need;
+  }
+}
+
+// current buffer must hold `slots` (append path / reserve): grow by copy
+void ensure_cur_capacity(te_pool* p, size_t slots) {
+  Buf& b = p->buf[p->cur];
+  if (slots <= b.cap) return;
+  size_t cap = std::max(slots, b.cap + b.cap / 2);
+  Buf nb;
+  alloc_buf(p, nb, cap);
+  if (p->n > 0) {
+    size_t tiles = (size_t)cdiv(p->n, te::TILE);
+    CK(cudaMemcpyAsync(nb.tiles, b.tiles, tiles * tile_doubles(p) * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    CK(cudaMemcpyAsync(nb.cold.ids, b.cold.ids, p->n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, p->stream));
+    CK(cudaMemcpyAsync(nb.cold.cls, b.cold.cls, p->n * sizeof(uint16_t), cudaMemcpyDeviceToDevice, p->stream));
+    CK(cudaMemcpyAsync(nb.cold.last_meas, b.cold.last_meas, p->n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    CK(cudaMemcpyAsync(nb.cold.meas, b.cold.meas, p->n * 7 * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+  }
+  CK(cudaStreamSynchronize(p->stream));
+  free_buf(b);
+  b = nb;
+  ensure_work(p, b.cap);
+}
+
+void ensure_other_capacity(te_pool* p, size_t slots) {
+  Buf& b = p->buf[1 - p->cur];
+  if (slots <= b.cap && b.tiles) return;
+  CK(cudaStreamSynchronize(p->stream));
+  free_buf(b);
+  alloc_buf(p, b, std::max(slots, p->buf[p->cur].cap));
+  ensure_work(p, b.cap);
+}
+
+void sync_host_ids(te_pool* p) {
+  if (p->h_ids_valid) return;
+  p->h_ids.resize((size_t)p->n);
+  if (p->n) {
+    CK(cudaMemcpyAsync(p->h_ids.data(), p->buf[p->cur].cold.ids, p->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+  }
+  p->h_ids_valid = true;
+}
+
+void upload_classes(te_pool* p) {
+  const int nc = (int)p->hQ.size();
+  if (nc > p->cls_cap) {
+    CK(cudaStreamSynchronize(p->stream));
+    cudaFree(p->dQ); cudaFree(p->dR); cudaFree(p->dP0);
+    int cap = std::max(nc, std::max(4, p->cls_cap * 2));
+    CK(cudaMalloc(&p->dQ, (size_t)cap * p->N * p->N * sizeof(double)));
+    CK(cudaMalloc(&p->dR, (size_t)cap * p->M * p->M * sizeof(double)));
+    CK(cudaMalloc(&p->dP0, (size_t)cap * p->N * p->N * sizeof(double)));
+    p->cls_cap = cap;
+    for (int c = 0; c < nc; ++c) {
+      CK(cudaMemcpyAsync(p->dQ + (size_t)c * p->N * p->N, p->hQ[c].data(), p->N * p->N * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+      CK(cudaMemcpyAsync(p->dR + (size_t)c * p->M * p->M, p->hR[c].data(), p->M * p->M * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+      CK(cudaMemcpyAsync(p->dP0 + (size_t)c * p->N * p->N, p->hP0[c].data(), p->N * p->N * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    }
+  } else {
+    const int c = nc - 1;
+    CK(cudaMemcpyAsync(p->dQ + (size_t)c * p->N * p->N, p->hQ[c].data(), p->N * p->N * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(p->dR + (size_t)c * p->M * p->M, p->hR[c].data(), p->M * p->M * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(p->dP0 + (size_t)c * p->N * p->N, p->hP0[c].data(), p->N * p->N * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+  }
+  CK(cudaStreamSynchronize(p->stream));
+}
+
+template <class T> T* to_dev(te_pool* p, const T* host, size_t n) {
+  if (!host || !n) return nullptr;
+  T* d = p->arena.get_n<T>(n);
+  CK(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, p->stream));
+  return d;
+}
+
+// ---- step kernel launch -----------------------------------------------------------------
+template <int TYPE, int WARPS, int STAGES>
+void launch_step_t(te_pool* p, const te::StepArgs& a, int n_work_hint) {
+  auto kern = te::kf_step_kernel<TYPE, WARPS, STAGES>;
+  const size_t smem = te::step_smem_bytes<TYPE>(WARPS, STAGES);
+  static thread_local int configured_dev = -1;
+  static bool configured[64] = {false};
+  (void)configured_dev;
+  if (!configured[p->device & 63]) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[p->device & 63] = true;
+  }
+  int grid = std::min(p->n_sm, std::max(1, cdiv(n_work_hint, WARPS)));
+  kern<<<grid, WARPS * 32, smem, p->stream>>>(a);
+  CK(cudaGetLastError());
+}
+
+// variant -> (warps, stages) per model.  Stage bytes: UV 13056, UA 25344, AV 43008, AR 90624.
+void launch_step(te_pool* p, const te::StepArgs& a, int n_work_hint) {
+  const int v = p->variant;
+  switch (p->model) {
+    case te::UNIFORM_VELOCITY:
+      if (v == 1) launch_step_t<te::UNIFORM_VELOCITY, 16, 1>(p, a, n_work_hint);
+      else if (v == 2) launch_step_t<te::UNIFORM_VELOCITY, 4, 4>(p, a, n_work_hint);
+      else launch_step_t<te::UNIFORM_VELOCITY, 8, 2>(p, a, n_work_hint);
+      break;
+    case te::UNIFORM_ACCELERATION:
+      if (v == 1) launch_step_t<te::UNIFORM_ACCELERATION, 8, 1>(p, a, n_work_hint);
+      else if (v == 2) launch_step_t<te::UNIFORM_ACCELERATION, 2, 4>(p, a, n_work_hint);
+      else launch_step_t<te::UNIFORM_ACCELERATION, 4, 2>(p, a, n_work_hint);
+      break;
+    case te::ANGULAR_VELOCITIES:
+      if (v == 1) launch_step_t<te::ANGULAR_VELOCITIES, 5, 1>(p, a, n_work_hint);
+      else launch_step_t<te::ANGULAR_VELOCITIES, 2, 2>(p, a, n_work_hint);
+      break;
+    default:
+      if (v == 1) launch_step_t<te::ANGULAR_RATES, 1, 2>(p, a, n_work_hint);
+      else launch_step_t<te::ANGULAR_RATES, 2, 1>(p, a, n_work_hint);
+      break;
+  }
+}
+
+te::StepArgs base_args(te_pool* p) {
+  te::StepArgs a{};
+  Buf& b = p->buf[p->cur];
+  a.tiles = b.tiles;
+  a.n_slots = (int)p->n;
+  a.n_tiles = cdiv(p->n, te::TILE);
+  a.cls = b.cold.cls;
+  a.Qtab = p->dQ;
+  a.Rtab = p->dR;
+  return a;
+}
+
+void check_meas_stride(te_pool* p, int stride) {
+  if (stride == 7) return;
+  if (stride == 3 && p->M == 3) return;
+  throw std::invalid_argument("meas_stride must be 7 (pose) or 3 (xyz, UV/UA pools only)");
+}
+
+// ---- rebuild (stable gather of survivors + init of new targets) ----------------------------
+template <int TYPE>
+void rebuild_t(te_pool* p, int n_new, const te::AddData& ad) {
+  Buf& ob = p->buf[p->cur];
+  Buf& nb = p->buf[1 - p->cur];
+  te::rebuild_kernel<TYPE><<<cdiv(n_new, 128), 128, 0, p->stream>>>(n_new, p->srcmap, ob.tiles, ob.cold, nb.tiles, nb.cold, ad, p->dP0);
+  CK(cudaGetLastError());
+}
+void rebuild(te_pool* p, int n_new, const te::AddData& ad) {
+  switch (p->model) {
+    case te::UNIFORM_VELOCITY: rebuild_t<te::UNIFORM_VELOCITY>(p, n_new, ad); break;
+    case te::UNIFORM_ACCELERATION: rebuild_t<te::UNIFORM_ACCELERATION>(p, n_new, ad); break;
+    case te::ANGULAR_VELOCITIES: rebuild_t<te::ANGULAR_VELOCITIES>(p, n_new, ad); break;
+    default: rebuild_t<te::ANGULAR_RATES>(p, n_new, ad); break;
+  }
+}
+template <int TYPE>
+void init_append_t(te_pool* p, int base, const te::AddData& ad, long long n) {
+  Buf& b = p->buf[p->cur];
+  te::init_append_kernel<TYPE><<<cdiv(n, 128), 128, 0, p->stream>>>(b.tiles, b.cold, base, ad, n, p->dP0);
+  CK(cudaGetLastError());
+}
+void init_append(te_pool* p, int base, const te::AddData& ad, long long n) {
+  switch (p->model) {
+    case te::UNIFORM_VELOCITY: init_append_t<te::UNIFORM_VELOCITY>(p, base, ad, n); break;
+    case te::UNIFORM_ACCELERATION: init_append_t<te::UNIFORM_ACCELERATION>(p, base, ad, n); break;
+    case te::ANGULAR_VELOCITIES: init_append_t<te::ANGULAR_VELOCITIES>(p, base, ad, n); break;
+    default: init_append_t<te::ANGULAR_RATES>(p, base, ad, n); break;
+  }
+}
+
+// alive[] (n_old entries) is set on the device; compacts survivors, merges `n_add` sorted new ids.
+// Returns the number of survivors.
+int compact_and_merge(te_pool* p, const te::AddData& ad, const uint32_t* d_add_ids, int n_add, uint32_t* d_erased /*or null*/) {
+  const int n_old = (int)p->n;
+  int total_alive = 0;
+  if (n_old > 0) {
+    size_t tmp = p->cub_bytes;
+    CK(cub::DeviceScan::ExclusiveSum(p->cub_tmp, tmp, p->alive, p->pos, n_old, p->stream));
+    int last_pos = 0, last_alive = 0;
+    CK(cudaMemcpyAsync(&last_pos, p->pos + n_old - 1, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(&last_alive, p->alive + n_old - 1, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    total_alive = last_pos + last_alive;
+  }
+  const int n_new = total_alive + n_add;
+  if (d_erased && n_old > total_alive) {
+    te::collect_erased_kernel<<<cdiv(n_old, 256), 256, 0, p->stream>>>(p->alive, p->pos, p->buf[p->cur].cold.ids, n_old, d_erased);
+    CK(cudaGetLastError());
+  }
+  if (n_new == n_old && n_add == 0) return total_alive;   // nothing erased, nothing added
+  ensure_other_capacity(p, (size_t)n_new);
+  if (n_old > 0) {
+    te::map_existing_kernel<<<cdiv(n_old, 256), 256, 0, p->stream>>>(n_old, p->alive, p->pos, p->buf[p->cur].cold.ids, d_add_ids, n_add, p->srcmap);
+    CK(cudaGetLastError());
+  }
+  if (n_add > 0) {
+    te::map_new_kernel<<<cdiv(n_add, 256), 256, 0, p->stream>>>(n_add, d_add_ids, p->buf[p->cur].cold.ids, n_old, p->pos, total_alive, p->srcmap);
+    CK(cudaGetLastError());
+  }
+  if (n_new > 0) rebuild(p, n_new, ad);
+  p->cur = 1 - p->cur;
+  p->n = n_new;
+  p->h_ids_valid = false;
+  return total_alive;
+}
+
+int* lookup_slots(te_pool* p, const uint32_t* d_ids, long long n) {
+  int* slots = p->arena.get_n<int>((size_t)n);
+  te::lookup_slots_kernel<<<cdiv(n, 256), 256, 0, p->stream>>>(p->buf[p->cur].cold.ids, (int)p->n, d_ids, n, slots);
+  CK(cudaGetLastError());
+  return slots;
+}
+
+template <class F> int guarded(te_pool* p, F&& f) {
+  try {
+    if (!p) throw std::invalid_argument("null pool");
+    DeviceGuard g(p->device);
+    p->arena.reset();
+    return f();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+template <class F> long long guarded_ll(te_pool* p, F&& f) {
+  try {
+    if (!p) throw std::invalid_argument("null pool");
+    DeviceGuard g(p->device);
+    p->arena.reset();
+    return f();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* te_last_error(void) { return g_err.c_str(); }
+
+int te_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int te_model_dims(int model, int* n, int* m) {
+  if (model < 0 || model > 3) return -1;
+  if (n) *n = te::model_n(model);
+  if (m) *m = te::model_m(model);
+  return 0;
+}
+
+size_t te_model_bytes_per_step(int model) {
+  // read x, P, measurement (+prev rpy), write x, P (+prev rpy), + 32 B of t / n_meas
+  switch (model) {
+    case TE_UNIFORM_VELOCITY: return 728;
+    case TE_UNIFORM_ACCELERATION: return 1496;
+    case TE_ANGULAR_VELOCITIES: return 2632;
+    case TE_ANGULAR_RATES: return 5608;
+    default: return 0;
+  }
+}
+
+te_pool* te_pool_create(int model, int device, void* cuda_stream) {
+  te_pool* p = nullptr;
+  try {
+    if (model < 0 || model > 3) throw std::invalid_argument("unknown model type");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+      cudaGetLastError();
+      throw std::runtime_error("no CUDA device available: the target pool has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) throw std::invalid_argument("bad device index");
+    DeviceGuard g(device);
+    p = new te_pool();
+    p->model = model;
+    p->device = device;
+    p->N = te::model_n(model);
+    p->M = te::model_m(model);
+    p->NF = te::model_nf(model);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) throw std::runtime_error("te_pool needs an sm_100a (Blackwell) device");
+    p->n_sm = prop.multiProcessorCount;
+    if (cuda_stream) {
+      p->stream = (cudaStream_t)cuda_stream;
+    } else {
+      CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+      p->own_stream = true;
+    }
+    CK(cudaMalloc(&p->d_counters, 4 * sizeof(int)));
+    CK(cudaMemsetAsync(p->d_counters, 0, 4 * sizeof(int), p->stream));
+    return p;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    delete p;
+    return nullptr;
+  }
+}
+
+void te_pool_destroy(te_pool* p) {
+  if (!p) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(p->device);
+  cudaStreamSynchronize(p->stream);
+  free_buf(p->buf[0]);
+  free_buf(p->buf[1]);
+  cudaFree(p->action); cudaFree(p->dt_slot); cudaFree(p->tile_flag); cudaFree(p->tile_list);
+  cudaFree(p->alive); cudaFree(p->pos); cudaFree(p->srcmap); cudaFree(p->d_counters); cudaFree(p->cub_tmp);
+  cudaFree(p->dQ); cudaFree(p->dR); cudaFree(p->dP0);
+  p->arena.destroy();
+  if (p->own_stream) cudaStreamDestroy(p->stream);
+  cudaSetDevice(prev);
+  delete p;
+}
+
+int te_pool_set_stream(te_pool* p, void* cuda_stream) {
+  return guarded(p, [&] {
+    CK(cudaStreamSynchronize(p->stream));
+    if (p->own_stream) cudaStreamDestroy(p->stream);
+    p->own_stream = false;
+    if (cuda_stream) {
+      p->stream = (cudaStream_t)cuda_stream;
+    } else {
+      CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+      p->own_stream = true;
+    }
+    return 0;
+  });
+}
+
+int te_pool_sync(te_pool* p) {
+  return guarded(p, [&] {
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+  });
+}
+
+int te_pool_set_variant(te_pool* p, int variant) {
+  if (!p) return -1;
+  p->variant = variant;
+  return 0;
+}
+
+int te_pool_reserve(te_pool* p, size_t n_targets) {
+  return guarded(p, [&] {
+    if (!p->buf[p->cur].tiles) {
+      alloc_buf(p, p->buf[p->cur], n_targets);
+      ensure_work(p, p->buf[p->cur].cap);
+    } else {
+      ensure_cur_capacity(p, n_targets);
+    }
+    return 0;
+  });
+}
+
+long long te_pool_size(te_pool* p) { return p ? p->n : -1; }
+
+size_t te_pool_device_bytes(te_pool* p) {
+  if (!p) return 0;
+  size_t b = 0;
+  for (int i = 0; i < 2; ++i)
+    if (p->buf[i].tiles) b += p->buf[i].cap / te::TILE * tile_doubles(p) * 8 + p->buf[i].cap * (4 + 2 + 8 + 56);
+  b += p->wcap * (1 + 8 + 4 + 4 + 4) + p->wcap / te::TILE * 5 + p->cub_bytes;
+  return b;
+}
+
+int te_pool_register_class(te_pool* p, const double* Q, const double* R, const double* P0) {
+  return guarded(p, [&] {
+    if (!Q || !R || !P0) throw std::invalid_argument("null model matrix");
+    const size_t nn = (size_t)p->N * p->N, mm = (size_t)p->M * p->M;
+    for (size_t c = 0; c < p->hQ.size(); ++c)
+      if (!std::memcmp(p->hQ[c].data(), Q, nn * 8) && !std::memcmp(p->hR[c].data(), R, mm * 8) && !std::memcmp(p->hP0[c].data(), P0, nn * 8))
+        return (int)c;
+    if (p->hQ.size() >= 65535) throw std::runtime_error("too many model classes (max 65535)");
+    p->hQ.emplace_back(Q, Q + nn);
+    p->hR.emplace_back(R, R + mm);
+    p->hP0.emplace_back(P0, P0 + nn);
+    upload_classes(p);
+    return (int)p->hQ.size() - 1;
+  });
+}
+
+int te_pool_class_count(te_pool* p) { return p ? (int)p->hQ.size() : -1; }
+
+int te_pool_get_class(te_pool* p, int cls, double* Q, double* R, double* P0) {
+  if (!p || cls < 0 || cls >= (int)p->hQ.size()) return -1;
+  if (Q) std::memcpy(Q, p->hQ[cls].data(), p->hQ[cls].size() * 8);
+  if (R) std::memcpy(R, p->hR[cls].data(), p->hR[cls].size() * 8);
+  if (P0) std::memcpy(P0, p->hP0[cls].data(), p->hP0[cls].size() * 8);
+  return 0;
+}
+
+long long te_pool_add_batch(te_pool* p, long long n, const uint32_t* ids, const uint16_t* cls, const double* t0, const double* p0,
+                            const double* v0, const double* a0, const double* p0_scale) {
+  return guarded_ll(p, [&]() -> long long {
+    if (n <= 0) return 0;
+    if (!ids || !p0) throw std::invalid_argument("ids and p0 are required");
+    if (p->hQ.empty()) throw std::runtime_error("no model class registered");
+    sync_host_ids(p);
+    // order the batch by id (first occurrence wins), drop ids that already exist
+    std::vector<long long> ord((size_t)n);
+    std::iota(ord.begin(), ord.end(), 0LL);
+    bool sorted = true;
+    for (long long k = 1; k < n && sorted; ++k) sorted = ids[k - 1] < ids[k];
+    if (!sorted) std::stable_sort(ord.begin(), ord.end(), [&](long long a, long long b) { return ids[a] < ids[b]; });
+    std::vector<long long> keep;
+    keep.reserve((size_t)n);
+    const bool append_only = p->h_ids.empty() || ids[ord[0]] > p->h_ids.back();
+    for (long long k = 0; k < n; ++k) {
+      const long long s = ord[k];
+      if (!keep.empty() && ids[keep.back()] == ids[s]) continue;
+      if (!append_only && std::binary_search(p->h_ids.begin(), p->h_ids.end(), ids[s])) continue;   // "already exists"
+      if (cls && cls[s] >= p->hQ.size()) throw std::invalid_argument("unknown model class in add batch");
+      keep.push_back(s);
+    }
+    const long long na = (long long)keep.size();
+    if (na == 0) return 0;
+    const bool identity = sorted && na == n;
+    // gather payload in id order
+    std::vector<uint32_t> g_ids;
+    std::vector<uint16_t> g_cls;
+    std::vector<double> g_t0, g_p0, g_v0, g_a0, g_sc;
+    const uint32_t* s_ids = ids;
+    const uint16_t* s_cls = cls;
+    const double *s_t0 = t0, *s_p0 = p0, *s_v0 = v0, *s_a0 = a0, *s_sc = p0_scale;
+    if (!identity) {
+      g_ids.resize(na);
+      for (long long k = 0; k < na; ++k) g_ids[k] = ids[keep[k]];
+      s_ids = g_ids.data();
+      auto gather = [&](const double* src, int w, std::vector<double>& dst) -> const double* {
+        if (!src) return nullptr;
+        dst.resize((size_t)na * w);
+        for (long long k = 0; k < na; ++k) std::memcpy(&dst[(size_t)k * w], src + (size_t)keep[k] * w, w * 8);
+        return dst.data();
+      };
+      s_t0 = gather(t0, 1, g_t0);
+      s_p0 = gather(p0, 7, g_p0);
+      s_v0 = gather(v0, 6, g_v0);
+      s_a0 = gather(a0, 6, g_a0);
+      s_sc = gather(p0_scale, 1, g_sc);
+      if (cls) {
+        g_cls.resize(na);
+        for (long long k = 0; k < na; ++k) g_cls[k] = cls[keep[k]];
+        s_cls = g_cls.data();
+      }
+    }
+    te::AddData ad{};
+    ad.ids = to_dev(p, s_ids, na);
+    ad.cls = to_dev(p, s_cls, na);
+    ad.t0 = to_dev(p, s_t0, na);
+    ad.p0 = to_dev(p, s_p0, na * 7);
+    ad.v0 = to_dev(p, s_v0, na * 6);
+    ad.a0 = to_dev(p, s_a0, na * 6);
+    ad.scale = to_dev(p, s_sc, na);
+    if (append_only) {
+      if (!p->buf[p->cur].tiles) {
+        alloc_buf(p, p->buf[p->cur], (size_t)na);
+        ensure_work(p, p->buf[p->cur].cap);
+      } else {
+        ensure_cur_capacity(p, (size_t)(p->n + na));
+      }
+      init_append(p, (int)p->n, ad, na);
+      p->n += na;
+      p->h_ids.insert(p->h_ids.end(), s_ids, s_ids + na);
+    } else {
+      ensure_work(p, (size_t)p->n);
+      te::fill_i32_kernel<<<cdiv(p->n, 256), 256, 0, p->stream>>>(p->alive, (int)p->n, 1);
+      CK(cudaGetLastError());
+      compact_and_merge(p, ad, ad.ids, (int)na, nullptr);
+      std::vector<uint32_t> merged(p->h_ids.size() + (size_t)na);
+      std::merge(p->h_ids.begin(), p->h_ids.end(), s_ids, s_ids + na, merged.begin());
+      p->h_ids.swap(merged);
+      p->h_ids_valid = true;
+    }
+    CK(cudaStreamSynchronize(p->stream));   // host payload vectors go out of scope
+    return na;
+  });
+}
+
+long long te_pool_erase_batch(te_pool* p, long long n, const uint32_t* ids) {
+  return guarded_ll(p, [&]() -> long long {
+    if (n <= 0 || p->n == 0) return 0;
+    if (!ids) throw std::invalid_argument("null ids");
+    ensure_work(p, (size_t)p->n);
+    uint32_t* d_ids = to_dev(p, ids, n);
+    int* slots = lookup_slots(p, d_ids, n);
+    te::fill_i32_kernel<<<cdiv(p->n, 256), 256, 0, p->stream>>>(p->alive, (int)p->n, 1);
+    te::clear_listed_kernel<<<cdiv(n, 256), 256, 0, p->stream>>>(p->alive, slots, n);
+    CK(cudaGetLastError());
+    const long long n_old = p->n;
+    te::AddData ad{};
+    const int alive = compact_and_merge(p, ad, nullptr, 0, nullptr);
+    return n_old - alive;
+  });
+}
+
+long long te_pool_ids(te_pool* p, uint32_t* out, long long cap) {
+  return guarded_ll(p, [&]() -> long long {
+    sync_host_ids(p);
+    if (out) std::memcpy(out, p->h_ids.data(), (size_t)std::min<long long>(cap, p->n) * sizeof(uint32_t));
+    return p->n;
+  });
+}
+
+int te_pool_contains(te_pool* p, uint32_t id) {
+  return guarded(p, [&] {
+    sync_host_ids(p);
+    return std::binary_search(p->h_ids.begin(), p->h_ids.end(), id) ? 1 : 0;
+  });
+}
+
+int te_pool_step_dense(te_pool* p, double dt, const double* dev_meas, int meas_stride, const uint8_t* dev_action, int default_action) {
+  return guarded(p, [&] {
+    if (p->n == 0) return 0;
+    if (!(dt >= 0.0)) throw std::invalid_argument("dt must be >= 0 (assert of src/target_interface.cpp:150)");
+    te::StepArgs a = base_args(p);
+    a.dt = dt;
+    a.meas = dev_meas;
+    a.meas_stride = meas_stride;
+    a.action = const_cast<uint8_t*>(dev_action);
+    a.default_action = default_action;
+    if (dev_meas) {
+      check_meas_stride(p, meas_stride);
+      a.meas_tma = ((uintptr_t)dev_meas % 16 == 0) ? 1 : 0;
+    } else if (dev_action || default_action == TE_ACT_UPDATE) {
+      if (default_action == TE_ACT_UPDATE || dev_action) {
+        if (!dev_meas && default_action == TE_ACT_UPDATE) throw std::invalid_argument("update tick without measurements");
+      }
+    }
+    launch_step(p, a, a.n_tiles);
+    return 0;
+  });
+}
+
+int te_pool_step_dense_host(te_pool* p, double dt, const double* meas, int meas_stride, const uint8_t* action, int default_action) {
+  return guarded(p, [&] {
+    if (p->n == 0) return 0;
+    if (!(dt >= 0.0)) throw std::invalid_argument("dt must be >= 0");
+    te::StepArgs a = base_args(p);
+    a.dt = dt;
+    a.default_action = default_action;
+    if (meas) {
+      check_meas_stride(p, meas_stride);
+      if (meas_stride == 7) {
+        // measured_pose_ = meas (src/target_interface.cpp:142-146): land the batch in the pool's own record
+        // for UPDATE slots only -> stage, then the kernel-side copy would cost a pass; instead keep the
+        // staged batch as this tick's measurement block and refresh measured_pose_ with one D2D copy
+        // when every slot is updated.
+        double* d = to_dev(p, meas, (size_t)p->n * 7);
+        a.meas = d;
+        if (!action && default_action == TE_ACT_UPDATE)
+          CK(cudaMemcpyAsync(p->buf[p->cur].cold.meas, d, (size_t)p->n * 7 * 8, cudaMemcpyDeviceToDevice, p->stream));
+      } else {
+        a.meas = to_dev(p, meas, (size_t)p->n * meas_stride);
+      }
+      a.meas_stride = meas_stride;
+      a.meas_tma = 1;
+    } else if (!action && default_action == TE_ACT_UPDATE) {
+      throw std::invalid_argument("update tick without measurements");
+    }
+    if (action) a.action = to_dev(p, action, (size_t)p->n);
+    launch_step(p, a, a.n_tiles);
+    if (action && meas && meas_stride == 7) {
+      // masked refresh of measured_pose_ for the UPDATE slots
+      te::copy_meas_masked_kernel<<<cdiv(p->n, 256), 256, 0, p->stream>>>(p->buf[p->cur].cold.meas, a.meas, a.action, (int)p->n);
+      CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+  });
+}
+
+long long te_pool_step_ids(te_pool* p, long long n, const uint32_t* ids, const double* dt, double dt_scalar, const double* meas,
+                           const uint8_t* action) {
+  return guarded_ll(p, [&]() -> long long {
+    if (n <= 0 || p->n == 0) return 0;
+    if (!ids) throw std::invalid_argument("null ids");
+    if (!dt && !(dt_scalar >= 0.0)) throw std::invalid_argument("dt must be >= 0");
+    ensure_work(p, (size_t)p->n);
+    Buf& b = p->buf[p->cur];
+    uint32_t* d_ids = to_dev(p, ids, n);
+    double* d_dt = to_dev(p, dt, n);
+    double* d_meas = to_dev(p, meas, n * 7);
+    uint8_t* d_act = to_dev(p, action, n);
+    if (!meas) {
+      bool needs = !action;
+      if (action) for (long long k = 0; k < n && !needs; ++k) needs = action[k] == TE_ACT_UPDATE;
+      if (needs) throw std::invalid_argument("update ops without measurements");
+    }
+    CK(cudaMemsetAsync(p->d_counters, 0, 2 * sizeof(int), p->stream));
+    te::scatter_ops_kernel<<<cdiv(n, 256), 256, 0, p->stream>>>(b.cold.ids, (int)p->n, n, d_ids, d_dt, dt_scalar, d_meas, d_act, p->action,
+                                                                 p->dt_slot, b.cold.meas, p->tile_flag, p->tile_list, p->d_counters);
+    CK(cudaGetLastError());
+    te::StepArgs a = base_args(p);
+    a.tile_list = p->tile_list;
+    a.d_nwork = p->d_counters;
+    a.dt = dt_scalar;
+    a.dt_slot = p->dt_slot;
+    a.meas = b.cold.meas;
+    a.meas_stride = 7;
+    a.meas_tma = 1;
+    a.action = p->action;
+    a.default_action = TE_ACT_NONE;
+    a.clear_action = 1;
+    a.tile_flag = p->tile_flag;
+    launch_step(p, a, (int)std::min<long long>(n, a.n_tiles));
+    int applied = 0;
+    CK(cudaMemcpyAsync(&applied, p->d_counters + 1, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return applied;
+  });
+}
+
+int te_pool_predict_all(te_pool* p, double dt) { return te_pool_step_dense(p, dt, nullptr, 7, nullptr, TE_ACT_PREDICT); }
+
+int te_pool_read_state(te_pool* p, long long n, const uint32_t* ids, double* x, double* P, double* t, long long* n_meas, double* prev_rpy,
+                       double* measured_pose) {
+  return guarded(p, [&] {
+    if (n <= 0) return 0;
+    if (!ids && n != p->n) throw std::invalid_argument("ids == NULL requires n == pool size");
+    const int N = p->N;
+    int* slots = nullptr;
+    if (ids) slots = lookup_slots(p, to_dev(p, ids, n), n);
+    double* dx = x ? p->arena.get_n<double>((size_t)n * N) : nullptr;
+    double* dP = P ? p->arena.get_n<double>((size_t)n * N * N) : nullptr;
+    double* dt_ = t ? p->arena.get_n<double>((size_t)n) : nullptr;
+    long long* dn = n_meas ? p->arena.get_n<long long>((size_t)n) : nullptr;
+    double* dprev = prev_rpy ? p->arena.get_n<double>((size_t)n * 3) : nullptr;
+    double* dmp = measured_pose ? p->arena.get_n<double>((size_t)n * 7) : nullptr;
+    if (dx) CK(cudaMemsetAsync(dx, 0, (size_t)n * N * 8, p->stream));
+    if (dP) CK(cudaMemsetAsync(dP, 0, (size_t)n * N * N * 8, p->stream));
+    if (dt_) CK(cudaMemsetAsync(dt_, 0, (size_t)n * 8, p->stream));
+    if (dn) CK(cudaMemsetAsync(dn, 0, (size_t)n * 8, p->stream));
+    if (dprev) CK(cudaMemsetAsync(dprev, 0, (size_t)n * 24, p->stream));
+    if (dmp) CK(cudaMemsetAsync(dmp, 0, (size_t)n * 56, p->stream));
+    Buf& b = p->buf[p->cur];
+    const int g = cdiv(n, 128);
+    switch (p->model) {
+      case te::UNIFORM_VELOCITY: te::gather_state_kernel<te::UNIFORM_VELOCITY><<<g, 128, 0, p->stream>>>(b.tiles, b.cold, slots, n, dx, dP, dt_, dn, dprev, dmp); break;
+      case te::UNIFORM_ACCELERATION: te::gather_state_kernel<te::UNIFORM_ACCELERATION><<<g, 128, 0, p->stream>>>(b.tiles, b.cold, slots, n, dx, dP, dt_, dn, dprev, dmp); break;
+      case te::ANGULAR_VELOCITIES: te::gather_state_kernel<te::ANGULAR_VELOCITIES><<<g, 128, 0, p->stream>>>(b.tiles, b.cold, slots, n, dx, dP, dt_, dn, dprev, dmp); break;
+      default: te::gather_state_kernel<te::ANGULAR_RATES><<<g, 128, 0, p->stream>>>(b.tiles, b.cold, slots, n, dx, dP, dt_, dn, dprev, dmp); break;
+    }
+    CK(cudaGetLastError());
+    if (x) CK(cudaMemcpyAsync(x, dx, (size_t)n * N * 8, cudaMemcpyDeviceToHost, p->stream));
+    if (P) CK(cudaMemcpyAsync(P, dP, (size_t)n * N * N * 8, cudaMemcpyDeviceToHost, p->stream));
+    if (t) CK(cudaMemcpyAsync(t, dt_, (size_t)n * 8, cudaMemcpyDeviceToHost, p->stream));
+    if (n_meas) CK(cudaMemcpyAsync(n_meas, dn, (size_t)n * 8, cudaMemcpyDeviceToHost, p->stream));
+    if (prev_rpy) CK(cudaMemcpyAsync(prev_rpy, dprev, (size_t)n * 24, cudaMemcpyDeviceToHost, p->stream));
+    if (measured_pose) CK(cudaMemcpyAsync(measured_pose, dmp, (size_t)n * 56, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+  });
+}
+
+static void launch_gather_estimates(te_pool* p, const int* slots, long long n, const double* d_t1, double* pose, double* twist, double* acc,
+                                    double* pose6, uint8_t* found, int rec13) {
+  Buf& b = p->buf[p->cur];
+  const int g = cdiv(n, 128);
+  switch (p->model) {
+    case te::UNIFORM_VELOCITY: te::gather_estimates_kernel<te::UNIFORM_VELOCITY><<<g, 128, 0, p->stream>>>(b.tiles, slots, n, d_t1, pose, twist, acc, pose6, found, rec13); break;
+    case te::UNIFORM_ACCELERATION: te::gather_estimates_kernel<te::UNIFORM_ACCELERATION><<<g, 128, 0, p->stream>>>(b.tiles, slots, n, d_t1, pose, twist, acc, pose6, found, rec13); break;
+    case te::ANGULAR_VELOCITIES: te::gather_estimates_kernel<te::ANGULAR_VELOCITIES><<<g, 128, 0, p->stream>>>(b.tiles, slots, n, d_t1, pose, twist, acc, pose6, found, rec13); break;
+    default: te::gather_estimates_kernel<te::ANGULAR_RATES><<<g, 128, 0, p->stream>>>(b.tiles, slots, n, d_t1, pose, twist, acc, pose6, found, rec13); break;
+  }
+  CK(cudaGetLastError());
+}
+
+int te_pool_read_estimates(te_pool* p, long long n, const uint32_t* ids, const double* t1, double* pose7, double* twist6, double* acc6,
+                           double* pose6_internal, uint8_t* found) {
+  return guarded(p, [&] {
+    if (n <= 0) return 0;
+    if (!ids && n != p->n) throw std::invalid_argument("ids == NULL requires n == pool size");
+    int* slots = nullptr;
+    if (ids) slots = lookup_slots(p, to_dev(p, ids, n), n);
+    const double* d_t1 = to_dev(p, t1, n);
+    double* dpose = pose7 ? p->arena.get_n<double>((size_t)n * 7) : nullptr;
+    double* dtw = twist6 ? p->arena.get_n<double>((size_t)n * 6) : nullptr;
+    double* dac = acc6 ? p->arena.get_n<double>((size_t)n * 6) : nullptr;
+    double* dp6 = pose6_internal ? p->arena.get_n<double>((size_t)n * 6) : nullptr;
+    uint8_t* dfound = found ? p->arena.get_n<uint8_t>((size_t)n) : nullptr;
+    if (dpose) CK(cudaMemsetAsync(dpose, 0, (size_t)n * 56, p->stream));
+    if (dtw) CK(cudaMemsetAsync(dtw, 0, (size_t)n * 48, p->stream));
+    if (dac) CK(cudaMemsetAsync(dac, 0, (size_t)n * 48, p->stream));
+    if (dp6) CK(cudaMemsetAsync(dp6, 0, (size_t)n * 48, p->stream));
+    launch_gather_estimates(p, slots, n, d_t1, dpose, dtw, dac, dp6, dfound, 0);
+    if (pose7) CK(cudaMemcpyAsync(pose7, dpose, (size_t)n * 56, cudaMemcpyDeviceToHost, p->stream));
+    if (twist6) CK(cudaMemcpyAsync(twist6, dtw, (size_t)n * 48, cudaMemcpyDeviceToHost, p->stream));
+    if (acc6) CK(cudaMemcpyAsync(acc6, dac, (size_t)n * 48, cudaMemcpyDeviceToHost, p->stream));
+    if (pose6_internal) CK(cudaMemcpyAsync(pose6_internal, dp6, (size_t)n * 48, cudaMemcpyDeviceToHost, p->stream));
+    if (found) CK(cudaMemcpyAsync(found, dfound, (size_t)n, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+  });
+}
+
+int te_pool_estimates_dev(te_pool* p, double* dev_out) {
+  return guarded(p, [&] {
+    if (p->n == 0) return 0;
+    if (!dev_out) throw std::invalid_argument("null output");
+    launch_gather_estimates(p, nullptr, p->n, nullptr, dev_out, nullptr, nullptr, nullptr, nullptr, 1);
+    return 0;
+  });
+}
+
+const uint32_t* te_pool_dev_ids(te_pool* p) { return p ? p->buf[p->cur].cold.ids : nullptr; }
+
+int te_pool_set_stamps(te_pool* p, long long n, const uint32_t* ids, const uint32_t* sec, const uint32_t* nsec) {
+  return guarded(p, [&] {
+    if (n <= 0 || p->n == 0) return 0;
+    if (!ids || !sec || !nsec) throw std::invalid_argument("null stamp arrays");
+    uint32_t* d_ids = to_dev(p, ids, n);
+    uint32_t* d_sec = to_dev(p, sec, n);
+    uint32_t* d_nsec = to_dev(p, nsec, n);
+    Buf& b = p->buf[p->cur];
+    te::set_stamps_kernel<<<cdiv(n, 256), 256, 0, p->stream>>>(b.cold.ids, (int)p->n, n, d_ids, d_sec, d_nsec, b.cold.last_meas);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+  });
+}
+
+long long te_pool_expire(te_pool* p, uint32_t now_sec, uint32_t now_nsec, double timeout, uint32_t* erased_out, long long cap) {
+  return guarded_ll(p, [&]() -> long long {
+    if (p->n == 0) return 0;
+    ensure_work(p, (size_t)p->n);
+    const long long n_old = p->n;
+    // toSec on the host in the same non-contracted arithmetic (utils.hpp:59-62)
+    volatile double ns = 1e-9 * (double)now_nsec;
+    const double now = (double)now_sec + ns;
+    te::expire_flags_kernel<<<cdiv(n_old, 256), 256, 0, p->stream>>>(p->buf[p->cur].cold.last_meas, (int)n_old, now, timeout, p->alive);
+    CK(cudaGetLastError());
+    uint32_t* d_erased = p->arena.get_n<uint32_t>((size_t)n_old);
+    te::AddData ad{};
+    const int alive = compact_and_merge(p, ad, nullptr, 0, d_erased);
+    const long long n_er = n_old - alive;
+    if (n_er > 0 && erased_out && cap > 0)
+      CK(cudaMemcpyAsync(erased_out, d_erased, (size_t)std::min(cap, n_er) * sizeof(uint32_t), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return n_er;
+  });
+}
+
+// ---- batched IntersectionSolver -------------------------------------------------------------
+te_isolver* te_isolver_create(te_pool* p, long long n_streams, unsigned filters_length) {
+  te_isolver* s = nullptr;
+  try {
+    if (!p || n_streams <= 0 || filters_length == 0) throw std::invalid_argument("bad isolver arguments");
+    DeviceGuard g(p->device);
+    s = new te_isolver();
+    s->pool = p;
+    s->st.n_streams = n_streams;
+    s->st.L = filters_length;
+    CK(cudaMalloc(&s->st.prev_pose, (size_t)n_streams * 7 * 8));
+    CK(cudaMalloc(&s->st.pos_win, (size_t)n_streams * filters_length * 8));
+    CK(cudaMalloc(&s->st.ang_win, (size_t)n_streams * filters_length * 8));
+    CK(cudaMalloc(&s->st.pos_sum, (size_t)n_streams * 8));
+    CK(cudaMalloc(&s->st.ang_sum, (size_t)n_streams * 8));
+    CK(cudaMalloc(&s->st.idx, (size_t)n_streams * 4));
+    CK(cudaMalloc(&s->st.complete, (size_t)n_streams));
+    CK(cudaMemsetAsync(s->st.pos_win, 0, (size_t)n_streams * filters_length * 8, p->stream));
+    CK(cudaMemsetAsync(s->st.ang_win, 0, (size_t)n_streams * filters_length * 8, p->stream));
+    CK(cudaMemsetAsync(s->st.pos_sum, 0, (size_t)n_streams * 8, p->stream));
+    CK(cudaMemsetAsync(s->st.ang_sum, 0, (size_t)n_streams * 8, p->stream));
+    CK(cudaMemsetAsync(s->st.idx, 0, (size_t)n_streams * 4, p->stream));
+    CK(cudaMemsetAsync(s->st.complete, 0, (size_t)n_streams, p->stream));
+    te::init_pose_kernel<<<cdiv(n_streams, 256), 256, 0, p->stream>>>(s->st.prev_pose, n_streams);   // initPose (:39)
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(p->stream));
+    return s;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    if (s) te_isolver_destroy(s);
+    return nullptr;
+  }
+}
+
+void te_isolver_destroy(te_isolver* s) {
+  if (!s) return;
+  cudaFree(s->st.prev_pose); cudaFree(s->st.pos_win); cudaFree(s->st.ang_win); cudaFree(s->st.pos_sum);
+  cudaFree(s->st.ang_sum); cudaFree(s->st.idx); cudaFree(s->st.complete);
+  delete s;
+}
+
+int te_isolver_query(te_isolver* s, long long n, const uint32_t* ids, const int32_t* stream, const double* t1, const double* origin,
+                     const double* radius, const double* pos_th, const double* ang_th, double* delta_t, double* pose7, uint8_t* converged) {
+  if (!s) { g_err = "null isolver"; return -1; }
+  te_pool* p = s->pool;
+  return guarded(p, [&] {
+    if (n <= 0) return 0;
+    if (!ids || !t1 || !origin || !radius) throw std::invalid_argument("ids, t1, origin and radius are required");
+    if (pose7 && (!pos_th || !ang_th)) throw std::invalid_argument("thresholds are required with pose7");
+    if (pose7 && !stream && n > s->st.n_streams) throw std::invalid_argument("more queries than solver streams");
+    if (stream) for (long long k = 0; k < n; ++k) if (stream[k] < 0 || stream[k] >= s->st.n_streams) throw std::invalid_argument("bad stream index");
+    int* slots = p->n ? lookup_slots(p, to_dev(p, ids, n), n) : nullptr;
+    if (!slots) {
+      slots = p->arena.get_n<int>((size_t)n);
+      CK(cudaMemsetAsync(slots, 0xff, (size_t)n * sizeof(int), p->stream));
+    }
+    const int* d_stream = to_dev(p, stream, n);
+    const double* d_t1 = to_dev(p, t1, n);
+    const double* d_origin = to_dev(p, origin, n * 3);
+    const double* d_radius = to_dev(p, radius, n);
+    const double* d_pth = to_dev(p, pos_th, n);
+    const double* d_ath = to_dev(p, ang_th, n);
+    double* d_delta = delta_t ? p->arena.get_n<double>((size_t)n) : nullptr;
+    double* d_pose = pose7 ? p->arena.get_n<double>((size_t)n * 7) : nullptr;
+    uint8_t* d_conv = converged ? p->arena.get_n<uint8_t>((size_t)n) : nullptr;
+    Buf& b = p->buf[p->cur];
+    const int g = cdiv(n, 128);
+    switch (p->model) {
+      case te::UNIFORM_VELOCITY: te::isolver_kernel<te::UNIFORM_VELOCITY><<<g, 128, 0, p->stream>>>(b.tiles, slots, d_stream, n, d_t1, d_origin, d_radius, d_pth, d_ath, s->st, d_delta, d_pose, d_conv); break;
+      case te::UNIFORM_ACCELERATION: te::isolver_kernel<te::UNIFORM_ACCELERATION><<<g, 128, 0, p->stream>>>(b.tiles, slots, d_stream, n, d_t1, d_origin, d_radius, d_pth, d_ath, s->st, d_delta, d_pose, d_conv); break;
+      case te::ANGULAR_VELOCITIES: te::isolver_kernel<te::ANGULAR_VELOCITIES><<<g, 128, 0, p->stream>>>(b.tiles, slots, d_stream, n, d_t1, d_origin, d_radius, d_pth, d_ath, s->st, d_delta, d_pose, d_conv); break;
+      default: te::isolver_kernel<te::ANGULAR_RATES><<<g, 128, 0, p->stream>>>(b.tiles, slots, d_stream, n, d_t1, d_origin, d_radius, d_pth, d_ath, s->st, d_delta, d_pose, d_conv); break;
+    }
+    CK(cudaGetLastError());
+    if (delta_t) CK(cudaMemcpyAsync(delta_t, d_delta, (size_t)n * 8, cudaMemcpyDeviceToHost, p->stream));
+    if (pose7) CK(cudaMemcpyAsync(pose7, d_pose, (size_t)n * 56, cudaMemcpyDeviceToHost, p->stream));
+    if (converged) CK(cudaMemcpyAsync(converged, d_conv, (size_t)n, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+  });
+}
+
+}  // extern "C"

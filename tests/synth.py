@@ -1,0 +1,64 @@
+"""Seeded synthetic measurement streams generated ON THE HOST so that the oracle and the
+GPU see bit-identical inputs."""
+import numpy as np
+
+
+def quat_mul(a, b):
+    """Hamilton product, arrays [..., 4] in [x y z w] order."""
+    ax, ay, az, aw = a[..., 0], a[..., 1], a[..., 2], a[..., 3]
+    bx, by, bz, bw = b[..., 0], b[..., 1], b[..., 2], b[..., 3]
+    return np.stack([aw * bx + ax * bw + ay * bz - az * by,
+                     aw * by + ay * bw + az * bx - ax * bz,
+                     aw * bz + az * bw + ax * by - ay * bx,
+                     aw * bw - ax * bx - ay * by - az * bz], axis=-1)
+
+
+def rpy_to_quat(rpy):
+    r, p, y = rpy[..., 0] / 2, rpy[..., 1] / 2, rpy[..., 2] / 2
+    cr, sr, cp, sp, cy, sy = np.cos(r), np.sin(r), np.cos(p), np.sin(p), np.cos(y), np.sin(y)
+    q = np.stack([sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy,
+                  cr * cp * cy + sr * sp * sy], axis=-1)
+    return q / np.linalg.norm(q, axis=-1, keepdims=True)
+
+
+def make_streams(n_targets, n_ticks, dt, seed=0x7A26E7, accel=True, angular=True, miss_prob=0.05, noise=0.01):
+    """Returns meas [n_ticks, n_targets, 7], action [n_ticks, n_targets] (2 = update, 1 = predict),
+    p0_scale [n_targets].  Attitude: rpy(t) = rpy0 + rate * t with |pitch| kept < 1.1 rad (H4: away from the
+    gimbal branch), yaw/roll free to wrap so the unwrap logic is exercised."""
+    rng = np.random.default_rng(seed)
+    p0 = rng.uniform(-5, 5, (n_targets, 3))
+    v0 = rng.uniform(-1, 1, (n_targets, 3))
+    a0 = np.zeros((n_targets, 3))
+    if accel:
+        a0[:, 2] = -9.81
+    t = (np.arange(n_ticks) * dt)[:, None, None]
+    pos = p0[None] + v0[None] * t + 0.5 * a0[None] * t * t
+    pos = pos + rng.normal(0.0, noise, pos.shape)
+    meas = np.zeros((n_ticks, n_targets, 7))
+    meas[..., :3] = pos
+    if angular:
+        rpy0 = np.stack([rng.uniform(-3, 3, n_targets), rng.uniform(-0.6, 0.6, n_targets), rng.uniform(-3, 3, n_targets)], axis=-1)
+        rate = np.stack([rng.uniform(-2, 2, n_targets), rng.uniform(-0.3, 0.3, n_targets), rng.uniform(-2, 2, n_targets)], axis=-1)
+        tt = t[..., 0]
+        rpy = rpy0[None] + rate[None] * t
+        # pitch oscillates instead of growing: stays within +-1.1 rad
+        rpy[..., 1] = rpy0[None, :, 1] + 0.5 * np.sin(rate[None, :, 1] * 4 * tt)
+        meas[..., 3:7] = rpy_to_quat(rpy)
+    else:
+        meas[..., 6] = 1.0
+    action = np.where(rng.uniform(size=(n_ticks, n_targets)) < miss_prob, 1, 2).astype(np.uint8)
+    action[0] = 2   # the ROS tick updates with the init measurement on first sight (H10)
+    p0_scale = rng.uniform(0.5, 2.0, n_targets)
+    return meas, action, p0_scale
+
+
+def compare_h2(got, ref, rtol=1e-9, floor=1e-6):
+    """SURVEY.md H2 norm: |d| <= rtol * max(|ref_ij|, max|ref| * floor) per matrix/vector.  Returns the max
+    ratio |d| / bound (<= 1 passes)."""
+    got = np.asarray(got); ref = np.asarray(ref)
+    flat_ref = ref.reshape(ref.shape[0], -1)
+    flat_got = got.reshape(got.shape[0], -1)
+    scale = np.abs(flat_ref).max(axis=1, keepdims=True)
+    bound = rtol * np.maximum(np.abs(flat_ref), scale * floor)
+    bound = np.maximum(bound, 1e-300)
+    return float((np.abs(flat_got - flat_ref) / bound).max())
