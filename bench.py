@@ -1,0 +1,376 @@
+#!/usr/bin/env python3
+"""bench.py -- KF predict+update target-steps/sec on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port) on host cores
+
+One "step" = one tick of the hot path over every target of the pool: TargetManager::update(id, dt, meas) for
+each target (predict + update + t / n_meas bookkeeping; a Philox-free 5 % of the targets miss their measurement
+each tick and take the predict-only path, SURVEY.md 8(d) anti-cohort rule).  Workload: BASELINE.json configs[1]'s
+model and arithmetic (uniform-acceleration, FP64 predict+update per measurement tick on 1 B200) at a target count
+whose state (720 B/target) is far larger than the 126 MB L2, so every tick streams from HBM; the literal 10k-target
+case is L2-resident and launch-bound and is reported beside it under "c2_10k".
+
+value    : targets x steps / device time, inputs (measurements, action masks) resident in HBM.
+e2e      : same ticks through te_pool_step_dense_host (HOST pinned buffers -> H2D inside the timed region, then the
+           tick, then a D2H read of every target's estimated position).
+roofline : achieved = algorithmic bytes per launch (UA 1496 B per update step, 1456 B per
+           predict-only step) / average kernel duration (CUDA events on the pool's stream); peak = MEASURED_PEAKS.json.
+cpu_baseline : the oracle port (oracle/, Eigen-free restatement of the reference TargetManager path) on host cores.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+DT = 1.0 / 250.0
+METRIC = "kf_predict_update_target_steps_per_sec"
+UNIT = "target-steps/s"
+MODEL_SHORT = {"uniform_velocity": "UV", "uniform_acceleration": "UA", "angular_velocities": "AV", "angular_rates": "AR"}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="uniform_acceleration", choices=list(MODEL_SHORT))
+    ap.add_argument("--targets", type=int, default=0, help="targets per GPU (default: 4Mi for UV/UA, 1Mi for AV/AR)")
+    ap.add_argument("--variant", type=int, default=-1)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-small", action="store_true")
+    ap.add_argument("--allgather", action="store_true", help="also time the optional all-gather of estimates (N>1)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi style clock/throttle sampling through NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = False
+        self.sm = []
+        self.reasons = set()
+        self.sm_max = None
+        self.power = []
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+            }
+            while not self.stop_flag:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:
+                    pass
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.02)
+        except Exception as e:  # NVML missing: report that instead of inventing clocks
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2.0)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "power_w_max": max(self.power) if self.power else None, "samples": len(self.sm), "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_run(model_name, threads, seconds, n_targets=10000):
+    import ctypes as C
+    from tests import orc
+    import target_estimation_b200.pool as tp  # load_model only (pure python)
+    mtype, _, Q, R, P0 = tp.load_model(model_name)
+    L = orc.lib()
+    rng = np.random.default_rng(7)
+    meas = np.zeros((n_targets, 7))
+    meas[:, :3] = rng.uniform(-5, 5, (n_targets, 3))
+    meas[:, 6] = 1.0
+    Qc, Rc, Pc = orc.colmajor(Q), orc.colmajor(R), orc.colmajor(P0)
+    n, m = Q.shape[0], R.shape[0]
+    chk = C.c_double()
+
+    def run(ticks):
+        return L.orc_bench_steps(mtype, orc.ptr(Qc), n, orc.ptr(Rc), m, orc.ptr(Pc), n_targets, ticks, threads, DT, orc.ptr(meas), 0.05,
+                                 C.byref(chk))
+    t_probe = run(2)
+    ticks = max(2, int(seconds / max(t_probe / 2, 1e-9)))
+    t = run(ticks)
+    return {"value": n_targets * ticks / t, "ticks": ticks, "targets": n_targets, "seconds": t, "threads": threads}
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return
+    from tests import orc
+    cores = orc.lib().orc_hardware_threads()
+    K = max(1, args.steps)
+    per_step = max(0.5, min(20.0, 120.0 / (K + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_run(args.model, cores, per_step / 4)
+    vals, secs = [], 0.0
+    sample = None
+    for _ in range(K):
+        r = cpu_run(args.model, cores, per_step)
+        vals.append(r["value"]); secs += r["seconds"]
+        sample = "%d %s targets x %d ticks per step, one oracle TargetManager per thread sharded by id %% %d" % (
+            r["targets"], MODEL_SHORT[args.model], r["ticks"], cores)
+    v = float(np.mean(vals))
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": args.warmup,
+           "ms_per_step": 1e3 * secs / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "config": {"workload": "BASELINE configs[1]: %s FP64 predict+update per measurement tick" % MODEL_SHORT[args.model],
+                                           "model": args.model, "note": "reference cannot be compiled here (Eigen/yaml-cpp absent): "
+                                           "timed the Eigen-free oracle port of its TargetManager path (-O2), all host threads"},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# the CUDA arm
+# ------------------------------------------------------------------------------------------------------
+def make_pool(te, torch, model_name, n, rank, world, stream, variant):
+    mtype, _, Q, R, P0 = te.load_model(model_name)
+    pool = te.TargetPool(mtype, device=torch.cuda.current_device(), stream=stream.cuda_stream)
+    if variant >= 0:
+        pool.set_variant(variant)
+    pool.register_class(Q, R, P0)
+    pool.reserve(n)
+    rng = np.random.default_rng(0x7A26E7 + rank)
+    chunk = 1 << 20
+    p0_all = []
+    for s in range(0, n, chunk):
+        k = min(chunk, n - s)
+        ids = (np.arange(s, s + k, dtype=np.int64) * world + rank).astype(np.uint32)   # owner(id) = id mod G
+        p0 = np.zeros((k, 7))
+        p0[:, :3] = rng.uniform(-5, 5, (k, 3))
+        ang = rng.uniform(-1, 1, (k, 3)) * np.array([3.0, 1.0, 3.0])
+        from tests.synth import rpy_to_quat
+        p0[:, 3:7] = rpy_to_quat(ang)
+        scale = rng.uniform(0.5, 2.0, k)                                                # anti-cohort P0 scale (H6)
+        pool.add(ids, p0, p0_scale=scale)
+        p0_all.append(p0)
+    return pool, mtype, np.concatenate(p0_all)
+
+
+def make_inputs(torch, p0, n_sets, stride, miss_prob, seed):
+    """n_sets rotating device-resident measurement blocks [n][stride] + action masks [n] (uint8)."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    base = torch.from_numpy(p0).cuda()
+    meas, act = [], []
+    for k in range(n_sets):
+        m = base[:, :stride].clone()
+        m[:, :3] += 0.01 * torch.randn((base.shape[0], 3), dtype=torch.float64, device="cuda", generator=g) + 0.004 * (k + 1)
+        meas.append(m.contiguous())
+        u = torch.rand((base.shape[0],), device="cuda", generator=g)
+        act.append(torch.where(u < miss_prob, 1, 2).to(torch.uint8).contiguous())
+    return meas, act
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import target_estimation_b200 as te   # raises if the CUDA library is missing: no fallback
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    model = args.model
+    short = MODEL_SHORT[model]
+    n = args.targets or ((4 << 20) if short in ("UV", "UA") else (1 << 20))
+    K, W = args.steps, max(args.warmup, 3)
+    stream = torch.cuda.Stream()
+    pool, mtype, p0 = make_pool(te, torch, model, n, rank, world, stream, args.variant)
+    N, M = te.model_dims(mtype)
+    stride = 7
+    n_sets = 4
+    meas, act = make_inputs(torch, p0, n_sets, stride, 0.05, 1234 + rank)
+    n_upd = [int((a == 2).sum().item()) for a in act]
+    B_upd = te.bytes_per_step(mtype)
+    B_pred = B_upd - 8 * (7 if M == 6 else 3) - 16          # no measurement read, n_meas untouched
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def tick(k):
+        pool.step_dense(DT, meas[k % n_sets], stride, act[k % n_sets])
+
+    # ---- resident-input throughput -----------------------------------------------------------------
+    for k in range(W):
+        tick(k)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for k in range(K):
+        tick(k)
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.result()
+    ms = ev0.elapsed_time(ev1)
+    t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    value = n * world * K / (ms_max * 1e-3)
+    alg_bytes = sum(n_upd[k % n_sets] * B_upd + (n - n_upd[k % n_sets]) * B_pred for k in range(K)) / K
+    peak, peak_src = peaks()
+    achieved = alg_bytes / (ms / K * 1e-3) / 1e9
+
+    # ---- e2e: host buffers through the C-ABI ---------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_meas = [m.cpu().pin_memory() for m in meas[:2]]
+        h_act = [a.cpu().pin_memory() for a in act[:2]]
+        h_out = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+        Ke = max(3, min(K, 20))
+
+        def tick_host(k):
+            check = te.lib.te_pool_tick_host(pool._h, DT, h_meas[k % 2].data_ptr(), stride, h_act[k % 2].data_ptr(), 2, h_out.data_ptr())
+            if check < 0:
+                raise RuntimeError(te._lib.last_error())
+        for k in range(3):
+            tick_host(k)
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for k in range(Ke):
+            tick_host(k)
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ems = max(e0.elapsed_time(e1), wall * 1e3)     # host-synchronous API: wall clock covers the copies
+        t_e = torch.tensor([ems], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": n * world * Ke / (float(t_e.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * (stride * 8 + 1),
+               "d2h_bytes_per_step": n * 24, "steps": Ke, "ms_per_step": float(t_e.item()) / Ke,
+               "api": "te_pool_tick_host (pinned host meas[n][7] + action[n] in, est. position [n][3] out)"}
+
+    # ---- optional all-gather of estimate records (off the hot path) -----------------------------------
+    allgather = None
+    if args.allgather and world > 1:
+        rec = torch.empty((n, 13), dtype=torch.float64, device="cuda")
+        out = torch.empty((world * n, 13), dtype=torch.float64, device="cuda")
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                pool.estimates_dev(rec)
+                dist.all_gather_into_tensor(out, rec)
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            for _ in range(5):
+                pool.estimates_dev(rec)
+                dist.all_gather_into_tensor(out, rec)
+            a1.record(stream)
+        barrier()
+        ag = torch.tensor([a0.elapsed_time(a1) / 5], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ag, op=dist.ReduceOp.MAX)
+        allgather = {"ms": float(ag.item()), "bytes_per_rank": n * 104, "records": "pose7|twist6 per target",
+                     "bus_gbs": (world - 1) * n * 104 / (float(ag.item()) * 1e-3) / 1e9}
+
+    # ---- BASELINE configs[1] literally: 10k targets, L2-resident, launch-bound (reported, not the headline) ----
+    small = None
+    if rank == 0 and not args.no_small:
+        ns = 10000
+        sp, _, p0s = make_pool(te, torch, model, ns, 0, 1, stream, args.variant)
+        ms_, as_ = make_inputs(torch, p0s, 2, stride, 0.05, 99)
+        for k in range(20):
+            sp.step_dense(DT, ms_[k % 2], stride, as_[k % 2])
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        Ks = 1000
+        s0.record(stream)
+        for k in range(Ks):
+            sp.step_dense(DT, ms_[k % 2], stride, as_[k % 2])
+        s1.record(stream)
+        torch.cuda.synchronize()
+        sms = s0.elapsed_time(s1)
+        small = {"targets": ns, "ticks": Ks, "us_per_tick": 1e3 * sms / Ks, "value": ns * Ks / (sms * 1e-3), "unit": UNIT,
+                 "note": "state 7.2 MB is L2-resident; back-to-back launches on one stream"}
+        sp.close()
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        from tests import orc
+        cores = orc.lib().orc_hardware_threads()
+        r1 = cpu_run(model, 1, args.cpu_seconds * 0.4)
+        rN = cpu_run(model, cores, args.cpu_seconds * 0.6)
+        cpu = {"value": rN["value"], "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d %s targets x %d ticks, oracle TargetManager per thread (id %% %d); 1-thread faithful figure: %.4g %s over %d ticks"
+               % (rN["targets"], short, rN["ticks"], cores, r1["value"], UNIT, r1["ticks"]),
+               "single_thread_value": r1["value"]}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": "BASELINE configs[1] (%s, FP64 predict+update per measurement tick) at %d targets per GPU" % (short, n),
+                          "model": model, "targets_per_gpu": n, "targets_total": n * world, "dt": DT, "missed_measurement_prob": 0.05,
+                          "measurement_layout": "[n][7] pose, device resident, %d rotating sets" % n_sets,
+                          "l2": "inputs larger than L2: state %.0f MB + %.0f MB of measurements per tick vs 126 MB L2" % (
+                              n * (N + N * N + 2) * 8 / 1e6, n * stride * 8 / 1e6),
+                          "sharding": "owner(id) = id mod n_gpus, no data-path collective", "kernel_variant": args.variant},
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                            "peak_source": peak_src, "kernel": "te::kf_step_kernel<%s>" % short, "alg_bytes_per_launch": alg_bytes,
+                            "alg_bytes_per_update_step": B_upd, "alg_bytes_per_predict_step": B_pred, "kernel_ms": ms / K},
+               "clocks": clocks, "gpu_launches": K, "e2e": e2e, "cpu_baseline": cpu, "c2_10k": small}
+        if allgather:
+            out["allgather"] = allgather
+        print(json.dumps(out), flush=True)
+    pool.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

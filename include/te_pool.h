@@ -74,6 +74,13 @@ int te_pool_step_dense(te_pool* p, double dt, const double* dev_meas, int meas_s
 /* Same with HOST buffers: host->device copies are part of the call. */
 int te_pool_step_dense_host(te_pool* p, double dt, const double* meas, int meas_stride, const uint8_t* action,
                             int default_action);
+/* One dense tick from HOST buffers with the per-tick result read back: meas [size][meas_stride] and action
+ * [size] (or NULL) go host->device, the tick runs, and est_pos_out (host, [size][3], may be NULL) receives
+ * every target's estimated position (what RosTargetManager broadcasts each tick,
+ * src/target_manager_ros.cpp:78-87).  Copies and kernels are pipelined in chunks of targets over internal
+ * streams.  Synchronous: returns when est_pos_out is complete. */
+int te_pool_tick_host(te_pool* p, double dt, const double* meas, int meas_stride, const uint8_t* action, int default_action,
+                      double* est_pos_out);
 /* Sparse tick by id (host buffers): op k applies action[k] with dt[k] (dt_scalar if dt NULL) and
  * meas[k][7] to ids[k]; unknown ids are skipped.  An id may appear once per call.  Returns #applied. */
 long long te_pool_step_ids(te_pool* p, long long n, const uint32_t* ids, const double* dt, double dt_scalar,

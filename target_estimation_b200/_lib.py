@@ -48,6 +48,7 @@ SIGNATURES = {
     "te_pool_contains": (_i, [_p, _u32]),
     "te_pool_step_dense": (_i, [_p, _d, _p, _i, _p, _i]),
     "te_pool_step_dense_host": (_i, [_p, _d, _p, _i, _p, _i]),
+    "te_pool_tick_host": (_i, [_p, _d, _p, _i, _p, _i, _p]),
     "te_pool_step_ids": (_ll, [_p, _ll, _p, _p, _d, _p, _p]),
     "te_pool_predict_all": (_i, [_p, _d]),
     "te_pool_read_state": (_i, [_p, _ll, _p, _p, _p, _p, _p, _p, _p]),

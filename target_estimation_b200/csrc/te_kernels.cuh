@@ -19,7 +19,9 @@ namespace te {
 struct StepArgs {
   double* tiles;            // [n_tiles][NF][32]
   int n_slots;
-  int n_tiles;
+  int n_tiles;               // tiles to process in dense mode: [tile_begin, tile_begin + n_tiles)
+  int tile_begin;
+  double* pos_out;           // optional [n_slots][3]: estimated position after the tick (publish record)
   const int* tile_list;     // sparse mode: tiles to process (device), else nullptr
   const int* d_nwork;       // sparse mode: number of entries in tile_list (device)
   double dt;
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_kernel(const StepArgs a
 
   auto tile_of = [&](int it) -> int {
     const int w = gw + it * GW;
-    return a.tile_list ? a.tile_list[w] : w;
+    return a.tile_list ? a.tile_list[w] : a.tile_begin + w;
   };
   auto use_meas_tma = [&](int tile) -> bool { return a.meas_tma && (tile * TILE + TILE <= a.n_slots); };
   // lane 0: fetch tile `it` into its stage
@@ -139,6 +141,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_kernel(const StepArgs a
         step_lane<TYPE>(st, lane, act, dt, meas, a.Qtab + (size_t)cls * MT::N * MT::N, a.Rtab + (size_t)cls * MT::M * MT::M);
         if (a.clear_action) a.action[slot] = 0;
       }
+      if (a.pos_out && valid) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a.pos_out[(size_t)slot * 3 + k] = st[(LY::F_X + k) * TILE + lane];
+      }
       fence_proxy_async();   // generic-proxy writes of the stage -> visible to the bulk store
       __syncwarp();
       if (lane == 0) {
@@ -147,6 +153,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_kernel(const StepArgs a
         if (a.clear_action) a.tile_flag[tile] = 0;
       }
     } else {
+      if (a.pos_out && valid) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a.pos_out[(size_t)slot * 3 + k] = st[(LY::F_X + k) * TILE + lane];
+      }
       __syncwarp();
     }
   }

@@ -116,6 +116,9 @@ struct te_pool {
   std::vector<uint32_t> h_ids;
   bool h_ids_valid = true;
   Arena arena;
+  // chunk pipeline of te_pool_tick_host
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  std::vector<cudaEvent_t> events;
 };
 
 struct te_isolver {
@@ -499,6 +502,9 @@ void te_pool_destroy(te_pool* p) {
   cudaFree(p->alive); cudaFree(p->pos); cudaFree(p->srcmap); cudaFree(p->d_counters); cudaFree(p->cub_tmp);
   cudaFree(p->dQ); cudaFree(p->dR); cudaFree(p->dP0);
   p->arena.destroy();
+  for (cudaEvent_t e : p->events) cudaEventDestroy(e);
+  if (p->h2d_stream) cudaStreamDestroy(p->h2d_stream);
+  if (p->d2h_stream) cudaStreamDestroy(p->d2h_stream);
   if (p->own_stream) cudaStreamDestroy(p->stream);
   cudaSetDevice(prev);
   delete p;
@@ -756,6 +762,68 @@ int te_pool_step_dense_host(te_pool* p, double dt, const double* meas, int meas_
       te::copy_meas_masked_kernel<<<cdiv(p->n, 256), 256, 0, p->stream>>>(p->buf[p->cur].cold.meas, a.meas, a.action, (int)p->n);
       CK(cudaGetLastError());
     }
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+  });
+}
+
+int te_pool_tick_host(te_pool* p, double dt, const double* meas, int meas_stride, const uint8_t* action, int default_action,
+                      double* est_pos_out) {
+  return guarded(p, [&] {
+    if (p->n == 0) return 0;
+    if (!(dt >= 0.0)) throw std::invalid_argument("dt must be >= 0");
+    if (meas) check_meas_stride(p, meas_stride);
+    else if (!action && default_action == TE_ACT_UPDATE) throw std::invalid_argument("update tick without measurements");
+    if (!p->h2d_stream) {
+      CK(cudaStreamCreateWithFlags(&p->h2d_stream, cudaStreamNonBlocking));
+      CK(cudaStreamCreateWithFlags(&p->d2h_stream, cudaStreamNonBlocking));
+    }
+    const long long n = p->n;
+    const int n_tiles = cdiv(n, te::TILE);
+    const int chunk_tiles = std::max(256, std::min(n_tiles, 8192));   // 262144 targets: 14.7 MB of pose measurements
+    const int n_chunks = cdiv(n_tiles, chunk_tiles);
+    while ((int)p->events.size() < 2 * n_chunks + 1) {
+      cudaEvent_t e;
+      CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      p->events.push_back(e);
+    }
+    double* d_meas = meas ? p->arena.get_n<double>((size_t)n * meas_stride) : nullptr;
+    uint8_t* d_act = action ? p->arena.get_n<uint8_t>((size_t)n) : nullptr;
+    double* d_pos = est_pos_out ? p->arena.get_n<double>((size_t)n * 3) : nullptr;
+    // staging buffers may have been carved by earlier work on the pool stream
+    CK(cudaEventRecord(p->events[2 * n_chunks], p->stream));
+    CK(cudaStreamWaitEvent(p->h2d_stream, p->events[2 * n_chunks], 0));
+    te::StepArgs a = base_args(p);
+    a.dt = dt;
+    a.meas = d_meas;
+    a.meas_stride = meas_stride;
+    a.meas_tma = d_meas ? 1 : 0;
+    a.action = d_act;
+    a.default_action = default_action;
+    a.pos_out = d_pos;
+    for (int c = 0; c < n_chunks; ++c) {
+      const long long s0 = (long long)c * chunk_tiles * te::TILE;
+      const long long s1 = std::min<long long>(n, s0 + (long long)chunk_tiles * te::TILE);
+      if (d_meas) CK(cudaMemcpyAsync(d_meas + s0 * meas_stride, meas + s0 * meas_stride, (size_t)(s1 - s0) * meas_stride * 8, cudaMemcpyHostToDevice, p->h2d_stream));
+      if (d_act) CK(cudaMemcpyAsync(d_act + s0, action + s0, (size_t)(s1 - s0), cudaMemcpyHostToDevice, p->h2d_stream));
+      CK(cudaEventRecord(p->events[2 * c], p->h2d_stream));
+      CK(cudaStreamWaitEvent(p->stream, p->events[2 * c], 0));
+      a.tile_begin = c * chunk_tiles;
+      a.n_tiles = std::min(chunk_tiles, n_tiles - c * chunk_tiles);
+      launch_step(p, a, a.n_tiles);
+      if (d_pos) {
+        CK(cudaEventRecord(p->events[2 * c + 1], p->stream));
+        CK(cudaStreamWaitEvent(p->d2h_stream, p->events[2 * c + 1], 0));
+        CK(cudaMemcpyAsync(est_pos_out + s0 * 3, d_pos + s0 * 3, (size_t)(s1 - s0) * 24, cudaMemcpyDeviceToHost, p->d2h_stream));
+      }
+    }
+    if (d_meas && meas_stride == 7) {   // measured_pose_ = meas for the updated slots (src/target_interface.cpp:142-146)
+      if (d_act) te::copy_meas_masked_kernel<<<cdiv(n, 256), 256, 0, p->stream>>>(p->buf[p->cur].cold.meas, d_meas, d_act, (int)n);
+      else if (default_action == TE_ACT_UPDATE)
+        CK(cudaMemcpyAsync(p->buf[p->cur].cold.meas, d_meas, (size_t)n * 56, cudaMemcpyDeviceToDevice, p->stream));
+      CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(p->d2h_stream));
     CK(cudaStreamSynchronize(p->stream));
     return 0;
   });
