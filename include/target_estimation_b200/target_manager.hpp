@@ -1,0 +1,195 @@
+// include/target_estimation_b200/target_manager.hpp -- host surface of the B200 target pool.
+//
+// Mirrors the reference's TargetManager / TargetInterface / IntersectionSolver API
+// (/root/reference/include/target_estimation/target_manager.hpp:30-270, target_interface.hpp:39-283,
+// intersection_solver.hpp:55-125; tick/expiry semantics of target_manager_ros.hpp:74-183) with the
+// same method names, argument order, return conventions and quirks.  Storage is not one heap object per
+// target: every call lands in the device-resident pools of include/te_pool.h.  Eigen is not a
+// dependency of this build (absent from the image), so Vector7d / Vector6d / MatrixXd are the
+// plain fixed/dynamic arrays below; INTEGRATION.md shows the Eigen::Map overloads a maintainer adds.
+//
+// Per-id calls (update(id,dt,meas), update(id,dt)) are queued and coalesced: the reference's
+// "for every id: update(id, dt, meas)" loop of one tick becomes ONE kernel launch at the next
+// getter / flush / repeated id.  Observable results are identical to immediate execution.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../te_pool.h"
+
+namespace target_estimation_b200 {
+
+typedef std::array<double, 3> Vector3d;
+typedef std::array<double, 6> Vector6d;
+typedef std::array<double, 7> Vector7d;
+
+struct MatrixXd {   // dense row-major dynamic matrix (only what the API needs)
+  int r = 0, c = 0;
+  std::vector<double> d;
+  MatrixXd() {}
+  MatrixXd(int rows, int cols) : r(rows), c(cols), d((size_t)rows * cols, 0.0) {}
+  double& operator()(int i, int j) { return d[(size_t)i * c + j]; }
+  double operator()(int i, int j) const { return d[(size_t)i * c + j]; }
+  int rows() const { return r; }
+  int cols() const { return c; }
+  const double* data() const { return d.data(); }
+};
+typedef std::vector<double> VectorXd;
+
+class TargetManager;
+
+// KalmanFilterInterface view (kalman.hpp:49-89): what test/target_manager_test.cpp:144 reads
+class EstimatorView {
+ public:
+  EstimatorView(TargetManager* m, unsigned id) : mgr_(m), id_(id) {}
+  VectorXd getState() const;
+  MatrixXd getP() const;
+  MatrixXd getQ() const;
+  MatrixXd getR() const;
+  MatrixXd getP0() const;
+ private:
+  TargetManager* mgr_;
+  unsigned id_;
+};
+
+// TargetInterface proxy (target_interface.hpp:58-160): every getter reads the target's slot back from
+// the device (a sync point).  A handle may outlive erase(); its getters then return zeros.
+class TargetInterface {
+ public:
+  typedef std::shared_ptr<TargetInterface> Ptr;
+  TargetInterface(TargetManager* m, unsigned id) : mgr_(m), id_(id), est_(m, id) {}
+  void addMeasurement(const double& dt, const Vector7d& meas);
+  void update(const double& dt);
+  Vector7d getEstimatedPose() const;
+  Vector6d getEstimatedTwist() const;
+  Vector6d getEstimatedAcceleration() const;
+  Vector7d getEstimatedPose(const double& t1) const;
+  Vector6d getEstimatedTwist(const double& t1) const;
+  Vector6d getEstimatedAcceleration(const double& t1) const;
+  Vector7d getMeasuredPose() const;
+  double getTime() const;
+  double getPeriodEstimate() const;   // src/target_interface.cpp:80-87
+  long long getNumberMeasurements() const;
+  unsigned getID() const { return id_; }
+  const EstimatorView* getEstimator() const { return &est_; }
+ private:
+  TargetManager* mgr_;
+  unsigned id_;
+  EstimatorView est_;
+};
+
+class TargetManager {
+ public:
+  typedef std::shared_ptr<TargetManager> Ptr;
+  enum target_t { ANGULAR_RATES = 0, ANGULAR_VELOCITIES, UNIFORM_ACCELERATION, UNIFORM_VELOCITY };   // target_manager.hpp:38
+
+  explicit TargetManager(int device = 0);
+  explicit TargetManager(const std::string& file, int device = 0);   // throws const char* like the reference (:110-118)
+  virtual ~TargetManager();
+
+  // reference API ---------------------------------------------------------------------------
+  void init(const unsigned int& id, const double& dt0, const double& t0, const Vector7d& p0, const Vector6d& v0 = Vector6d{},
+            const Vector6d& a0 = Vector6d{});
+  void init(const target_t& type, const unsigned int& id, const double& dt0, const double& t0, const MatrixXd& Q, const MatrixXd& R,
+            const MatrixXd& P0, const Vector7d& p0, const Vector6d& v0 = Vector6d{}, const Vector6d& a0 = Vector6d{});
+  void init(const std::string& file, const unsigned int& id, const double& dt0, const double& t0, const Vector7d& p0,
+            const Vector6d& v0 = Vector6d{}, const Vector6d& a0 = Vector6d{});
+  bool update(const unsigned int& id, const double& dt, const Vector7d& meas);
+  bool update(const unsigned int& id, const double& dt);
+  virtual void update(const double& dt);
+  bool erase(const unsigned int& id);
+  TargetInterface::Ptr getTarget(const unsigned int& id);
+  bool getTargetPose(const unsigned int& id, Vector7d& pose);
+  bool getTargetTwist(const unsigned int& id, Vector6d& twist);
+  bool getTargetAcceleration(const unsigned int& id, Vector6d& acc);
+  long long getNumberMeasurements(const unsigned int& id);
+  void log();
+  std::vector<unsigned int> getAvailableTargets();
+  bool selectTargetType(const std::string& type_str, target_t& type);
+  bool loadYamlFile(const std::string& file, MatrixXd& Q, MatrixXd& R, MatrixXd& P, target_t& type);
+
+  // batched extensions (one kernel launch per call) ---------------------------------------------
+  long long initBatch(long long n, const unsigned* ids, double dt0, const double* t0, const double* p0 /*[n][7]*/,
+                      const double* v0 = nullptr, const double* a0 = nullptr);
+  long long initBatch(target_t type, const MatrixXd& Q, const MatrixXd& R, const MatrixXd& P0, long long n, const unsigned* ids, double dt0,
+                      const double* t0, const double* p0, const double* v0 = nullptr, const double* a0 = nullptr,
+                      const double* p0_scale = nullptr);
+  long long updateBatch(long long n, const unsigned* ids, double dt, const double* meas /*[n][7]*/, const unsigned char* action = nullptr);
+  long long eraseBatch(long long n, const unsigned* ids);
+  void getEstimatesBatch(long long n, const unsigned* ids, const double* t1, double* pose7, double* twist6, double* acc6,
+                         unsigned char* found);
+  void flush();
+  bool quiet = false;   // suppress the reference's stdout messages ("does not exist", "already exists", ...)
+
+  // access for the proxies / solver
+  struct Slot { int type; };
+  bool typeOf(unsigned id, int& type);
+  te_pool* poolOf(int type, bool create);
+  int device() const { return device_; }
+  std::recursive_mutex& lock() { return target_lock_; }
+
+ protected:
+  struct Pending {
+    std::vector<uint32_t> ids;
+    std::vector<double> dt, meas;
+    std::vector<uint8_t> action;
+  };
+  void flushLocked();
+  int registerClass(int type, const MatrixXd& Q, const MatrixXd& R, const MatrixXd& P0);
+  void queue(int type, unsigned id, double dt, const double* meas, int action);
+
+  int device_;
+  te_pool* pools_[4] = {nullptr, nullptr, nullptr, nullptr};
+  Pending pending_[4];
+  std::unordered_map<unsigned, uint8_t> pending_ids_;
+  std::map<unsigned, uint8_t> targets_;   // id -> model type, ascending like the reference's std::map
+  std::recursive_mutex target_lock_;
+  MatrixXd default_Q_, default_P_, default_R_;
+  target_t default_type_ = UNIFORM_VELOCITY;
+  bool default_values_loaded_ = false;
+};
+
+// utils.hpp:206-265 (host copy used by nothing on the hot path; kept for API completeness)
+class MovingAvgFilter {
+ public:
+  typedef std::shared_ptr<MovingAvgFilter> Ptr;
+  explicit MovingAvgFilter(unsigned n) : sum_(0.0), variance_(0.0), window_(n, 0.0), idx_(0), complete_(false) {}
+  double update(double value);
+  double getVariance() const { return variance_; }
+ private:
+  double sum_, variance_;
+  std::vector<double> window_;
+  unsigned idx_;
+  bool complete_;
+};
+
+// intersection_solver.hpp:55-125.  One object = one reference solver (one pair of moving-average
+// filters + previous intersection pose shared by every id queried through it).
+class IntersectionSolver {
+ public:
+  typedef std::shared_ptr<IntersectionSolver> Ptr;
+  IntersectionSolver(TargetManager::Ptr target_manager, const unsigned int filters_length = 250);
+  ~IntersectionSolver();
+  double getIntersectionTimeWithSphere(const unsigned int& id, const double& t1, const Vector3d& origin, const double& radius);
+  bool getIntersectionPoseWithSphere(const unsigned int& id, const double& t1, const double& pos_th, const double& ang_th,
+                                     const Vector3d& origin, const double& radius, Vector7d& intersection_pose);
+ private:
+  te_isolver* solverFor(int type);
+  TargetManager::Ptr target_manager_;
+  unsigned filters_length_;
+  // the filters live on the device with the pool they were last used with; a reference solver used
+  // across model types would share them -- documented limitation: one solver state per model type
+  te_isolver* solvers_[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+// utils.hpp:273-313
+std::vector<std::string> splitString(const std::string& s, const std::string& delimiter = "_");
+bool getId(const std::string& s, unsigned int& id);
+
+}  // namespace target_estimation_b200

@@ -1,0 +1,72 @@
+/* include/target_manager_c.h -- reference-facing C-ABI of the B200 target manager.
+ *
+ * The first ten entry points are exactly the symbols of the reference's C wrapper
+ * (/root/reference/include/target_estimation/target_manager_c.h:28-37, implemented in
+ * /root/reference/src/target_manager_c.cpp:15-76): same names, argument order and meaning, so
+ * libtarget_c.so of this repo can be loaded in place of the reference's libtarget_c.so.
+ * Differences in error behaviour, all on paths where the reference has undefined behaviour:
+ *   - target_manager_new returns NULL when the YAML file cannot be loaded (the reference lets a
+ *     `throw "..."` cross the extern "C" boundary, src/target_manager.cpp:115);
+ *   - target_manager_init on a manager without default model is a no-op (reference: same throw).
+ * Getters return false for an unknown id and then copy the previous successful value of the same
+ * getter into the output, like the reference's file-static scratch vectors
+ * (src/target_manager_c.cpp:8-9,39-42).
+ *
+ * The *_batch entry points are extensions (the reference ABI is one target per call and has no
+ * erase): one call = one kernel launch over the device-resident pool.  All buffers are caller-owned
+ * host memory; nothing here exposes CUDA or torch types.
+ */
+#ifndef TARGET_MANAGER_C_B200_H
+#define TARGET_MANAGER_C_B200_H
+#ifndef __cplusplus
+#include <stdbool.h>
+#endif
+
+typedef void target_manager_c;
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* ---- reference ABI (target_manager_c.h:28-37) ---- */
+target_manager_c* target_manager_new(const char* file);
+void target_manager_init(const target_manager_c* self, const unsigned int id, const double dt0, double p0[], const double t0);
+void target_manager_update_meas(const target_manager_c* self, const unsigned int id, const double dt, double meas[]);
+void target_manager_update(const target_manager_c* self, const unsigned int id, const double dt);
+bool target_manager_get_est_pose(const target_manager_c* self, const unsigned int id, double pose[]);
+bool target_manager_get_est_twist(const target_manager_c* self, const unsigned int id, double twist[]);
+bool target_manager_get_est_acceleration(const target_manager_c* self, const unsigned int id, double acceleration[]);
+int target_manager_get_n_measurements(const target_manager_c* self, const unsigned int id);
+void target_manager_log(const target_manager_c* self);
+void target_manager_delete(target_manager_c* self);
+
+/* ---- batched extensions (not in the reference) ---- */
+/* same as target_manager_new, on an explicit CUDA device */
+target_manager_c* target_manager_new_on_device(const char* file, int device);
+/* TargetManager::init for n ids (default model): p0 [n][7]; returns #created (existing ids skipped) */
+long long target_manager_init_batch(const target_manager_c* self, long long n, const unsigned int* ids, double dt0, const double* p0,
+                                    const double* t0 /* [n] or NULL = 0 */);
+/* one tick: action[k] 2 = update(id,dt,meas[k]) / 1 = update(id,dt) / 0 = skip; action NULL = all 2.
+ * Returns #applied (unknown ids are skipped like the reference's "does not exist"). */
+long long target_manager_update_batch(const target_manager_c* self, long long n, const unsigned int* ids, double dt, const double* meas,
+                                      const unsigned char* action);
+/* TargetManager::update(dt): predict every target */
+void target_manager_update_all(const target_manager_c* self, double dt);
+/* TargetManager::erase; returns #erased */
+long long target_manager_erase_batch(const target_manager_c* self, long long n, const unsigned int* ids);
+bool target_manager_erase(const target_manager_c* self, unsigned int id);
+/* estimates for n ids: any output may be NULL; found[k] = id exists.  t1 NULL = current estimates,
+ * else getEstimatedPose/Twist/Acceleration(t1[k]) */
+int target_manager_get_estimates_batch(const target_manager_c* self, long long n, const unsigned int* ids, const double* t1, double* pose7,
+                                       double* twist6, double* acc6, unsigned char* found);
+/* getAvailableTargets: ascending ids; returns the count (call with cap 0 to size the buffer) */
+long long target_manager_get_ids(const target_manager_c* self, unsigned int* out, long long cap);
+/* filter state of one target: x [n], P [n*n] row-major; returns n (0 = unknown id) */
+int target_manager_get_state(const target_manager_c* self, unsigned int id, double* x, double* P, double* t);
+/* pending per-id calls are coalesced into one launch per tick; force them out */
+void target_manager_flush(const target_manager_c* self);
+const char* target_manager_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -64,6 +64,8 @@ long long te_pool_erase_batch(te_pool* p, long long n, const uint32_t* ids);
 /* ascending ids (getAvailableTargets, src/target_manager.cpp:126-133); returns pool size */
 long long te_pool_ids(te_pool* p, uint32_t* out, long long cap);
 int te_pool_contains(te_pool* p, uint32_t id);
+/* model class of one target (-1 with te_last_error() if the id is unknown) */
+int te_pool_class_of(te_pool* p, uint32_t id);
 
 /* ---- stepping (the hot path) -------------------------------------------------------- */
 /* One tick over every slot, slot order = ascending id.  dev_meas: [size][meas_stride] doubles

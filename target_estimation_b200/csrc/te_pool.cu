@@ -706,6 +706,18 @@ int te_pool_contains(te_pool* p, uint32_t id) {
   });
 }
 
+int te_pool_class_of(te_pool* p, uint32_t id) {
+  return guarded(p, [&] {
+    sync_host_ids(p);
+    auto it = std::lower_bound(p->h_ids.begin(), p->h_ids.end(), id);
+    if (it == p->h_ids.end() || *it != id) throw std::invalid_argument("unknown target id");
+    uint16_t c = 0;
+    CK(cudaMemcpyAsync(&c, p->buf[p->cur].cold.cls + (it - p->h_ids.begin()), sizeof(uint16_t), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return (int)c;
+  });
+}
+
 int te_pool_step_dense(te_pool* p, double dt, const double* dev_meas, int meas_stride, const uint8_t* dev_action, int default_action) {
   return guarded(p, [&] {
     if (p->n == 0) return 0;

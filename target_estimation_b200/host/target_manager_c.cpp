@@ -1,0 +1,142 @@
+// target_manager_c.cpp -- extern "C" wrapper of the host TargetManager: the ten symbols of the reference's
+// C-ABI (/root/reference/src/target_manager_c.cpp:15-76) plus the batched extensions of
+// include/target_manager_c.h.  No exception crosses the boundary.
+#include "target_manager_c.h"
+
+#include <cstring>
+#include <string>
+
+#include "target_estimation_b200/target_manager.hpp"
+
+using namespace target_estimation_b200;
+
+namespace {
+// the reference keeps file-static scratch vectors and copies them out even when the id is unknown
+// (src/target_manager_c.cpp:8-9,39-42): an unknown id returns false and the previous value
+Vector7d vector7d_tmp_{};
+Vector6d vector6d_tmp_{};
+thread_local std::string g_err;
+
+template <class F, class R> R guard(R fallback, F&& f) {
+  try {
+    return f();
+  } catch (const char* msg) {
+    g_err = msg;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+  } catch (...) {
+    g_err = "unknown error";
+  }
+  return fallback;
+}
+inline TargetManager* M(const target_manager_c* self) { return (TargetManager*)self; }
+}  // namespace
+
+extern "C" {
+
+target_manager_c* target_manager_new_on_device(const char* file, int device) {
+  return guard((target_manager_c*)nullptr, [&]() -> target_manager_c* {
+    TargetManager* m = (file && file[0]) ? new TargetManager(std::string(file), device) : new TargetManager(device);
+    return (target_manager_c*)m;
+  });
+}
+target_manager_c* target_manager_new(const char* file) { return target_manager_new_on_device(file, 0); }
+
+void target_manager_init(const target_manager_c* self, const unsigned int id, const double dt0, double p0[], const double t0) {
+  guard(0, [&] {
+    Vector7d p;
+    std::memcpy(p.data(), p0, sizeof(double) * 7);
+    M(self)->init(id, dt0, t0, p);
+    return 0;
+  });
+}
+
+void target_manager_update_meas(const target_manager_c* self, const unsigned int id, const double dt, double meas[]) {
+  guard(0, [&] {
+    Vector7d m;
+    std::memcpy(m.data(), meas, sizeof(double) * 7);
+    M(self)->update(id, dt, m);
+    return 0;
+  });
+}
+
+void target_manager_update(const target_manager_c* self, const unsigned int id, const double dt) {
+  guard(0, [&] {
+    M(self)->update(id, dt);
+    return 0;
+  });
+}
+
+bool target_manager_get_est_pose(const target_manager_c* self, const unsigned int id, double pose[]) {
+  bool res = guard(false, [&] { return M(self)->getTargetPose(id, vector7d_tmp_); });
+  std::memcpy(pose, vector7d_tmp_.data(), sizeof(double) * 7);
+  return res;
+}
+bool target_manager_get_est_twist(const target_manager_c* self, const unsigned int id, double twist[]) {
+  bool res = guard(false, [&] { return M(self)->getTargetTwist(id, vector6d_tmp_); });
+  std::memcpy(twist, vector6d_tmp_.data(), sizeof(double) * 6);
+  return res;
+}
+bool target_manager_get_est_acceleration(const target_manager_c* self, const unsigned int id, double acceleration[]) {
+  bool res = guard(false, [&] { return M(self)->getTargetAcceleration(id, vector6d_tmp_); });
+  std::memcpy(acceleration, vector6d_tmp_.data(), sizeof(double) * 6);
+  return res;
+}
+int target_manager_get_n_measurements(const target_manager_c* self, const unsigned int id) {
+  return guard(0, [&] { return (int)M(self)->getNumberMeasurements(id); });   // long long -> int like the reference (:64)
+}
+void target_manager_log(const target_manager_c* self) {
+  guard(0, [&] { M(self)->log(); return 0; });
+}
+void target_manager_delete(target_manager_c* self) { delete M(self); }
+
+// ---- batched extensions ------------------------------------------------------------------------
+long long target_manager_init_batch(const target_manager_c* self, long long n, const unsigned int* ids, double dt0, const double* p0,
+                                    const double* t0) {
+  return guard(-1LL, [&] { return M(self)->initBatch(n, ids, dt0, t0, p0); });
+}
+long long target_manager_update_batch(const target_manager_c* self, long long n, const unsigned int* ids, double dt, const double* meas,
+                                      const unsigned char* action) {
+  return guard(-1LL, [&] { return M(self)->updateBatch(n, ids, dt, meas, action); });
+}
+void target_manager_update_all(const target_manager_c* self, double dt) {
+  guard(0, [&] { M(self)->update(dt); return 0; });
+}
+long long target_manager_erase_batch(const target_manager_c* self, long long n, const unsigned int* ids) {
+  return guard(-1LL, [&] { return M(self)->eraseBatch(n, ids); });
+}
+bool target_manager_erase(const target_manager_c* self, unsigned int id) {
+  return guard(false, [&] { return M(self)->erase(id); });
+}
+int target_manager_get_estimates_batch(const target_manager_c* self, long long n, const unsigned int* ids, const double* t1, double* pose7,
+                                       double* twist6, double* acc6, unsigned char* found) {
+  return guard(-1, [&] { M(self)->getEstimatesBatch(n, ids, t1, pose7, twist6, acc6, found); return 0; });
+}
+long long target_manager_get_ids(const target_manager_c* self, unsigned int* out, long long cap) {
+  return guard(-1LL, [&] {
+    auto ids = M(self)->getAvailableTargets();
+    const long long n = (long long)ids.size();
+    if (out && cap > 0) std::memcpy(out, ids.data(), sizeof(unsigned) * (size_t)(n < cap ? n : cap));
+    return n;
+  });
+}
+int target_manager_get_state(const target_manager_c* self, unsigned int id, double* x, double* P, double* t) {
+  return guard(0, [&] {
+    auto tg = M(self)->getTarget(id);
+    if (!tg) return 0;
+    VectorXd xs = tg->getEstimator()->getState();
+    if (x) std::memcpy(x, xs.data(), sizeof(double) * xs.size());
+    if (P) {
+      MatrixXd Pm = tg->getEstimator()->getP();
+      std::memcpy(P, Pm.data(), sizeof(double) * Pm.d.size());
+    }
+    if (t) *t = tg->getTime();
+    return (int)xs.size();
+  });
+}
+void target_manager_flush(const target_manager_c* self) {
+  guard(0, [&] { M(self)->flush(); return 0; });
+}
+const char* target_manager_last_error(void) { return g_err.c_str(); }
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+"""ctypes binding of include/target_manager_c.h (the reference-facing C-ABI, lib/libtarget_c.so)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+so_path = os.path.join(_HERE, "lib", "libtarget_c.so")
+if not os.path.exists(so_path):
+    raise ImportError("target_estimation_b200: %s is missing -- run __graft_entry__.build()" % so_path)
+clib = C.CDLL(so_path)
+
+_p, _u, _d, _ll, _i = C.c_void_p, C.c_uint, C.c_double, C.c_longlong, C.c_int
+_SIG = {
+    "target_manager_new": (_p, [C.c_char_p]),
+    "target_manager_new_on_device": (_p, [C.c_char_p, _i]),
+    "target_manager_init": (None, [_p, _u, _d, _p, _d]),
+    "target_manager_update_meas": (None, [_p, _u, _d, _p]),
+    "target_manager_update": (None, [_p, _u, _d]),
+    "target_manager_get_est_pose": (C.c_bool, [_p, _u, _p]),
+    "target_manager_get_est_twist": (C.c_bool, [_p, _u, _p]),
+    "target_manager_get_est_acceleration": (C.c_bool, [_p, _u, _p]),
+    "target_manager_get_n_measurements": (_i, [_p, _u]),
+    "target_manager_log": (None, [_p]),
+    "target_manager_delete": (None, [_p]),
+    "target_manager_init_batch": (_ll, [_p, _ll, _p, _d, _p, _p]),
+    "target_manager_update_batch": (_ll, [_p, _ll, _p, _d, _p, _p]),
+    "target_manager_update_all": (None, [_p, _d]),
+    "target_manager_erase_batch": (_ll, [_p, _ll, _p]),
+    "target_manager_erase": (C.c_bool, [_p, _u]),
+    "target_manager_get_estimates_batch": (_i, [_p, _ll, _p, _p, _p, _p, _p, _p]),
+    "target_manager_get_ids": (_ll, [_p, _p, _ll]),
+    "target_manager_get_state": (_i, [_p, _u, _p, _p, _p]),
+    "target_manager_flush": (None, [_p]),
+    "target_manager_last_error": (C.c_char_p, []),
+}
+for _n, (_r, _a) in _SIG.items():
+    _f = getattr(clib, _n)
+    _f.restype = _r
+    _f.argtypes = _a
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class TargetManagerC:
+    """Python view of one `target_manager_c*` handle; method names follow the C symbols."""
+
+    def __init__(self, yaml_file, device=0):
+        self.h = clib.target_manager_new_on_device(yaml_file.encode() if yaml_file else None, device)
+        if not self.h:
+            raise RuntimeError("target_manager_new failed: %s" % clib.target_manager_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            clib.target_manager_delete(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def init(self, id_, dt0, p0, t0):
+        p0 = np.ascontiguousarray(p0, dtype=np.float64)
+        clib.target_manager_init(self.h, id_, dt0, _ptr(p0), t0)
+
+    def update_meas(self, id_, dt, meas):
+        meas = np.ascontiguousarray(meas, dtype=np.float64)
+        clib.target_manager_update_meas(self.h, id_, dt, _ptr(meas))
+
+    def update(self, id_, dt):
+        clib.target_manager_update(self.h, id_, dt)
+
+    def _get(self, fn, id_, k, out=None):
+        out = np.zeros(k) if out is None else out
+        return bool(fn(self.h, id_, _ptr(out))), out
+
+    def get_est_pose(self, id_, out=None): return self._get(clib.target_manager_get_est_pose, id_, 7, out)
+    def get_est_twist(self, id_, out=None): return self._get(clib.target_manager_get_est_twist, id_, 6, out)
+    def get_est_acceleration(self, id_, out=None): return self._get(clib.target_manager_get_est_acceleration, id_, 6, out)
+    def get_n_measurements(self, id_): return int(clib.target_manager_get_n_measurements(self.h, id_))
+
+    def init_batch(self, ids, dt0, p0, t0=None):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        p0 = np.ascontiguousarray(p0, dtype=np.float64)
+        t0 = np.ascontiguousarray(t0, dtype=np.float64) if t0 is not None else None
+        return int(clib.target_manager_init_batch(self.h, ids.size, _ptr(ids), dt0, _ptr(p0), _ptr(t0)))
+
+    def update_batch(self, ids, dt, meas=None, action=None):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        meas = np.ascontiguousarray(meas, dtype=np.float64) if meas is not None else None
+        action = np.ascontiguousarray(action, dtype=np.uint8) if action is not None else None
+        return int(clib.target_manager_update_batch(self.h, ids.size, _ptr(ids), dt, _ptr(meas), _ptr(action)))
+
+    def update_all(self, dt):
+        clib.target_manager_update_all(self.h, dt)
+
+    def erase(self, id_):
+        return bool(clib.target_manager_erase(self.h, id_))
+
+    def erase_batch(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        return int(clib.target_manager_erase_batch(self.h, ids.size, _ptr(ids)))
+
+    def get_estimates_batch(self, ids, t1=None):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        n = ids.size
+        t1 = np.ascontiguousarray(np.broadcast_to(t1, (n,)), dtype=np.float64) if t1 is not None else None
+        pose, twist, acc, found = np.zeros((n, 7)), np.zeros((n, 6)), np.zeros((n, 6)), np.zeros(n, dtype=np.uint8)
+        rc = clib.target_manager_get_estimates_batch(self.h, n, _ptr(ids), _ptr(t1), _ptr(pose), _ptr(twist), _ptr(acc), _ptr(found))
+        if rc < 0:
+            raise RuntimeError(clib.target_manager_last_error().decode())
+        return pose, twist, acc, found
+
+    def ids(self):
+        n = int(clib.target_manager_get_ids(self.h, None, 0))
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        clib.target_manager_get_ids(self.h, _ptr(out), n)
+        return out[:n]
+
+    def state(self, id_, n_max=18):
+        x = np.zeros(n_max); P = np.zeros(n_max * n_max); t = C.c_double()
+        n = int(clib.target_manager_get_state(self.h, id_, _ptr(x), _ptr(P), C.byref(t)))
+        if n == 0:
+            return None
+        return {"x": x[:n].copy(), "P": P[: n * n].reshape(n, n).copy(), "t": t.value}
+
+    def flush(self):
+        clib.target_manager_flush(self.h)

@@ -1,0 +1,118 @@
+"""-m gpu: add / erase churn and expiry -- track ids and erase decisions bit-exact against the oracle's
+RosTargetManager-tick restatement (src/target_manager_ros.cpp:41-92), state parity after compaction."""
+import numpy as np
+import pytest
+
+from tests import orc, synth
+
+pytestmark = pytest.mark.gpu
+DT = 1.0 / 250.0
+
+
+def test_add_erase_order_and_state():
+    import target_estimation_b200 as te
+    mtype, _, Q, R, P0 = te.load_model("uniform_velocity")
+    pool = te.TargetPool(mtype); pool.register_class(Q, R, P0)
+    ref = orc.Manager()
+    rng = np.random.default_rng(0)
+    live = set()
+    next_meas = lambda n: np.hstack([rng.normal(size=(n, 3)), np.tile([0, 0, 0, 1.0], (n, 1))])
+    for rnd in range(12):
+        # add a random batch (some duplicates of live ids, unsorted, interleaved with existing ids)
+        new = rng.choice(5000, size=rng.integers(1, 200), replace=False).astype(np.uint32)
+        p0 = next_meas(new.size)
+        added = pool.add(new, p0, t0=np.full(new.size, 0.1 * rnd))
+        fresh = [int(i) for i in new if int(i) not in live]
+        assert added == len(fresh)
+        for k, i in enumerate(new):
+            if int(i) not in live:
+                ref.init_full(mtype, int(i), DT, 0.1 * rnd, Q, R, P0, p0[k]); live.add(int(i))
+        ids = pool.ids()
+        assert np.array_equal(ids, ref.ids()) and np.array_equal(ids, np.sort(ids))
+        for _ in range(3):
+            m = next_meas(ids.size); act = rng.integers(0, 3, ids.size).astype(np.uint8)
+            pool.step_dense_host(DT, m, act); ref.step_batch(ids, DT, m, act)
+        gone = rng.choice(ids, size=min(ids.size // 3, 150), replace=False)
+        assert pool.erase(np.concatenate([gone, [9999999]])) == gone.size
+        for g in gone:
+            ref.erase(int(g)); live.discard(int(g))
+        ids = pool.ids()
+        assert np.array_equal(ids, ref.ids())
+        got, want = pool.read_state(), ref.states(ids, 6)
+        assert synth.compare_h2(got["x"], want["x"]) <= 1.0 and synth.compare_h2(got["P"], want["P"]) <= 1.0
+        assert np.array_equal(got["n_meas"], want["n_meas"]) and np.array_equal(got["t"], want["t"])
+    pool.close()
+
+
+def test_expiry_bit_exact():
+    """SURVEY.md C3 sub-run: synthetic clock (sec, nsec) with epoch 1000 s, per tick 1 % of the live ids stop
+    receiving measurements, expire after timeout = 8 dt by `last > 0 && now - last >= timeout`, and as many fresh ids
+    appear.  The set and order of live ids and every tick's erase list must match the oracle exactly."""
+    import target_estimation_b200 as te
+    name = "angular_rates"
+    mtype, _, Q, R, P0 = te.load_model(name)
+    n0, ticks = 2048, 48
+    timeout = 8 * DT
+    pool = te.TargetPool(mtype); pool.register_class(Q, R, P0)
+    L = orc.lib()
+    h = L.orc_tick_new(mtype, orc.ptr(orc.colmajor(Q)), Q.shape[0], orc.ptr(orc.colmajor(R)), R.shape[0], orc.ptr(orc.colmajor(P0)))
+    L.orc_tick_set_expiration(h, timeout)
+    rng = np.random.default_rng(17)
+    next_id = n0
+    active = list(range(n0))            # ids still producing measurements
+    t_tick = 0.0
+    def stamp(k):                        # clock at tick k: 1000 s + k * 4 ms, in integer nanoseconds
+        ns = 1000 * 10 ** 9 + k * 4000000
+        return ns // 10 ** 9, ns % 10 ** 9
+    for k in range(ticks):
+        sec, nsec = stamp(k)
+        if k > 0:
+            quit_ = rng.choice(len(active), size=max(1, len(active) // 100), replace=False)
+            active = [a for j, a in enumerate(active) if j not in set(quit_.tolist())]
+            fresh = list(range(next_id, next_id + len(quit_))); next_id += len(quit_)
+            active += fresh
+        ids = np.array(active, dtype=np.uint32)
+        quat = synth.rpy_to_quat(rng.uniform(-1, 1, (ids.size, 3)))
+        poses = np.hstack([rng.normal(size=(ids.size, 3)), quat])
+        stamps = np.tile(np.array([sec, nsec], dtype=np.uint32), (ids.size, 1))
+        # ---- oracle: /tf callback then the tick
+        L.orc_tick_callback_ids(h, ids.size, orc.ptr(ids), orc.ptr(np.ascontiguousarray(stamps)), orc.ptr(np.ascontiguousarray(poses)))
+        erased_ref = np.zeros(8192, dtype=np.uint32)
+        n_er = L.orc_tick_update(h, DT, sec, nsec, orc.ptr(erased_ref), 8192)
+        # ---- device: the same tick expressed with the pool primitives
+        have = set(pool.ids().tolist())
+        new_mask = np.array([int(i) not in have for i in ids])
+        if new_mask.any():                                   # init on first sight with the measurement as p0, t0 = t_
+            pool.add(ids[new_mask], poses[new_mask], t0=np.full(int(new_mask.sum()), t_tick))
+        pool.set_stamps(ids, stamps[:, 0], stamps[:, 1])
+        # every live target: update if its mailbox has a (possibly stale) measurement -- the reference's new_meas_
+        # flag is sticky (H10), so silent targets re-apply their last pose until they expire
+        live = pool.ids()
+        last = dict(zip(ids.tolist(), poses))
+        if k == 0:
+            mailbox = {}
+        mailbox.update(last)
+        m = np.array([mailbox[int(i)] for i in live])
+        pool.step_ids(live, DT, m)
+        erased = pool.expire(sec, nsec, timeout)
+        for e in erased:
+            mailbox.pop(int(e), None)
+        t_tick = t_tick + DT
+        assert n_er == erased.size and np.array_equal(erased, erased_ref[:n_er]), k
+        ref_ids = np.zeros(max(L.orc_num_targets(h), 1), dtype=np.uint32)
+        n_ref = L.orc_get_ids(h, orc.ptr(ref_ids), ref_ids.size)
+        assert np.array_equal(pool.ids(), ref_ids[:n_ref]), k
+    assert next_id > n0 + 500 and len(pool) > 0
+    # state parity of a sample of survivors after all the compaction
+    live = pool.ids()
+    sample = live[:: max(1, live.size // 64)]
+    got = pool.read_state(sample)
+    N = Q.shape[0]
+    xs = np.zeros((sample.size, N)); Ps = np.zeros((sample.size, N, N))
+    import ctypes as C
+    for j, i in enumerate(sample):
+        t = C.c_double(); nm = C.c_longlong()
+        L.orc_get_state(h, int(i), orc.ptr(xs[j]), orc.ptr(Ps[j]), C.byref(t), C.byref(nm), None)
+        assert got["n_meas"][j] == nm.value and got["t"][j] == t.value
+    assert synth.compare_h2(got["x"], xs) <= 1.0 and synth.compare_h2(got["P"], Ps) <= 1.0
+    pool.close()

@@ -1,0 +1,164 @@
+"""-m gpu: the reference-facing C-ABI (include/target_manager_c.h, lib/libtarget_c.so) against the oracle's
+TargetManager on identical inputs -- reads like the reference's own test/target_manager_test.cpp, plus the paths
+that test never touches (erase, predict-only, unknown ids, stale getter scratch, batched extensions)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import orc, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DT = 1.0 / 250.0
+CASES = [(0, "uniform_velocity"), (1, "uniform_acceleration"), (2, "angular_rates"), (3, "angular_velocities")]
+
+
+def _yaml(name):
+    return os.path.join(ROOT, "models", "model_%s_params.yaml" % name)
+
+
+def _reftest(n_points):
+    meas = np.zeros((4, n_points, 7)); real = np.zeros((4, n_points, 7))
+    orc.lib().orc_reftest_streams(DT, n_points, 4, orc.ptr(meas), orc.ptr(real))
+    return meas
+
+
+@pytest.mark.parametrize("idx,name", CASES)
+def test_reference_scenario_through_c_abi(idx, name):
+    """BASELINE configs[0]: target_manager_test (1 target, 10 000 steps, libstdc++ noise stream), per-id calls
+    update_meas -> get_est_pose -> get_est_twist every step, against the oracle and the reference tolerances."""
+    from target_estimation_b200.manager import TargetManagerC
+    n = 10000
+    meas = _reftest(n)[idx]
+    mgr = TargetManagerC(_yaml(name))
+    ref = orc.Manager(_yaml(name))
+    mgr.init(idx, DT, meas[0], 0.0)
+    ref.init_default(idx, DT, meas[0], 0.0)
+    pose = np.zeros((n, 7)); twist = np.zeros((n, 6))
+    rpose = np.zeros((n, 7)); rtwist = np.zeros((n, 6))
+    N = orc.load_yaml(_yaml(name))["Q"].shape[0]
+    xs = np.zeros((n // 500, N)); Ps = np.zeros((n // 500, N, N))
+    orc.lib().orc_run_stream(ref.h, idx, n, DT, orc.ptr(np.ascontiguousarray(meas)), None, 500, orc.ptr(xs), orc.ptr(Ps), orc.ptr(rpose),
+                             orc.ptr(rtwist))
+    k_rec = 0
+    for k in range(n):
+        mgr.update_meas(idx, DT, meas[k])
+        ok1, _ = mgr.get_est_pose(idx, pose[k])
+        ok2, _ = mgr.get_est_twist(idx, twist[k])
+        assert ok1 and ok2
+        if (k + 1) % 500 == 0:
+            st = mgr.state(idx)
+            assert synth.compare_h2(st["x"][None], xs[k_rec][None]) <= 1.0, k
+            assert synth.compare_h2(st["P"][None], Ps[k_rec][None]) <= 1.0, k
+            k_rec += 1
+    assert mgr.get_n_measurements(idx) == n == ref.n_measurements(idx)
+    # reference tolerances (test/target_manager_test.cpp:179-189, 335-340)
+    goal = np.array([0.2, 0.3, 0.4])
+    assert np.all(np.abs(pose[-1, :3] - goal) < 0.01)
+    assert np.all(np.abs(twist[:, :3].mean(axis=0) - goal / (n * DT)) < 0.01)
+    if name == "angular_velocities":
+        omega = np.array([3.0, 0.01, 0.1])
+        assert np.all(np.abs(twist[:, 3:].mean(axis=0) - omega) < 0.05) and np.all(np.abs(twist[-1, 3:] - omega) < 0.01)
+    # and against the oracle, every step: positions / twists 1e-9 relative (scale = max |ref|)
+    assert np.abs(pose[:, :3] - rpose[:, :3]).max() <= 1e-9 * max(1.0, np.abs(rpose[:, :3]).max())
+    assert np.abs(twist - rtwist).max() <= 1e-9 * max(1.0, np.abs(rtwist).max())
+    # quaternion outputs: sign-insensitive
+    dq = np.minimum(np.abs(pose[:, 3:] - rpose[:, 3:]).max(axis=1), np.abs(pose[:, 3:] + rpose[:, 3:]).max(axis=1))
+    assert dq.max() <= 1e-9
+    mgr.close()
+
+
+def test_registry_semantics():
+    """init twice, unknown ids, erase, predict-only, ascending ids, getter scratch (src/target_manager.cpp:144-295,
+    src/target_manager_c.cpp:37-59)."""
+    from target_estimation_b200.manager import TargetManagerC
+    name = "uniform_acceleration"
+    mgr = TargetManagerC(_yaml(name)); ref = orc.Manager(_yaml(name))
+    rng = np.random.default_rng(11)
+    p = rng.normal(size=(6, 7)); p[:, 3:] = [0, 0, 0, 1]
+    for i, id_ in enumerate([42, 7, 1000000, 3]):
+        mgr.init(id_, DT, p[i], 0.5 * i); ref.init_default(id_, DT, p[i], 0.5 * i)
+    mgr.init(7, DT, p[5], 9.0); ref.init_default(7, DT, p[5], 9.0)            # "already exists": no-op
+    assert list(mgr.ids()) == list(ref.ids()) == [3, 7, 42, 1000000]
+    for k in range(30):
+        for id_ in (42, 7, 3):
+            m = p[0] + 0.01 * k
+            if (k + id_) % 4 == 0:
+                mgr.update(id_, DT); ref.update(id_, DT)                         # predict only
+            else:
+                mgr.update_meas(id_, DT, m); ref.update_meas(id_, DT, m)
+        mgr.update_meas(555, DT, p[0])                                           # unknown id: skipped
+        assert not ref.update_meas(555, DT, p[0])
+    for id_ in (3, 7, 42, 1000000):
+        st, rs = mgr.state(id_), ref.state(id_, 9)
+        assert synth.compare_h2(st["x"][None], rs["x"][None]) <= 1.0
+        assert synth.compare_h2(st["P"][None], rs["P"][None]) <= 1.0
+        assert st["t"] == rs["t"]
+        assert mgr.get_n_measurements(id_) == ref.n_measurements(id_)
+    # unknown id: false and the previous successful value stays in the output
+    ok, good = mgr.get_est_pose(42)
+    ok2, stale = mgr.get_est_pose(999)
+    assert ok and not ok2 and np.array_equal(good, stale)
+    assert mgr.get_n_measurements(999) == 0
+    # update(dt) for all targets
+    mgr.update_all(DT); ref.update_all(DT)
+    for id_ in (3, 1000000):
+        assert synth.compare_h2(mgr.state(id_)["P"][None], ref.state(id_, 9)["P"][None]) <= 1.0
+    # erase
+    assert mgr.erase(7) and ref.erase(7)
+    assert not mgr.erase(7) and not ref.erase(7)
+    assert list(mgr.ids()) == list(ref.ids()) == [3, 42, 1000000]
+    assert mgr.state(7) is None
+    st, rs = mgr.state(42), ref.state(42, 9)
+    assert synth.compare_h2(st["P"][None], rs["P"][None]) <= 1.0
+    # re-create the erased id: fresh filter
+    mgr.init(7, DT, p[2], 1.0); ref.init_default(7, DT, p[2], 1.0)
+    assert mgr.get_n_measurements(7) == 0
+    assert synth.compare_h2(mgr.state(7)["x"][None], ref.state(7, 9)["x"][None]) <= 1.0
+    mgr.close()
+
+
+@pytest.mark.parametrize("name", ["uniform_velocity", "angular_rates"])
+def test_batched_extensions(name):
+    from target_estimation_b200.manager import TargetManagerC
+    y = orc.load_yaml(_yaml(name))
+    N = y["Q"].shape[0]
+    n, ticks = 300, 25
+    meas, action, _ = synth.make_streams(n, ticks, DT, accel=name == "angular_rates", angular=y["R"].shape[0] == 6, seed=5)
+    rng = np.random.default_rng(3)
+    ids = rng.permutation(np.arange(n, dtype=np.uint32) * 5 + 1)               # unsorted ids
+    mgr = TargetManagerC(_yaml(name)); ref = orc.Manager(_yaml(name))
+    t0 = rng.uniform(0, 2, n)
+    assert mgr.init_batch(ids, DT, meas[0], t0) == n
+    assert mgr.init_batch(ids[:10], DT, meas[0][:10]) == 0                      # all exist
+    for k in range(n):
+        ref.init_default(int(ids[k]), DT, meas[0, k], float(t0[k]))
+    assert list(mgr.ids()) == sorted(ids.tolist())
+    for k in range(ticks):
+        act = action[k].copy()
+        act[rng.uniform(size=n) < 0.1] = 0                                       # some targets untouched this tick
+        assert mgr.update_batch(ids, DT, meas[k], act) == int((act != 0).sum())
+        ref.step_batch(ids, DT, meas[k], act)
+    order = np.argsort(ids)
+    got_pose, got_twist, got_acc, found = mgr.get_estimates_batch(ids)
+    assert found.all()
+    for j in order[:: max(1, n // 40)]:
+        st, rs = mgr.state(int(ids[j])), ref.state(int(ids[j]), N)
+        assert synth.compare_h2(st["x"][None], rs["x"][None]) <= 1.0
+        assert synth.compare_h2(st["P"][None], rs["P"][None]) <= 1.0
+        ok, rp = ref.pose(int(ids[j])); _, rt = ref.twist(int(ids[j])); _, ra = ref.acc(int(ids[j]))
+        assert np.abs(got_pose[j, :3] - rp[:3]).max() <= 1e-9 * max(1, np.abs(rp[:3]).max())
+        assert min(np.abs(got_pose[j, 3:] - rp[3:]).max(), np.abs(got_pose[j, 3:] + rp[3:]).max()) <= 1e-9
+        assert np.abs(got_twist[j] - rt).max() <= 1e-9 * max(1, np.abs(rt).max())
+        assert np.abs(got_acc[j] - ra).max() <= 1e-9 * max(1, np.abs(ra).max())
+    # erase a batch (with unknown ids mixed in) and compare the surviving id set
+    gone = np.concatenate([ids[::7], np.array([999999], dtype=np.uint32)])
+    assert mgr.erase_batch(gone) == len(ids[::7])
+    for g in ids[::7]:
+        ref.erase(int(g))
+    assert np.array_equal(mgr.ids(), ref.ids())
+    j = int(order[1]) if ids[order[1]] not in set(ids[::7].tolist()) else int(order[2])
+    st, rs = mgr.state(int(ids[j])), ref.state(int(ids[j]), N)
+    assert synth.compare_h2(st["P"][None], rs["P"][None]) <= 1.0
+    mgr.close()
