@@ -18,6 +18,7 @@
 
 #include "../../include/te_pool.h"
 #include "te_kernels.cuh"
+#include "te_split.cuh"
 
 namespace {
 
@@ -35,46 +36,47 @@ struct CudaError : std::runtime_error {
 
 inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
-// grow-only device scratch, bump-allocated per call
+// grow-only device scratch, bump-allocated per call: one main block sized by the previous call's demand,
+// overflow goes to one-off blocks that are folded into the main block at the next reset
 struct Arena {
-  std::vector<void*> chunks;
-  std::vector<size_t> caps;
-  size_t off = 0, want = 0;
+  char* main = nullptr;
+  size_t main_cap = 0, off = 0, want = 0;
+  std::vector<void*> extra;
   void reset() {
-    if (chunks.size() > 1 || (chunks.size() == 1 && want > caps[0])) {
-      for (void* c : chunks) cudaFree(c);
-      chunks.clear();
-      caps.clear();
-    }
-    if (chunks.empty() && want) {
-      void* p = nullptr;
-      size_t cap = want + want / 2;
-      CK(cudaMalloc(&p, cap));
-      chunks.push_back(p);
-      caps.push_back(cap);
+    for (void* c : extra) cudaFree(c);
+    extra.clear();
+    if (want > main_cap) {
+      cudaFree(main);
+      main = nullptr;
+      main_cap = 0;
+      const size_t cap = want + want / 2;
+      CK(cudaMalloc((void**)&main, cap));
+      main_cap = cap;
     }
     off = 0;
     want = 0;
   }
   void* get(size_t bytes) {
     bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
     want += bytes;
-    if (!chunks.empty() && chunks.size() == 1 && off + bytes <= caps[0]) {
-      void* p = (char*)chunks[0] + off;
+    if (off + bytes <= main_cap) {
+      void* p = main + off;
       off += bytes;
       return p;
     }
     void* p = nullptr;
-    CK(cudaMalloc(&p, bytes ? bytes : 256));
-    chunks.push_back(p);
-    caps.push_back(bytes);
+    CK(cudaMalloc(&p, bytes));
+    extra.push_back(p);
     return p;
   }
   template <class T> T* get_n(size_t n) { return (T*)get(n * sizeof(T)); }
   void destroy() {
-    for (void* c : chunks) cudaFree(c);
-    chunks.clear();
-    caps.clear();
+    for (void* c : extra) cudaFree(c);
+    extra.clear();
+    cudaFree(main);
+    main = nullptr;
+    main_cap = 0;
   }
 };
 
@@ -218,7 +220,8 @@ void ensure_other_capacity(te_pool* p, size_t slots) {
   CK(cudaStreamSynchronize(p->stream));
   free_buf(b);
   alloc_buf(p, b, std::max(slots, p->buf[p->cur].cap));
-  ensure_work(p, b.cap);
+  // the work arrays hold the live alive[] / pos[] of the running compaction: callers size them up-front
+  if (p->wcap < slots) throw std::logic_error("work arrays not sized before compaction");
 }
 
 void sync_host_ids(te_pool* p) {
@@ -279,6 +282,21 @@ void launch_step_t(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   CK(cudaGetLastError());
 }
 
+// row-split kernel (te_split.cuh): one CTA of RS warps per tile, STAGES stages per CTA, CTAS CTAs per SM
+template <int TYPE, int STAGES, int CTAS>
+void launch_split_t(te_pool* p, const te::StepArgs& a, int n_work_hint) {
+  auto kern = te::kf_step_split_kernel<TYPE, STAGES, CTAS>;
+  const size_t smem = te::split_smem_bytes<TYPE>(STAGES);
+  static bool configured[64] = {false};
+  if (!configured[p->device & 63]) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[p->device & 63] = true;
+  }
+  int grid = std::min(p->n_sm * CTAS, std::max(1, n_work_hint));
+  kern<<<grid, te::Split<TYPE>::RS * 32, smem, p->stream>>>(a);
+  CK(cudaGetLastError());
+}
+
 // variant -> (warps, stages) per model.  Stage bytes: UV 13056, UA 25344, AV 43008, AR 90624.
 void launch_step(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   const int v = p->variant;
@@ -295,11 +313,14 @@ void launch_step(te_pool* p, const te::StepArgs& a, int n_work_hint) {
       break;
     case te::ANGULAR_VELOCITIES:
       if (v == 1) launch_step_t<te::ANGULAR_VELOCITIES, 5, 1>(p, a, n_work_hint);
-      else launch_step_t<te::ANGULAR_VELOCITIES, 2, 2>(p, a, n_work_hint);
+      else if (v == 2) launch_split_t<te::ANGULAR_VELOCITIES, 1, 5>(p, a, n_work_hint);
+      else if (v == 3) launch_split_t<te::ANGULAR_VELOCITIES, 3, 1>(p, a, n_work_hint);
+      else launch_split_t<te::ANGULAR_VELOCITIES, 2, 2>(p, a, n_work_hint);
       break;
     default:
-      if (v == 1) launch_step_t<te::ANGULAR_RATES, 1, 2>(p, a, n_work_hint);
-      else launch_step_t<te::ANGULAR_RATES, 2, 1>(p, a, n_work_hint);
+      if (v == 1) launch_step_t<te::ANGULAR_RATES, 2, 1>(p, a, n_work_hint);
+      else if (v == 2) launch_split_t<te::ANGULAR_RATES, 1, 2>(p, a, n_work_hint);
+      else launch_split_t<te::ANGULAR_RATES, 2, 1>(p, a, n_work_hint);
       break;
   }
 }
@@ -660,7 +681,7 @@ long long te_pool_add_batch(te_pool* p, long long n, const uint32_t* ids, const 
       p->n += na;
       p->h_ids.insert(p->h_ids.end(), s_ids, s_ids + na);
     } else {
-      ensure_work(p, (size_t)p->n);
+      ensure_work(p, (size_t)(p->n + na));
       te::fill_i32_kernel<<<cdiv(p->n, 256), 256, 0, p->stream>>>(p->alive, (int)p->n, 1);
       CK(cudaGetLastError());
       compact_and_merge(p, ad, ad.ids, (int)na, nullptr);

@@ -158,7 +158,8 @@ def test_batched_extensions(name):
     for g in ids[::7]:
         ref.erase(int(g))
     assert np.array_equal(mgr.ids(), ref.ids())
-    j = int(order[1]) if ids[order[1]] not in set(ids[::7].tolist()) else int(order[2])
+    gone_set = set(ids[::7].tolist())
+    j = next(int(o) for o in order if int(ids[o]) not in gone_set)
     st, rs = mgr.state(int(ids[j])), ref.state(int(ids[j]), N)
     assert synth.compare_h2(st["P"][None], rs["P"][None]) <= 1.0
     mgr.close()
