@@ -316,23 +316,30 @@ __device__ __forceinline__ void predict_av(PAcc& P, double* x, double dt, const 
 // partial-pivot-LU inverse only in rounding (measured < 1e-12 relative, tests/).
 // -------------------------------------------------------------------------------------
 template <int M> struct Chol {
-  double L[M * (M + 1) / 2];   // row-packed lower triangle; diagonal holds 1/L_jj
-  __device__ __forceinline__ double& at(int i, int j) { return L[i * (i + 1) / 2 + j]; }
+  // lower triangle in a full M x M register array (the upper half is never touched and costs nothing);
+  // the diagonal holds 1/L_jj.  Every loop runs over a constant range with compile-time guards so that the
+  // unroller resolves all indices (triangular trip counts left the factor in local memory).
+  double L[M][M];
+  __device__ __forceinline__ double& at(int i, int j) { return L[i][j]; }
   __device__ __forceinline__ void factor() {
 #pragma unroll
     for (int j = 0; j < M; ++j) {
-      double d = at(j, j);
+      double d = L[j][j];
 #pragma unroll
-      for (int k = 0; k < j; ++k) d -= at(j, k) * at(j, k);
+      for (int k = 0; k < M; ++k)
+        if (k < j) d -= L[j][k] * L[j][k];
       const double inv = 1.0 / sqrt(d);
 #pragma unroll
-      for (int i = j + 1; i < M; ++i) {
-        double s = at(i, j);
+      for (int i = 0; i < M; ++i) {
+        if (i > j) {
+          double s = L[i][j];
 #pragma unroll
-        for (int k = 0; k < j; ++k) s -= at(i, k) * at(j, k);
-        at(i, j) = s * inv;
+          for (int k = 0; k < M; ++k)
+            if (k < j) s -= L[i][k] * L[j][k];
+          L[i][j] = s * inv;
+        }
       }
-      at(j, j) = inv;
+      L[j][j] = inv;
     }
   }
   // solve (L L^T) z = b in place
@@ -341,15 +348,18 @@ template <int M> struct Chol {
     for (int i = 0; i < M; ++i) {
       double s = b[i];
 #pragma unroll
-      for (int k = 0; k < i; ++k) s -= at(i, k) * b[k];
-      b[i] = s * at(i, i);
+      for (int k = 0; k < M; ++k)
+        if (k < i) s -= L[i][k] * b[k];
+      b[i] = s * L[i][i];
     }
 #pragma unroll
-    for (int i = M - 1; i >= 0; --i) {
+    for (int ii = 0; ii < M; ++ii) {
+      const int i = M - 1 - ii;
       double s = b[i];
 #pragma unroll
-      for (int k = i + 1; k < M; ++k) s -= at(k, i) * b[k];
-      b[i] = s * at(i, i);
+      for (int k = 0; k < M; ++k)
+        if (k > i) s -= L[k][i] * b[k];
+      b[i] = s * L[i][i];
     }
   }
 };
@@ -361,7 +371,8 @@ __device__ __forceinline__ void kf_update(PAcc& P, double* x, const double* y, c
 #pragma unroll
   for (int i = 0; i < M; ++i)
 #pragma unroll
-    for (int j = 0; j <= i; ++j) ch.at(i, j) = P(i, j) + __ldg(&R[i * M + j]);
+    for (int j = 0; j < M; ++j)
+      if (j <= i) ch.at(i, j) = P(i, j) + __ldg(&R[i * M + j]);
   ch.factor();
   double v[M];
 #pragma unroll

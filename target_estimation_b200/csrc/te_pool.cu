@@ -313,13 +313,13 @@ void launch_step(te_pool* p, const te::StepArgs& a, int n_work_hint) {
       break;
     case te::ANGULAR_VELOCITIES:
       if (v == 1) launch_step_t<te::ANGULAR_VELOCITIES, 5, 1>(p, a, n_work_hint);
-      else if (v == 2) launch_split_t<te::ANGULAR_VELOCITIES, 1, 5>(p, a, n_work_hint);
-      else if (v == 3) launch_split_t<te::ANGULAR_VELOCITIES, 3, 1>(p, a, n_work_hint);
+      else if (v == 2) launch_split_t<te::ANGULAR_VELOCITIES, 1, 3>(p, a, n_work_hint);
+      else if (v == 3) launch_split_t<te::ANGULAR_VELOCITIES, 4, 1>(p, a, n_work_hint);
       else launch_split_t<te::ANGULAR_VELOCITIES, 2, 2>(p, a, n_work_hint);
       break;
     default:
       if (v == 1) launch_step_t<te::ANGULAR_RATES, 2, 1>(p, a, n_work_hint);
-      else if (v == 2) launch_split_t<te::ANGULAR_RATES, 1, 2>(p, a, n_work_hint);
+      else if (v == 2) launch_split_t<te::ANGULAR_RATES, 1, 1>(p, a, n_work_hint);
       else launch_split_t<te::ANGULAR_RATES, 2, 1>(p, a, n_work_hint);
       break;
   }
