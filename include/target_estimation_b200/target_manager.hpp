@@ -188,6 +188,70 @@ class IntersectionSolver {
   te_isolver* solvers_[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
+// ---------------------------------------------------------------------------------------------------
+// RosTargetManager without ROS (target_manager_ros.hpp:74-183, src/target_manager_ros.cpp:6-107): the /tf
+// mailbox per id, the per-tick init-on-first-sight / update / predict loop, expiry erase and the list of
+// filtered poses the node broadcasts.  ros::Time stamps are (sec, nsec) pairs; ros::Time::now() is passed in.
+// One tick = at most one add, one sparse step launch, one expiry compaction and one estimate gather.
+// ---------------------------------------------------------------------------------------------------
+struct StampedPose {
+  uint32_t sec = 0, nsec = 0;
+  Vector7d pose{};   // geometry_msgs default-constructs to zeros
+};
+double toSec(uint32_t sec, uint32_t nsec);   // utils.hpp:59-62 (never contracted to an FMA)
+
+class Measurement {   // target_manager_ros.hpp:74-134
+ public:
+  Measurement() : last_meas_time_(0.0), new_meas_(true) {}
+  bool read(StampedPose& tr) const {
+    if (new_meas_) { tr = tr_; return true; }   // new_meas_ is NOT cleared by read()
+    return false;
+  }
+  void update(const StampedPose& tr);
+  double getTime() const { return last_meas_time_; }
+  // the accepted stamp behind last_meas_time_, and whether the device copy of it is stale
+  uint32_t acceptedSec() const { return acc_sec_; }
+  uint32_t acceptedNsec() const { return acc_nsec_; }
+  bool stampDirty() const { return stamp_dirty_; }
+  void clearStampDirty() { stamp_dirty_ = false; }
+ private:
+  double last_meas_time_;
+  bool new_meas_;
+  StampedPose tr_;
+  uint32_t acc_sec_ = 0, acc_nsec_ = 0;
+  bool stamp_dirty_ = false;
+};
+
+class TickTargetManager : public TargetManager {
+ public:
+  TickTargetManager(target_t type, const MatrixXd& Q, const MatrixXd& R, const MatrixXd& P, int device = 0);
+  explicit TickTargetManager(const std::string& yaml_file, int device = 0);
+  // /tf callback (src/target_manager_ros.cpp:26-39): frame "<token>_<id>"; a frame that contains the token but does
+  // not parse BREAKS the loop (the rest of the message is dropped), like the reference
+  void measurementCallBack(long long n, const char* const* child_frame_ids, const uint32_t* sec, const uint32_t* nsec, const double* poses);
+  void measurementCallBackIds(long long n, const unsigned* ids, const uint32_t* sec, const uint32_t* nsec, const double* poses);
+  // RosTargetManager::update(dt) (:41-92) with ros::Time::now() = (now_sec, now_nsec).  erased (optional) receives
+  // the ids removed by the expiry rule in ascending order.
+  void tick(const double& dt, uint32_t now_sec, uint32_t now_nsec, std::vector<unsigned>* erased = nullptr);
+  // the poses the node would broadcast after the last tick: ascending ids + [n][7]
+  const std::vector<unsigned>& publishedIds() const { return pub_ids_; }
+  const std::vector<double>& publishedPoses() const { return pub_poses_; }
+  void setTargetTokenName(const std::string& token_name) { token_name_ = token_name; }
+  void setExpirationTime(double t);
+  double time() const { return t_; }
+  size_t mailboxCount() const { return measurements_.size(); }
+  bool publish = true;   // gather the filtered poses every tick (the TF broadcast of :78-87)
+ private:
+  target_t type_;
+  MatrixXd Q_, P_, R_;
+  std::string token_name_;
+  double t_;
+  std::map<unsigned, Measurement> measurements_;
+  double expiration_time_;
+  std::vector<unsigned> pub_ids_;
+  std::vector<double> pub_poses_;
+};
+
 // utils.hpp:273-313
 std::vector<std::string> splitString(const std::string& s, const std::string& delimiter = "_");
 bool getId(const std::string& s, unsigned int& id);

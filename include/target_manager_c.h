@@ -64,6 +64,25 @@ long long target_manager_get_ids(const target_manager_c* self, unsigned int* out
 int target_manager_get_state(const target_manager_c* self, unsigned int id, double* x, double* P, double* t);
 /* pending per-id calls are coalesced into one launch per tick; force them out */
 void target_manager_flush(const target_manager_c* self);
+
+/* ---- tick front-end: RosTargetManager semantics without ROS (src/target_manager_ros.cpp:26-92) ----
+ * The handle is also a valid target_manager_c* for every function above. */
+target_manager_c* target_tick_manager_new(const char* file, int device);
+void target_tick_manager_set_expiration(const target_manager_c* self, double timeout_s);
+void target_tick_manager_set_token(const target_manager_c* self, const char* token);
+/* /tf callback: n transforms with child frame "<token>_<id>" (frames) or already-parsed ids */
+void target_tick_manager_callback_frames(const target_manager_c* self, long long n, const char* const* child_frame_ids,
+                                         const unsigned int* sec, const unsigned int* nsec, const double* poses /*[n][7]*/);
+void target_tick_manager_callback_ids(const target_manager_c* self, long long n, const unsigned int* ids, const unsigned int* sec,
+                                      const unsigned int* nsec, const double* poses /*[n][7]*/);
+/* RosTargetManager::update(dt) with ros::Time::now() = (now_sec, now_nsec); returns #targets erased by the expiry
+ * rule (their ids, ascending, into erased_out up to cap), or -1 on error */
+long long target_tick_manager_update(const target_manager_c* self, double dt, unsigned int now_sec, unsigned int now_nsec,
+                                     unsigned int* erased_out, long long cap);
+/* the filtered poses broadcast by the last tick: ascending ids + [n][7]; returns n */
+long long target_tick_manager_published(const target_manager_c* self, unsigned int* ids_out, double* poses_out, long long cap);
+double target_tick_manager_time(const target_manager_c* self);
+long long target_tick_manager_mailboxes(const target_manager_c* self);
 const char* target_manager_last_error(void);
 
 #ifdef __cplusplus

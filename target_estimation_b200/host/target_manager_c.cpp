@@ -4,7 +4,9 @@
 #include "target_manager_c.h"
 
 #include <cstring>
+#include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "target_estimation_b200/target_manager.hpp"
 
@@ -138,5 +140,61 @@ void target_manager_flush(const target_manager_c* self) {
   guard(0, [&] { M(self)->flush(); return 0; });
 }
 const char* target_manager_last_error(void) { return g_err.c_str(); }
+
+// ---- tick front-end ---------------------------------------------------------------------------------
+static TickTargetManager* T(const target_manager_c* self) {
+  TickTargetManager* t = dynamic_cast<TickTargetManager*>(M(self));
+  if (!t) throw std::invalid_argument("handle is not a tick manager");
+  return t;
+}
+target_manager_c* target_tick_manager_new(const char* file, int device) {
+  return guard((target_manager_c*)nullptr, [&]() -> target_manager_c* {
+    if (!file || !file[0]) throw std::invalid_argument("a model file is required");
+    TargetManager* m = new TickTargetManager(std::string(file), device);
+    m->quiet = true;
+    return (target_manager_c*)m;
+  });
+}
+void target_tick_manager_set_expiration(const target_manager_c* self, double timeout_s) {
+  guard(0, [&] { T(self)->setExpirationTime(timeout_s); return 0; });
+}
+void target_tick_manager_set_token(const target_manager_c* self, const char* token) {
+  guard(0, [&] { T(self)->setTargetTokenName(token ? token : ""); return 0; });
+}
+void target_tick_manager_callback_frames(const target_manager_c* self, long long n, const char* const* frames, const unsigned int* sec,
+                                         const unsigned int* nsec, const double* poses) {
+  guard(0, [&] { T(self)->measurementCallBack(n, frames, sec, nsec, poses); return 0; });
+}
+void target_tick_manager_callback_ids(const target_manager_c* self, long long n, const unsigned int* ids, const unsigned int* sec,
+                                      const unsigned int* nsec, const double* poses) {
+  guard(0, [&] { T(self)->measurementCallBackIds(n, ids, sec, nsec, poses); return 0; });
+}
+long long target_tick_manager_update(const target_manager_c* self, double dt, unsigned int now_sec, unsigned int now_nsec,
+                                     unsigned int* erased_out, long long cap) {
+  return guard(-1LL, [&]() -> long long {
+    std::vector<unsigned> er;
+    T(self)->tick(dt, now_sec, now_nsec, &er);
+    const long long n = (long long)er.size();
+    if (erased_out && cap > 0) std::memcpy(erased_out, er.data(), sizeof(unsigned) * (size_t)(n < cap ? n : cap));
+    return n;
+  });
+}
+long long target_tick_manager_published(const target_manager_c* self, unsigned int* ids_out, double* poses_out, long long cap) {
+  return guard(-1LL, [&]() -> long long {
+    const auto& ids = T(self)->publishedIds();
+    const auto& po = T(self)->publishedPoses();
+    const long long n = (long long)ids.size();
+    const long long k = n < cap ? n : cap;
+    if (ids_out && k > 0) std::memcpy(ids_out, ids.data(), sizeof(unsigned) * (size_t)k);
+    if (poses_out && k > 0) std::memcpy(poses_out, po.data(), sizeof(double) * 7 * (size_t)k);
+    return n;
+  });
+}
+double target_tick_manager_time(const target_manager_c* self) {
+  return guard(-1.0, [&] { return T(self)->time(); });
+}
+long long target_tick_manager_mailboxes(const target_manager_c* self) {
+  return guard(-1LL, [&] { return (long long)T(self)->mailboxCount(); });
+}
 
 }  // extern "C"

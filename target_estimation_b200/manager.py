@@ -33,6 +33,15 @@ _SIG = {
     "target_manager_get_state": (_i, [_p, _u, _p, _p, _p]),
     "target_manager_flush": (None, [_p]),
     "target_manager_last_error": (C.c_char_p, []),
+    "target_tick_manager_new": (_p, [C.c_char_p, _i]),
+    "target_tick_manager_set_expiration": (None, [_p, _d]),
+    "target_tick_manager_set_token": (None, [_p, C.c_char_p]),
+    "target_tick_manager_callback_frames": (None, [_p, _ll, _p, _p, _p, _p]),
+    "target_tick_manager_callback_ids": (None, [_p, _ll, _p, _p, _p, _p]),
+    "target_tick_manager_update": (_ll, [_p, _d, _u, _u, _p, _ll]),
+    "target_tick_manager_published": (_ll, [_p, _p, _p, _ll]),
+    "target_tick_manager_time": (_d, [_p]),
+    "target_tick_manager_mailboxes": (_ll, [_p]),
 }
 for _n, (_r, _a) in _SIG.items():
     _f = getattr(clib, _n)
@@ -130,3 +139,48 @@ class TargetManagerC:
 
     def flush(self):
         clib.target_manager_flush(self.h)
+
+
+class TickManagerC(TargetManagerC):
+    """RosTargetManager semantics without ROS (target_tick_manager_* of include/target_manager_c.h)."""
+
+    def __init__(self, yaml_file, device=0):
+        self.h = clib.target_tick_manager_new(yaml_file.encode(), device)
+        if not self.h:
+            raise RuntimeError("target_tick_manager_new failed: %s" % clib.target_manager_last_error().decode())
+
+    def set_expiration(self, t):
+        clib.target_tick_manager_set_expiration(self.h, float(t))
+
+    def set_token(self, s):
+        clib.target_tick_manager_set_token(self.h, s.encode())
+
+    def callback_ids(self, ids, sec, nsec, poses):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32); sec = np.ascontiguousarray(sec, dtype=np.uint32)
+        nsec = np.ascontiguousarray(nsec, dtype=np.uint32); poses = np.ascontiguousarray(poses, dtype=np.float64)
+        clib.target_tick_manager_callback_ids(self.h, ids.size, _ptr(ids), _ptr(sec), _ptr(nsec), _ptr(poses))
+
+    def callback_frames(self, frames, sec, nsec, poses):
+        arr = (C.c_char_p * len(frames))(*[f.encode() for f in frames])
+        sec = np.ascontiguousarray(sec, dtype=np.uint32); nsec = np.ascontiguousarray(nsec, dtype=np.uint32)
+        poses = np.ascontiguousarray(poses, dtype=np.float64)
+        clib.target_tick_manager_callback_frames(self.h, len(frames), arr, _ptr(sec), _ptr(nsec), _ptr(poses))
+
+    def tick(self, dt, now_sec, now_nsec, cap=1 << 20):
+        out = np.zeros(cap, dtype=np.uint32)
+        n = int(clib.target_tick_manager_update(self.h, dt, now_sec, now_nsec, _ptr(out), cap))
+        if n < 0:
+            raise RuntimeError(clib.target_manager_last_error().decode())
+        return out[:n].copy()
+
+    def published(self):
+        n = int(clib.target_tick_manager_published(self.h, None, None, 0))
+        ids = np.zeros(max(n, 1), dtype=np.uint32); poses = np.zeros((max(n, 1), 7))
+        clib.target_tick_manager_published(self.h, _ptr(ids), _ptr(poses), n)
+        return ids[:n], poses[:n]
+
+    def time(self):
+        return float(clib.target_tick_manager_time(self.h))
+
+    def mailboxes(self):
+        return int(clib.target_tick_manager_mailboxes(self.h))
