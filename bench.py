@@ -12,8 +12,8 @@ whose state (720 B/target) is far larger than the 126 MB L2, so every tick strea
 case is L2-resident and launch-bound and is reported beside it under "c2_10k".
 
 value    : targets x steps / device time, inputs (measurements, action masks) resident in HBM.
-e2e      : same ticks through te_pool_step_dense_host (HOST pinned buffers -> H2D inside the timed region, then the
-           tick, then a D2H read of every target's estimated position).
+e2e      : same ticks through te_pool_tick_host (HOST pinned buffers -> H2D inside the timed region, the tick, and a
+           D2H read of every target's estimated position, pipelined in chunks over three streams).
 roofline : achieved = algorithmic bytes per launch (UA 1496 B per update step, 1456 B per
            predict-only step) / average kernel duration (CUDA events on the pool's stream); peak = MEASURED_PEAKS.json.
 cpu_baseline : the oracle port (oracle/, Eigen-free restatement of the reference TargetManager path) on host cores.
@@ -40,8 +40,8 @@ MODEL_SHORT = {"uniform_velocity": "UV", "uniform_acceleration": "UA", "angular_
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="uniform_acceleration", choices=list(MODEL_SHORT))
     ap.add_argument("--targets", type=int, default=0, help="targets per GPU (default: 4Mi for UV/UA, 1Mi for AV/AR)")
@@ -52,6 +52,17 @@ def parse():
     ap.add_argument("--allgather", action="store_true", help="also time the optional all-gather of estimates (N>1)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
+
+
+def ncu_traffic(model, n):
+    """per-launch DRAM bytes of the dominant kernel from the committed ncu capture of this configuration"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            e = json.load(f).get("%s@%d" % (model, n))
+        if e:
+            return e["traffic_bytes"], e["source"]
+    return None, None
 
 
 def peaks():
@@ -134,13 +145,29 @@ def cpu_run(model_name, threads, seconds, n_targets=10000):
     return {"value": n_targets * ticks / t, "ticks": ticks, "targets": n_targets, "seconds": t, "threads": threads}
 
 
+def default_targets(model):
+    return (4 << 20) if MODEL_SHORT[model] in ("UV", "UA") else (1 << 20)
+
+
+def make_config(model, n, world, variant, n_sets=4, stride=7):
+    import target_estimation_b200.pool as tp
+    N, M = tp.model_dims(tp.MODEL_TYPES[model])
+    short = MODEL_SHORT[model]
+    return {"workload": "BASELINE configs[1] (%s, FP64 predict+update per measurement tick) at %d targets per GPU" % (short, n),
+            "model": model, "targets_per_gpu": n, "targets_total": n * world, "dt": DT, "missed_measurement_prob": 0.05,
+            "measurement_layout": "[n][7] pose, device resident, %d rotating sets" % n_sets,
+            "l2": "inputs larger than L2: state %.0f MB + %.0f MB of measurements per tick vs 126 MB L2" % (
+                n * (N + N * N + 2) * 8 / 1e6, n * stride * 8 / 1e6),
+            "sharding": "owner(id) = id mod n_gpus, no data-path collective", "kernel_variant": variant}
+
+
 def reference_arm(args, rank):
     if rank != 0:
         return
     from tests import orc
     cores = orc.lib().orc_hardware_threads()
     K = max(1, args.steps)
-    per_step = max(0.5, min(20.0, 120.0 / (K + args.warmup)))
+    per_step = min(5.0, 150.0 / (K + args.warmup))   # bounded sample: the whole run stays within a few minutes
     for _ in range(args.warmup):
         cpu_run(args.model, cores, per_step / 4)
     vals, secs = [], 0.0
@@ -153,9 +180,9 @@ def reference_arm(args, rank):
     v = float(np.mean(vals))
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": args.warmup,
            "ms_per_step": 1e3 * secs / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-           "data": "synthetic", "config": {"workload": "BASELINE configs[1]: %s FP64 predict+update per measurement tick" % MODEL_SHORT[args.model],
-                                           "model": args.model, "note": "reference cannot be compiled here (Eigen/yaml-cpp absent): "
-                                           "timed the Eigen-free oracle port of its TargetManager path (-O2), all host threads"},
+           "data": "synthetic", "config": dict(make_config(args.model, args.targets or default_targets(args.model), args.gpus, args.variant),
+                                               reference_arm="reference cannot be compiled here (Eigen / yaml-cpp absent, no network): the Eigen-free "
+                                               "oracle port of its TargetManager path (-O2, -ffp-contract=off), all host threads, bounded sample: " + sample),
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(out), flush=True)
@@ -221,7 +248,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     model = args.model
     short = MODEL_SHORT[model]
-    n = args.targets or ((4 << 20) if short in ("UV", "UA") else (1 << 20))
+    n = args.targets or default_targets(model)
     K, W = args.steps, max(args.warmup, 3)
     stream = torch.cuda.Stream()
     pool, mtype, p0 = make_pool(te, torch, model, n, rank, world, stream, args.variant)
@@ -265,6 +292,7 @@ def main():
     alg_bytes = sum(n_upd[k % n_sets] * B_upd + (n - n_upd[k % n_sets]) * B_pred for k in range(K)) / K
     peak, peak_src = peaks()
     achieved = alg_bytes / (ms / K * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(model, n)
 
     # ---- e2e: host buffers through the C-ABI ---------------------------------------------------------
     e2e = None
@@ -354,13 +382,8 @@ def main():
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": "BASELINE configs[1] (%s, FP64 predict+update per measurement tick) at %d targets per GPU" % (short, n),
-                          "model": model, "targets_per_gpu": n, "targets_total": n * world, "dt": DT, "missed_measurement_prob": 0.05,
-                          "measurement_layout": "[n][7] pose, device resident, %d rotating sets" % n_sets,
-                          "l2": "inputs larger than L2: state %.0f MB + %.0f MB of measurements per tick vs 126 MB L2" % (
-                              n * (N + N * N + 2) * 8 / 1e6, n * stride * 8 / 1e6),
-                          "sharding": "owner(id) = id mod n_gpus, no data-path collective", "kernel_variant": args.variant},
-               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+               "config": make_config(model, n, world, args.variant, n_sets, stride),
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                             "peak_source": peak_src, "kernel": "te::kf_step_kernel<%s>" % short, "alg_bytes_per_launch": alg_bytes,
                             "alg_bytes_per_update_step": B_upd, "alg_bytes_per_predict_step": B_pred, "kernel_ms": ms / K},
                "clocks": clocks, "gpu_launches": K, "e2e": e2e, "cpu_baseline": cpu, "c2_10k": small}

@@ -283,10 +283,10 @@ void launch_step_t(te_pool* p, const te::StepArgs& a, int n_work_hint) {
 }
 
 // row-split kernel (te_split.cuh): one CTA of RS warps per tile, STAGES stages per CTA, CTAS CTAs per SM
-template <int TYPE, int STAGES, int CTAS>
+template <int TYPE, int STAGES, int CTAS, bool WSEP>
 void launch_split_t(te_pool* p, const te::StepArgs& a, int n_work_hint) {
-  auto kern = te::kf_step_split_kernel<TYPE, STAGES, CTAS>;
-  const size_t smem = te::split_smem_bytes<TYPE>(STAGES);
+  auto kern = te::kf_step_split_kernel<TYPE, STAGES, CTAS, WSEP>;
+  const size_t smem = te::split_smem_bytes<TYPE>(STAGES, WSEP);
   static bool configured[64] = {false};
   if (!configured[p->device & 63]) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -313,14 +313,17 @@ void launch_step(te_pool* p, const te::StepArgs& a, int n_work_hint) {
       break;
     case te::ANGULAR_VELOCITIES:
       if (v == 1) launch_step_t<te::ANGULAR_VELOCITIES, 5, 1>(p, a, n_work_hint);
-      else if (v == 2) launch_split_t<te::ANGULAR_VELOCITIES, 1, 3>(p, a, n_work_hint);
-      else if (v == 3) launch_split_t<te::ANGULAR_VELOCITIES, 4, 1>(p, a, n_work_hint);
-      else launch_split_t<te::ANGULAR_VELOCITIES, 2, 2>(p, a, n_work_hint);
+      else if (v == 2) launch_split_t<te::ANGULAR_VELOCITIES, 1, 3, true>(p, a, n_work_hint);
+      else if (v == 3) launch_split_t<te::ANGULAR_VELOCITIES, 1, 4, false>(p, a, n_work_hint);
+      else if (v == 4) launch_split_t<te::ANGULAR_VELOCITIES, 2, 2, false>(p, a, n_work_hint);
+      else launch_split_t<te::ANGULAR_VELOCITIES, 2, 2, true>(p, a, n_work_hint);
       break;
     default:
       if (v == 1) launch_step_t<te::ANGULAR_RATES, 2, 1>(p, a, n_work_hint);
-      else if (v == 2) launch_split_t<te::ANGULAR_RATES, 1, 1>(p, a, n_work_hint);
-      else launch_split_t<te::ANGULAR_RATES, 2, 1>(p, a, n_work_hint);
+      else if (v == 2) launch_split_t<te::ANGULAR_RATES, 1, 1, true>(p, a, n_work_hint);
+      else if (v == 3) launch_split_t<te::ANGULAR_RATES, 1, 2, false>(p, a, n_work_hint);
+      else if (v == 4) launch_split_t<te::ANGULAR_RATES, 2, 1, false>(p, a, n_work_hint);
+      else launch_split_t<te::ANGULAR_RATES, 2, 1, true>(p, a, n_work_hint);
       break;
   }
 }

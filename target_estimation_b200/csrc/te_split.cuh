@@ -26,8 +26,8 @@ namespace te {
 template <int TYPE> struct Split { static constexpr int RS = 6; };   // AR: rows r, 6+r, 12+r ; AV: rows r, 6+r
 
 // shared memory of one CTA: [mbarriers 1 KB][STAGES x (tile + measurement block)][W: M x N x 32][y: 6 x 32]
-template <int TYPE> __host__ __device__ constexpr size_t split_smem_bytes(int stages) {
-  return 1024 + ((size_t)stages * stage_doubles<TYPE>() + (size_t)Model<TYPE>::M * Model<TYPE>::N * TILE + 6 * TILE) * 8;
+template <int TYPE> __host__ __device__ constexpr size_t split_smem_bytes(int stages, bool wsep) {
+  return 1024 + ((size_t)stages * stage_doubles<TYPE>() + (wsep ? (size_t)Model<TYPE>::M * Model<TYPE>::N * TILE : 0) + 6 * TILE) * 8;
 }
 
 __device__ __forceinline__ double sel3(const double a[3], int r) { return r == 0 ? a[0] : (r == 1 ? a[1] : a[2]); }
@@ -42,7 +42,9 @@ __device__ __forceinline__ double quat_to_rpy_comp(const Quat& q, int k) {
   return atan2(2 * (q.x * q.y + q.w * q.z), (q.w * q.w + q.x * q.x - q.y * q.y - q.z * q.z));
 }
 
-template <int TYPE, int STAGES, int MIN_CTAS>
+// WSEP: W goes to its own buffer (3 barriers per tile) or overwrites the published top rows in place (2 more
+// barriers, 27 KB less shared memory for AR -> two CTAs per SM)
+template <int TYPE, int STAGES, int MIN_CTAS, bool WSEP>
 __global__ void __launch_bounds__(Split<TYPE>::RS * 32, MIN_CTAS) kf_step_split_kernel(const StepArgs a) {
   using MT = Model<TYPE>;
   using LY = Layout<TYPE>;
@@ -55,8 +57,8 @@ __global__ void __launch_bounds__(Split<TYPE>::RS * 32, MIN_CTAS) kf_step_split_
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   double* stage0 = reinterpret_cast<double*>(smem_raw + 1024);
-  double* Wbuf = stage0 + (size_t)STAGES * STAGE_DOUBLES;   // [M][N][32]
-  double* ybuf = Wbuf + (size_t)M * N * TILE;               // [6][32]
+  double* Wsep = stage0 + (size_t)STAGES * STAGE_DOUBLES;   // [M][N][32] (WSEP only)
+  double* ybuf = Wsep + (WSEP ? (size_t)M * N * TILE : 0);  // [6][32]
   const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool producer = threadIdx.x == 0;
 
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(Split<TYPE>::RS * 32, MIN_CTAS) kf_step_split_
       issue(it + STAGES - 1);
     }
     double* st = stage0 + (size_t)s * STAGE_DOUBLES;
+    double* Wbuf = WSEP ? Wsep : st + LY::F_P * TILE;   // in place: W(k,c) takes the slot of P'(k,c), k < M
     mbar_wait(&bars[s], parity);
 
     // lane = target in every warp, so a warp ballot already is the tile-wide answer
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(Split<TYPE>::RS * 32, MIN_CTAS) kf_step_split_
       __syncthreads();
 
       // ---- phase B: S = P'[0:M,0:M] + R, v, this warp's columns of W -> Wbuf ---------------------------
-      double v[M];
+      double Wc[M][CW];
       if (upd) {
         Chol<M> ch;
 #pragma unroll
@@ -259,6 +262,7 @@ __global__ void __launch_bounds__(Split<TYPE>::RS * 32, MIN_CTAS) kf_step_split_
           for (int j = 0; j < M; ++j)
             if (j <= i) ch.at(i, j) = st[(LY::F_P + i * N + j) * TILE + lane] + __ldg(&R[i * M + j]);
         ch.factor();
+        double v[M];
 #pragma unroll
         for (int k = 0; k < M; ++k) v[k] = ybuf[k * TILE + lane] - st[(LY::F_X + k) * TILE + lane];
         ch.solve(v);
@@ -270,24 +274,33 @@ __global__ void __launch_bounds__(Split<TYPE>::RS * 32, MIN_CTAS) kf_step_split_
           for (int k = 0; k < M; ++k) col[k] = st[(LY::F_P + k * N + c) * TILE + lane];
           ch.solve(col);
 #pragma unroll
-          for (int k = 0; k < M; ++k) Wbuf[(k * N + c) * TILE + lane] = col[k];
+          for (int k = 0; k < M; ++k) Wc[k][cc] = col[k];
         }
-      }
-      __syncthreads();
-
-      // ---- phase C: own rows: x += P'[rows,0:M] v ; P[rows,:] -= P'[rows,0:M] W ---------------------------
-      if (upd) {
-        double Pk[RPT][M];
+        // x += P'[rows,0:M] v (K (y - C x'), src/kalman.cpp:93) here, so that v is dead before phase C
 #pragma unroll
         for (int q = 0; q < RPT; ++q) {
           double sacc = 0.0;
 #pragma unroll
-          for (int k = 0; k < M; ++k) {
-            Pk[q][k] = Pr[q][k];
-            sacc += Pr[q][k] * v[k];
-          }
+          for (int k = 0; k < M; ++k) sacc += Pr[q][k] * v[k];
           xr[q] += sacc;
         }
+      }
+      if (!WSEP) __syncthreads();   // in place: every warp has read S and its columns of P'[0:M,:]
+      if (upd) {
+#pragma unroll
+        for (int cc = 0; cc < CW; ++cc)
+#pragma unroll
+          for (int k = 0; k < M; ++k) Wbuf[(k * N + r * CW + cc) * TILE + lane] = Wc[k][cc];
+      }
+      __syncthreads();
+
+      // ---- phase C: own rows: P[rows,:] -= P'[rows,0:M] W ((I - K C) P, src/kalman.cpp:94) ----------------
+      if (upd) {
+        double Pk[RPT][M];
+#pragma unroll
+        for (int q = 0; q < RPT; ++q)
+#pragma unroll
+          for (int k = 0; k < M; ++k) Pk[q][k] = Pr[q][k];
 #pragma unroll
         for (int c = N - 1; c >= 0; --c) {
           double w[M];
@@ -302,6 +315,7 @@ __global__ void __launch_bounds__(Split<TYPE>::RS * 32, MIN_CTAS) kf_step_split_
           }
         }
       }
+      if (!WSEP) __syncthreads();   // in place: every warp has read W before rows 0..M-1 are rewritten
 
       // ---- phase D: own rows back into the stage (nobody reads the published top rows after phase B) ------
       if (active) {

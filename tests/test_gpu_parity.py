@@ -58,7 +58,7 @@ def test_step_parity_small(model):
 
 
 @pytest.mark.parametrize("model", MODELS)
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_step_parity_variants(model, variant):
     w = _run(model, 200, 40, variant=variant, check_every=20)
     assert w["x"] <= 1.0 and w["P"] <= 1.0, w
