@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "te_fmod.h"
+
 namespace te {
 
 enum : int { ANGULAR_RATES = 0, ANGULAR_VELOCITIES = 1, UNIFORM_ACCELERATION = 2, UNIFORM_VELOCITY = 3 };
@@ -77,20 +79,20 @@ template <int N> struct SmemP {
 #define TE_PI 3.14159265358979323846
 
 __device__ __forceinline__ double constrain_angle(double x) {   // geometry.hpp:31-36
-  x = fmod(x + TE_PI, 2 * TE_PI);
+  x = fmod_exact(x + TE_PI, 2 * TE_PI);
   if (x < 0) x += 2 * TE_PI;
   return x - TE_PI;
 }
-__device__ __forceinline__ double angle_conv(double a) { return fmod(constrain_angle(a), 2 * TE_PI); }   // :43-45
+__device__ __forceinline__ double angle_conv(double a) { return fmod_exact(constrain_angle(a), 2 * TE_PI); }   // :43-45
 __device__ __forceinline__ double angle_diff(double a, double b) {   // geometry.hpp:53-58
-  double dif = fmod(b - a + TE_PI, 2 * TE_PI);
+  double dif = fmod_exact(b - a + TE_PI, 2 * TE_PI);
   if (dif < 0) dif += 2 * TE_PI;
   return dif - TE_PI;
 }
 __device__ __forceinline__ double unwrap1(double prev, double nw) {   // geometry.hpp:70-76
   return prev - angle_diff(nw, angle_conv(prev));
 }
-__device__ __forceinline__ double wrap_max(double x, double mx) { return fmod(mx + fmod(x, mx), mx); }          // :79-83
+__device__ __forceinline__ double wrap_max(double x, double mx) { return fmod_exact(mx + fmod_exact(x, mx), mx); }          // :79-83
 __device__ __forceinline__ double wrap_min_max(double x, double mn, double mx) { return mn + wrap_max(x - mn, mx - mn); }  // :85-88
 
 struct Quat { double x, y, z, w; };
@@ -328,7 +330,9 @@ template <int M> struct Chol {
 #pragma unroll
       for (int k = 0; k < M; ++k)
         if (k < j) d -= L[j][k] * L[j][k];
-      const double inv = 1.0 / sqrt(d);
+      // reciprocal square root: one MUFU seed + Newton steps instead of sqrt followed by a division -- this scalar sits
+      // on the longest dependent chain of the whole step (six of them in a row for M = 6); <= 2 ulp, far inside 1e-9
+      const double inv = rsqrt(d);
 #pragma unroll
       for (int i = 0; i < M; ++i) {
         if (i > j) {

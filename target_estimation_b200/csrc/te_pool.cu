@@ -282,18 +282,18 @@ void launch_step_t(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   CK(cudaGetLastError());
 }
 
-// row-split kernel (te_split.cuh): one CTA of RS warps per tile, STAGES stages per CTA, CTAS CTAs per SM
-template <int TYPE, int STAGES, int CTAS, bool WSEP>
+// row/column-split kernel (te_split.cuh): one CTA of 6*CS warps per tile, STAGES stages per CTA, CTAS CTAs per SM
+template <int TYPE, int CS, int STAGES, int CTAS>
 void launch_split_t(te_pool* p, const te::StepArgs& a, int n_work_hint) {
-  auto kern = te::kf_step_split_kernel<TYPE, STAGES, CTAS, WSEP>;
-  const size_t smem = te::split_smem_bytes<TYPE>(STAGES, WSEP);
+  auto kern = te::kf_step_split_kernel<TYPE, CS, STAGES, CTAS>;
+  const size_t smem = te::split_smem_bytes<TYPE>(STAGES);
   static bool configured[64] = {false};
   if (!configured[p->device & 63]) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[p->device & 63] = true;
   }
   int grid = std::min(p->n_sm * CTAS, std::max(1, n_work_hint));
-  kern<<<grid, te::Split<TYPE>::RS * 32, smem, p->stream>>>(a);
+  kern<<<grid, (te::SPLIT_RS * CS + te::split_nt<TYPE>()) * 32, smem, p->stream>>>(a);
   CK(cudaGetLastError());
 }
 
@@ -313,17 +313,15 @@ void launch_step(te_pool* p, const te::StepArgs& a, int n_work_hint) {
       break;
     case te::ANGULAR_VELOCITIES:
       if (v == 1) launch_step_t<te::ANGULAR_VELOCITIES, 5, 1>(p, a, n_work_hint);
-      else if (v == 2) launch_split_t<te::ANGULAR_VELOCITIES, 1, 3, true>(p, a, n_work_hint);
-      else if (v == 3) launch_split_t<te::ANGULAR_VELOCITIES, 1, 4, false>(p, a, n_work_hint);
-      else if (v == 4) launch_split_t<te::ANGULAR_VELOCITIES, 2, 2, false>(p, a, n_work_hint);
-      else launch_split_t<te::ANGULAR_VELOCITIES, 2, 2, true>(p, a, n_work_hint);
+      else if (v == 2) launch_split_t<te::ANGULAR_VELOCITIES, 1, 2, 1>(p, a, n_work_hint);
+      else if (v == 3) launch_split_t<te::ANGULAR_VELOCITIES, 1, 1, 3>(p, a, n_work_hint);
+      else if (v == 4) launch_split_t<te::ANGULAR_VELOCITIES, 1, 3, 1>(p, a, n_work_hint);
+      else launch_split_t<te::ANGULAR_VELOCITIES, 1, 2, 2>(p, a, n_work_hint);
       break;
     default:
       if (v == 1) launch_step_t<te::ANGULAR_RATES, 2, 1>(p, a, n_work_hint);
-      else if (v == 2) launch_split_t<te::ANGULAR_RATES, 1, 1, true>(p, a, n_work_hint);
-      else if (v == 3) launch_split_t<te::ANGULAR_RATES, 1, 2, false>(p, a, n_work_hint);
-      else if (v == 4) launch_split_t<te::ANGULAR_RATES, 2, 1, false>(p, a, n_work_hint);
-      else launch_split_t<te::ANGULAR_RATES, 2, 1, true>(p, a, n_work_hint);
+      else if (v == 2) launch_split_t<te::ANGULAR_RATES, 1, 1, 1>(p, a, n_work_hint);
+      else launch_split_t<te::ANGULAR_RATES, 1, 2, 1>(p, a, n_work_hint);
       break;
   }
 }
@@ -1119,3 +1117,10 @@ int te_isolver_query(te_isolver* s, long long n, const uint32_t* ids, const int3
 }
 
 }  // extern "C"
+
+#ifdef TE_TIMELINE
+// debug build only (tools/timeline.py): phase timestamps of CTA 0 recorded by kf_step_split_kernel
+extern "C" int te_debug_timeline(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, te::g_timeline, sizeof(long long) * 2 * 64 * 12);
+}
+#endif

@@ -1,36 +1,77 @@
-// te_split.cuh -- row-split KF step kernel for the large-state models (AR n=18, AV n=12).
+// te_split.cuh -- warp-specialised row/column-split KF step kernel for the large-state models (AR n=18, AV n=12).
 //
-// One CTA of RS = 6 warps works on one tile of 32 targets: lane = target, warp r owns the rows
-// {q*6 + r} of every target's covariance (AR: rows r, 6+r, 12+r = one row of each kinematic block;
-// AV: rows r, 6+r = (p_r, v_r) for r < 3 and (rpy_i, w_i) for r = 3 + i), held in registers.  The tile itself is staged in
-// shared memory by one TMA bulk copy and written back by one bulk store, as in kf_step_kernel; what the
-// row owners must exchange -- the top M rows of the predicted covariance and W = S^-1 P'[0:M,:] -- goes
-// through the staged tile in place, with CTA barriers between the phases:
+// One CTA works on one tile of 32 targets (lane = target) with two groups of warps:
 //
-//   A  predict own rows (x' = A x | f(x), P' = A P A^T + Q); warps 0..2 convert one Euler angle each
-//      (quat -> rpy -> unwrap); publish row r of P', x'[r], y                                              | barrier
-//   B  every warp factors S = P'[0:M,0:M] + R (in-register Cholesky), solves v = S^-1 (y - x'[0:M]) and
-//      its N/6 columns of W into a separate W buffer                                                     | barrier
-//   C  own rows: x += P'[rows,0:M] v ; P[rows,:] = P'[rows,:] - P'[rows,0:M] W
-//   D  own rows back into the stage, t / n_meas bookkeeping                                              | barrier, bulk store
-// (AV has one more barrier in A: warps 3..5 read the original rows 3..5 / 9..11 before they are republished.)
+//  * 6*CS MAIN warps.  Warp (r, h) owns, for every target of the tile, the rows {q*6 + r} and the columns
+//    {b*6 + 3h + cc} (CS = 2; all columns for CS = 1) of the covariance, in registers.  With that ownership the predict
+//    of the kinematic models is thread-local (row r of each kinematic block, and the columns c, 6+c, 12+c that the
+//    banded A(dt) couples), and the EKF predict of AV needs only the original rows 3..5 / 9..11 from the staged tile.
+//  * NT CONVERTER warps, running up to STAGES-1 tiles AHEAD of the main warps: one Euler angle of the measurement
+//    each (normalise quaternion -> rpy -> unwrap against the previous unwrapped angle: sqrt, divisions, atan2 / asin
+//    and three fmods -- a ~4000-cycle dependent chain that used to sit on the critical path of every tile), and for AV
+//    a fourth warp that evaluates the Euler-rate Jacobians J_rpy, J_w and E^-1 once per target.  They hand y (and J) to
+//    the main warps through shared memory and a named barrier (bar.arrive / bar.sync) per stage.
 //
-// Same arithmetic as te_device.cuh's step_lane (predict_kinematic / predict_av / kf_update); only the
-// ownership of the rows differs.  Reference: src/kalman.cpp:84-95,129-140, src/types/angular_rates.cpp:72-115,
+// The tile is staged in shared memory by one TMA bulk copy (mbarrier completion; both groups wait on it) and written
+// back by one bulk store, as in kf_step_kernel.  Main-warp phases, separated by named barriers of the main group:
+//
+//   A  predict own block (x' = A x | f(x), P' = A P A^T + Q); publish in place: row r of P', x'[r], P'[own rows, 0:6]  | barrier
+//   B  warp 0: S = P'[0:6,0:6] + R (in-register Cholesky), v = S^-1 (y - x'[0:6]); warps 1..: factor S, columns of
+//      W = S^-1 P'[0:6,:] -> W buffer; the last warp's lane 0 is the TMA producer and refills the other stage here   | barrier
+//   C  own block: x += P'[rows, 0:6] v ; P[rows, cols] = P'[rows, cols] - P'[rows, 0:6] W[:, cols]
+//   D  own block back into the stage, t / n_meas bookkeeping                                               | barrier, bulk store
+// (AV: the r >= 3 warps read the original rows 3..5 / 9..11 in A; a named barrier among them orders those reads
+//  before the in-place publish.)
+//
+// Same arithmetic as te_device.cuh's step_lane (predict_kinematic / predict_av / kf_update); only the ownership of
+// the elements differs.  Reference: src/kalman.cpp:84-95,129-140, src/types/angular_rates.cpp:72-115,
 // src/types/angular_velocities.cpp:80-151.
 #pragma once
 #include "te_kernels.cuh"
 
 namespace te {
 
-template <int TYPE> struct Split { static constexpr int RS = 6; };   // AR: rows r, 6+r, 12+r ; AV: rows r, 6+r
+#ifdef TE_TIMELINE
+// debug build only: CTA 0 / thread 0 records clock64() at the phase boundaries of its first 64 tiles
+__device__ long long g_timeline[2 * 64 * 12];
+#define TE_MARK(k) do { if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 96) && it < 64) g_timeline[((threadIdx.x ? 1 : 0) * 64 + it) * 12 + (k)] = clock64(); } while (0)
+#else
+#define TE_MARK(k) do { } while (0)
+#endif
 
-// shared memory of one CTA: [mbarriers 1 KB][STAGES x (tile + measurement block)][W: M x N x 32][y: 6 x 32]
-template <int TYPE> __host__ __device__ constexpr size_t split_smem_bytes(int stages, bool wsep) {
-  return 1024 + ((size_t)stages * stage_doubles<TYPE>() + (wsep ? (size_t)Model<TYPE>::M * Model<TYPE>::N * TILE : 0) + 6 * TILE) * 8;
+#ifndef TE_BULK_CHUNK_DOUBLES
+#define TE_BULK_CHUNK_DOUBLES (1 << 20)   // whole tile in one bulk copy (8 KB chunks measured slightly slower)
+#endif
+constexpr int BULK_CHUNK_DOUBLES = TE_BULK_CHUNK_DOUBLES;
+#ifndef TE_SKIP
+#define TE_SKIP 0   // timing experiments only (results become wrong): 1 skip phase B, 2 skip phase C, 4 skip predict, 16 skip converters
+#endif
+constexpr int SPLIT_RS = 6;     // row owners per target (= M for both angular models)
+constexpr int JBUF_FIELDS = 14; // AV: J_rpy (5 non-trivial) + J_w (6) + predicted rpy (3)
+constexpr int SPLIT_BAR_BYTES = 128;   // mbarriers in front of the stages
+
+// converter warps: 2, so that 6 main + 2 = 8 warps = two per scheduler partition and every thread may keep 255 registers
+// (a 9th warp would cap all of them at 168: registers are allocated per partition)
+template <int TYPE> __host__ __device__ constexpr int split_nt() { return 2; }
+
+// shared memory of one CTA: [mbarriers 128 B][STAGES x (tile + measurement block)][W: 6 x N x 32][STAGES x y: 6 x 32]
+// [STAGES x jbuf: 14 x 32 (AV)]   (AV, 2 stages: 115 712 B -> two CTAs per SM)
+template <int TYPE> __host__ __device__ constexpr size_t split_smem_bytes(int stages) {
+  return SPLIT_BAR_BYTES + ((size_t)stages * stage_doubles<TYPE>() + (size_t)Model<TYPE>::M * Model<TYPE>::N * TILE +
+                 (size_t)stages * (6 * TILE + (TYPE == ANGULAR_VELOCITIES ? JBUF_FIELDS * TILE : 0))) * 8;
 }
 
-__device__ __forceinline__ double sel3(const double a[3], int r) { return r == 0 ? a[0] : (r == 1 ? a[1] : a[2]); }
+// named barriers with immediate ids (a register id makes ptxas reserve all 16 hardware barriers, i.e. one CTA per SM)
+template <int ID, int COUNT> __device__ __forceinline__ void named_bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
+template <int ID, int COUNT> __device__ __forceinline__ void named_bar_arrive() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
+template <int BASE, int COUNT> __device__ __forceinline__ void stage_bar_sync(int s) {
+  if (s == 0) named_bar_sync<BASE, COUNT>(); else if (s == 1) named_bar_sync<BASE + 1, COUNT>();
+  else if (s == 2) named_bar_sync<BASE + 2, COUNT>(); else named_bar_sync<BASE + 3, COUNT>();
+}
+template <int BASE, int COUNT> __device__ __forceinline__ void stage_bar_arrive(int s) {
+  if (s == 0) named_bar_arrive<BASE, COUNT>(); else if (s == 1) named_bar_arrive<BASE + 1, COUNT>();
+  else if (s == 2) named_bar_arrive<BASE + 2, COUNT>(); else named_bar_arrive<BASE + 3, COUNT>();
+}
 
 // component k of quatToRpy (geometry.hpp:154-176), same expressions as quat_to_rpy()
 __device__ __forceinline__ double quat_to_rpy_comp(const Quat& q, int k) {
@@ -42,25 +83,34 @@ __device__ __forceinline__ double quat_to_rpy_comp(const Quat& q, int k) {
   return atan2(2 * (q.x * q.y + q.w * q.z), (q.w * q.w + q.x * q.x - q.y * q.y - q.z * q.z));
 }
 
-// WSEP: W goes to its own buffer (3 barriers per tile) or overwrites the published top rows in place (2 more
-// barriers, 27 KB less shared memory for AR -> two CTAs per SM)
-template <int TYPE, int STAGES, int MIN_CTAS, bool WSEP>
-__global__ void __launch_bounds__(Split<TYPE>::RS * 32, MIN_CTAS) kf_step_split_kernel(const StepArgs a) {
+template <int TYPE, int CS, int STAGES, int MIN_CTAS>
+__global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_CTAS) kf_step_split_kernel(const StepArgs a) {
   using MT = Model<TYPE>;
   using LY = Layout<TYPE>;
-  constexpr int N = MT::N, M = MT::M, RS = Split<TYPE>::RS;
+  constexpr int N = MT::N, M = MT::M, RS = SPLIT_RS;
+  constexpr int NW = RS * CS;        // warps per CTA
   constexpr int RPT = N / RS;        // rows per thread: AR 3, AV 2
-  constexpr int CW = N / RS;         // W columns per warp
+  constexpr int NCOL = N / CS;       // columns per thread
+  constexpr int BL = 6 / CS;         // own columns per block of 6
+  constexpr int NT = split_nt<TYPE>();         // converter warps
+  constexpr int NMAIN = NW * 32;               // threads of the main group
+  constexpr int WPW = (N + NW - 2) / (NW - 1); // W columns per warp 1.. (warp 0 solves v)
+  // named barriers: 0 = __syncthreads at start-up, 1 = AV r >= 3 group, BAR_MAIN = main group,
+  // BAR_Y + s = converters -> main (y / J of the tile in stage s), BAR_DONE + s = main -> producer (tile in stage s finished)
+  constexpr int BAR_MAIN = 2, BAR_Y = 3, BAR_DONE = BAR_Y + STAGES;
   constexpr int STAGE_DOUBLES = stage_doubles<TYPE>();
-  static_assert(N % RS == 0 && M == RS, "one measured row per thread");
+  static_assert(M == RS && (CS == 1 || CS == 2) && STAGES <= 4 && 3 + 2 * STAGES <= 16, "one measured row per row owner");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  double* stage0 = reinterpret_cast<double*>(smem_raw + 1024);
-  double* Wsep = stage0 + (size_t)STAGES * STAGE_DOUBLES;   // [M][N][32] (WSEP only)
-  double* ybuf = Wsep + (WSEP ? (size_t)M * N * TILE : 0);  // [6][32]
-  const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool producer = threadIdx.x == 0;
+  double* stage0 = reinterpret_cast<double*>(smem_raw + SPLIT_BAR_BYTES);
+  double* Wbuf = stage0 + (size_t)STAGES * STAGE_DOUBLES;   // [M][N][32]
+  double* ybuf0 = Wbuf + (size_t)M * N * TILE;              // [STAGES][6][32]
+  double* jbuf0 = ybuf0 + (size_t)STAGES * 6 * TILE;        // [STAGES][17][32] (AV)
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = w % RS, h = (w / RS) % CS;
+  const bool producer = threadIdx.x == (NW + 1) * 32;       // lane 0 of converter warp 1: every TMA issue / wait lives there
+  auto colof = [&](int j) -> int { return CS == 1 ? j : (j / BL) * 6 + BL * h + (j % BL); };
 
   if (producer) {
 #pragma unroll
@@ -72,8 +122,8 @@ __global__ void __launch_bounds__(Split<TYPE>::RS * 32, MIN_CTAS) kf_step_split_
   const int n_work = a.d_nwork ? *a.d_nwork : a.n_tiles;
   const int n_my = (n_work > (int)blockIdx.x) ? (n_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   auto tile_of = [&](int it) -> int {
-    const int w = blockIdx.x + it * gridDim.x;
-    return a.tile_list ? a.tile_list[w] : a.tile_begin + w;
+    const int ww = blockIdx.x + it * gridDim.x;
+    return a.tile_list ? a.tile_list[ww] : a.tile_begin + ww;
   };
   auto use_meas_tma = [&](int tile) -> bool { return a.meas_tma && (tile * TILE + TILE <= a.n_slots); };
   auto issue = [&](int it) {
@@ -83,11 +133,18 @@ __global__ void __launch_bounds__(Split<TYPE>::RS * 32, MIN_CTAS) kf_step_split_
     const bool mt = use_meas_tma(tile);
     const uint32_t mbytes = mt ? (uint32_t)a.meas_stride * TILE * 8u : 0u;
     mbar_expect_tx(&bars[s], (uint32_t)LY::TILE_BYTES + mbytes);
-    bulk_g2s(st, a.tiles + (size_t)tile * LY::TILE_DOUBLES, LY::TILE_BYTES, &bars[s]);
+    // the tile travels as several bulk copies on one mbarrier: a single 40-90 KB copy is served at ~18 B/clk, several
+    // smaller ones overlap in the copy engine
+    const double* src = a.tiles + (size_t)tile * LY::TILE_DOUBLES;
+#pragma unroll 1
+    for (int off = 0; off < LY::TILE_DOUBLES; off += BULK_CHUNK_DOUBLES) {
+      const int nd = (LY::TILE_DOUBLES - off) < BULK_CHUNK_DOUBLES ? (LY::TILE_DOUBLES - off) : BULK_CHUNK_DOUBLES;
+      bulk_g2s(st + off, src + off, (uint32_t)nd * 8u, &bars[s]);
+    }
     if (mt) bulk_g2s(st + LY::TILE_DOUBLES, a.meas + (size_t)tile * TILE * a.meas_stride, mbytes, &bars[s]);
   };
   if (producer) {
-    for (int pre = 0; pre < STAGES - 1 && pre < n_my; ++pre) issue(pre);
+    for (int pre = 0; pre < STAGES && pre < n_my; ++pre) issue(pre);
   }
 
   // per-lane control words, fetched one tile ahead so that their global-load latency never sits in front of a tile
@@ -106,6 +163,109 @@ __global__ void __launch_bounds__(Split<TYPE>::RS * 32, MIN_CTAS) kf_step_split_
   };
   load_ctrl(0);
 
+  // =========================== converter warps ===========================
+  if (w >= NW) {
+    const int tw = w - NW;
+    // converter 1 is also the TMA producer: when the main warps have finished tile jd (named barrier BAR_DONE + stage) it
+    // issues the bulk store, waits until the store has drained the stage and refills it with tile jd + STAGES -- the main
+    // warps never wait on a copy
+    unsigned anyh[4] = {0u, 0u, 0u, 0u};   // "tile has work" per stage, noted when the converter handled the tile
+    auto retire = [&](int jd) {
+      if (jd < 0 || jd >= n_my) return;
+      const int sd = jd % STAGES;
+      const int tile_d = tile_of(jd);
+      const unsigned any_d = sd == 0 ? anyh[0] : (sd == 1 ? anyh[1] : (sd == 2 ? anyh[2] : anyh[3]));
+      stage_bar_sync<BAR_DONE, NMAIN + 32>(sd);
+      if (producer) {
+        double* std_ = stage0 + (size_t)sd * STAGE_DOUBLES;
+        if (any_d) {
+          bulk_s2g(a.tiles + (size_t)tile_d * LY::TILE_DOUBLES, std_, LY::TILE_BYTES);
+          bulk_commit();
+          if (a.clear_action) a.tile_flag[tile_d] = 0;
+        }
+        if (jd + STAGES < n_my) {
+          bulk_wait_read<0>();
+          issue(jd + STAGES);
+        }
+      }
+    };
+    for (int it = 0; it < n_my; ++it) {
+      const int s = it % STAGES;
+      const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
+      const int tile = tile_of(it);
+      const int slot = tile * TILE + lane;
+      const int act = act_n;
+      const double dt = dt_n;
+      load_ctrl(it + 1);
+      const bool mt = use_meas_tma(tile);
+      double* st = stage0 + (size_t)s * STAGE_DOUBLES;
+      double* ybuf = ybuf0 + (size_t)s * 6 * TILE;
+      {
+        const unsigned any_t = __ballot_sync(0xffffffffu, act != ACT_NONE);
+        if (s == 0) anyh[0] = any_t; else if (s == 1) anyh[1] = any_t; else if (s == 2) anyh[2] = any_t; else anyh[3] = any_t;
+      }
+      mbar_wait(&bars[s], parity);
+      if (act == ACT_UPDATE && !(TE_SKIP & 16)) {   // angular_rates.cpp:79-88 / angular_velocities.cpp:87-96
+        // converter 0: roll and pitch (two independent chains, interleaved by the scheduler); converter 1: yaw
+        const double* mp = mt ? (st + LY::TILE_DOUBLES + lane * a.meas_stride) : (a.meas + (size_t)slot * a.meas_stride);
+        Quat qm{mp[3], mp[4], mp[5], mp[6]};
+        quat_normalize(qm);
+        if (tw == 0) {
+          const double a0 = quat_to_rpy_comp(qm, 0), a1 = quat_to_rpy_comp(qm, 1);
+          const double u0 = unwrap1(st[(LY::F_PREV + 0) * TILE + lane], a0);
+          const double u1 = unwrap1(st[(LY::F_PREV + 1) * TILE + lane], a1);
+          st[(LY::F_PREV + 0) * TILE + lane] = u0;   // meas_rpy_internal_ = unwrapped
+          st[(LY::F_PREV + 1) * TILE + lane] = u1;
+          ybuf[3 * TILE + lane] = u0;
+          ybuf[4 * TILE + lane] = u1;
+          ybuf[0 * TILE + lane] = mp[0];
+          ybuf[1 * TILE + lane] = mp[1];
+        } else {
+          const double a2 = quat_to_rpy_comp(qm, 2);
+          const double u2 = unwrap1(st[(LY::F_PREV + 2) * TILE + lane], a2);
+          st[(LY::F_PREV + 2) * TILE + lane] = u2;
+          ybuf[5 * TILE + lane] = u2;
+          ybuf[2 * TILE + lane] = mp[2];
+        }
+      }
+      if (TYPE == ANGULAR_VELOCITIES && tw == 1) {
+        if (act != ACT_NONE) {   // Jacobians at the previous posterior (angular_velocities.cpp:116-124, geometry.hpp:359-426)
+          double s_r, c_r, s_p, c_p;
+          sincos(st[(LY::F_X + 3) * TILE + lane], &s_r, &c_r);
+          sincos(st[(LY::F_X + 4) * TILE + lane], &s_p, &c_p);
+          const double wy = st[(LY::F_X + 10) * TILE + lane], wz = st[(LY::F_X + 11) * TILE + lane];
+          double* jb = jbuf0 + (size_t)s * JBUF_FIELDS * TILE + lane;
+          jb[0 * TILE] = (dt * (wy * c_r * s_p - wz * s_p * s_r)) / c_p + 1;   // J1[0][0]
+          jb[1 * TILE] = (dt * (wz * c_r + wy * s_r)) / (c_p * c_p);           // J1[0][1]
+          jb[2 * TILE] = -dt * (wz * c_r + wy * s_r);                          // J1[1][0]
+          jb[3 * TILE] = (dt * (wy * c_r - wz * s_r)) / c_p;                   // J1[2][0]
+          jb[4 * TILE] = (dt * s_p * (wz * c_r + wy * s_r)) / (c_p * c_p);     // J1[2][1]
+          jb[5 * TILE] = (dt * s_p * s_r) / c_p;                               // J2[0][1]
+          jb[6 * TILE] = (dt * c_r * s_p) / c_p;                               // J2[0][2]
+          jb[7 * TILE] = dt * c_r;                                             // J2[1][1]
+          jb[8 * TILE] = -dt * s_r;                                            // J2[1][2]
+          jb[9 * TILE] = (dt * s_r) / c_p;                                     // J2[2][1]
+          jb[10 * TILE] = (dt * c_r) / c_p;                                    // J2[2][2]
+          // f(x) for the Euler angles: rpy += dt * EarBaseInv(rpy) * w (angular_velocities.cpp:126-140, geometry.hpp:359-374)
+          const double wx = st[(LY::F_X + 9) * TILE + lane];
+          const double E01 = (s_p * s_r) / c_p, E02 = (c_r * s_p) / c_p, E11 = c_r, E12 = -s_r, E21 = s_r / c_p, E22 = c_r / c_p;
+          jb[11 * TILE] = st[(LY::F_X + 3) * TILE + lane] + ((dt * 1.0) * wx + (dt * E01) * wy + (dt * E02) * wz);
+          jb[12 * TILE] = st[(LY::F_X + 4) * TILE + lane] + ((dt * 0.0) * wx + (dt * E11) * wy + (dt * E12) * wz);
+          jb[13 * TILE] = st[(LY::F_X + 5) * TILE + lane] + ((dt * 0.0) * wx + (dt * E21) * wy + (dt * E22) * wz);
+        }
+      }
+      stage_bar_arrive<BAR_Y, NMAIN + NT * 32>(s);   // y / J of this tile are in shared memory
+      if (tw == 1) retire(it - (STAGES - 1));         // write back the tile the main warps finish next, refill its stage
+    }
+    if (tw == 1) {
+      for (int jd = n_my - (STAGES - 1); jd < n_my; ++jd) retire(jd);
+      if (producer) bulk_wait<0>();
+    }
+    return;
+  }
+
+  // ============================= main warps =============================
+
   for (int it = 0; it < n_my; ++it) {
     const int s = it % STAGES;
     const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
@@ -119,142 +279,181 @@ __global__ void __launch_bounds__(Split<TYPE>::RS * 32, MIN_CTAS) kf_step_split_
     const double* __restrict__ R = a.Rtab + (size_t)cls * M * M;
     const bool mt = use_meas_tma(tile);
 
-    if (producer && it + STAGES - 1 < n_my) {
-      bulk_wait_read<0>();   // the previous iteration's store has drained its stage
-      issue(it + STAGES - 1);
-    }
+    TE_MARK(0);
+    TE_MARK(1);
     double* st = stage0 + (size_t)s * STAGE_DOUBLES;
-    double* Wbuf = WSEP ? Wsep : st + LY::F_P * TILE;   // in place: W(k,c) takes the slot of P'(k,c), k < M
+    double* ybuf = ybuf0 + (size_t)s * 6 * TILE;
+    double* jbuf = jbuf0 + (size_t)s * JBUF_FIELDS * TILE;
     mbar_wait(&bars[s], parity);
+    stage_bar_sync<BAR_Y, NMAIN + NT * 32>(s);   // the converters finished this tile (normally long ago)
+    TE_MARK(2);
 
     // lane = target in every warp, so a warp ballot already is the tile-wide answer
     const unsigned any = __ballot_sync(0xffffffffu, act != ACT_NONE);
     if (any) {
       const bool active = act != ACT_NONE;
       const bool upd = act == ACT_UPDATE;
-      double Pr[RPT][N];
+
+      double Pr[RPT][NCOL];
       double xr[RPT];
 #pragma unroll
       for (int q = 0; q < RPT; ++q) {
         const int g = q * RS + r;
         xr[q] = st[(LY::F_X + g) * TILE + lane];
 #pragma unroll
-        for (int c = 0; c < N; ++c) Pr[q][c] = st[(LY::F_P + g * N + c) * TILE + lane];
+        for (int j = 0; j < NCOL; ++j) Pr[q][j] = st[(LY::F_P + g * N + colof(j)) * TILE + lane];
       }
 
-      // ---- phase A: measurement conversion (one Euler angle per warp 0..2) + predict of the own rows ----
-      if (r < 3 && upd) {
-        const double* mp = mt ? (st + LY::TILE_DOUBLES + lane * a.meas_stride) : (a.meas + (size_t)slot * a.meas_stride);
-        Quat qm{mp[3], mp[4], mp[5], mp[6]};
-        quat_normalize(qm);
-        const double ang = quat_to_rpy_comp(qm, r);
-        const double un = unwrap1(st[(LY::F_PREV + r) * TILE + lane], ang);
-        st[(LY::F_PREV + r) * TILE + lane] = un;   // meas_rpy_internal_ = unwrapped (angular_rates.cpp:85-88)
-        ybuf[(3 + r) * TILE + lane] = un;
-        ybuf[r * TILE + lane] = mp[r];
-      }
-
-      if (active) {
+      // ---- phase A: predict of the own block ----
+      if (active && !(TE_SKIP & 4)) {
         if (TYPE == ANGULAR_RATES) {
-          constexpr int B = MT::B;
-          const double h = 0.5 * dt * dt;
-          xr[0] = xr[0] + dt * xr[1] + h * xr[2];
+          const double hh = 0.5 * dt * dt;
+          xr[0] = xr[0] + dt * xr[1] + hh * xr[2];
           xr[1] = xr[1] + dt * xr[2];
 #pragma unroll
-          for (int j = 0; j < N; ++j) {   // A P on the three rows of this thread (one per kinematic block)
-            Pr[0][j] = Pr[0][j] + dt * Pr[1][j] + h * Pr[2][j];
+          for (int j = 0; j < NCOL; ++j) {   // A P on the three rows of this thread (one per kinematic block)
+            Pr[0][j] = Pr[0][j] + dt * Pr[1][j] + hh * Pr[2][j];
             Pr[1][j] = Pr[1][j] + dt * Pr[2][j];
           }
 #pragma unroll
-          for (int q = 0; q < RPT; ++q) {   // (A P) A^T + Q within each row
+          for (int q = 0; q < RPT; ++q) {   // (A P) A^T + Q within each row: columns c, 6+c, 12+c
 #pragma unroll
-            for (int c = 0; c < B; ++c) {
-              Pr[q][c] = Pr[q][c] + dt * Pr[q][B + c] + h * Pr[q][2 * B + c];
-              Pr[q][B + c] = Pr[q][B + c] + dt * Pr[q][2 * B + c];
+            for (int c = 0; c < BL; ++c) {
+              Pr[q][c] = Pr[q][c] + dt * Pr[q][BL + c] + hh * Pr[q][2 * BL + c];
+              Pr[q][BL + c] = Pr[q][BL + c] + dt * Pr[q][2 * BL + c];
             }
 #pragma unroll
-            for (int j = 0; j < N; ++j) Pr[q][j] = Pr[q][j] + __ldg(&Q[(q * RS + r) * N + j]);
+            for (int j = 0; j < NCOL; ++j) Pr[q][j] = Pr[q][j] + __ldg(&Q[(q * RS + r) * N + colof(j)]);
           }
         } else {
-          // EKF (angular_velocities.cpp:116-140): A linearised at the previous posterior, read from the stage.
-          // Thread r < 3 owns rows (p_r, v_r); thread r >= 3 owns rows (rpy_i, w_i), i = r - 3.
-          double s_r, c_r, s_p, c_p;
-          sincos(st[(LY::F_X + 3) * TILE + lane], &s_r, &c_r);
-          sincos(st[(LY::F_X + 4) * TILE + lane], &s_p, &c_p);
-          const double wx = st[(LY::F_X + 9) * TILE + lane], wy = st[(LY::F_X + 10) * TILE + lane], wz = st[(LY::F_X + 11) * TILE + lane];
-          double J1[3][3], J2[3][3];
-          J1[0][0] = (dt * (wy * c_r * s_p - wz * s_p * s_r)) / c_p + 1;
-          J1[0][1] = (dt * (wz * c_r + wy * s_r)) / (c_p * c_p);
-          J1[0][2] = 0;
-          J1[1][0] = -dt * (wz * c_r + wy * s_r);
-          J1[1][1] = 1;
-          J1[1][2] = 0;
-          J1[2][0] = (dt * (wy * c_r - wz * s_r)) / c_p;
-          J1[2][1] = (dt * s_p * (wz * c_r + wy * s_r)) / (c_p * c_p);
-          J1[2][2] = 1;
-          J2[0][0] = dt; J2[0][1] = (dt * s_p * s_r) / c_p; J2[0][2] = (dt * c_r * s_p) / c_p;
-          J2[1][0] = 0;  J2[1][1] = dt * c_r;               J2[1][2] = -dt * s_r;
-          J2[2][0] = 0;  J2[2][1] = (dt * s_r) / c_p;       J2[2][2] = (dt * c_r) / c_p;
+          // EKF: thread r < 3 owns rows (p_r, v_r); thread r >= 3 owns rows (rpy_i, w_i), i = r - 3
+          const double* jb = jbuf + lane;
           if (r < 3) {
             xr[0] = xr[0] + dt * xr[1];
 #pragma unroll
-            for (int j = 0; j < N; ++j) Pr[0][j] = Pr[0][j] + dt * Pr[1][j];
+            for (int j = 0; j < NCOL; ++j) Pr[0][j] = Pr[0][j] + dt * Pr[1][j];
           } else {
             const int i = r - 3;
-            double E[3][3];
-            E[0][0] = 1; E[0][1] = (s_p * s_r) / c_p; E[0][2] = (c_r * s_p) / c_p;
-            E[1][0] = 0; E[1][1] = c_r;               E[1][2] = -s_r;
-            E[2][0] = 0; E[2][1] = s_r / c_p;         E[2][2] = c_r / c_p;
-            double j1r[3], j2r[3], er[3];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const double c0[3] = {J1[0][j], J1[1][j], J1[2][j]}, c1[3] = {J2[0][j], J2[1][j], J2[2][j]}, c2[3] = {E[0][j], E[1][j], E[2][j]};
-              j1r[j] = sel3(c0, i); j2r[j] = sel3(c1, i); er[j] = sel3(c2, i);
-            }
-            xr[0] = xr[0] + ((dt * er[0]) * wx + (dt * er[1]) * wy + (dt * er[2]) * wz);
+            // rows i of J_rpy, J_w, E^-1 (structural 0 / 1 / dt entries are not stored)
+            double j1r[3], j2r[3];
+            j1r[0] = i == 0 ? jb[0 * TILE] : (i == 1 ? jb[2 * TILE] : jb[3 * TILE]);
+            j1r[1] = i == 0 ? jb[1 * TILE] : (i == 1 ? 1.0 : jb[4 * TILE]);
+            j1r[2] = i == 2 ? 1.0 : 0.0;
+            j2r[0] = i == 0 ? dt : 0.0;
+            j2r[1] = i == 0 ? jb[5 * TILE] : (i == 1 ? jb[7 * TILE] : jb[9 * TILE]);
+            j2r[2] = i == 0 ? jb[6 * TILE] : (i == 1 ? jb[8 * TILE] : jb[10 * TILE]);
+            xr[0] = jb[(11 + i) * TILE];   // predicted Euler angle, evaluated by the converter warp
             // row 3+i of A P = J1[i,:] rows 3..5 + J2[i,:] rows 9..11 (original rows, from the stage)
 #pragma unroll
-            for (int j = 0; j < N; ++j) {
+            for (int j = 0; j < NCOL; ++j) {
               double p1[3], p3[3];
 #pragma unroll
               for (int k = 0; k < 3; ++k) {
-                p1[k] = st[(LY::F_P + (3 + k) * N + j) * TILE + lane];
-                p3[k] = st[(LY::F_P + (9 + k) * N + j) * TILE + lane];
+                p1[k] = st[(LY::F_P + (3 + k) * N + colof(j)) * TILE + lane];
+                p3[k] = st[(LY::F_P + (9 + k) * N + colof(j)) * TILE + lane];
               }
               Pr[0][j] = j1r[0] * p1[0] + j1r[1] * p1[1] + j1r[2] * p1[2] + j2r[0] * p3[0] + j2r[1] * p3[1] + j2r[2] * p3[2];
             }
           }
-          // (A P) A^T + Q within each row
+          // (A P) A^T + Q within each row; linear columns {0..2, 6..8} and angular columns {3..5, 9..11} are closed sets
+          const bool lin = (CS == 1) || h == 0, angc = (CS == 1) || h == 1;
+          double J1[3][3], J2[3][3];
+          if (angc) {
+            J1[0][0] = jb[0 * TILE]; J1[0][1] = jb[1 * TILE]; J1[0][2] = 0;
+            J1[1][0] = jb[2 * TILE]; J1[1][1] = 1;            J1[1][2] = 0;
+            J1[2][0] = jb[3 * TILE]; J1[2][1] = jb[4 * TILE]; J1[2][2] = 1;
+            J2[0][0] = dt; J2[0][1] = jb[5 * TILE]; J2[0][2] = jb[6 * TILE];
+            J2[1][0] = 0;  J2[1][1] = jb[7 * TILE]; J2[1][2] = jb[8 * TILE];
+            J2[2][0] = 0;  J2[2][1] = jb[9 * TILE]; J2[2][2] = jb[10 * TILE];
+          }
 #pragma unroll
           for (int q = 0; q < RPT; ++q) {
-            double rw[N];
-#pragma unroll
-            for (int j = 0; j < N; ++j) rw[j] = Pr[q][j];
             const int g = q * RS + r;
+            if (CS == 1) {
+              double rw[N];
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              Pr[q][j] = (rw[j] + rw[6 + j] * dt) + __ldg(&Q[g * N + j]);
-              const double sacc = rw[3] * J1[j][0] + rw[4] * J1[j][1] + rw[5] * J1[j][2] + rw[9] * J2[j][0] + rw[10] * J2[j][1] + rw[11] * J2[j][2];
-              Pr[q][3 + j] = sacc + __ldg(&Q[g * N + 3 + j]);
-              Pr[q][6 + j] = rw[6 + j] + __ldg(&Q[g * N + 6 + j]);
-              Pr[q][9 + j] = rw[9 + j] + __ldg(&Q[g * N + 9 + j]);
+              for (int j = 0; j < N; ++j) rw[j] = Pr[q][j];
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                Pr[q][j] = (rw[j] + rw[6 + j] * dt) + __ldg(&Q[g * N + j]);
+                const double sacc = rw[3] * J1[j][0] + rw[4] * J1[j][1] + rw[5] * J1[j][2] + rw[9] * J2[j][0] + rw[10] * J2[j][1] + rw[11] * J2[j][2];
+                Pr[q][3 + j] = sacc + __ldg(&Q[g * N + 3 + j]);
+                Pr[q][6 + j] = rw[6 + j] + __ldg(&Q[g * N + 6 + j]);
+                Pr[q][9 + j] = rw[9 + j] + __ldg(&Q[g * N + 9 + j]);
+              }
+            } else if (lin) {   // local 0..2 = cols 0..2, local 3..5 = cols 6..8
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                Pr[q][j] = (Pr[q][j] + Pr[q][3 + j] * dt) + __ldg(&Q[g * N + j]);
+                Pr[q][3 + j] = Pr[q][3 + j] + __ldg(&Q[g * N + 6 + j]);
+              }
+            } else {            // local 0..2 = cols 3..5, local 3..5 = cols 9..11
+              double rw[6];
+#pragma unroll
+              for (int j = 0; j < 6; ++j) rw[j] = Pr[q][j];
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                const double sacc = rw[0] * J1[j][0] + rw[1] * J1[j][1] + rw[2] * J1[j][2] + rw[3] * J2[j][0] + rw[4] * J2[j][1] + rw[5] * J2[j][2];
+                Pr[q][j] = sacc + __ldg(&Q[g * N + 3 + j]);
+                Pr[q][3 + j] = rw[3 + j] + __ldg(&Q[g * N + 9 + j]);
+              }
             }
           }
         }
       }
-      if (TYPE == ANGULAR_VELOCITIES) __syncthreads();   // warps 3..5 have read the original rows 3..5 / 9..11
-
-      // publish the predicted measured row r and x'[r] in place
-      if (upd) {
-        st[(LY::F_X + r) * TILE + lane] = xr[0];
-#pragma unroll
-        for (int c = 0; c < N; ++c) st[(LY::F_P + r * N + c) * TILE + lane] = Pr[0][c];
+      if (TYPE == ANGULAR_VELOCITIES && r >= 3) {
+        // the r >= 3 warps have read the original rows 3..5 / 9..11; nobody else does.  Order those reads before the
+        // in-place publish of rows 3..5 (and of P'[9..11, 0:6] when CS = 2) with a named barrier among them.
+        asm volatile("bar.sync 1, %0;" ::"n"(3 * CS * 32) : "memory");
       }
-      __syncthreads();
 
-      // ---- phase B: S = P'[0:M,0:M] + R, v, this warp's columns of W -> Wbuf ---------------------------
-      double Wc[M][CW];
+      // publish in place: predicted measured row r and x'[r]; with CS = 2 also P'[own rows q >= 1, own part of 0:6]
       if (upd) {
+        if (h == 0) st[(LY::F_X + r) * TILE + lane] = xr[0];
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) st[(LY::F_P + r * N + colof(j)) * TILE + lane] = Pr[0][j];
+        if (CS == 2) {
+#pragma unroll
+          for (int q = 1; q < RPT; ++q)
+#pragma unroll
+            for (int c = 0; c < BL; ++c) st[(LY::F_P + (q * RS + r) * N + BL * h + c) * TILE + lane] = Pr[q][c];
+        }
+      }
+      TE_MARK(3);
+      named_bar_sync<BAR_MAIN, NMAIN>();
+      TE_MARK(4);
+      TE_MARK(5);
+
+      // ---- phase B: warp 0 factors S = P'[0:M,0:M] + R and solves v = S^-1 (y - x'[0:M]); warps 1..: factor S, columns
+      //      of W -> Wbuf ----
+      double Pk[RPT][M];   // P'[own rows, 0:M]: own part from registers, the partner's part from the stage
+      if (upd) {
+#pragma unroll
+        for (int q = 0; q < RPT; ++q)
+#pragma unroll
+          for (int k = 0; k < M; ++k) {
+            if (CS == 1) Pk[q][k] = Pr[q][k];
+            else Pk[q][k] = (k / BL == h) ? Pr[q][k % BL] : st[(LY::F_P + (q * RS + r) * N + k) * TILE + lane];
+          }
+      }
+      if (TE_SKIP & 1) {
+      } else if (w == 0) {
+        if (upd) {
+          Chol<M> ch;
+#pragma unroll
+          for (int i = 0; i < M; ++i)
+#pragma unroll
+            for (int j = 0; j < M; ++j)
+              if (j <= i) ch.at(i, j) = st[(LY::F_P + i * N + j) * TILE + lane] + __ldg(&R[i * M + j]);
+          ch.factor();
+          double v[M];
+#pragma unroll
+          for (int k = 0; k < M; ++k) v[k] = ybuf[k * TILE + lane] - st[(LY::F_X + k) * TILE + lane];
+          ch.solve(v);
+#pragma unroll
+          for (int k = 0; k < M; ++k) ybuf[k * TILE + lane] = v[k];   // y -> v in place (only this lane reads y[.][lane])
+        }
+      } else if (upd) {
         Chol<M> ch;
 #pragma unroll
         for (int i = 0; i < M; ++i)
@@ -262,71 +461,65 @@ __global__ void __launch_bounds__(Split<TYPE>::RS * 32, MIN_CTAS) kf_step_split_
           for (int j = 0; j < M; ++j)
             if (j <= i) ch.at(i, j) = st[(LY::F_P + i * N + j) * TILE + lane] + __ldg(&R[i * M + j]);
         ch.factor();
-        double v[M];
+        TE_MARK(6);
 #pragma unroll
-        for (int k = 0; k < M; ++k) v[k] = ybuf[k * TILE + lane] - st[(LY::F_X + k) * TILE + lane];
-        ch.solve(v);
+        for (int cc = 0; cc < WPW; ++cc) {
+          const int c = (w - 1) + cc * (NW - 1);
+          if (c < N) {
+            double col[M];
 #pragma unroll
-        for (int cc = 0; cc < CW; ++cc) {
-          const int c = r * CW + cc;
-          double col[M];
+            for (int k = 0; k < M; ++k) col[k] = st[(LY::F_P + k * N + c) * TILE + lane];
+            ch.solve(col);
 #pragma unroll
-          for (int k = 0; k < M; ++k) col[k] = st[(LY::F_P + k * N + c) * TILE + lane];
-          ch.solve(col);
-#pragma unroll
-          for (int k = 0; k < M; ++k) Wc[k][cc] = col[k];
-        }
-        // x += P'[rows,0:M] v (K (y - C x'), src/kalman.cpp:93) here, so that v is dead before phase C
-#pragma unroll
-        for (int q = 0; q < RPT; ++q) {
-          double sacc = 0.0;
-#pragma unroll
-          for (int k = 0; k < M; ++k) sacc += Pr[q][k] * v[k];
-          xr[q] += sacc;
-        }
-      }
-      if (!WSEP) __syncthreads();   // in place: every warp has read S and its columns of P'[0:M,:]
-      if (upd) {
-#pragma unroll
-        for (int cc = 0; cc < CW; ++cc)
-#pragma unroll
-          for (int k = 0; k < M; ++k) Wbuf[(k * N + r * CW + cc) * TILE + lane] = Wc[k][cc];
-      }
-      __syncthreads();
-
-      // ---- phase C: own rows: P[rows,:] -= P'[rows,0:M] W ((I - K C) P, src/kalman.cpp:94) ----------------
-      if (upd) {
-        double Pk[RPT][M];
-#pragma unroll
-        for (int q = 0; q < RPT; ++q)
-#pragma unroll
-          for (int k = 0; k < M; ++k) Pk[q][k] = Pr[q][k];
-#pragma unroll
-        for (int c = N - 1; c >= 0; --c) {
-          double w[M];
-#pragma unroll
-          for (int k = 0; k < M; ++k) w[k] = Wbuf[(k * N + c) * TILE + lane];
-#pragma unroll
-          for (int q = 0; q < RPT; ++q) {
-            double sacc = Pr[q][c];
-#pragma unroll
-            for (int k = 0; k < M; ++k) sacc -= Pk[q][k] * w[k];
-            Pr[q][c] = sacc;
+            for (int k = 0; k < M; ++k) Wbuf[(k * N + c) * TILE + lane] = col[k];
           }
         }
       }
-      if (!WSEP) __syncthreads();   // in place: every warp has read W before rows 0..M-1 are rewritten
+      TE_MARK(8);
+      named_bar_sync<BAR_MAIN, NMAIN>();
+      TE_MARK(9);
 
-      // ---- phase D: own rows back into the stage (nobody reads the published top rows after phase B) ------
+      // ---- phase C: own block: P[rows, cols] -= P'[rows,0:M] W[:, cols]  ((I - K C) P, src/kalman.cpp:94) ----
+      if (upd && !(TE_SKIP & 2)) {
+        if (h == 0) {   // x += P'[rows,0:M] v  (K (y - C x'), src/kalman.cpp:93)
+#pragma unroll
+          for (int q = 0; q < RPT; ++q) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int k = 0; k < M; ++k) sacc += Pk[q][k] * ybuf[k * TILE + lane];
+            xr[q] += sacc;
+          }
+        }
+#pragma unroll
+        for (int jj = 0; jj < NCOL; ++jj) {
+          const int j = NCOL - 1 - jj;
+          double wv[M];
+#pragma unroll
+          for (int k = 0; k < M; ++k) wv[k] = Wbuf[(k * N + colof(j)) * TILE + lane];
+#pragma unroll
+          for (int q = 0; q < RPT; ++q) {
+            // two interleaved chains of three instead of one of six: halves the dependent-FMA depth of the inner product
+            double s0 = Pr[q][j], s1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < M; k += 2) {
+              s0 -= Pk[q][k] * wv[k];
+              s1 -= Pk[q][k + 1] * wv[k + 1];
+            }
+            Pr[q][j] = s0 + s1;
+          }
+        }
+      }
+
+      // ---- phase D: own block back into the stage (nobody reads the published entries after phase B) ----
       if (active) {
 #pragma unroll
         for (int q = 0; q < RPT; ++q) {
           const int g = q * RS + r;
-          st[(LY::F_X + g) * TILE + lane] = xr[q];
+          if (h == 0) st[(LY::F_X + g) * TILE + lane] = xr[q];
 #pragma unroll
-          for (int c = 0; c < N; ++c) st[(LY::F_P + g * N + c) * TILE + lane] = Pr[q][c];
+          for (int j = 0; j < NCOL; ++j) st[(LY::F_P + g * N + colof(j)) * TILE + lane] = Pr[q][j];
         }
-        if (r == 0) {
+        if (w == 0) {
           st[LY::F_T * TILE + lane] = st[LY::F_T * TILE + lane] + dt;   // updateTime
           if (upd) {
             long long* nm = reinterpret_cast<long long*>(st + LY::F_NMEAS * TILE + lane);
@@ -335,20 +528,17 @@ __global__ void __launch_bounds__(Split<TYPE>::RS * 32, MIN_CTAS) kf_step_split_
           if (a.clear_action) a.action[slot] = 0;
         }
       }
-      if (a.pos_out && valid && r < 3) a.pos_out[(size_t)slot * 3 + r] = xr[0];
-      fence_proxy_async();
-      __syncthreads();   // also orders this tile's Wbuf / ybuf reads before the next tile's writes
-      if (producer) {
-        bulk_s2g(a.tiles + (size_t)tile * LY::TILE_DOUBLES, st, LY::TILE_BYTES);
-        bulk_commit();
-        if (a.clear_action) a.tile_flag[tile] = 0;
-      }
+      if (a.pos_out && valid && w < 3) a.pos_out[(size_t)slot * 3 + w] = xr[0];
+      fence_proxy_async();   // generic-proxy writes of the stage -> visible to the producer's bulk store
+      TE_MARK(10);
+      stage_bar_arrive<BAR_DONE, NMAIN + 32>(s);   // no wait: the next tile lives in another stage, and W / y reuse is ordered by
+                                                   // the next tile's first main barrier
     } else {
-      if (a.pos_out && valid && r < 3) a.pos_out[(size_t)slot * 3 + r] = st[(LY::F_X + r) * TILE + lane];
-      __syncthreads();   // the stage may be refilled by the producer in the next iteration
+      if (a.pos_out && valid && w < 3) a.pos_out[(size_t)slot * 3 + w] = st[(LY::F_X + w) * TILE + lane];
+      stage_bar_arrive<BAR_DONE, NMAIN + 32>(s);
     }
   }
-  if (producer) bulk_wait<0>();
 }
+
 
 }  // namespace te
