@@ -130,9 +130,7 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
     const int tile = tile_of(it);
     const int s = it % STAGES;
     double* st = stage0 + (size_t)s * STAGE_DOUBLES;
-    const bool mt = use_meas_tma(tile);
-    const uint32_t mbytes = mt ? (uint32_t)a.meas_stride * TILE * 8u : 0u;
-    mbar_expect_tx(&bars[s], (uint32_t)LY::TILE_BYTES + mbytes);
+    mbar_expect_tx(&bars[s], (uint32_t)LY::TILE_BYTES);   // measurements are read from global memory by the converters
     // the tile travels as several bulk copies on one mbarrier: a single 40-90 KB copy is served at ~18 B/clk, several
     // smaller ones overlap in the copy engine
     const double* src = a.tiles + (size_t)tile * LY::TILE_DOUBLES;
@@ -141,7 +139,6 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
       const int nd = (LY::TILE_DOUBLES - off) < BULK_CHUNK_DOUBLES ? (LY::TILE_DOUBLES - off) : BULK_CHUNK_DOUBLES;
       bulk_g2s(st + off, src + off, (uint32_t)nd * 8u, &bars[s]);
     }
-    if (mt) bulk_g2s(st + LY::TILE_DOUBLES, a.meas + (size_t)tile * TILE * a.meas_stride, mbytes, &bars[s]);
   };
   if (producer) {
     for (int pre = 0; pre < STAGES && pre < n_my; ++pre) issue(pre);
@@ -175,7 +172,7 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
       const int sd = jd % STAGES;
       const int tile_d = tile_of(jd);
       const unsigned any_d = sd == 0 ? anyh[0] : (sd == 1 ? anyh[1] : (sd == 2 ? anyh[2] : anyh[3]));
-      stage_bar_sync<BAR_DONE, NMAIN + 32>(sd);
+      stage_bar_sync<BAR_DONE, NMAIN + NT * 32>(sd);   // both converters: y / J buffer sd may be rewritten from here on
       if (producer) {
         double* std_ = stage0 + (size_t)sd * STAGE_DOUBLES;
         if (any_d) {
@@ -189,51 +186,82 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
         }
       }
     };
+    // The converters never touch the staged tile: measurement, previous unwrapped angles and (AV) the previous posterior
+    // come straight from global memory -- this tick has not rewritten the tile yet -- so they run while the tile's bulk
+    // copy is still in flight, up to STAGES tiles ahead of the main warps.  Their inputs are fetched one tile ahead too.
+    double in_n[12];   // [0..6] measurement pose, [7..8] previous unwrapped angle(s) of this converter, AV: [6..11] reused below
+    double xin_n[6];   // AV converter 1: x[3..5], x[9..11]
+    auto load_inputs = [&](int it) {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) in_n[k] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) xin_n[k] = 0.0;
+      if (it < n_my) {
+        const int tile = tile_of(it);
+        const int slot = tile * TILE + lane;
+        if (slot < a.n_slots) {
+          const double* gt = a.tiles + (size_t)tile * LY::TILE_DOUBLES + lane;   // this lane's column of the tile in HBM
+          if (a.meas) {
+            const double* mp = a.meas + (size_t)slot * a.meas_stride;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) in_n[k] = __ldg(mp + k);
+          }
+          if (tw == 0) {
+            in_n[7] = gt[(LY::F_PREV + 0) * TILE];
+            in_n[8] = gt[(LY::F_PREV + 1) * TILE];
+          } else {
+            in_n[7] = gt[(LY::F_PREV + 2) * TILE];
+            if (TYPE == ANGULAR_VELOCITIES) {
+#pragma unroll
+              for (int k = 0; k < 3; ++k) {
+                xin_n[k] = gt[(LY::F_X + 3 + k) * TILE];
+                xin_n[3 + k] = gt[(LY::F_X + 9 + k) * TILE];
+              }
+            }
+          }
+        }
+      }
+    };
+    load_inputs(0);
     for (int it = 0; it < n_my; ++it) {
       const int s = it % STAGES;
-      const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
-      const int tile = tile_of(it);
-      const int slot = tile * TILE + lane;
       const int act = act_n;
       const double dt = dt_n;
+      double in[9], xin[6];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) in[k] = in_n[k];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) xin[k] = xin_n[k];
       load_ctrl(it + 1);
-      const bool mt = use_meas_tma(tile);
-      double* st = stage0 + (size_t)s * STAGE_DOUBLES;
+      load_inputs(it + 1);
       double* ybuf = ybuf0 + (size_t)s * 6 * TILE;
       {
         const unsigned any_t = __ballot_sync(0xffffffffu, act != ACT_NONE);
         if (s == 0) anyh[0] = any_t; else if (s == 1) anyh[1] = any_t; else if (s == 2) anyh[2] = any_t; else anyh[3] = any_t;
       }
-      mbar_wait(&bars[s], parity);
       if (act == ACT_UPDATE && !(TE_SKIP & 16)) {   // angular_rates.cpp:79-88 / angular_velocities.cpp:87-96
         // converter 0: roll and pitch (two independent chains, interleaved by the scheduler); converter 1: yaw
-        const double* mp = mt ? (st + LY::TILE_DOUBLES + lane * a.meas_stride) : (a.meas + (size_t)slot * a.meas_stride);
-        Quat qm{mp[3], mp[4], mp[5], mp[6]};
+        Quat qm{in[3], in[4], in[5], in[6]};
         quat_normalize(qm);
         if (tw == 0) {
           const double a0 = quat_to_rpy_comp(qm, 0), a1 = quat_to_rpy_comp(qm, 1);
-          const double u0 = unwrap1(st[(LY::F_PREV + 0) * TILE + lane], a0);
-          const double u1 = unwrap1(st[(LY::F_PREV + 1) * TILE + lane], a1);
-          st[(LY::F_PREV + 0) * TILE + lane] = u0;   // meas_rpy_internal_ = unwrapped
-          st[(LY::F_PREV + 1) * TILE + lane] = u1;
-          ybuf[3 * TILE + lane] = u0;
-          ybuf[4 * TILE + lane] = u1;
-          ybuf[0 * TILE + lane] = mp[0];
-          ybuf[1 * TILE + lane] = mp[1];
+          ybuf[3 * TILE + lane] = unwrap1(in[7], a0);
+          ybuf[4 * TILE + lane] = unwrap1(in[8], a1);
+          ybuf[0 * TILE + lane] = in[0];
+          ybuf[1 * TILE + lane] = in[1];
         } else {
           const double a2 = quat_to_rpy_comp(qm, 2);
-          const double u2 = unwrap1(st[(LY::F_PREV + 2) * TILE + lane], a2);
-          st[(LY::F_PREV + 2) * TILE + lane] = u2;
-          ybuf[5 * TILE + lane] = u2;
-          ybuf[2 * TILE + lane] = mp[2];
+          ybuf[5 * TILE + lane] = unwrap1(in[7], a2);
+          ybuf[2 * TILE + lane] = in[2];
         }
       }
       if (TYPE == ANGULAR_VELOCITIES && tw == 1) {
         if (act != ACT_NONE) {   // Jacobians at the previous posterior (angular_velocities.cpp:116-124, geometry.hpp:359-426)
           double s_r, c_r, s_p, c_p;
-          sincos(st[(LY::F_X + 3) * TILE + lane], &s_r, &c_r);
-          sincos(st[(LY::F_X + 4) * TILE + lane], &s_p, &c_p);
-          const double wy = st[(LY::F_X + 10) * TILE + lane], wz = st[(LY::F_X + 11) * TILE + lane];
+          const double x3 = xin[0], x4 = xin[1], x5 = xin[2];
+          sincos(x3, &s_r, &c_r);
+          sincos(x4, &s_p, &c_p);
+          const double wx = xin[3], wy = xin[4], wz = xin[5];
           double* jb = jbuf0 + (size_t)s * JBUF_FIELDS * TILE + lane;
           jb[0 * TILE] = (dt * (wy * c_r * s_p - wz * s_p * s_r)) / c_p + 1;   // J1[0][0]
           jb[1 * TILE] = (dt * (wz * c_r + wy * s_r)) / (c_p * c_p);           // J1[0][1]
@@ -247,20 +275,17 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
           jb[9 * TILE] = (dt * s_r) / c_p;                                     // J2[2][1]
           jb[10 * TILE] = (dt * c_r) / c_p;                                    // J2[2][2]
           // f(x) for the Euler angles: rpy += dt * EarBaseInv(rpy) * w (angular_velocities.cpp:126-140, geometry.hpp:359-374)
-          const double wx = st[(LY::F_X + 9) * TILE + lane];
           const double E01 = (s_p * s_r) / c_p, E02 = (c_r * s_p) / c_p, E11 = c_r, E12 = -s_r, E21 = s_r / c_p, E22 = c_r / c_p;
-          jb[11 * TILE] = st[(LY::F_X + 3) * TILE + lane] + ((dt * 1.0) * wx + (dt * E01) * wy + (dt * E02) * wz);
-          jb[12 * TILE] = st[(LY::F_X + 4) * TILE + lane] + ((dt * 0.0) * wx + (dt * E11) * wy + (dt * E12) * wz);
-          jb[13 * TILE] = st[(LY::F_X + 5) * TILE + lane] + ((dt * 0.0) * wx + (dt * E21) * wy + (dt * E22) * wz);
+          jb[11 * TILE] = x3 + ((dt * 1.0) * wx + (dt * E01) * wy + (dt * E02) * wz);
+          jb[12 * TILE] = x4 + ((dt * 0.0) * wx + (dt * E11) * wy + (dt * E12) * wz);
+          jb[13 * TILE] = x5 + ((dt * 0.0) * wx + (dt * E21) * wy + (dt * E22) * wz);
         }
       }
       stage_bar_arrive<BAR_Y, NMAIN + NT * 32>(s);   // y / J of this tile are in shared memory
-      if (tw == 1) retire(it - (STAGES - 1));         // write back the tile the main warps finish next, refill its stage
+      retire(it - (STAGES - 1));   // write back the tile the main warps finish next, refill its stage
     }
-    if (tw == 1) {
-      for (int jd = n_my - (STAGES - 1); jd < n_my; ++jd) retire(jd);
-      if (producer) bulk_wait<0>();
-    }
+    for (int jd = n_my - (STAGES - 1); jd < n_my; ++jd) retire(jd);
+    if (producer) bulk_wait<0>();
     return;
   }
 
@@ -448,7 +473,11 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
           ch.factor();
           double v[M];
 #pragma unroll
-          for (int k = 0; k < M; ++k) v[k] = ybuf[k * TILE + lane] - st[(LY::F_X + k) * TILE + lane];
+          for (int k = 0; k < M; ++k) v[k] = ybuf[k * TILE + lane];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) st[(LY::F_PREV + k) * TILE + lane] = v[3 + k];   // meas_rpy_internal_ = unwrapped rpy
+#pragma unroll
+          for (int k = 0; k < M; ++k) v[k] = v[k] - st[(LY::F_X + k) * TILE + lane];
           ch.solve(v);
 #pragma unroll
           for (int k = 0; k < M; ++k) ybuf[k * TILE + lane] = v[k];   // y -> v in place (only this lane reads y[.][lane])
@@ -531,11 +560,11 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
       if (a.pos_out && valid && w < 3) a.pos_out[(size_t)slot * 3 + w] = xr[0];
       fence_proxy_async();   // generic-proxy writes of the stage -> visible to the producer's bulk store
       TE_MARK(10);
-      stage_bar_arrive<BAR_DONE, NMAIN + 32>(s);   // no wait: the next tile lives in another stage, and W / y reuse is ordered by
+      stage_bar_arrive<BAR_DONE, NMAIN + NT * 32>(s);   // no wait: the next tile lives in another stage, and W / y reuse is ordered by
                                                    // the next tile's first main barrier
     } else {
       if (a.pos_out && valid && w < 3) a.pos_out[(size_t)slot * 3 + w] = st[(LY::F_X + w) * TILE + lane];
-      stage_bar_arrive<BAR_DONE, NMAIN + 32>(s);
+      stage_bar_arrive<BAR_DONE, NMAIN + NT * 32>(s);
     }
   }
 }
