@@ -519,22 +519,37 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
             xr[q] += sacc;
           }
         }
+        if (MIN_CTAS == 1) {
+          // rank-1 updates, k outermost: every step touches all RPT x NCOL owned elements independently (full ILP), the
+          // dependent chain per element is the same k = 0..M-1 order as the reference's inner product
 #pragma unroll
-        for (int jj = 0; jj < NCOL; ++jj) {
-          const int j = NCOL - 1 - jj;
-          double wv[M];
+          for (int k = 0; k < M; ++k) {
+            double wrow[NCOL];
 #pragma unroll
-          for (int k = 0; k < M; ++k) wv[k] = Wbuf[(k * N + colof(j)) * TILE + lane];
+            for (int j = 0; j < NCOL; ++j) wrow[j] = Wbuf[(k * N + colof(j)) * TILE + lane];
 #pragma unroll
-          for (int q = 0; q < RPT; ++q) {
-            // two interleaved chains of three instead of one of six: halves the dependent-FMA depth of the inner product
-            double s0 = Pr[q][j], s1 = 0.0;
+            for (int q = 0; q < RPT; ++q)
 #pragma unroll
-            for (int k = 0; k < M; k += 2) {
-              s0 -= Pk[q][k] * wv[k];
-              s1 -= Pk[q][k + 1] * wv[k + 1];
+              for (int j = 0; j < NCOL; ++j) Pr[q][j] -= Pk[q][k] * wrow[j];
+          }
+        } else {
+          // register-lean form for the 128-register budget of two CTAs per SM: one column at a time, two chains of three
+#pragma unroll
+          for (int jj = 0; jj < NCOL; ++jj) {
+            const int j = NCOL - 1 - jj;
+            double wv[M];
+#pragma unroll
+            for (int k = 0; k < M; ++k) wv[k] = Wbuf[(k * N + colof(j)) * TILE + lane];
+#pragma unroll
+            for (int q = 0; q < RPT; ++q) {
+              double s0 = Pr[q][j], s1 = 0.0;
+#pragma unroll
+              for (int k = 0; k < M; k += 2) {
+                s0 -= Pk[q][k] * wv[k];
+                s1 -= Pk[q][k + 1] * wv[k + 1];
+              }
+              Pr[q][j] = s0 + s1;
             }
-            Pr[q][j] = s0 + s1;
           }
         }
       }
