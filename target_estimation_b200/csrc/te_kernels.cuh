@@ -36,6 +36,12 @@ struct StepArgs {
   const uint16_t* cls;      // [n_slots] model class
   const double* Qtab;       // [n_classes][N*N] row-major
   const double* Rtab;       // [n_classes][M*M]
+  // Q / R of one class (normally the pool's only one) travel in the kernel-parameter constant bank: a tile whose
+  // lanes all use that class reads them as c[0][..] operands / LDC instead of 50+ global loads per target through an
+  // L1 that the staged tiles leave almost no room for (AV with two CTAs per SM: < 4 KB)
+  int cls_c;                // class held in Qc / Rc, -1 = none
+  double Rc[36];
+  double Qc[324];
 };
 
 constexpr int MEAS_DOUBLES = 7 * TILE;   // measurement block of a stage (max stride 7)

@@ -335,6 +335,12 @@ te::StepArgs base_args(te_pool* p) {
   a.cls = b.cold.cls;
   a.Qtab = p->dQ;
   a.Rtab = p->dR;
+  a.cls_c = -1;
+  if (!p->hQ.empty()) {   // class 0 rides in the parameter constant bank
+    a.cls_c = 0;
+    std::memcpy(a.Qc, p->hQ[0].data(), sizeof(double) * p->N * p->N);
+    std::memcpy(a.Rc, p->hR[0].data(), sizeof(double) * p->M * p->M);
+  }
   return a;
 }
 

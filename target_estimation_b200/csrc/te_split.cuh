@@ -54,10 +54,10 @@ constexpr int SPLIT_BAR_BYTES = 128;   // mbarriers in front of the stages
 // (a 9th warp would cap all of them at 168: registers are allocated per partition)
 template <int TYPE> __host__ __device__ constexpr int split_nt() { return 2; }
 
-// shared memory of one CTA: [mbarriers 128 B][STAGES x (tile + measurement block)][W: 6 x N x 32][STAGES x y: 6 x 32]
-// [STAGES x jbuf: 14 x 32 (AV)]   (AV, 2 stages: 115 712 B -> two CTAs per SM)
+// shared memory of one CTA: [mbarriers 128 B][STAGES x tile][W: 6 x N x 32][STAGES x y: 6 x 32][STAGES x jbuf: 14 x 32 (AV)]
+// (AV, 2 stages: 112 128 B -> two CTAs per SM)
 template <int TYPE> __host__ __device__ constexpr size_t split_smem_bytes(int stages) {
-  return SPLIT_BAR_BYTES + ((size_t)stages * stage_doubles<TYPE>() + (size_t)Model<TYPE>::M * Model<TYPE>::N * TILE +
+  return SPLIT_BAR_BYTES + ((size_t)stages * Layout<TYPE>::TILE_DOUBLES + (size_t)Model<TYPE>::M * Model<TYPE>::N * TILE +
                  (size_t)stages * (6 * TILE + (TYPE == ANGULAR_VELOCITIES ? JBUF_FIELDS * TILE : 0))) * 8;
 }
 
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
   // named barriers: 0 = __syncthreads at start-up, 1 = AV r >= 3 group, BAR_MAIN = main group,
   // BAR_Y + s = converters -> main (y / J of the tile in stage s), BAR_DONE + s = main -> producer (tile in stage s finished)
   constexpr int BAR_MAIN = 2, BAR_Y = 3, BAR_DONE = BAR_Y + STAGES;
-  constexpr int STAGE_DOUBLES = stage_doubles<TYPE>();
+  constexpr int STAGE_DOUBLES = LY::TILE_DOUBLES;   // no measurement block: the converters read measurements from global memory
   static_assert(M == RS && (CS == 1 || CS == 2) && STAGES <= 4 && 3 + 2 * STAGES <= 16, "one measured row per row owner");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -302,7 +302,11 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
     load_ctrl(it + 1);
     const double* __restrict__ Q = a.Qtab + (size_t)cls * N * N;
     const double* __restrict__ R = a.Rtab + (size_t)cls * M * M;
-    const bool mt = use_meas_tma(tile);
+    // warp-uniform: every lane of the tile uses the class whose Q / R sit in the parameter constant bank
+    // (only where the L1 is starved: with one CTA per SM the L1 keeps the tables and indexed LDCs were slower, AR 0.90 -> 0.69)
+    const bool ctab = (MIN_CTAS > 1) && __all_sync(0xffffffffu, cls == a.cls_c);
+    auto Qv = [&](int idx) -> double { return ctab ? a.Qc[idx] : __ldg(&Q[idx]); };
+    auto Rv = [&](int idx) -> double { return ctab ? a.Rc[idx] : __ldg(&R[idx]); };
 
     TE_MARK(0);
     TE_MARK(1);
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
               Pr[q][BL + c] = Pr[q][BL + c] + dt * Pr[q][2 * BL + c];
             }
 #pragma unroll
-            for (int j = 0; j < NCOL; ++j) Pr[q][j] = Pr[q][j] + __ldg(&Q[(q * RS + r) * N + colof(j)]);
+            for (int j = 0; j < NCOL; ++j) Pr[q][j] = Pr[q][j] + Qv((q * RS + r) * N + colof(j));
           }
         } else {
           // EKF: thread r < 3 owns rows (p_r, v_r); thread r >= 3 owns rows (rpy_i, w_i), i = r - 3
@@ -400,17 +404,17 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
               for (int j = 0; j < N; ++j) rw[j] = Pr[q][j];
 #pragma unroll
               for (int j = 0; j < 3; ++j) {
-                Pr[q][j] = (rw[j] + rw[6 + j] * dt) + __ldg(&Q[g * N + j]);
+                Pr[q][j] = (rw[j] + rw[6 + j] * dt) + Qv(g * N + j);
                 const double sacc = rw[3] * J1[j][0] + rw[4] * J1[j][1] + rw[5] * J1[j][2] + rw[9] * J2[j][0] + rw[10] * J2[j][1] + rw[11] * J2[j][2];
-                Pr[q][3 + j] = sacc + __ldg(&Q[g * N + 3 + j]);
-                Pr[q][6 + j] = rw[6 + j] + __ldg(&Q[g * N + 6 + j]);
-                Pr[q][9 + j] = rw[9 + j] + __ldg(&Q[g * N + 9 + j]);
+                Pr[q][3 + j] = sacc + Qv(g * N + 3 + j);
+                Pr[q][6 + j] = rw[6 + j] + Qv(g * N + 6 + j);
+                Pr[q][9 + j] = rw[9 + j] + Qv(g * N + 9 + j);
               }
             } else if (lin) {   // local 0..2 = cols 0..2, local 3..5 = cols 6..8
 #pragma unroll
               for (int j = 0; j < 3; ++j) {
-                Pr[q][j] = (Pr[q][j] + Pr[q][3 + j] * dt) + __ldg(&Q[g * N + j]);
-                Pr[q][3 + j] = Pr[q][3 + j] + __ldg(&Q[g * N + 6 + j]);
+                Pr[q][j] = (Pr[q][j] + Pr[q][3 + j] * dt) + Qv(g * N + j);
+                Pr[q][3 + j] = Pr[q][3 + j] + Qv(g * N + 6 + j);
               }
             } else {            // local 0..2 = cols 3..5, local 3..5 = cols 9..11
               double rw[6];
@@ -419,8 +423,8 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
 #pragma unroll
               for (int j = 0; j < 3; ++j) {
                 const double sacc = rw[0] * J1[j][0] + rw[1] * J1[j][1] + rw[2] * J1[j][2] + rw[3] * J2[j][0] + rw[4] * J2[j][1] + rw[5] * J2[j][2];
-                Pr[q][j] = sacc + __ldg(&Q[g * N + 3 + j]);
-                Pr[q][3 + j] = rw[3 + j] + __ldg(&Q[g * N + 9 + j]);
+                Pr[q][j] = sacc + Qv(g * N + 3 + j);
+                Pr[q][3 + j] = rw[3 + j] + Qv(g * N + 9 + j);
               }
             }
           }
@@ -452,14 +456,12 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
       // ---- phase B: warp 0 factors S = P'[0:M,0:M] + R and solves v = S^-1 (y - x'[0:M]); warps 1..: factor S, columns
       //      of W -> Wbuf ----
       double Pk[RPT][M];   // P'[own rows, 0:M]: own part from registers, the partner's part from the stage
-      if (upd) {
+      if (upd && CS == 2) {   // (CS = 1: copied at the start of phase C, keeps 2*RPT*M registers free during the solves)
 #pragma unroll
         for (int q = 0; q < RPT; ++q)
 #pragma unroll
-          for (int k = 0; k < M; ++k) {
-            if (CS == 1) Pk[q][k] = Pr[q][k];
-            else Pk[q][k] = (k / BL == h) ? Pr[q][k % BL] : st[(LY::F_P + (q * RS + r) * N + k) * TILE + lane];
-          }
+          for (int k = 0; k < M; ++k)
+            Pk[q][k] = (k / BL == h) ? Pr[q][k % BL] : st[(LY::F_P + (q * RS + r) * N + k) * TILE + lane];
       }
       if (TE_SKIP & 1) {
       } else if (w == 0) {
@@ -469,7 +471,7 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
           for (int i = 0; i < M; ++i)
 #pragma unroll
             for (int j = 0; j < M; ++j)
-              if (j <= i) ch.at(i, j) = st[(LY::F_P + i * N + j) * TILE + lane] + __ldg(&R[i * M + j]);
+              if (j <= i) ch.at(i, j) = st[(LY::F_P + i * N + j) * TILE + lane] + Rv(i * M + j);
           ch.factor();
           double v[M];
 #pragma unroll
@@ -488,7 +490,7 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
         for (int i = 0; i < M; ++i)
 #pragma unroll
           for (int j = 0; j < M; ++j)
-            if (j <= i) ch.at(i, j) = st[(LY::F_P + i * N + j) * TILE + lane] + __ldg(&R[i * M + j]);
+            if (j <= i) ch.at(i, j) = st[(LY::F_P + i * N + j) * TILE + lane] + Rv(i * M + j);
         ch.factor();
         TE_MARK(6);
 #pragma unroll
@@ -510,6 +512,12 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
 
       // ---- phase C: own block: P[rows, cols] -= P'[rows,0:M] W[:, cols]  ((I - K C) P, src/kalman.cpp:94) ----
       if (upd && !(TE_SKIP & 2)) {
+        if (CS == 1) {
+#pragma unroll
+          for (int q = 0; q < RPT; ++q)
+#pragma unroll
+            for (int k = 0; k < M; ++k) Pk[q][k] = Pr[q][k];
+        }
         if (h == 0) {   // x += P'[rows,0:M] v  (K (y - C x'), src/kalman.cpp:93)
 #pragma unroll
           for (int q = 0; q < RPT; ++q) {
