@@ -107,6 +107,9 @@ const uint32_t* te_pool_dev_ids(te_pool* p);
 /* ---- expiry (RosTargetManager::update, src/target_manager_ros.cpp:67-72) ---------------- */
 /* Record per-target last measurement stamps (toSec(sec,nsec), utils.hpp:59-62) for ids. */
 int te_pool_set_stamps(te_pool* p, long long n, const uint32_t* ids, const uint32_t* sec, const uint32_t* nsec);
+/* Dense form of the above for device-resident ticks: every slot whose action (dev_action[slot], or default_action when
+ * NULL) is TE_ACT_UPDATE gets toSec(sec, nsec) as its last measurement stamp.  Asynchronous on the pool's stream. */
+int te_pool_stamp_dense(te_pool* p, const uint8_t* dev_action, int default_action, uint32_t sec, uint32_t nsec);
 /* Erase every target with last_meas_time > 0 && (now - last_meas_time) >= timeout, evaluated on
  * the device in non-contracted FP64 (bit-exact with the reference compare).  erased_out receives the
  * ascending erased ids (up to cap).  Returns #erased. */
@@ -124,6 +127,11 @@ void te_isolver_destroy(te_isolver* s);
 int te_isolver_query(te_isolver* s, long long n, const uint32_t* ids, const int32_t* stream, const double* t1,
                      const double* origin /*[n][3]*/, const double* radius, const double* pos_th, const double* ang_th,
                      double* delta_t, double* pose7, uint8_t* converged);
+
+/* Dense device-resident form: one query per slot (query k = slot k = solver stream k; needs n_streams >= pool size).
+ * dev_t1 NULL = each target's own time; dev_delta / dev_pose7 / dev_converged may be NULL.  Asynchronous. */
+int te_isolver_query_dense(te_isolver* s, const double* dev_t1, const double* dev_origin /*[size][3]*/, const double* dev_radius,
+                           double pos_th, double ang_th, double* dev_delta, double* dev_pose7, uint8_t* dev_converged);
 
 #ifdef __cplusplus
 }

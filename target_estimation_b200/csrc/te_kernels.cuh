@@ -425,6 +425,13 @@ __global__ void set_stamps_kernel(const uint32_t* __restrict__ ids_sorted, int n
   if (s >= n_slots || ids_sorted[s] != q[k]) return;
   last_meas[s] = to_sec_rn(sec[k], nsec[k]);
 }
+// dense tick: every slot updated this tick gets the tick's stamp as last_meas_time_
+__global__ void stamp_dense_kernel(const uint8_t* __restrict__ action, int default_action, int n_slots, double stamp, double* last_meas) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  const int a = action ? (int)action[s] : default_action;
+  if (a == ACT_UPDATE) last_meas[s] = stamp;
+}
 // alive[s] = !(last > 0.0 && (now - last) >= timeout)   (src/target_manager_ros.cpp:67)
 __global__ void expire_flags_kernel(const double* __restrict__ last_meas, int n_slots, double now, double timeout, int* alive) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -560,6 +567,7 @@ struct IsolverState {
   double* ang_sum;
   unsigned* idx;         // [n_streams] window_idx_
   uint8_t* complete;     // [n_streams] filter_complete_
+  double pos_th_all, ang_th_all;   // thresholds of the dense form (per-query arrays absent)
 };
 
 // MovingAvgFilter::update (utils.hpp:222-251) without the variance by-product (never read by
@@ -585,7 +593,7 @@ __global__ void isolver_kernel(const double* __restrict__ tiles, const int* __re
   using LY = Layout<TYPE>;
   long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const int s = slots[k];
+  const int s = slots ? slots[k] : (int)k;   // dense form: query k = slot k
   double delta = -1.0;
   double pose[7] = {0, 0, 0, 0, 0, 0, 1};   // initPose(intersection_pose) (:99)
   bool converged = false;
@@ -595,8 +603,9 @@ __global__ void isolver_kernel(const double* __restrict__ tiles, const int* __re
 #pragma unroll
     for (int i = 0; i < MT::N; ++i) x[i] = rec[(LY::F_X + i) * TILE];
     const double t = rec[LY::F_T * TILE];
+    const double tq = t1 ? t1[k] : t;           // dense form without t1: the target's own time
     double po[7], tw[6], ac[6];
-    derive_outputs<TYPE>(x, t, true, t1[k], po, tw, ac, nullptr);
+    derive_outputs<TYPE>(x, t, true, tq, po, tw, ac, nullptr);
     const double px = po[0] - origin[3 * k + 0], py = po[1] - origin[3 * k + 1], pz = po[2] - origin[3 * k + 2];
     const double vx = tw[0], vy = tw[1], vz = tw[2];
     const double ax = ac[0], ay = ac[1], az = ac[2];
@@ -610,7 +619,7 @@ __global__ void isolver_kernel(const double* __restrict__ tiles, const int* __re
     delta = lowest_real_root4(c);
     if (delta < 0) delta = -1.0;
     if (pose_out && delta > -1.0) {   // :102-121
-      derive_outputs<TYPE>(x, t, true, delta + t1[k], pose, nullptr, nullptr, nullptr);
+      derive_outputs<TYPE>(x, t, true, delta + tq, pose, nullptr, nullptr, nullptr);
       const long long sidx = stream ? stream[k] : k;
       double* prev = st.prev_pose + sidx * 7;
       const double dx = pose[0] - prev[0], dy = pose[1] - prev[1], dz = pose[2] - prev[2];
@@ -633,7 +642,7 @@ __global__ void isolver_kernel(const double* __restrict__ tiles, const int* __re
       st.complete[sidx] = complete ? 1 : 0;
 #pragma unroll
       for (int e = 0; e < 7; ++e) prev[e] = pose[e];
-      if (pf <= pos_th[k] && af <= ang_th[k]) converged = true;
+      if (pf <= (pos_th ? pos_th[k] : st.pos_th_all) && af <= (ang_th ? ang_th[k] : st.ang_th_all)) converged = true;
     }
   }
   if (delta_out) delta_out[k] = delta;

@@ -1019,6 +1019,17 @@ int te_pool_set_stamps(te_pool* p, long long n, const uint32_t* ids, const uint3
   });
 }
 
+int te_pool_stamp_dense(te_pool* p, const uint8_t* dev_action, int default_action, uint32_t sec, uint32_t nsec) {
+  return guarded(p, [&] {
+    if (p->n == 0) return 0;
+    volatile double ns = 1e-9 * (double)nsec;   // toSec (utils.hpp:59-62), never contracted
+    const double stamp = (double)sec + ns;
+    te::stamp_dense_kernel<<<cdiv(p->n, 256), 256, 0, p->stream>>>(dev_action, default_action, (int)p->n, stamp, p->buf[p->cur].cold.last_meas);
+    CK(cudaGetLastError());
+    return 0;
+  });
+}
+
 long long te_pool_expire(te_pool* p, uint32_t now_sec, uint32_t now_nsec, double timeout, uint32_t* erased_out, long long cap) {
   return guarded_ll(p, [&]() -> long long {
     if (p->n == 0) return 0;
@@ -1118,6 +1129,31 @@ int te_isolver_query(te_isolver* s, long long n, const uint32_t* ids, const int3
     if (pose7) CK(cudaMemcpyAsync(pose7, d_pose, (size_t)n * 56, cudaMemcpyDeviceToHost, p->stream));
     if (converged) CK(cudaMemcpyAsync(converged, d_conv, (size_t)n, cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
+    return 0;
+  });
+}
+
+int te_isolver_query_dense(te_isolver* s, const double* dev_t1, const double* dev_origin, const double* dev_radius, double pos_th,
+                           double ang_th, double* dev_delta, double* dev_pose7, uint8_t* dev_converged) {
+  if (!s) { g_err = "null isolver"; return -1; }
+  te_pool* p = s->pool;
+  return guarded(p, [&] {
+    const long long n = p->n;
+    if (n == 0) return 0;
+    if (!dev_origin || !dev_radius) throw std::invalid_argument("origin and radius are required");
+    if (n > s->st.n_streams) throw std::invalid_argument("more targets than solver streams");
+    te::IsolverState st = s->st;
+    st.pos_th_all = pos_th;
+    st.ang_th_all = ang_th;
+    Buf& b = p->buf[p->cur];
+    const int g = cdiv(n, 128);
+    switch (p->model) {
+      case te::UNIFORM_VELOCITY: te::isolver_kernel<te::UNIFORM_VELOCITY><<<g, 128, 0, p->stream>>>(b.tiles, nullptr, nullptr, n, dev_t1, dev_origin, dev_radius, nullptr, nullptr, st, dev_delta, dev_pose7, dev_converged); break;
+      case te::UNIFORM_ACCELERATION: te::isolver_kernel<te::UNIFORM_ACCELERATION><<<g, 128, 0, p->stream>>>(b.tiles, nullptr, nullptr, n, dev_t1, dev_origin, dev_radius, nullptr, nullptr, st, dev_delta, dev_pose7, dev_converged); break;
+      case te::ANGULAR_VELOCITIES: te::isolver_kernel<te::ANGULAR_VELOCITIES><<<g, 128, 0, p->stream>>>(b.tiles, nullptr, nullptr, n, dev_t1, dev_origin, dev_radius, nullptr, nullptr, st, dev_delta, dev_pose7, dev_converged); break;
+      default: te::isolver_kernel<te::ANGULAR_RATES><<<g, 128, 0, p->stream>>>(b.tiles, nullptr, nullptr, n, dev_t1, dev_origin, dev_radius, nullptr, nullptr, st, dev_delta, dev_pose7, dev_converged); break;
+    }
+    CK(cudaGetLastError());
     return 0;
   });
 }

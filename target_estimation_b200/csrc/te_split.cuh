@@ -76,11 +76,14 @@ template <int BASE, int COUNT> __device__ __forceinline__ void stage_bar_arrive(
 // component k of quatToRpy (geometry.hpp:154-176), same expressions as quat_to_rpy()
 __device__ __forceinline__ double quat_to_rpy_comp(const Quat& q, int k) {
   const double s = -2 * (q.x * q.z - q.w * q.y);
-  if (s > 0.9999) return k == 0 ? 0.0 : (k == 1 ? TE_PI / 2 : 2 * atan2(q.z, q.w));
-  if (s < -0.9999) return k == 0 ? 0.0 : (k == 1 ? -TE_PI / 2 : 2 * atan2(q.z, q.w));
-  if (k == 0) return atan2(2 * (q.y * q.z + q.w * q.x), (q.w * q.w - q.x * q.x - q.y * q.y + q.z * q.z));
-  if (k == 1) return asin(s);
-  return atan2(2 * (q.x * q.y + q.w * q.z), (q.w * q.w + q.x * q.x - q.y * q.y - q.z * q.z));
+  const bool gimbal = (s > 0.9999) || (s < -0.9999);
+  if (k == 0) return gimbal ? 0.0 : atan2(2 * (q.y * q.z + q.w * q.x), (q.w * q.w - q.x * q.x - q.y * q.y + q.z * q.z));
+  if (k == 1) return s > 0.9999 ? TE_PI / 2 : (s < -0.9999 ? -TE_PI / 2 : asin(s));
+  // one atan2 call site for both branches (the function is ~150 instructions inlined)
+  const double ay = gimbal ? q.z : 2 * (q.x * q.y + q.w * q.z);
+  const double ax = gimbal ? q.w : (q.w * q.w + q.x * q.x - q.y * q.y - q.z * q.z);
+  const double at = atan2(ay, ax);
+  return gimbal ? 2 * at : at;
 }
 
 template <int TYPE, int CS, int STAGES, int MIN_CTAS>
@@ -463,28 +466,8 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
           for (int k = 0; k < M; ++k)
             Pk[q][k] = (k / BL == h) ? Pr[q][k % BL] : st[(LY::F_P + (q * RS + r) * N + k) * TILE + lane];
       }
-      if (TE_SKIP & 1) {
-      } else if (w == 0) {
-        if (upd) {
-          Chol<M> ch;
-#pragma unroll
-          for (int i = 0; i < M; ++i)
-#pragma unroll
-            for (int j = 0; j < M; ++j)
-              if (j <= i) ch.at(i, j) = st[(LY::F_P + i * N + j) * TILE + lane] + Rv(i * M + j);
-          ch.factor();
-          double v[M];
-#pragma unroll
-          for (int k = 0; k < M; ++k) v[k] = ybuf[k * TILE + lane];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) st[(LY::F_PREV + k) * TILE + lane] = v[3 + k];   // meas_rpy_internal_ = unwrapped rpy
-#pragma unroll
-          for (int k = 0; k < M; ++k) v[k] = v[k] - st[(LY::F_X + k) * TILE + lane];
-          ch.solve(v);
-#pragma unroll
-          for (int k = 0; k < M; ++k) ybuf[k * TILE + lane] = v[k];   // y -> v in place (only this lane reads y[.][lane])
-        }
-      } else if (upd) {
+      if (upd && !(TE_SKIP & 1)) {
+        // one copy of the factorisation for every warp (code size: the kernel is I-cache bound enough as it is)
         Chol<M> ch;
 #pragma unroll
         for (int i = 0; i < M; ++i)
@@ -493,17 +476,29 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
             if (j <= i) ch.at(i, j) = st[(LY::F_P + i * N + j) * TILE + lane] + Rv(i * M + j);
         ch.factor();
         TE_MARK(6);
-#pragma unroll
-        for (int cc = 0; cc < WPW; ++cc) {
+        // right-hand sides: warp 0 solves the innovation, warps 1.. their columns of P'[0:M,:]
+        const int n_rhs = (w == 0) ? 1 : WPW;
+#pragma unroll 1
+        for (int cc = 0; cc < n_rhs; ++cc) {
           const int c = (w - 1) + cc * (NW - 1);
-          if (c < N) {
-            double col[M];
+          if (w != 0 && c >= N) break;
+          double col[M];
+          if (w == 0) {
+#pragma unroll
+            for (int k = 0; k < M; ++k) col[k] = ybuf[k * TILE + lane];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) st[(LY::F_PREV + k) * TILE + lane] = col[3 + k];   // meas_rpy_internal_ = unwrapped rpy
+#pragma unroll
+            for (int k = 0; k < M; ++k) col[k] = col[k] - st[(LY::F_X + k) * TILE + lane];
+          } else {
 #pragma unroll
             for (int k = 0; k < M; ++k) col[k] = st[(LY::F_P + k * N + c) * TILE + lane];
-            ch.solve(col);
-#pragma unroll
-            for (int k = 0; k < M; ++k) Wbuf[(k * N + c) * TILE + lane] = col[k];
           }
+          ch.solve(col);
+          double* dst = (w == 0) ? (ybuf + lane) : (Wbuf + (size_t)c * TILE + lane);   // y -> v in place | W(:, c)
+          const int stride = (w == 0) ? TILE : N * TILE;
+#pragma unroll
+          for (int k = 0; k < M; ++k) dst[k * stride] = col[k];
         }
       }
       TE_MARK(8);

@@ -204,6 +204,9 @@ class TargetPool:
         ids = _np(ids, np.uint32); sec = _np(sec, np.uint32); nsec = _np(nsec, np.uint32)
         check(lib.te_pool_set_stamps(self._h, ids.size, _ptr(ids), _ptr(sec), _ptr(nsec)))
 
+    def stamp_dense(self, sec, nsec, dev_action=None, default_action=ACT_UPDATE):
+        check(lib.te_pool_stamp_dense(self._h, _dev_ptr(dev_action), int(default_action), int(sec), int(nsec)))
+
     def expire(self, now_sec, now_nsec, timeout):
         cap = len(self)
         out = np.zeros(max(cap, 1), dtype=np.uint32)
@@ -231,6 +234,11 @@ class IntersectionSolver:
             self.close()
         except Exception:
             pass
+
+    def query_dense(self, dev_origin, dev_radius, pos_th, ang_th, dev_t1=None, dev_delta=None, dev_pose=None, dev_conv=None):
+        """device-resident: one query per slot (torch CUDA tensors), asynchronous on the pool's stream"""
+        check(lib.te_isolver_query_dense(self._h, _dev_ptr(dev_t1), _dev_ptr(dev_origin), _dev_ptr(dev_radius), float(pos_th), float(ang_th),
+                                         _dev_ptr(dev_delta), _dev_ptr(dev_pose), _dev_ptr(dev_conv)))
 
     def query(self, ids, t1, origin, radius, pos_th=None, ang_th=None, stream=None, with_pose=True):
         ids = _np(ids, np.uint32)

@@ -120,3 +120,33 @@ def test_intersection_batched_streams():
     for r in refs:
         orc.lib().orc_isolver_delete(r)
     solver.close(); pool.close()
+
+
+def test_dense_entry_points_match_id_entry_points():
+    """te_isolver_query_dense / te_pool_stamp_dense (device-resident forms) == the id-based host forms"""
+    import torch
+    te, pool, ref, ids, meas, action = _setup("uniform_acceleration", 70, 15, seed=31)
+    n = len(ids)
+    s_id = te.IntersectionSolver(pool, n_streams=n, filters_length=7)
+    s_dn = te.IntersectionSolver(pool, n_streams=n, filters_length=7)
+    rng = np.random.default_rng(4)
+    st = pool.read_state(ids)
+    origin = np.zeros((n, 3)); radius = rng.uniform(0.2, 0.6, n)
+    for j, i in enumerate(ids):
+        _, p = ref.pose_at(int(i), float(st["t"][j]) + 0.25)
+        origin[j] = p[:3] + rng.normal(0, 0.02, 3)
+    d_o, d_r = torch.from_numpy(origin).cuda(), torch.from_numpy(radius).cuda()
+    d_delta = torch.empty(n, dtype=torch.float64, device="cuda"); d_pose = torch.empty((n, 7), dtype=torch.float64, device="cuda")
+    d_conv = torch.empty(n, dtype=torch.uint8, device="cuda")
+    for rep in range(3):
+        d, pose, conv = s_id.query(ids, st["t"], origin, radius, 0.5, 0.5)
+        s_dn.query_dense(d_o, d_r, 0.5, 0.5, None, d_delta, d_pose, d_conv)
+        pool.sync()
+        assert np.array_equal(d, d_delta.cpu().numpy()) and np.array_equal(pose, d_pose.cpu().numpy())
+        assert np.array_equal(conv, d_conv.cpu().numpy())
+    # stamp_dense + expire == set_stamps + expire
+    act = np.where(np.arange(n) % 3 == 0, 1, 2).astype(np.uint8)
+    pool.stamp_dense(1000, 0, torch.from_numpy(act).cuda())
+    gone = pool.expire(1000, 50000000, 0.04)     # 1000.05 - 1000.0 >= 0.04 (1000.04 - 1000.0 rounds to just below 0.04)
+    assert np.array_equal(gone, ids[act == 2])
+    s_id.close(); s_dn.close(); pool.close()

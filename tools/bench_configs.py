@@ -1,0 +1,132 @@
+#!/usr/bin/env python3
+"""Secondary measurements for BASELINE.json configs[2..3] (not the bench.py headline): prints one JSON object.
+
+  C3  1 Mi angular-rates targets with per-tick add/erase churn: every tick 1 % of the live ids fall silent (expire
+      8 ticks later by the reference's predicate), as many fresh ids appear; tick = dense step + stamp + expiry
+      compaction + append.
+  C4  1 Mi targets + one IntersectionSolver query per target per tick (device resident), for uniform-velocity (reference
+      semantics: every query returns -1) and uniform-acceleration (the quartic path is exercised).
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import target_estimation_b200 as te  # noqa: E402
+from tests.synth import rpy_to_quat  # noqa: E402
+
+DT = 1.0 / 250.0
+
+
+def make_pool(model, n, stream, v0=None):
+    mtype, _, Q, R, P0 = te.load_model(model)
+    pool = te.TargetPool(mtype, stream=stream.cuda_stream)
+    pool.register_class(Q, R, P0)
+    pool.reserve(int(n * 1.3))
+    rng = np.random.default_rng(1)
+    p0 = np.zeros((n, 7)); p0[:, :3] = rng.uniform(-5, 5, (n, 3))
+    p0[:, 3:] = rpy_to_quat(rng.uniform(-0.4, 0.4, (n, 3)))
+    pool.add(np.arange(n, dtype=np.uint32), p0, p0_scale=rng.uniform(0.5, 2.0, n), v0=v0)
+    return pool, p0
+
+
+def c3_churn(n=1 << 20, ticks=48):
+    stream = torch.cuda.Stream()
+    pool, p0 = make_pool("angular_rates", n, stream)
+    rng = np.random.default_rng(2)
+    ids = pool.ids()
+    silent_at = np.full(ids.size, 1 << 30, dtype=np.int64)       # tick at which an id stops producing measurements
+    next_id = int(ids.max()) + 1
+    timeout = 8 * DT
+    base = torch.from_numpy(p0).cuda()
+    n_erased = n_added = 0
+    steps = 0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(ticks):
+        ns = 1000 * 10 ** 9 + k * 4000000
+        sec, nsec = ns // 10 ** 9, ns % 10 ** 9
+        live = ids.size
+        # 1 % of the speaking ids fall silent from this tick on
+        speaking = np.nonzero(silent_at > k)[0]
+        quit_ = rng.choice(speaking, size=max(1, speaking.size // 100), replace=False)
+        silent_at[quit_] = k
+        act = np.where(silent_at > k, 2, 1).astype(np.uint8)
+        d_act = torch.from_numpy(act).cuda()
+        if base.shape[0] != live:
+            base = torch.cat([base, base[: live - base.shape[0]]]) if base.shape[0] < live else base[:live]
+        meas = base  # pose layout [n][7]; values are irrelevant to the cost
+        pool.step_dense(DT, meas, 7, d_act)
+        pool.stamp_dense(sec, nsec, d_act)
+        erased = pool.expire(sec, nsec, timeout)
+        steps += live
+        if erased.size:
+            keep = np.ones(ids.size, dtype=bool)
+            keep[np.searchsorted(ids, erased)] = False
+            ids, silent_at = ids[keep], silent_at[keep]
+            base = base[torch.from_numpy(np.nonzero(keep)[0]).cuda()]
+            n_erased += erased.size
+        fresh = np.arange(next_id, next_id + quit_.size, dtype=np.uint32)
+        next_id += quit_.size
+        pf = np.zeros((fresh.size, 7)); pf[:, :3] = rng.uniform(-5, 5, (fresh.size, 3)); pf[:, 6] = 1.0
+        pool.add(fresh, pf, t0=np.full(fresh.size, k * DT))
+        ids = np.concatenate([ids, fresh]); silent_at = np.concatenate([silent_at, np.full(fresh.size, 1 << 30, dtype=np.int64)])
+        base = torch.cat([base, torch.from_numpy(pf).cuda()])
+        n_added += fresh.size
+    pool.sync()
+    dt_wall = time.perf_counter() - t0
+    assert np.array_equal(pool.ids(), ids)
+    out = {"targets": n, "ticks": ticks, "erased": int(n_erased), "added": int(n_added), "ms_per_tick": 1e3 * dt_wall / ticks,
+           "target_steps_per_s": steps / dt_wall, "note": "wall clock incl. host-side mask generation, expiry compaction (stable gather of the "
+           "whole pool into the second buffer) and append; ids verified against the host model of the churn"}
+    pool.close()
+    return out
+
+
+def c4_intersect(model, n=1 << 20, ticks=20):
+    stream = torch.cuda.Stream()
+    v0 = np.zeros((n, 6)); v0[:, 0] = 1.0                       # every target flies along +x at 1 m/s ...
+    pool, p0 = make_pool(model, n, stream, v0=v0)
+    solver = te.IntersectionSolver(pool, n_streams=n, filters_length=250)
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    base = torch.from_numpy(p0).cuda()
+    origin = base[:, :3].clone()
+    origin[:, 0] += 2.0                                         # ... towards a sphere 2 m ahead (the target starts outside it)
+    origin += 0.1 * (torch.rand((n, 3), dtype=torch.float64, device="cuda", generator=g) - 0.5)
+    origin = origin.contiguous()
+    radius = (0.3 + 0.4 * torch.rand((n,), dtype=torch.float64, device="cuda", generator=g)).contiguous()
+    delta = torch.empty(n, dtype=torch.float64, device="cuda")
+    pose = torch.empty((n, 7), dtype=torch.float64, device="cuda")
+    conv = torch.empty(n, dtype=torch.uint8, device="cuda")
+    meas = base.clone(); meas[:, 0] += DT; meas[:, 2] -= 0.0001   # consistent with the motion, slight downward pull -> non-zero acceleration estimate
+    for _ in range(3):
+        pool.step_dense(DT, meas, 7, None, te.ACT_UPDATE)
+        solver.query_dense(origin, radius, 0.05, 0.1, None, delta, pose, conv)
+    pool.sync()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    tq = 0.0
+    e0.record(stream)
+    for _ in range(ticks):
+        pool.step_dense(DT, meas, 7, None, te.ACT_UPDATE)
+    e1.record(stream)
+    for _ in range(ticks):
+        solver.query_dense(origin, radius, 0.05, 0.1, None, delta, pose, conv)
+    e2.record(stream)
+    pool.sync(); torch.cuda.synchronize()
+    ms_step, ms_q = e0.elapsed_time(e1) / ticks, e1.elapsed_time(e2) / ticks
+    found = int((delta >= 0).sum().item())
+    out = {"model": model, "targets": n, "queries_per_tick": n, "ms_per_tick_step": ms_step, "ms_per_tick_queries": ms_q,
+           "queries_per_s": n / (ms_q * 1e-3), "interceptions_found": found, "converged": int(conv.sum().item())}
+    solver.close(); pool.close()
+    return out
+
+
+if __name__ == "__main__":
+    res = {"c3_churn_angular_rates": c3_churn(), "c4_intersect_uniform_velocity": c4_intersect("uniform_velocity"),
+           "c4_intersect_uniform_acceleration": c4_intersect("uniform_acceleration")}
+    print(json.dumps(res))
