@@ -476,29 +476,47 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
             if (j <= i) ch.at(i, j) = st[(LY::F_P + i * N + j) * TILE + lane] + Rv(i * M + j);
         ch.factor();
         TE_MARK(6);
-        // right-hand sides: warp 0 solves the innovation, warps 1.. their columns of P'[0:M,:]
-        const int n_rhs = (w == 0) ? 1 : WPW;
-#pragma unroll 1
-        for (int cc = 0; cc < n_rhs; ++cc) {
-          const int c = (w - 1) + cc * (NW - 1);
-          if (w != 0 && c >= N) break;
+        if (w == 0) {   // innovation: v = S^-1 (y - x'[0:M])
           double col[M];
-          if (w == 0) {
 #pragma unroll
-            for (int k = 0; k < M; ++k) col[k] = ybuf[k * TILE + lane];
+          for (int k = 0; k < M; ++k) col[k] = ybuf[k * TILE + lane];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) st[(LY::F_PREV + k) * TILE + lane] = col[3 + k];   // meas_rpy_internal_ = unwrapped rpy
+          for (int k = 0; k < 3; ++k) st[(LY::F_PREV + k) * TILE + lane] = col[3 + k];   // meas_rpy_internal_ = unwrapped rpy
 #pragma unroll
-            for (int k = 0; k < M; ++k) col[k] = col[k] - st[(LY::F_X + k) * TILE + lane];
-          } else {
+          for (int k = 0; k < M; ++k) col[k] = col[k] - st[(LY::F_X + k) * TILE + lane];
+          ch.solve(col);
+#pragma unroll
+          for (int k = 0; k < M; ++k) ybuf[k * TILE + lane] = col[k];   // y -> v in place (only this lane reads y[.][lane])
+        } else if (MIN_CTAS > 1) {   // register-lean: one column at a time
+#pragma unroll 1
+          for (int cc = 0; cc < WPW; ++cc) {
+            const int c = (w - 1) + cc * (NW - 1);
+            if (c >= N) break;
+            double col[M];
 #pragma unroll
             for (int k = 0; k < M; ++k) col[k] = st[(LY::F_P + k * N + c) * TILE + lane];
-          }
-          ch.solve(col);
-          double* dst = (w == 0) ? (ybuf + lane) : (Wbuf + (size_t)c * TILE + lane);   // y -> v in place | W(:, c)
-          const int stride = (w == 0) ? TILE : N * TILE;
+            ch.solve(col);
 #pragma unroll
-          for (int k = 0; k < M; ++k) dst[k * stride] = col[k];
+            for (int k = 0; k < M; ++k) Wbuf[(k * N + c) * TILE + lane] = col[k];
+          }
+        } else {        // this warp's columns of W = S^-1 P'[0:M,:], solved together (independent chains interleave)
+          double col[WPW][M];
+#pragma unroll
+          for (int cc = 0; cc < WPW; ++cc) {
+            const int c = (w - 1) + cc * (NW - 1);
+#pragma unroll
+            for (int k = 0; k < M; ++k) col[cc][k] = (c < N) ? st[(LY::F_P + k * N + c) * TILE + lane] : 0.0;
+          }
+#pragma unroll
+          for (int cc = 0; cc < WPW; ++cc) ch.solve(col[cc]);
+#pragma unroll
+          for (int cc = 0; cc < WPW; ++cc) {
+            const int c = (w - 1) + cc * (NW - 1);
+            if (c < N) {
+#pragma unroll
+              for (int k = 0; k < M; ++k) Wbuf[(k * N + c) * TILE + lane] = col[cc][k];
+            }
+          }
         }
       }
       TE_MARK(8);
