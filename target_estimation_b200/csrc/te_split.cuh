@@ -99,10 +99,11 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
   constexpr int NMAIN = NW * 32;               // threads of the main group
   constexpr int WPW = (N + NW - 2) / (NW - 1); // W columns per warp 1.. (warp 0 solves v)
   // named barriers: 0 = __syncthreads at start-up, 1 = AV r >= 3 group, BAR_MAIN = main group,
-  // BAR_Y + s = converters -> main (y / J of the tile in stage s), BAR_DONE + s = main -> producer (tile in stage s finished)
-  constexpr int BAR_MAIN = 2, BAR_Y = 3, BAR_DONE = BAR_Y + STAGES;
+  // BAR_Y + s = converters -> main (y / J of the tile in stage s).  "tile in stage s finished" (main -> converters /
+  // producer) is an mbarrier, done[s], so that the two converters can wait for different tiles independently.
+  constexpr int BAR_MAIN = 2, BAR_Y = 3;
   constexpr int STAGE_DOUBLES = LY::TILE_DOUBLES;   // no measurement block: the converters read measurements from global memory
-  static_assert(M == RS && (CS == 1 || CS == 2) && STAGES <= 4 && 3 + 2 * STAGES <= 16, "one measured row per row owner");
+  static_assert(M == RS && (CS == 1 || CS == 2) && STAGES <= 4, "one measured row per row owner");
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -117,7 +118,10 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
 
   if (producer) {
 #pragma unroll
-    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&bars[s], 1);                 // full[s]: tile landed (one expect_tx arrival + the copy's bytes)
+      mbar_init(&bars[STAGES + s], NW);       // done[s]: every main warp finished the tile in stage s (lane 0 arrives)
+    }
     fence_mbar_init();
   }
   __syncthreads();
@@ -170,12 +174,15 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
     // issues the bulk store, waits until the store has drained the stage and refills it with tile jd + STAGES -- the main
     // warps never wait on a copy
     unsigned anyh[4] = {0u, 0u, 0u, 0u};   // "tile has work" per stage, noted when the converter handled the tile
-    auto retire = [&](int jd) {
+    auto wait_done = [&](int jd) {   // the main warps have finished tile jd (and with it the y / J buffers of its stage)
+      if (jd >= 0 && jd < n_my) mbar_wait(&bars[STAGES + jd % STAGES], (uint32_t)(jd / STAGES) & 1u);
+    };
+    auto retire = [&](int jd) {      // converter 1 / producer: write tile jd back, refill its stage with tile jd + STAGES
       if (jd < 0 || jd >= n_my) return;
       const int sd = jd % STAGES;
       const int tile_d = tile_of(jd);
       const unsigned any_d = sd == 0 ? anyh[0] : (sd == 1 ? anyh[1] : (sd == 2 ? anyh[2] : anyh[3]));
-      stage_bar_sync<BAR_DONE, NMAIN + NT * 32>(sd);   // both converters: y / J buffer sd may be rewritten from here on
+      wait_done(jd);
       if (producer) {
         double* std_ = stage0 + (size_t)sd * STAGE_DOUBLES;
         if (any_d) {
@@ -193,7 +200,7 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
     // come straight from global memory -- this tick has not rewritten the tile yet -- so they run while the tile's bulk
     // copy is still in flight, up to STAGES tiles ahead of the main warps.  Their inputs are fetched one tile ahead too.
     double in_n[12];   // [0..6] measurement pose, [7..8] previous unwrapped angle(s) of this converter, AV: [6..11] reused below
-    double xin_n[6];   // AV converter 1: x[3..5], x[9..11]
+    double xin_n[6];   // AV converter 0: x[3..5], x[9..11]
     auto load_inputs = [&](int it) {
 #pragma unroll
       for (int k = 0; k < 12; ++k) in_n[k] = 0.0;
@@ -211,9 +218,7 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
           }
           if (tw == 0) {
             in_n[7] = gt[(LY::F_PREV + 0) * TILE];
-            in_n[8] = gt[(LY::F_PREV + 1) * TILE];
-          } else {
-            in_n[7] = gt[(LY::F_PREV + 2) * TILE];
+            in_n[8] = gt[(LY::F_PREV + 2) * TILE];
             if (TYPE == ANGULAR_VELOCITIES) {
 #pragma unroll
               for (int k = 0; k < 3; ++k) {
@@ -221,6 +226,8 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
                 xin_n[3 + k] = gt[(LY::F_X + 9 + k) * TILE];
               }
             }
+          } else {
+            in_n[7] = gt[(LY::F_PREV + 1) * TILE];
           }
         }
       }
@@ -237,28 +244,32 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
       for (int k = 0; k < 6; ++k) xin[k] = xin_n[k];
       load_ctrl(it + 1);
       load_inputs(it + 1);
+      // y / J buffers of stage s were last used by tile it - STAGES.  Converter 1 has already waited for that tile in its
+      // retire(); converter 0 is not tied to the producer and may run up to STAGES tiles ahead of the main warps.
+      if (tw == 0) wait_done(it - STAGES);
       double* ybuf = ybuf0 + (size_t)s * 6 * TILE;
       {
         const unsigned any_t = __ballot_sync(0xffffffffu, act != ACT_NONE);
         if (s == 0) anyh[0] = any_t; else if (s == 1) anyh[1] = any_t; else if (s == 2) anyh[2] = any_t; else anyh[3] = any_t;
       }
       if (act == ACT_UPDATE && !(TE_SKIP & 16)) {   // angular_rates.cpp:79-88 / angular_velocities.cpp:87-96
-        // converter 0: roll and pitch (two independent chains, interleaved by the scheduler); converter 1: yaw
+        // converter 0: roll and yaw (two atan2 chains; with the AV Jacobians a third independent chain, all interleaved by
+        // the scheduler); converter 1, which is also the TMA producer and must react quickly, only pitch (asin)
         Quat qm{in[3], in[4], in[5], in[6]};
         quat_normalize(qm);
         if (tw == 0) {
-          const double a0 = quat_to_rpy_comp(qm, 0), a1 = quat_to_rpy_comp(qm, 1);
+          const double a0 = quat_to_rpy_comp(qm, 0), a2 = quat_to_rpy_comp(qm, 2);
           ybuf[3 * TILE + lane] = unwrap1(in[7], a0);
-          ybuf[4 * TILE + lane] = unwrap1(in[8], a1);
+          ybuf[5 * TILE + lane] = unwrap1(in[8], a2);
           ybuf[0 * TILE + lane] = in[0];
-          ybuf[1 * TILE + lane] = in[1];
-        } else {
-          const double a2 = quat_to_rpy_comp(qm, 2);
-          ybuf[5 * TILE + lane] = unwrap1(in[7], a2);
           ybuf[2 * TILE + lane] = in[2];
+        } else {
+          const double a1 = quat_to_rpy_comp(qm, 1);
+          ybuf[4 * TILE + lane] = unwrap1(in[7], a1);
+          ybuf[1 * TILE + lane] = in[1];
         }
       }
-      if (TYPE == ANGULAR_VELOCITIES && tw == 1) {
+      if (TYPE == ANGULAR_VELOCITIES && tw == 0) {
         if (act != ACT_NONE) {   // Jacobians at the previous posterior (angular_velocities.cpp:116-124, geometry.hpp:359-426)
           double s_r, c_r, s_p, c_p;
           const double x3 = xin[0], x4 = xin[1], x5 = xin[2];
@@ -285,10 +296,12 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
         }
       }
       stage_bar_arrive<BAR_Y, NMAIN + NT * 32>(s);   // y / J of this tile are in shared memory
-      retire(it - (STAGES - 1));   // write back the tile the main warps finish next, refill its stage
+      if (tw == 1) retire(it - (STAGES - 1));   // write back the tile the main warps finish next, refill its stage
     }
-    for (int jd = n_my - (STAGES - 1); jd < n_my; ++jd) retire(jd);
-    if (producer) bulk_wait<0>();
+    if (tw == 1) {
+      for (int jd = n_my - (STAGES - 1); jd < n_my; ++jd) retire(jd);
+      if (producer) bulk_wait<0>();
+    }
     return;
   }
 
@@ -596,11 +609,13 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
       if (a.pos_out && valid && w < 3) a.pos_out[(size_t)slot * 3 + w] = xr[0];
       fence_proxy_async();   // generic-proxy writes of the stage -> visible to the producer's bulk store
       TE_MARK(10);
-      stage_bar_arrive<BAR_DONE, NMAIN + NT * 32>(s);   // no wait: the next tile lives in another stage, and W / y reuse is ordered by
-                                                   // the next tile's first main barrier
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[STAGES + s]);   // no wait: the next tile lives in another stage, and W reuse is ordered
+                                                       // by the next tile's first main barrier
     } else {
       if (a.pos_out && valid && w < 3) a.pos_out[(size_t)slot * 3 + w] = st[(LY::F_X + w) * TILE + lane];
-      stage_bar_arrive<BAR_DONE, NMAIN + NT * 32>(s);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[STAGES + s]);
     }
   }
 }
