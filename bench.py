@@ -366,6 +366,23 @@ def main():
         sms = s0.elapsed_time(s1)
         small = {"targets": ns, "ticks": Ks, "us_per_tick": 1e3 * sms / Ks, "value": ns * Ks / (sms * 1e-3), "unit": UNIT,
                  "note": "state 7.2 MB is L2-resident; back-to-back launches on one stream"}
+        # the same 10k targets in replay launches: 64 buffered ticks per launch, tiles stay on chip across ticks
+        T = 64
+        mt = torch.stack([ms_[k % 2] for k in range(T)]).contiguous()
+        at = torch.stack([as_[k % 2] for k in range(T)]).contiguous()
+        for _ in range(3):
+            sp.step_dense_ticks(T, DT, mt, stride, at)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        Kr = 50
+        r0.record(stream)
+        for _ in range(Kr):
+            sp.step_dense_ticks(T, DT, mt, stride, at)
+        r1.record(stream)
+        torch.cuda.synchronize()
+        rms = r0.elapsed_time(r1)
+        small["replay64"] = {"ticks_per_launch": T, "launches": Kr, "us_per_tick": 1e3 * rms / (Kr * T), "value": ns * Kr * T / (rms * 1e-3),
+                             "unit": UNIT, "note": "te_pool_step_dense_ticks: 64 buffered ticks per launch (batched ingestion / catch-up)"}
         sp.close()
 
     cpu = None

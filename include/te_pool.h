@@ -73,6 +73,12 @@ int te_pool_class_of(te_pool* p, uint32_t id);
  * dev_action: [size] bytes of TE_ACT_* or NULL = default_action for all.  Device pointers. */
 int te_pool_step_dense(te_pool* p, double dt, const double* dev_meas, int meas_stride, const uint8_t* dev_action,
                        int default_action);
+/* Replay: n_ticks consecutive dense ticks in ONE launch.  dev_meas: [n_ticks][size][meas_stride], dev_action:
+ * [n_ticks][size] or NULL.  Results are bit-identical to n_ticks calls of te_pool_step_dense (same arithmetic, same
+ * order); each tile stays on chip for all its ticks, so state and covariance cross HBM once per launch instead of once
+ * per tick (targets are independent: temporal blocking is exact).  For batched ingestion / catch-up / offline replay. */
+int te_pool_step_dense_ticks(te_pool* p, int n_ticks, double dt, const double* dev_meas, int meas_stride, const uint8_t* dev_action,
+                             int default_action);
 /* Same with HOST buffers: host->device copies are part of the call. */
 int te_pool_step_dense_host(te_pool* p, double dt, const double* meas, int meas_stride, const uint8_t* action,
                             int default_action);

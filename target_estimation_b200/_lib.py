@@ -48,6 +48,7 @@ SIGNATURES = {
     "te_pool_contains": (_i, [_p, _u32]),
     "te_pool_class_of": (_i, [_p, _u32]),
     "te_pool_step_dense": (_i, [_p, _d, _p, _i, _p, _i]),
+    "te_pool_step_dense_ticks": (_i, [_p, _i, _d, _p, _i, _p, _i]),
     "te_pool_step_dense_host": (_i, [_p, _d, _p, _i, _p, _i]),
     "te_pool_tick_host": (_i, [_p, _d, _p, _i, _p, _i, _p]),
     "te_pool_step_ids": (_ll, [_p, _ll, _p, _p, _d, _p, _p]),

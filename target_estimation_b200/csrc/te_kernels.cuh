@@ -39,6 +39,11 @@ struct StepArgs {
   // Q / R of one class (normally the pool's only one) travel in the kernel-parameter constant bank: a tile whose
   // lanes all use that class reads them as c[0][..] operands / LDC instead of 50+ global loads per target through an
   // L1 that the staged tiles leave almost no room for (AV with two CTAs per SM: < 4 KB)
+  // multi-tick ("replay") launches: tick k reads meas + k * meas_tick_stride and action + k * action_tick_stride; a tile
+  // stays on chip for all n_ticks ticks (temporal blocking: targets are independent)
+  int n_ticks;
+  long long meas_tick_stride;     // doubles
+  long long action_tick_stride;   // bytes
   int cls_c;                // class held in Qc / Rc, -1 = none
   double Rc[36];
   double Qc[324];
@@ -51,7 +56,7 @@ template <int TYPE> __host__ __device__ constexpr size_t step_smem_bytes(int war
   return 1024 + (size_t)warps * stages * stage_doubles<TYPE>() * 8;
 }
 
-template <int TYPE, int WARPS, int STAGES>
+template <int TYPE, int WARPS, int STAGES, bool MULTI = false>
 __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_kernel(const StepArgs a) {
   using MT = Model<TYPE>;
   using LY = Layout<TYPE>;
@@ -131,6 +136,55 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_kernel(const StepArgs a
 
     double* st = mystage + (size_t)s * STAGE_DOUBLES;
     mbar_wait(&mybar[s], parity);
+
+    if (MULTI) {
+      // replay: all n_ticks ticks of this tile while it is staged; the next tick's control word and measurement are
+      // fetched while the current one is computed (they are the only global traffic per tick: <= 57 B per target)
+      unsigned any_tile = 0u;
+      int act_t = act;
+      double meas_t[7];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) meas_t[k] = meas[k];
+      for (int tick = 0; tick < a.n_ticks; ++tick) {
+        int act_nx = ACT_NONE;
+        double meas_nx[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) meas_nx[k] = 0.0;
+        if (tick + 1 < a.n_ticks && valid) {
+          act_nx = a.action ? (int)a.action[(size_t)(tick + 1) * a.action_tick_stride + slot] : a.default_action;
+          if (a.meas) {
+            const double* mp = a.meas + (size_t)(tick + 1) * a.meas_tick_stride + (size_t)slot * a.meas_stride;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) meas_nx[k] = __ldg(mp + k);
+            if (MT::M == 6) {
+#pragma unroll
+              for (int k = 3; k < 7; ++k) meas_nx[k] = __ldg(mp + k);
+            }
+          }
+        }
+        any_tile |= __ballot_sync(0xffffffffu, act_t != ACT_NONE);
+        if (act_t != ACT_NONE)
+          step_lane<TYPE>(st, lane, act_t, dt, meas_t, a.Qtab + (size_t)cls * MT::N * MT::N, a.Rtab + (size_t)cls * MT::M * MT::M);
+        act_t = act_nx;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) meas_t[k] = meas_nx[k];
+      }
+      if (a.pos_out && valid) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a.pos_out[(size_t)slot * 3 + k] = st[(LY::F_X + k) * TILE + lane];
+      }
+      if (any_tile) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          bulk_s2g(a.tiles + (size_t)tile * LY::TILE_DOUBLES, st, LY::TILE_BYTES);
+          bulk_commit();
+        }
+      } else {
+        __syncwarp();
+      }
+      continue;
+    }
 
     const unsigned any = __ballot_sync(0xffffffffu, act != ACT_NONE);
     if (any) {

@@ -266,9 +266,9 @@ template <class T> T* to_dev(te_pool* p, const T* host, size_t n) {
 }
 
 // ---- step kernel launch -----------------------------------------------------------------
-template <int TYPE, int WARPS, int STAGES>
+template <int TYPE, int WARPS, int STAGES, bool MULTI = false>
 void launch_step_t(te_pool* p, const te::StepArgs& a, int n_work_hint) {
-  auto kern = te::kf_step_kernel<TYPE, WARPS, STAGES>;
+  auto kern = te::kf_step_kernel<TYPE, WARPS, STAGES, MULTI>;
   const size_t smem = te::step_smem_bytes<TYPE>(WARPS, STAGES);
   static thread_local int configured_dev = -1;
   static bool configured[64] = {false};
@@ -295,6 +295,16 @@ void launch_split_t(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   int grid = std::min(p->n_sm * CTAS, std::max(1, n_work_hint));
   kern<<<grid, (te::SPLIT_RS * CS + te::split_nt<TYPE>()) * 32, smem, p->stream>>>(a);
   CK(cudaGetLastError());
+}
+
+// multi-tick replay: the per-warp kernel with the tile resident across ticks (every model)
+void launch_step_multi(te_pool* p, const te::StepArgs& a, int n_work_hint) {
+  switch (p->model) {
+    case te::UNIFORM_VELOCITY: launch_step_t<te::UNIFORM_VELOCITY, 8, 2, true>(p, a, n_work_hint); break;
+    case te::UNIFORM_ACCELERATION: launch_step_t<te::UNIFORM_ACCELERATION, 4, 2, true>(p, a, n_work_hint); break;
+    case te::ANGULAR_VELOCITIES: launch_step_t<te::ANGULAR_VELOCITIES, 5, 1, true>(p, a, n_work_hint); break;
+    default: launch_step_t<te::ANGULAR_RATES, 2, 1, true>(p, a, n_work_hint); break;
+  }
 }
 
 // variant -> (warps, stages) per model.  Stage bytes: UV 13056, UA 25344, AV 43008, AR 90624.
@@ -335,6 +345,7 @@ te::StepArgs base_args(te_pool* p) {
   a.cls = b.cold.cls;
   a.Qtab = p->dQ;
   a.Rtab = p->dR;
+  a.n_ticks = 1;
   a.cls_c = -1;
   if (!p->hQ.empty()) {   // class 0 rides in the parameter constant bank
     a.cls_c = 0;
@@ -765,6 +776,28 @@ int te_pool_step_dense(te_pool* p, double dt, const double* dev_meas, int meas_s
       }
     }
     launch_step(p, a, a.n_tiles);
+    return 0;
+  });
+}
+
+int te_pool_step_dense_ticks(te_pool* p, int n_ticks, double dt, const double* dev_meas, int meas_stride, const uint8_t* dev_action,
+                             int default_action) {
+  return guarded(p, [&] {
+    if (p->n == 0 || n_ticks <= 0) return 0;
+    if (!(dt >= 0.0)) throw std::invalid_argument("dt must be >= 0");
+    if (dev_meas) check_meas_stride(p, meas_stride);
+    else if (default_action == TE_ACT_UPDATE || dev_action) throw std::invalid_argument("update ticks without measurements");
+    te::StepArgs a = base_args(p);
+    a.dt = dt;
+    a.meas = dev_meas;
+    a.meas_stride = meas_stride;
+    a.meas_tma = 0;
+    a.action = const_cast<uint8_t*>(dev_action);
+    a.default_action = default_action;
+    a.n_ticks = n_ticks;
+    a.meas_tick_stride = (long long)p->n * meas_stride;
+    a.action_tick_stride = p->n;
+    launch_step_multi(p, a, a.n_tiles);
     return 0;
   });
 }

@@ -136,6 +136,11 @@ class TargetPool:
     def step_dense(self, dt, dev_meas=None, meas_stride=7, dev_action=None, default_action=ACT_UPDATE):
         check(lib.te_pool_step_dense(self._h, float(dt), _dev_ptr(dev_meas), int(meas_stride), _dev_ptr(dev_action), int(default_action)))
 
+    def step_dense_ticks(self, n_ticks, dt, dev_meas=None, meas_stride=7, dev_action=None, default_action=ACT_UPDATE):
+        """n_ticks ticks in one launch: dev_meas [n_ticks][n][stride], dev_action [n_ticks][n] (torch CUDA tensors)"""
+        check(lib.te_pool_step_dense_ticks(self._h, int(n_ticks), float(dt), _dev_ptr(dev_meas), int(meas_stride), _dev_ptr(dev_action),
+                                           int(default_action)))
+
     def step_dense_host(self, dt, meas=None, action=None, default_action=ACT_UPDATE, meas_ptr=None, meas_stride=7, action_ptr=None):
         """Host buffers (numpy) or raw host pointers (pinned torch tensors: pass data_ptr())."""
         if meas is not None:

@@ -76,3 +76,41 @@ def test_step_parity_4096x2000(model):
     n = 4096 if model in ("uniform_velocity", "uniform_acceleration") else 1024
     w = _run(model, n, n_ticks, check_every=100)
     assert w["x"] <= 1.0 and w["P"] <= 1.0, w
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_replay_launch_is_bit_identical_to_sequential_ticks(model):
+    """te_pool_step_dense_ticks (one launch, tile resident across ticks) == the same ticks launched one by one"""
+    import torch
+    import target_estimation_b200 as te
+    mtype, _, Q, R, P0 = te.load_model(model)
+    N, M = te.model_dims(mtype)
+    n, ticks = 333, 24
+    meas, action, scale = synth.make_streams(n, ticks, DT, accel=model in ("uniform_acceleration", "angular_rates"), angular=M == 6, seed=13)
+    action[3:, ::5] = 0    # some targets untouched on some ticks
+    ids = np.arange(n, dtype=np.uint32) * 2 + 1
+    pools = []
+    for _ in range(2):
+        p = te.TargetPool(mtype)
+        p.set_variant(1)   # the per-warp kernel for every model: the replay path runs the same code per tick
+        p.register_class(Q, R, P0)
+        p.add(ids, meas[0], p0_scale=scale)
+        pools.append(p)
+    d_meas = torch.from_numpy(meas).cuda().contiguous()
+    d_act = torch.from_numpy(action).cuda().contiguous()
+    for k in range(ticks):
+        pools[0].step_dense(DT, d_meas[k], 7, d_act[k])
+    pools[1].step_dense_ticks(ticks, DT, d_meas, 7, d_act)
+    a, b = pools[0].read_state(), pools[1].read_state()
+    for key in ("x", "P", "t", "n_meas", "prev_rpy"):
+        assert np.array_equal(a[key], b[key]), key
+    # and against the oracle
+    mgr = orc.Manager()
+    for k, i in enumerate(ids):
+        mgr.init_full(mtype, int(i), DT, 0.0, Q, R, scale[k] * P0, meas[0, k])
+    for k in range(ticks):
+        mgr.step_batch(ids, DT, meas[k], action[k])
+    ref = mgr.states(ids, N)
+    assert synth.compare_h2(b["x"], ref["x"]) <= 1.0 and synth.compare_h2(b["P"], ref["P"]) <= 1.0
+    for p in pools:
+        p.close()

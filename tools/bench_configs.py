@@ -126,7 +126,35 @@ def c4_intersect(model, n=1 << 20, ticks=20):
     return out
 
 
+def replay(model="uniform_acceleration", n=4 << 20, T=16, launches=10):
+    """temporal blocking: T buffered ticks per launch, state crosses HBM once per launch"""
+    stream = torch.cuda.Stream()
+    pool, p0 = make_pool(model, n, stream)
+    base = torch.from_numpy(p0).cuda()
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    meas = base.unsqueeze(0).repeat(T, 1, 1).contiguous()
+    meas[:, :, :3] += 0.01 * torch.randn((T, n, 3), dtype=torch.float64, device="cuda", generator=g)
+    act = torch.where(torch.rand((T, n), device="cuda", generator=g) < 0.05, 1, 2).to(torch.uint8).contiguous()
+    for _ in range(2):
+        pool.step_dense_ticks(T, DT, meas, 7, act)
+    pool.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(launches):
+        pool.step_dense_ticks(T, DT, meas, 7, act)
+    e1.record(stream)
+    pool.sync(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    out = {"model": model, "targets": n, "ticks_per_launch": T, "launches": launches, "ms_per_launch": ms / launches,
+           "target_steps_per_s": n * T * launches / (ms * 1e-3),
+           "note": "te_pool_step_dense_ticks: same arithmetic and results as T single ticks; HBM traffic per target-step = "
+                   "(state in + out) / T + measurement"}
+    pool.close()
+    return out
+
+
 if __name__ == "__main__":
     res = {"c3_churn_angular_rates": c3_churn(), "c4_intersect_uniform_velocity": c4_intersect("uniform_velocity"),
-           "c4_intersect_uniform_acceleration": c4_intersect("uniform_acceleration")}
+           "c4_intersect_uniform_acceleration": c4_intersect("uniform_acceleration"),
+           "replay16_uniform_acceleration_4Mi": replay()}
     print(json.dumps(res))
