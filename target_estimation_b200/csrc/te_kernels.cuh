@@ -145,6 +145,22 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_kernel(const StepArgs a
       double meas_t[7];
 #pragma unroll
       for (int k = 0; k < 7; ++k) meas_t[k] = meas[k];
+      const double* __restrict__ Qc = a.Qtab + (size_t)cls * MT::N * MT::N;
+      const double* __restrict__ Rc = a.Rtab + (size_t)cls * MT::M * MT::M;
+      // register-resident models (UV / UA): state and covariance stay in registers across the ticks
+      constexpr int NR = MT::REGS ? MT::N : 1;
+      RegP<NR> Preg;
+      double xreg[NR];
+      double t_reg = 0.0;
+      long long nm_reg = 0;
+      if (MT::REGS) {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) xreg[i] = st[(LY::F_X + i) * TILE + lane];
+#pragma unroll
+        for (int k = 0; k < NR * NR; ++k) Preg.v[k] = st[(LY::F_P + k) * TILE + lane];
+        t_reg = st[LY::F_T * TILE + lane];
+        nm_reg = reinterpret_cast<const long long*>(st)[LY::F_NMEAS * TILE + lane];
+      }
       for (int tick = 0; tick < a.n_ticks; ++tick) {
         int act_nx = ACT_NONE;
         double meas_nx[7];
@@ -163,11 +179,29 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_kernel(const StepArgs a
           }
         }
         any_tile |= __ballot_sync(0xffffffffu, act_t != ACT_NONE);
-        if (act_t != ACT_NONE)
-          step_lane<TYPE>(st, lane, act_t, dt, meas_t, a.Qtab + (size_t)cls * MT::N * MT::N, a.Rtab + (size_t)cls * MT::M * MT::M);
+        if (act_t != ACT_NONE) {
+          if constexpr (MT::REGS) {   // same calls, in the same order, as step_lane()
+            predict_kinematic<NR, MT::B, MT::NB>(Preg, xreg, dt, Qc);
+            if (act_t == ACT_UPDATE) {
+              kf_update<NR, MT::M>(Preg, xreg, meas_t, Rc);
+              nm_reg += 1;
+            }
+            t_reg = t_reg + dt;
+          } else {
+            step_lane<TYPE>(st, lane, act_t, dt, meas_t, Qc, Rc);
+          }
+        }
         act_t = act_nx;
 #pragma unroll
         for (int k = 0; k < 7; ++k) meas_t[k] = meas_nx[k];
+      }
+      if (MT::REGS) {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) st[(LY::F_X + i) * TILE + lane] = xreg[i];
+#pragma unroll
+        for (int k = 0; k < NR * NR; ++k) st[(LY::F_P + k) * TILE + lane] = Preg.v[k];
+        st[LY::F_T * TILE + lane] = t_reg;
+        reinterpret_cast<long long*>(st)[LY::F_NMEAS * TILE + lane] = nm_reg;
       }
       if (a.pos_out && valid) {
 #pragma unroll
