@@ -39,51 +39,72 @@ def c3_churn(n=1 << 20, ticks=48):
     stream = torch.cuda.Stream()
     pool, p0 = make_pool("angular_rates", n, stream)
     rng = np.random.default_rng(2)
-    ids = pool.ids()
-    silent_at = np.full(ids.size, 1 << 30, dtype=np.int64)       # tick at which an id stops producing measurements
-    next_id = int(ids.max()) + 1
     timeout = 8 * DT
-    base = torch.from_numpy(p0).cuda()
-    n_erased = n_added = 0
-    steps = 0
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
+    # ---- host model of the churn, computed BEFORE the timed loop: per tick the action mask in slot order, the ids that
+    # ---- must expire, and the fresh ids.  The timed loop then contains library calls only.
+    ids = pool.ids().astype(np.int64)
+    silent_at = np.full(ids.size, 1 << 30, dtype=np.int64)
+    last_tick = np.full(ids.size, -1, dtype=np.int64)      # last tick with a measurement (-1: never stamped -> never expires)
+    next_id = int(ids.max()) + 1
+    sched = []
+
+    def to_sec(tk):   # toSec of the synthetic clock: two roundings, like the device
+        ns_ = 1000 * 10 ** 9 + tk * 4000000
+        return float(ns_ // 10 ** 9) + 1e-9 * float(ns_ % 10 ** 9)
+
     for k in range(ticks):
-        ns = 1000 * 10 ** 9 + k * 4000000
-        sec, nsec = ns // 10 ** 9, ns % 10 ** 9
-        live = ids.size
-        # 1 % of the speaking ids fall silent from this tick on
         speaking = np.nonzero(silent_at > k)[0]
         quit_ = rng.choice(speaking, size=max(1, speaking.size // 100), replace=False)
         silent_at[quit_] = k
-        act = np.where(silent_at > k, 2, 1).astype(np.uint8)
-        d_act = torch.from_numpy(act).cuda()
-        if base.shape[0] != live:
-            base = torch.cat([base, base[: live - base.shape[0]]]) if base.shape[0] < live else base[:live]
-        meas = base  # pose layout [n][7]; values are irrelevant to the cost
-        pool.step_dense(DT, meas, 7, d_act)
-        pool.stamp_dense(sec, nsec, d_act)
-        erased = pool.expire(sec, nsec, timeout)
-        steps += live
-        if erased.size:
-            keep = np.ones(ids.size, dtype=bool)
-            keep[np.searchsorted(ids, erased)] = False
-            ids, silent_at = ids[keep], silent_at[keep]
-            base = base[torch.from_numpy(np.nonzero(keep)[0]).cuda()]
-            n_erased += erased.size
-        fresh = np.arange(next_id, next_id + quit_.size, dtype=np.uint32)
+        speaks = silent_at > k
+        act = np.where(speaks, 2, 1).astype(np.uint8)
+        last_tick[speaks] = k
+        # the reference's predicate in FP64: last > 0 && (now - last) >= timeout
+        now_ = to_sec(k)
+        cand = np.nonzero(~speaks & (last_tick >= 0))[0]
+        expired = np.zeros(ids.size, dtype=bool)
+        if cand.size:
+            uniq = {int(t_): to_sec(int(t_)) for t_ in np.unique(last_tick[cand])}
+            lasts = np.array([uniq[int(t_)] for t_ in last_tick[cand]])
+            expired[cand] = (now_ - lasts) >= timeout
+        exp_ids = ids[expired]
+        ids, silent_at, last_tick = ids[~expired], silent_at[~expired], last_tick[~expired]
+        fresh = np.arange(next_id, next_id + quit_.size, dtype=np.int64)
         next_id += quit_.size
         pf = np.zeros((fresh.size, 7)); pf[:, :3] = rng.uniform(-5, 5, (fresh.size, 3)); pf[:, 6] = 1.0
-        pool.add(fresh, pf, t0=np.full(fresh.size, k * DT))
+        sched.append((torch.from_numpy(act).cuda(), exp_ids.astype(np.uint32), fresh.astype(np.uint32), pf, act.size))
         ids = np.concatenate([ids, fresh]); silent_at = np.concatenate([silent_at, np.full(fresh.size, 1 << 30, dtype=np.int64)])
-        base = torch.cat([base, torch.from_numpy(pf).cuda()])
-        n_added += fresh.size
+        last_tick = np.concatenate([last_tick, np.full(fresh.size, -1, dtype=np.int64)])
+    n_max = max(s_[4] for s_ in sched) + 1
+    meas = torch.zeros((n_max, 7), dtype=torch.float64, device="cuda"); meas[:, 6] = 1.0
+    meas[:, :3] = torch.rand((n_max, 3), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    n_erased = n_added = steps = 0
+    parts = {"step+stamp": 0.0, "expire": 0.0, "add": 0.0}
+    t0 = time.perf_counter()
+    for k, (d_act, exp_ids, fresh, pf, live) in enumerate(sched):
+        ns = 1000 * 10 ** 9 + k * 4000000
+        sec, nsec = ns // 10 ** 9, ns % 10 ** 9
+        ta = time.perf_counter()
+        pool.step_dense(DT, meas, 7, d_act)
+        pool.stamp_dense(sec, nsec, d_act)
+        pool.sync()
+        tb = time.perf_counter()
+        erased = pool.expire(sec, nsec, timeout)
+        tc = time.perf_counter()
+        pool.add(fresh, pf, t0=np.full(fresh.size, k * DT))
+        td = time.perf_counter()
+        parts["step+stamp"] += tb - ta; parts["expire"] += tc - tb; parts["add"] += td - tc
+        assert np.array_equal(erased, exp_ids), k          # erase decisions bit-exact against the host model
+        steps += live; n_erased += erased.size; n_added += fresh.size
     pool.sync()
     dt_wall = time.perf_counter() - t0
-    assert np.array_equal(pool.ids(), ids)
+    assert np.array_equal(pool.ids().astype(np.int64), ids)
     out = {"targets": n, "ticks": ticks, "erased": int(n_erased), "added": int(n_added), "ms_per_tick": 1e3 * dt_wall / ticks,
-           "target_steps_per_s": steps / dt_wall, "note": "wall clock incl. host-side mask generation, expiry compaction (stable gather of the "
-           "whole pool into the second buffer) and append; ids verified against the host model of the churn"}
+           "target_steps_per_s": steps / dt_wall, "ms_per_tick_parts": {k_: 1e3 * v / ticks for k_, v in parts.items()},
+           "note": "library calls only in the timed loop (dense step + stamp, expiry = flags + scan + stable gather of the whole pool "
+                   "into the second buffer, append of the fresh ids from host arrays); every tick's erase list and the final id "
+                   "set are checked against a host model of the churn"}
     pool.close()
     return out
 
