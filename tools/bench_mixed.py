@@ -4,8 +4,9 @@
     python tools/bench_mixed.py [--targets-per-gpu 8388608] [--ticks 32]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 tools/bench_mixed.py ...
 
-owner(id) = id mod G; model(id) by id mod 10: 0-3 uniform velocity, 4-7 uniform acceleration, 8 angular velocities,
-9 angular rates.  One pool per model per rank, four launches per tick on one stream, no collective on
+owner(id) = id mod G; model(id) by (id div 16) mod 10: 0-3 uniform velocity, 4-7 uniform acceleration, 8 angular
+velocities, 9 angular rates (SURVEY.md 8(d) C5 says "id mod 10", which is not independent of id mod G for even G -- rank 0 of 2
+would own every AV and no AR target; taking the residue of id div 16 keeps the 40/40/10/10 mix on every rank for G | 16).  One pool per model per rank, four launches per tick on one stream, no collective on
 the hot path; afterwards every rank contributes its [pose7 | twist6] records to an NCCL all-gather.  Prints one JSON line.
 """
 import argparse
@@ -42,7 +43,7 @@ def main():
     rng = np.random.default_rng(100 + rank)
     pools, inputs, alg_bytes = [], [], 0.0
     for name, residues in MIX:
-        ids = ids_all[np.isin(ids_all % 10, residues)].astype(np.uint32)
+        ids = ids_all[np.isin((ids_all // 16) % 10, residues)].astype(np.uint32)
         mtype, _, Q, R, P0 = te.load_model(name)
         pool = te.TargetPool(mtype, device=local, stream=stream.cuda_stream)
         pool.register_class(Q, R, P0)
@@ -111,7 +112,7 @@ def main():
     torch.cuda.synchronize()
     if rank == 0:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-        res = {"config": "C5 mixed models (40% UV / 40% UA / 10% AV / 10% AR by id mod 10), owner = id mod G", "n_gpus": world,
+        res = {"config": "C5 mixed models (40% UV / 40% UA / 10% AV / 10% AR by (id div 16) mod 10), owner = id mod G", "n_gpus": world,
                "targets_per_gpu": n, "targets_total": n * world, "ticks": args.ticks, "ms_per_tick": ms / args.ticks,
                "target_steps_per_s": n * world * args.ticks / (ms * 1e-3), "per_gpu_counts": dict(zip([m for m, _ in MIX], counts)),
                "alg_gbs_per_gpu": alg_bytes / (ms / args.ticks * 1e-3) / 1e9, "frac_of_hbm_peak": alg_bytes / (ms / args.ticks * 1e-3) / 1e9 / peak,
