@@ -324,6 +324,26 @@ def main():
         e2e = {"value": n * world * Ke / (float(t_e.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * (stride * 8 + 1),
                "d2h_bytes_per_step": n * 24, "steps": Ke, "ms_per_step": float(t_e.item()) / Ke,
                "api": "te_pool_tick_host (pinned host meas[n][7] + action[n] in, est. position [n][3] out)"}
+        if M == 3:
+            # the linear models only read x y z of the pose: a caller that hands over [n][3] positions moves 2.3x fewer bytes
+            h3 = [m[:, :3].contiguous().cpu().pin_memory() for m in meas[:2]]
+
+            def tick_host3(k):
+                if te.lib.te_pool_tick_host(pool._h, DT, h3[k % 2].data_ptr(), 3, h_act[k % 2].data_ptr(), 2, h_out.data_ptr()) < 0:
+                    raise RuntimeError(te._lib.last_error())
+            for k in range(3):
+                tick_host3(k)
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(Ke):
+                tick_host3(k)
+            barrier()
+            t3 = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+            e2e["xyz_only"] = {"value": n * world * Ke / (float(t3.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * (3 * 8 + 1),
+                               "d2h_bytes_per_step": n * 24, "ms_per_step": float(t3.item()) / Ke,
+                               "api": "te_pool_tick_host with meas_stride 3 (positions only)"}
 
     # ---- optional all-gather of estimate records (off the hot path) -----------------------------------
     allgather = None
