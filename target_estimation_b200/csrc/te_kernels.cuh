@@ -4,6 +4,7 @@
 //   isolver_kernel     : batched IntersectionSolver
 #pragma once
 #include "te_device.cuh"
+#include "te_quartic.h"
 
 namespace te {
 
@@ -382,7 +383,11 @@ __global__ void map_new_kernel(int n_add, const uint32_t* __restrict__ add_ids, 
   srcmap[k + before] = -1 - k;
 }
 
-// stable gather of every field of every surviving target into the other buffer + init of new ones
+// stable gather of every field of every surviving target into the other buffer + init of new ones.  blockIdx.y selects a
+// chunk of REBUILD_FPT fields, all of whose loads are issued before the first store (a single thread walking the 347
+// fields of an AR slot one after the other keeps too few bytes in flight: 2.0 TB/s; chunked: see DESIGN.md section 7);
+// chunk 0 also moves the cold arrays and initialises the new slots.
+constexpr int REBUILD_FPT = 16;
 template <int TYPE>
 __global__ void rebuild_kernel(int n_new, const int* __restrict__ srcmap, const double* __restrict__ old_tiles, ColdArrays old_cold,
                                double* __restrict__ new_tiles, ColdArrays new_cold, AddData ad, const double* P0tab) {
@@ -390,17 +395,23 @@ __global__ void rebuild_kernel(int n_new, const int* __restrict__ srcmap, const 
   int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= n_new) return;
   int s = srcmap[d];
+  const int f0 = blockIdx.y * REBUILD_FPT;
   if (s >= 0) {
     const double* src = old_tiles + (size_t)(s / TILE) * LY::TILE_DOUBLES + (s % TILE);
     double* dst = new_tiles + (size_t)(d / TILE) * LY::TILE_DOUBLES + (d % TILE);
-#pragma unroll 8
-    for (int f = 0; f < LY::NF; ++f) dst[f * TILE] = src[f * TILE];
-    new_cold.ids[d] = old_cold.ids[s];
-    new_cold.cls[d] = old_cold.cls[s];
-    new_cold.last_meas[d] = old_cold.last_meas[s];
+    double v[REBUILD_FPT];
 #pragma unroll
-    for (int e = 0; e < 7; ++e) new_cold.meas[(size_t)d * 7 + e] = old_cold.meas[(size_t)s * 7 + e];
-  } else {
+    for (int k = 0; k < REBUILD_FPT; ++k) if (f0 + k < LY::NF) v[k] = __ldcs(src + (size_t)(f0 + k) * TILE);
+#pragma unroll
+    for (int k = 0; k < REBUILD_FPT; ++k) if (f0 + k < LY::NF) __stcs(dst + (size_t)(f0 + k) * TILE, v[k]);
+    if (blockIdx.y == 0) {
+      new_cold.ids[d] = old_cold.ids[s];
+      new_cold.cls[d] = old_cold.cls[s];
+      new_cold.last_meas[d] = old_cold.last_meas[s];
+#pragma unroll
+      for (int e = 0; e < 7; ++e) new_cold.meas[(size_t)d * 7 + e] = old_cold.meas[(size_t)s * 7 + e];
+    }
+  } else if (blockIdx.y == 0) {
     init_slot<TYPE>(new_tiles, new_cold, d, ad, (long long)(-1 - s), P0tab);
   }
 }
@@ -537,114 +548,11 @@ __global__ void collect_erased_kernel(const int* __restrict__ alive, const int* 
 
 // -------------------------------------------------------------------------------------
 // Batched IntersectionSolver (src/intersection_solver.cpp:42-124).
-// Roots of the quartic: Aberth-Ehrlich simultaneous iteration in complex FP64 (the reference
-// uses Eigen's companion-matrix QR; both are backward stable -- they differ only for
-// near-multiple roots), then the reference's selection rule: smallest real part
-// among roots with |imag| < 1e-10, -1 if none / leading coefficient 0 / negative.
+// Roots of the quartic: te_quartic.h (Ferrari split + Newton polish in real FP64, Aberth-Ehrlich fallback; the
+// reference uses Eigen's companion-matrix QR; all are backward stable -- they differ only for near-multiple roots,
+// SURVEY.md H9), then the reference's selection rule: smallest real part among roots with |imag| < 1e-10, -1 if none /
+// leading coefficient 0 / negative.
 // -------------------------------------------------------------------------------------
-struct Cplx { double re, im; };
-__device__ __forceinline__ Cplx cadd(Cplx a, Cplx b) { return {a.re + b.re, a.im + b.im}; }
-__device__ __forceinline__ Cplx csub(Cplx a, Cplx b) { return {a.re - b.re, a.im - b.im}; }
-__device__ __forceinline__ Cplx cmul(Cplx a, Cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
-__device__ __forceinline__ Cplx cdiv(Cplx a, Cplx b) {
-  // Smith's algorithm
-  if (fabs(b.re) >= fabs(b.im)) {
-    double r = b.im / b.re, d = b.re + b.im * r;
-    return {(a.re + a.im * r) / d, (a.im - a.re * r) / d};
-  }
-  double r = b.re / b.im, d = b.re * r + b.im;
-  return {(a.re * r + a.im) / d, (a.im * r - a.re) / d};
-}
-__device__ __forceinline__ double cabs2(Cplx a) { return a.re * a.re + a.im * a.im; }
-
-__device__ __forceinline__ void horner4(const double c[5], Cplx z, Cplx& p, Cplx& dp) {
-  p = {c[4], 0.0};
-  dp = {0.0, 0.0};
-#pragma unroll
-  for (int i = 3; i >= 0; --i) {
-    dp = cadd(cmul(dp, z), p);
-    p = cadd(cmul(p, z), Cplx{c[i], 0.0});
-  }
-}
-// (Eigen) poly_eval: Horner for |x| <= 1, reversed Horner otherwise
-__device__ __forceinline__ double poly_abs4(const double c[5], Cplx x) {
-  if (cabs2(x) <= 1.0) {
-    Cplx v{c[4], 0.0};
-#pragma unroll
-    for (int i = 3; i >= 0; --i) v = cadd(cmul(v, x), Cplx{c[i], 0.0});
-    return sqrt(cabs2(v));
-  }
-  Cplx inv = cdiv(Cplx{1.0, 0.0}, x);
-  Cplx v{c[0], 0.0};
-#pragma unroll
-  for (int i = 1; i <= 4; ++i) v = cadd(cmul(v, inv), Cplx{c[i], 0.0});
-  Cplx x2 = cmul(x, x), x4 = cmul(x2, x2);
-  return sqrt(cabs2(cmul(x4, v)));
-}
-
-__device__ inline double lowest_real_root4(const double c[5]) {
-  if (!(fabs(c[4]) > 0.0)) return -1.0;
-  // monic coefficients for the root bound / starting circle
-  const double b3 = c[3] / c[4], b2 = c[2] / c[4], b1 = c[1] / c[4], b0 = c[0] / c[4];
-  // Fujiwara bound
-  double rad = fabs(b3);
-  rad = fmax(rad, sqrt(fabs(b2)));
-  rad = fmax(rad, cbrt(fabs(b1)));
-  rad = fmax(rad, sqrt(sqrt(fabs(b0) * 0.5)));
-  rad = 2.0 * rad;
-  if (!(rad > 0.0)) rad = 1.0;
-  const double ctr = -b3 * 0.25;
-  Cplx z[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    double sn, cs;
-    sincos(0.7 + 1.5707963267948966 * k, &sn, &cs);
-    z[k] = {ctr + 0.5 * rad * cs, 0.5 * rad * sn};
-  }
-  for (int iter = 0; iter < 200; ++iter) {
-    double worst = 0.0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      Cplx p, dp;
-      horner4(c, z[k], p, dp);
-      if (p.re == 0.0 && p.im == 0.0) continue;
-      if (dp.re == 0.0 && dp.im == 0.0) { z[k].re += 1e-3 * rad; z[k].im += 1e-3 * rad; worst = 1.0; continue; }
-      Cplx w = cdiv(p, dp);
-      Cplx ssum{0.0, 0.0};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (j == k) continue;
-        Cplx d = csub(z[k], z[j]);
-        if (d.re == 0.0 && d.im == 0.0) d = {1e-300, 1e-300};
-        ssum = cadd(ssum, cdiv(Cplx{1.0, 0.0}, d));
-      }
-      Cplx den = csub(Cplx{1.0, 0.0}, cmul(w, ssum));
-      Cplx dz = (den.re == 0.0 && den.im == 0.0) ? w : cdiv(w, den);
-      z[k] = csub(z[k], dz);
-      const double rel = sqrt(cabs2(dz)) / fmax(sqrt(cabs2(z[k])), 1e-300);
-      worst = fmax(worst, rel);
-    }
-    if (worst < 4e-16) break;
-  }
-  // (Eigen 3.4) clean imaginary noise of real roots
-  const double coarse_prec = 4096.0 * 2.220446049250313e-16;   // 4^(5+1) * eps
-  bool found = false;
-  double best = 0.0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (fabs(z[k].im) <= fabs(z[k].re) * coarse_prec) {
-      Cplx r{z[k].re, 0.0};
-      if (poly_abs4(c, r) <= poly_abs4(c, z[k])) z[k] = r;
-    }
-    if (fabs(z[k].im) < 1e-10) {
-      if (!found) { found = true; best = z[k].re; }
-      else if (z[k].re < best) best = z[k].re;
-    }
-  }
-  if (!found) return -1.0;
-  return best;
-}
-
 struct IsolverState {
   long long n_streams;
   unsigned L;            // filters_length

@@ -366,7 +366,8 @@ template <int TYPE>
 void rebuild_t(te_pool* p, int n_new, const te::AddData& ad) {
   Buf& ob = p->buf[p->cur];
   Buf& nb = p->buf[1 - p->cur];
-  te::rebuild_kernel<TYPE><<<cdiv(n_new, 128), 128, 0, p->stream>>>(n_new, p->srcmap, ob.tiles, ob.cold, nb.tiles, nb.cold, ad, p->dP0);
+  const dim3 grid(cdiv(n_new, 128), (te::Layout<TYPE>::NF + te::REBUILD_FPT - 1) / te::REBUILD_FPT);
+  te::rebuild_kernel<TYPE><<<grid, 128, 0, p->stream>>>(n_new, p->srcmap, ob.tiles, ob.cold, nb.tiles, nb.cold, ad, p->dP0);
   CK(cudaGetLastError());
 }
 void rebuild(te_pool* p, int n_new, const te::AddData& ad) {
