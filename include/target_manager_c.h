@@ -83,6 +83,22 @@ long long target_tick_manager_update(const target_manager_c* self, double dt, un
 long long target_tick_manager_published(const target_manager_c* self, unsigned int* ids_out, double* poses_out, long long cap);
 double target_tick_manager_time(const target_manager_c* self);
 long long target_tick_manager_mailboxes(const target_manager_c* self);
+
+/* ---- recorded /tf input: rosbag v2.0 reader + the node's loop on the recording (bag_reader.hpp) ----
+ * One record per transform, in record order; `msg` groups the transforms of one TFMessage (= one callback). */
+typedef struct target_tf_record {
+  unsigned int rec_sec, rec_nsec;   /* receive time of the message record */
+  unsigned int msg;                 /* index of the message the transform came in */
+  unsigned int seq, sec, nsec;      /* header.seq, header.stamp */
+  char frame_id[64], child_frame_id[64];
+  double pose[7];                   /* translation xyz, rotation xyzw (target_manager_ros.hpp:36-46) */
+} target_tf_record;
+/* returns the number of transforms on `topic` (NULL = "/tf"), the first `cap` of them in out; -1 on error */
+long long target_bag_read_tf(const char* path, const char* topic, target_tf_record* out, long long cap);
+/* src/target_node.cpp:36-44 on the bag's clock at `frequency` Hz, `extra_ticks` ticks past the last message.
+ * stats_out (optional): ticks, messages, transforms, erased.  Returns the number of ticks, -1 on error. */
+long long target_tick_manager_replay_bag(const target_manager_c* self, const char* path, const char* topic, double frequency,
+                                         long long extra_ticks, long long stats_out[4]);
 const char* target_manager_last_error(void);
 
 #ifdef __cplusplus

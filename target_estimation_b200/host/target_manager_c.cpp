@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 
+#include "target_estimation_b200/bag_reader.hpp"
 #include "target_estimation_b200/target_manager.hpp"
 
 using namespace target_estimation_b200;
@@ -192,6 +193,34 @@ long long target_tick_manager_published(const target_manager_c* self, unsigned i
 }
 double target_tick_manager_time(const target_manager_c* self) {
   return guard(-1.0, [&] { return T(self)->time(); });
+}
+long long target_bag_read_tf(const char* path, const char* topic, target_tf_record* out, long long cap) {
+  return guard(-1LL, [&]() -> long long {
+    if (!path) throw std::invalid_argument("path is NULL");
+    const std::vector<TfRecord> rec = readBagTf(path, topic ? topic : "/tf");
+    const long long n = (long long)rec.size();
+    for (long long i = 0; i < n && i < cap && out; ++i) {
+      target_tf_record& o = out[i];
+      const TfRecord& r = rec[(size_t)i];
+      o.rec_sec = r.rec_sec; o.rec_nsec = r.rec_nsec; o.msg = r.msg; o.seq = r.seq; o.sec = r.sec; o.nsec = r.nsec;
+      std::memset(o.frame_id, 0, sizeof(o.frame_id));
+      std::memset(o.child_frame_id, 0, sizeof(o.child_frame_id));
+      std::strncpy(o.frame_id, r.frame_id.c_str(), sizeof(o.frame_id) - 1);
+      std::strncpy(o.child_frame_id, r.child_frame_id.c_str(), sizeof(o.child_frame_id) - 1);
+      std::memcpy(o.pose, r.pose, sizeof(o.pose));
+    }
+    return n;
+  });
+}
+long long target_tick_manager_replay_bag(const target_manager_c* self, const char* path, const char* topic, double frequency,
+                                         long long extra_ticks, long long stats_out[4]) {
+  return guard(-1LL, [&]() -> long long {
+    if (!path) throw std::invalid_argument("path is NULL");
+    const std::vector<TfRecord> rec = readBagTf(path, topic ? topic : "/tf");
+    const ReplayStats st = replayBag(*T(self), rec, frequency, extra_ticks);
+    if (stats_out) { stats_out[0] = st.ticks; stats_out[1] = st.messages; stats_out[2] = st.transforms; stats_out[3] = st.erased; }
+    return st.ticks;
+  });
 }
 long long target_tick_manager_mailboxes(const target_manager_c* self) {
   return guard(-1LL, [&] { return (long long)T(self)->mailboxCount(); });

@@ -42,6 +42,8 @@ _SIG = {
     "target_tick_manager_published": (_ll, [_p, _p, _p, _ll]),
     "target_tick_manager_time": (_d, [_p]),
     "target_tick_manager_mailboxes": (_ll, [_p]),
+    "target_bag_read_tf": (_ll, [C.c_char_p, C.c_char_p, _p, _ll]),
+    "target_tick_manager_replay_bag": (_ll, [_p, C.c_char_p, C.c_char_p, _d, _ll, _p]),
 }
 for _n, (_r, _a) in _SIG.items():
     _f = getattr(clib, _n)
@@ -141,6 +143,21 @@ class TargetManagerC:
         clib.target_manager_flush(self.h)
 
 
+# target_tf_record of include/target_manager_c.h
+TF_RECORD_DTYPE = np.dtype([("rec_sec", np.uint32), ("rec_nsec", np.uint32), ("msg", np.uint32), ("seq", np.uint32), ("sec", np.uint32),
+                            ("nsec", np.uint32), ("frame_id", "S64"), ("child_frame_id", "S64"), ("pose", np.float64, (7,))], align=True)
+
+
+def read_bag_tf(path, topic="/tf"):
+    """every transform of a rosbag v2.0 /tf recording, in record order (target_bag_read_tf)"""
+    n = int(clib.target_bag_read_tf(path.encode(), topic.encode(), None, 0))
+    if n < 0:
+        raise RuntimeError(clib.target_manager_last_error().decode())
+    out = np.zeros(max(n, 1), dtype=TF_RECORD_DTYPE)
+    clib.target_bag_read_tf(path.encode(), topic.encode(), _ptr(out), n)
+    return out[:n]
+
+
 class TickManagerC(TargetManagerC):
     """RosTargetManager semantics without ROS (target_tick_manager_* of include/target_manager_c.h)."""
 
@@ -181,6 +198,13 @@ class TickManagerC(TargetManagerC):
 
     def time(self):
         return float(clib.target_tick_manager_time(self.h))
+
+    def replay_bag(self, path, frequency, topic="/tf", extra_ticks=0):
+        """the node's loop (update; spinOnce; sleep) on a recording; returns dict(ticks, messages, transforms, erased)"""
+        st = np.zeros(4, dtype=np.int64)
+        if int(clib.target_tick_manager_replay_bag(self.h, path.encode(), topic.encode(), float(frequency), int(extra_ticks), _ptr(st))) < 0:
+            raise RuntimeError(clib.target_manager_last_error().decode())
+        return dict(zip(("ticks", "messages", "transforms", "erased"), (int(v) for v in st)))
 
     def mailboxes(self):
         return int(clib.target_tick_manager_mailboxes(self.h))
