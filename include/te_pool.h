@@ -122,6 +122,17 @@ int te_pool_stamp_dense(te_pool* p, const uint8_t* dev_action, int default_actio
 long long te_pool_expire(te_pool* p, uint32_t now_sec, uint32_t now_nsec, double timeout, uint32_t* erased_out,
                          long long cap);
 
+/* One whole churn tick of RosTargetManager::update (src/target_manager_ros.cpp:52-76) for a device-resident stream:
+ * te_pool_step_dense(dt, dev_meas, ...) + te_pool_stamp_dense(dev_action, default_action, stamp_*) +
+ * te_pool_expire(now_*, timeout, ...), with identical results (survivor state bit-identical, same erased ids, same slot
+ * order), but the stable compaction is FUSED into the step: the kernel reads each tile in place and writes the
+ * survivors' columns straight to their compacted slots in the pool's second buffer, so an expiry tick moves the state
+ * through HBM once instead of twice.  Targets that expire at the end of this tick are not stepped (their step is
+ * unobservable).  Ticks on which nothing expires run the ordinary in-place step.  Returns #erased. */
+long long te_pool_step_dense_expire(te_pool* p, double dt, const double* dev_meas, int meas_stride, const uint8_t* dev_action,
+                                    int default_action, uint32_t stamp_sec, uint32_t stamp_nsec, uint32_t now_sec, uint32_t now_nsec,
+                                    double timeout, uint32_t* erased_out, long long cap);
+
 /* ---- batched IntersectionSolver (src/intersection_solver.cpp) ---------------------------- */
 /* n_streams independent solver states (each = one reference IntersectionSolver object: two moving
  * average filters of filters_length samples + previous intersection pose). */

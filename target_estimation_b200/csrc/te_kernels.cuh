@@ -45,6 +45,12 @@ struct StepArgs {
   int n_ticks;
   long long meas_tick_stride;     // doubles
   long long action_tick_stride;   // bytes
+  // compacting tick (te_pool_step_dense_expire): the tile is read from `tiles` as usual, but every surviving target's
+  // column goes to slot dst_pos[slot] of `dst_tiles` (the pool's other buffer) instead of back in place, so the stable
+  // compaction after an expiry costs no pass of its own.  nullptr = in place.
+  double* dst_tiles;
+  const int* dst_alive;     // [n_slots] 1 = survives
+  const int* dst_pos;       // [n_slots] exclusive scan of dst_alive
   int cls_c;                // class held in Qc / Rc, -1 = none
   double Rc[36];
   double Qc[324];
@@ -112,11 +118,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_kernel(const StepArgs a
     int act = ACT_NONE;
     double dt = a.dt;
     int cls = 0;
+    int dst = -1;   // compacting tick: destination slot, -1 = erased
     if (valid) {
       act = a.action ? (int)a.action[slot] : a.default_action;
       if (a.dt_slot) dt = a.dt_slot[slot];
       cls = (int)a.cls[slot];
+      if (a.dst_tiles && a.dst_alive[slot]) dst = a.dst_pos[slot];
     }
+    if (a.dst_tiles && dst < 0) act = ACT_NONE;   // erased at the end of this tick: its step is unobservable
     const bool mt = use_meas_tma(tile);
     double meas[7];
     if (!mt && act == ACT_UPDATE) {
@@ -236,10 +245,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_kernel(const StepArgs a
         step_lane<TYPE>(st, lane, act, dt, meas, a.Qtab + (size_t)cls * MT::N * MT::N, a.Rtab + (size_t)cls * MT::M * MT::M);
         if (a.clear_action) a.action[slot] = 0;
       }
-      if (a.pos_out && valid) {
+    }
+    if (a.pos_out && valid) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) a.pos_out[(size_t)slot * 3 + k] = st[(LY::F_X + k) * TILE + lane];
+      for (int k = 0; k < 3; ++k) a.pos_out[(size_t)slot * 3 + k] = st[(LY::F_X + k) * TILE + lane];
+    }
+    if (a.dst_tiles) {
+      // compacting tick: every lane moves its own column (the only one it wrote) to its destination slot; consecutive
+      // survivors are consecutive there, so each field is one or two coalesced segments per warp
+      if (dst >= 0) {
+        double* dr = a.dst_tiles + (size_t)(dst / TILE) * LY::TILE_DOUBLES + (dst % TILE);
+#pragma unroll 8
+        for (int f = 0; f < LY::NF; ++f) __stcs(dr + (size_t)f * TILE, st[f * TILE + lane]);
       }
+      __syncwarp();   // all columns read before lane 0 refills this stage in the next iteration
+    } else if (any) {
       fence_proxy_async();   // generic-proxy writes of the stage -> visible to the bulk store
       __syncwarp();
       if (lane == 0) {
@@ -248,10 +268,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_kernel(const StepArgs a
         if (a.clear_action) a.tile_flag[tile] = 0;
       }
     } else {
-      if (a.pos_out && valid) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) a.pos_out[(size_t)slot * 3 + k] = st[(LY::F_X + k) * TILE + lane];
-      }
       __syncwarp();
     }
   }
@@ -544,6 +560,19 @@ __global__ void collect_erased_kernel(const int* __restrict__ alive, const int* 
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_slots || alive[s]) return;
   erased[s - pos[s]] = ids[s];
+}
+
+// compacting tick: the cold arrays of the survivors move to their destination slots (the tile fields are moved by the step
+// kernel itself)
+__global__ void compact_cold_kernel(int n_old, const int* __restrict__ alive, const int* __restrict__ pos, ColdArrays old_cold, ColdArrays new_cold) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_old || !alive[s]) return;
+  const int d = pos[s];
+  new_cold.ids[d] = old_cold.ids[s];
+  new_cold.cls[d] = old_cold.cls[s];
+  new_cold.last_meas[d] = old_cold.last_meas[s];
+#pragma unroll
+  for (int e = 0; e < 7; ++e) new_cold.meas[(size_t)d * 7 + e] = old_cold.meas[(size_t)s * 7 + e];
 }
 
 // -------------------------------------------------------------------------------------

@@ -117,6 +117,10 @@ struct te_pool {
   // host mirror of the sorted ids (lazy)
   std::vector<uint32_t> h_ids;
   bool h_ids_valid = true;
+  // largest live id, kept across compactions: enough to recognise an append-only add batch (monotonically increasing
+  // track ids, the common case) without downloading the whole id array again
+  uint32_t h_last_id = 0;
+  bool h_last_valid = false;
   Arena arena;
   // chunk pipeline of te_pool_tick_host
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
@@ -232,6 +236,7 @@ void sync_host_ids(te_pool* p) {
     CK(cudaStreamSynchronize(p->stream));
   }
   p->h_ids_valid = true;
+  if (p->n) { p->h_last_id = p->h_ids.back(); p->h_last_valid = true; }
 }
 
 void upload_classes(te_pool* p) {
@@ -283,9 +288,9 @@ void launch_step_t(te_pool* p, const te::StepArgs& a, int n_work_hint) {
 }
 
 // row/column-split kernel (te_split.cuh): one CTA of 6*CS warps per tile, STAGES stages per CTA, CTAS CTAs per SM
-template <int TYPE, int CS, int STAGES, int CTAS>
-void launch_split_t(te_pool* p, const te::StepArgs& a, int n_work_hint) {
-  auto kern = te::kf_step_split_kernel<TYPE, CS, STAGES, CTAS>;
+template <int TYPE, int CS, int STAGES, int CTAS, bool COMPACT>
+void launch_split_k(te_pool* p, const te::StepArgs& a, int n_work_hint) {
+  auto kern = te::kf_step_split_kernel<TYPE, CS, STAGES, CTAS, COMPACT>;
   const size_t smem = te::split_smem_bytes<TYPE>(STAGES);
   static bool configured[64] = {false};
   if (!configured[p->device & 63]) {
@@ -296,8 +301,9 @@ void launch_split_t(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   kern<<<grid, (te::SPLIT_RS * CS + te::split_nt<TYPE>()) * 32, smem, p->stream>>>(a);
   CK(cudaGetLastError());
 }
+template <int TYPE, int CS, int STAGES, int CTAS>
+void launch_split_t(te_pool* p, const te::StepArgs& a, int n_work_hint) { launch_split_k<TYPE, CS, STAGES, CTAS, false>(p, a, n_work_hint); }
 
-// multi-tick replay: the per-warp kernel with the tile resident across ticks (every model)
 void launch_step_multi(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   switch (p->model) {
     case te::UNIFORM_VELOCITY: launch_step_t<te::UNIFORM_VELOCITY, 8, 2, true>(p, a, n_work_hint); break;
@@ -310,6 +316,12 @@ void launch_step_multi(te_pool* p, const te::StepArgs& a, int n_work_hint) {
 // variant -> (warps, stages) per model.  Stage bytes: UV 13056, UA 25344, AV 43008, AR 90624.
 void launch_step(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   const int v = p->variant;
+  if (a.dst_tiles) {
+    // compacting tick: separate instantiations of the default split configurations, so that the in-place kernels carry
+    // none of its code (the AV kernel at 128 registers lost 6 % to a few extra runtime branches)
+    if (p->model == te::ANGULAR_VELOCITIES) return launch_split_k<te::ANGULAR_VELOCITIES, 1, 2, 2, true>(p, a, n_work_hint);
+    if (p->model == te::ANGULAR_RATES) return launch_split_k<te::ANGULAR_RATES, 1, 2, 1, true>(p, a, n_work_hint);
+  }
   switch (p->model) {
     case te::UNIFORM_VELOCITY:
       if (v == 1) launch_step_t<te::UNIFORM_VELOCITY, 16, 1>(p, a, n_work_hint);
@@ -393,6 +405,16 @@ void init_append(te_pool* p, int base, const te::AddData& ad, long long n) {
   }
 }
 
+// after a compaction: the largest surviving id (4 bytes; the callers synchronise the stream before they return)
+void fetch_last_id(te_pool* p) {
+  p->h_last_valid = false;
+  if (p->n > 0) {
+    CK(cudaMemcpyAsync(&p->h_last_id, p->buf[p->cur].cold.ids + p->n - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    p->h_last_valid = true;
+  }
+}
+
 // alive[] (n_old entries) is set on the device; compacts survivors, merges `n_add` sorted new ids.
 // Returns the number of survivors.
 int compact_and_merge(te_pool* p, const te::AddData& ad, const uint32_t* d_add_ids, int n_add, uint32_t* d_erased /*or null*/) {
@@ -426,6 +448,7 @@ int compact_and_merge(te_pool* p, const te::AddData& ad, const uint32_t* d_add_i
   p->cur = 1 - p->cur;
   p->n = n_new;
   p->h_ids_valid = false;
+  fetch_last_id(p);
   return total_alive;
 }
 
@@ -633,7 +656,6 @@ long long te_pool_add_batch(te_pool* p, long long n, const uint32_t* ids, const 
     if (n <= 0) return 0;
     if (!ids || !p0) throw std::invalid_argument("ids and p0 are required");
     if (p->hQ.empty()) throw std::runtime_error("no model class registered");
-    sync_host_ids(p);
     // order the batch by id (first occurrence wins), drop ids that already exist
     std::vector<long long> ord((size_t)n);
     std::iota(ord.begin(), ord.end(), 0LL);
@@ -642,7 +664,10 @@ long long te_pool_add_batch(te_pool* p, long long n, const uint32_t* ids, const 
     if (!sorted) std::stable_sort(ord.begin(), ord.end(), [&](long long a, long long b) { return ids[a] < ids[b]; });
     std::vector<long long> keep;
     keep.reserve((size_t)n);
-    const bool append_only = p->h_ids.empty() || ids[ord[0]] > p->h_ids.back();
+    if (p->n == 0) { p->h_ids.clear(); p->h_ids_valid = true; }
+    if (p->n > 0 && !p->h_ids_valid && !p->h_last_valid) sync_host_ids(p);
+    const bool append_only = p->n == 0 || ids[ord[0]] > (p->h_ids_valid ? p->h_ids.back() : p->h_last_id);
+    if (!append_only) sync_host_ids(p);   // membership test and merge need the whole sorted id array
     for (long long k = 0; k < n; ++k) {
       const long long s = ord[k];
       if (!keep.empty() && ids[keep.back()] == ids[s]) continue;
@@ -698,7 +723,9 @@ long long te_pool_add_batch(te_pool* p, long long n, const uint32_t* ids, const 
       }
       init_append(p, (int)p->n, ad, na);
       p->n += na;
-      p->h_ids.insert(p->h_ids.end(), s_ids, s_ids + na);
+      if (p->h_ids_valid) p->h_ids.insert(p->h_ids.end(), s_ids, s_ids + na);
+      p->h_last_id = s_ids[na - 1];
+      p->h_last_valid = true;
     } else {
       ensure_work(p, (size_t)(p->n + na));
       te::fill_i32_kernel<<<cdiv(p->n, 256), 256, 0, p->stream>>>(p->alive, (int)p->n, 1);
@@ -1079,6 +1106,70 @@ long long te_pool_expire(te_pool* p, uint32_t now_sec, uint32_t now_nsec, double
     const int alive = compact_and_merge(p, ad, nullptr, 0, d_erased);
     const long long n_er = n_old - alive;
     if (n_er > 0 && erased_out && cap > 0)
+      CK(cudaMemcpyAsync(erased_out, d_erased, (size_t)std::min(cap, n_er) * sizeof(uint32_t), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return n_er;
+  });
+}
+
+long long te_pool_step_dense_expire(te_pool* p, double dt, const double* dev_meas, int meas_stride, const uint8_t* dev_action,
+                                    int default_action, uint32_t stamp_sec, uint32_t stamp_nsec, uint32_t now_sec, uint32_t now_nsec,
+                                    double timeout, uint32_t* erased_out, long long cap) {
+  return guarded_ll(p, [&]() -> long long {
+    if (p->n == 0) return 0;
+    if (!(dt >= 0.0)) throw std::invalid_argument("dt must be >= 0 (assert of src/target_interface.cpp:150)");
+    if (dev_meas) check_meas_stride(p, meas_stride);
+    else if (dev_action || default_action == TE_ACT_UPDATE) throw std::invalid_argument("update tick without measurements");
+    const int n_old = (int)p->n;
+    ensure_work(p, (size_t)n_old);
+    Buf& ob = p->buf[p->cur];
+    // 1. this tick's stamps, then the expiry predicate (both as in te_pool_stamp_dense / te_pool_expire)
+    volatile double sns = 1e-9 * (double)stamp_nsec;
+    const double stamp = (double)stamp_sec + sns;
+    volatile double nns = 1e-9 * (double)now_nsec;
+    const double now = (double)now_sec + nns;
+    te::stamp_dense_kernel<<<cdiv(n_old, 256), 256, 0, p->stream>>>(dev_action, default_action, n_old, stamp, ob.cold.last_meas);
+    CK(cudaGetLastError());
+    te::expire_flags_kernel<<<cdiv(n_old, 256), 256, 0, p->stream>>>(ob.cold.last_meas, n_old, now, timeout, p->alive);
+    CK(cudaGetLastError());
+    size_t tmp = p->cub_bytes;
+    CK(cub::DeviceScan::ExclusiveSum(p->cub_tmp, tmp, p->alive, p->pos, n_old, p->stream));
+    int last_pos = 0, last_alive = 0;
+    CK(cudaMemcpyAsync(&last_pos, p->pos + n_old - 1, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(&last_alive, p->alive + n_old - 1, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    const int n_alive = last_pos + last_alive;
+    const long long n_er = n_old - n_alive;
+    // 2. the step: in place when nobody expired, else into the compacted slots of the other buffer
+    te::StepArgs a = base_args(p);
+    a.dt = dt;
+    a.meas = dev_meas;
+    a.meas_stride = meas_stride;
+    a.meas_tma = (dev_meas && (uintptr_t)dev_meas % 16 == 0) ? 1 : 0;
+    a.action = const_cast<uint8_t*>(dev_action);
+    a.default_action = default_action;
+    if (n_er == 0) {
+      launch_step(p, a, a.n_tiles);
+      return 0;
+    }
+    uint32_t* d_erased = p->arena.get_n<uint32_t>((size_t)n_er);
+    te::collect_erased_kernel<<<cdiv(n_old, 256), 256, 0, p->stream>>>(p->alive, p->pos, ob.cold.ids, n_old, d_erased);
+    CK(cudaGetLastError());
+    if (n_alive > 0) {
+      ensure_other_capacity(p, (size_t)n_alive);
+      Buf& nb = p->buf[1 - p->cur];
+      te::compact_cold_kernel<<<cdiv(n_old, 256), 256, 0, p->stream>>>(n_old, p->alive, p->pos, p->buf[p->cur].cold, nb.cold);
+      CK(cudaGetLastError());
+      a.dst_tiles = nb.tiles;
+      a.dst_alive = p->alive;
+      a.dst_pos = p->pos;
+      launch_step(p, a, a.n_tiles);
+    }
+    p->cur = 1 - p->cur;
+    p->n = n_alive;
+    p->h_ids_valid = false;
+    fetch_last_id(p);
+    if (erased_out && cap > 0)
       CK(cudaMemcpyAsync(erased_out, d_erased, (size_t)std::min(cap, n_er) * sizeof(uint32_t), cudaMemcpyDeviceToHost, p->stream));
     CK(cudaStreamSynchronize(p->stream));
     return n_er;

@@ -86,7 +86,7 @@ __device__ __forceinline__ double quat_to_rpy_comp(const Quat& q, int k) {
   return gimbal ? 2 * at : at;
 }
 
-template <int TYPE, int CS, int STAGES, int MIN_CTAS>
+template <int TYPE, int CS, int STAGES, int MIN_CTAS, bool COMPACT = false>
 __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_CTAS) kf_step_split_kernel(const StepArgs a) {
   using MT = Model<TYPE>;
   using LY = Layout<TYPE>;
@@ -152,16 +152,20 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
   }
 
   // per-lane control words, fetched one tile ahead so that their global-load latency never sits in front of a tile
-  int act_n = ACT_NONE, cls_n = 0;
+  int act_n = ACT_NONE, cls_n = 0, dst_n = -1;   // dst_n: compacting tick, destination slot of this lane's target (-1 = erased)
   double dt_n = a.dt;
   auto load_ctrl = [&](int it) {
-    act_n = ACT_NONE; cls_n = 0; dt_n = a.dt;
+    act_n = ACT_NONE; cls_n = 0; dt_n = a.dt; dst_n = -1;
     if (it < n_my) {
       const int slot = tile_of(it) * TILE + lane;
       if (slot < a.n_slots) {
         act_n = a.action ? (int)a.action[slot] : a.default_action;
         if (a.dt_slot) dt_n = a.dt_slot[slot];
         cls_n = (int)a.cls[slot];
+        if (COMPACT) {
+          if (a.dst_alive[slot]) dst_n = a.dst_pos[slot];
+          else act_n = ACT_NONE;   // erased at the end of this tick: its step is unobservable
+        }
       }
     }
   };
@@ -183,8 +187,14 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
       const int tile_d = tile_of(jd);
       const unsigned any_d = sd == 0 ? anyh[0] : (sd == 1 ? anyh[1] : (sd == 2 ? anyh[2] : anyh[3]));
       wait_done(jd);
+      double* std_ = stage0 + (size_t)sd * STAGE_DOUBLES;
+      if (COMPACT) {
+        // compacting tick (te_pool_step_dense_expire): the main warps have already written the survivors' columns to their
+        // destination slots in the other buffer -- no bulk store, and the source buffer is never written
+        if (producer && jd + STAGES < n_my) issue(jd + STAGES);
+        return;
+      }
       if (producer) {
-        double* std_ = stage0 + (size_t)sd * STAGE_DOUBLES;
         if (any_d) {
           bulk_s2g(a.tiles + (size_t)tile_d * LY::TILE_DOUBLES, std_, LY::TILE_BYTES);
           bulk_commit();
@@ -313,9 +323,26 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
     const int tile = tile_of(it);
     const int slot = tile * TILE + lane;
     const bool valid = slot < a.n_slots;
-    const int act = act_n, cls = cls_n;
+    const int act = act_n, cls = cls_n, dst = dst_n;
     const double dt = dt_n;
     load_ctrl(it + 1);
+    // compacting tick: this warp moves the entries it owns (its rows; warp 0 also t / n_meas / prev_rpy) from the stage to
+    // the target's destination slot -- entries it wrote itself or that nobody writes, so no barrier is needed
+    auto compact_out = [&](const double* stg) {
+      if (dst < 0) return;
+      double* dr = a.dst_tiles + (size_t)(dst / TILE) * LY::TILE_DOUBLES + (dst % TILE);
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) {
+        const int g = q * RS + r;
+        if (h == 0) __stcs(dr + (size_t)(LY::F_X + g) * TILE, stg[(LY::F_X + g) * TILE + lane]);
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) __stcs(dr + (size_t)(LY::F_P + g * N + colof(j)) * TILE, stg[(LY::F_P + g * N + colof(j)) * TILE + lane]);
+      }
+      if (w == 0) {
+#pragma unroll
+        for (int f = LY::F_P + N * N; f < LY::NF; ++f) __stcs(dr + (size_t)f * TILE, stg[f * TILE + lane]);
+      }
+    };
     const double* __restrict__ Q = a.Qtab + (size_t)cls * N * N;
     const double* __restrict__ R = a.Rtab + (size_t)cls * M * M;
     // warp-uniform: every lane of the tile uses the class whose Q / R sit in the parameter constant bank
@@ -607,6 +634,7 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
         }
       }
       if (a.pos_out && valid && w < 3) a.pos_out[(size_t)slot * 3 + w] = xr[0];
+      if (COMPACT) compact_out(st);
       fence_proxy_async();   // generic-proxy writes of the stage -> visible to the producer's bulk store
       TE_MARK(10);
       __syncwarp();
@@ -614,6 +642,7 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
                                                        // by the next tile's first main barrier
     } else {
       if (a.pos_out && valid && w < 3) a.pos_out[(size_t)slot * 3 + w] = st[(LY::F_X + w) * TILE + lane];
+      if (COMPACT) compact_out(st);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[STAGES + s]);
     }

@@ -220,6 +220,17 @@ class TargetPool:
         n = check(lib.te_pool_expire(self._h, int(now_sec), int(now_nsec), float(timeout), _ptr(buf), cap))
         return buf[:n].copy()
 
+    def step_dense_expire(self, dt, dev_meas, meas_stride, dev_action, default_action, stamp, now, timeout):
+        """one churn tick = step_dense + stamp_dense(stamp) + expire(now, timeout) with the compaction fused into the step;
+        stamp / now are (sec, nsec) pairs.  Returns the erased ids (ascending)."""
+        cap = len(self)
+        buf = getattr(self, "_erase_buf", None)
+        if buf is None or buf.size < cap:
+            buf = self._erase_buf = np.empty(max(cap + cap // 4, 1), dtype=np.uint32)
+        n = check(lib.te_pool_step_dense_expire(self._h, float(dt), _dev_ptr(dev_meas), int(meas_stride), _dev_ptr(dev_action), int(default_action),
+                                                int(stamp[0]), int(stamp[1]), int(now[0]), int(now[1]), float(timeout), _ptr(buf), cap))
+        return buf[:n].copy()
+
 
 class IntersectionSolver:
     """Batched IntersectionSolver: n_streams independent reference solver objects (include/te_pool.h)."""

@@ -116,3 +116,59 @@ def test_expiry_bit_exact():
         assert got["n_meas"][j] == nm.value and got["t"][j] == t.value
     assert synth.compare_h2(got["x"], xs) <= 1.0 and synth.compare_h2(got["P"], Ps) <= 1.0
     pool.close()
+
+
+@pytest.mark.parametrize("name", ["uniform_velocity", "uniform_acceleration", "angular_velocities", "angular_rates"])
+def test_fused_step_expire_is_bit_identical(name):
+    """te_pool_step_dense_expire (compaction fused into the step kernel: survivors' columns go straight to their compacted
+    slots in the second buffer) == te_pool_step_dense + te_pool_stamp_dense + te_pool_expire, bit for bit: erased ids,
+    surviving ids and order, x, P, t, n_meas, prev_rpy.  Pool size not a multiple of the tile, ticks with and without
+    expiries, heavy (30 %) and light churn, fresh ids appended in between."""
+    import torch
+    import target_estimation_b200 as te
+    mtype, _, Q, R, P0 = te.load_model(name)
+    angular = name.startswith("angular")
+    n0, ticks = 3000 + 13, 30
+    timeout = 3 * DT
+    meas_all, action_all, scale = synth.make_streams(n0 + 40 * ticks, ticks, DT, accel=True, angular=angular, seed=11)
+    pools = []
+    for _ in range(2):
+        p = te.TargetPool(mtype); p.register_class(Q, R, P0)
+        p.add(np.arange(n0, dtype=np.uint32), meas_all[0, :n0], p0_scale=scale[:n0])
+        pools.append(p)
+    rng = np.random.default_rng(23)
+    next_id = n0
+    silent = np.zeros(n0 + 40 * ticks, dtype=bool)     # by id: no more measurements
+    stamp = lambda k: ((1000 * 10 ** 9 + k * 4000000) // 10 ** 9, (1000 * 10 ** 9 + k * 4000000) % 10 ** 9)
+    total = 0
+    for k in range(ticks):
+        ids = pools[0].ids()
+        assert np.array_equal(ids, pools[1].ids())
+        if k in (2, 9):        # a burst: 30 % fall silent at once
+            silent[rng.choice(ids, size=ids.size * 3 // 10, replace=False)] = True
+        elif k % 4 != 3:       # light churn; every fourth tick nobody new falls silent
+            silent[rng.choice(ids, size=max(1, ids.size // 100), replace=False)] = True
+        act = np.where(silent[ids], te.ACT_PREDICT, action_all[k % ticks, ids]).astype(np.uint8)
+        act[silent[ids] & (rng.random(ids.size) < 0.1)] = te.ACT_NONE
+        m = torch.from_numpy(np.ascontiguousarray(meas_all[k % ticks, ids])).cuda()
+        a = torch.from_numpy(act).cuda()
+        sec, nsec = stamp(k)
+        pools[0].step_dense(DT, m, 7, a, te.ACT_UPDATE)
+        pools[0].stamp_dense(sec, nsec, a)
+        er0 = pools[0].expire(sec, nsec, timeout)
+        er1 = pools[1].step_dense_expire(DT, m, 7, a, te.ACT_UPDATE, (sec, nsec), (sec, nsec), timeout)
+        assert np.array_equal(er0, er1), k
+        total += er0.size
+        s0, s1 = pools[0].read_state(), pools[1].read_state()
+        assert np.array_equal(pools[0].ids(), pools[1].ids())
+        for f in ("x", "P", "t", "n_meas") + (("prev_rpy",) if angular else ()):
+            assert np.array_equal(s0[f].view(np.uint64) if s0[f].dtype == np.float64 else s0[f],
+                                  s1[f].view(np.uint64) if s1[f].dtype == np.float64 else s1[f]), (k, f)
+        # fresh ids (appended: larger than every live id), first measurement as p0
+        nf = 40
+        fresh = np.arange(next_id, next_id + nf, dtype=np.uint32); next_id += nf
+        for p in pools:
+            p.add(fresh, meas_all[k % ticks, fresh], t0=np.full(nf, k * DT), p0_scale=scale[fresh])
+    assert total > n0 // 3
+    for p in pools:
+        p.close()

@@ -35,7 +35,7 @@ def make_pool(model, n, stream, v0=None):
     return pool, p0
 
 
-def c3_churn(n=1 << 20, ticks=48):
+def c3_churn(n=1 << 20, ticks=48, fused=False):
     stream = torch.cuda.Stream()
     pool, p0 = make_pool("angular_rates", n, stream)
     rng = np.random.default_rng(2)
@@ -80,21 +80,25 @@ def c3_churn(n=1 << 20, ticks=48):
     meas[:, :3] = torch.rand((n_max, 3), dtype=torch.float64, device="cuda")
     torch.cuda.synchronize()
     n_erased = n_added = steps = 0
-    parts = {"step+stamp": 0.0, "expire": 0.0, "add": 0.0}
+    parts = {"step+stamp+expire (fused)" if fused else "step+stamp": 0.0, "expire": 0.0, "add": 0.0}
     t0 = time.perf_counter()
     for k, (d_act, exp_ids, fresh, pf, live) in enumerate(sched):
         ns = 1000 * 10 ** 9 + k * 4000000
         sec, nsec = ns // 10 ** 9, ns % 10 ** 9
         ta = time.perf_counter()
-        pool.step_dense(DT, meas, 7, d_act)
-        pool.stamp_dense(sec, nsec, d_act)
-        pool.sync()
-        tb = time.perf_counter()
-        erased = pool.expire(sec, nsec, timeout)
-        tc = time.perf_counter()
+        if fused:   # one call: stamps + expiry flags + scan, then the step writes the survivors to their compacted slots
+            erased = pool.step_dense_expire(DT, meas, 7, d_act, te.ACT_UPDATE, (sec, nsec), (sec, nsec), timeout)
+            tb = tc = time.perf_counter()
+        else:
+            pool.step_dense(DT, meas, 7, d_act)
+            pool.stamp_dense(sec, nsec, d_act)
+            pool.sync()
+            tb = time.perf_counter()
+            erased = pool.expire(sec, nsec, timeout)
+            tc = time.perf_counter()
         pool.add(fresh, pf, t0=np.full(fresh.size, k * DT))
         td = time.perf_counter()
-        parts["step+stamp"] += tb - ta; parts["expire"] += tc - tb; parts["add"] += td - tc
+        parts["step+stamp+expire (fused)" if fused else "step+stamp"] += tb - ta; parts["expire"] += tc - tb; parts["add"] += td - tc
         assert np.array_equal(erased, exp_ids), k          # erase decisions bit-exact against the host model
         steps += live; n_erased += erased.size; n_added += fresh.size
     pool.sync()
@@ -102,9 +106,12 @@ def c3_churn(n=1 << 20, ticks=48):
     assert np.array_equal(pool.ids().astype(np.int64), ids)
     out = {"targets": n, "ticks": ticks, "erased": int(n_erased), "added": int(n_added), "ms_per_tick": 1e3 * dt_wall / ticks,
            "target_steps_per_s": steps / dt_wall, "ms_per_tick_parts": {k_: 1e3 * v / ticks for k_, v in parts.items()},
-           "note": "library calls only in the timed loop (dense step + stamp, expiry = flags + scan + stable gather of the whole pool "
-                   "into the second buffer, append of the fresh ids from host arrays); every tick's erase list and the final id "
-                   "set are checked against a host model of the churn"}
+           "note": ("library calls only in the timed loop (te_pool_step_dense_expire: stamps, expiry flags, scan, then ONE pass in which "
+                    "the step kernel writes the survivors to their compacted slots; append of the fresh ids from host arrays)"
+                    if fused else
+                    "library calls only in the timed loop (dense step + stamp, expiry = flags + scan + stable gather of the whole pool "
+                    "into the second buffer, append of the fresh ids from host arrays)") +
+                   "; every tick's erase list and the final id set are checked against a host model of the churn"}
     pool.close()
     return out
 
@@ -175,7 +182,7 @@ def replay(model="uniform_acceleration", n=4 << 20, T=16, launches=10):
 
 
 if __name__ == "__main__":
-    res = {"c3_churn_angular_rates": c3_churn(), "c4_intersect_uniform_velocity": c4_intersect("uniform_velocity"),
+    res = {"c3_churn_angular_rates": c3_churn(), "c3_churn_angular_rates_fused": c3_churn(fused=True), "c4_intersect_uniform_velocity": c4_intersect("uniform_velocity"),
            "c4_intersect_uniform_acceleration": c4_intersect("uniform_acceleration"),
            "replay16_uniform_acceleration_4Mi": replay()}
     print(json.dumps(res))
