@@ -34,6 +34,9 @@ import numpy as np  # noqa: E402
 DT = 1.0 / 250.0
 METRIC = "kf_predict_update_target_steps_per_sec"
 UNIT = "target-steps/s"
+# dominant kernel per model with the default variant (te_pool.cu launch_step)
+KERNEL_NAME = {"uniform_velocity": "te::kf_step_kernel", "uniform_acceleration": "te::kf_step_kernel",
+               "angular_velocities": "te::kf_step_av_direct_kernel", "angular_rates": "te::kf_step_split_kernel"}
 MODEL_SHORT = {"uniform_velocity": "UV", "uniform_acceleration": "UA", "angular_velocities": "AV", "angular_rates": "AR"}
 
 
@@ -421,7 +424,7 @@ def main():
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": make_config(model, n, world, args.variant, n_sets, stride),
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                            "peak_source": peak_src, "kernel": "te::kf_step_kernel<%s>" % short, "alg_bytes_per_launch": alg_bytes,
+                            "peak_source": peak_src, "kernel": KERNEL_NAME.get(model, "te::kf_step_kernel") + "<%s>" % short, "alg_bytes_per_launch": alg_bytes,
                             "alg_bytes_per_update_step": B_upd, "alg_bytes_per_predict_step": B_pred, "kernel_ms": ms / K},
                "clocks": clocks, "gpu_launches": K, "e2e": e2e, "cpu_baseline": cpu, "c2_10k": small}
         if allgather:

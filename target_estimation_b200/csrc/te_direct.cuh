@@ -1,0 +1,78 @@
+// te_direct.cuh -- direct (register-streaming) step kernel of the angular-velocities model.
+//
+// kf_step_kernel stages whole tiles in shared memory by TMA so that data in flight occupies no registers; that pays when
+// a thread's working set is the whole tile (UV / UA).  The symmetric AV step (te_av_sym.cuh) needs only 95 of the tile's 161
+// fields as INPUT -- state, upper triangle of the covariance, t, n_meas, previous unwrapped angles -- and keeps them in
+// registers from the first instruction to the last, so staging buys nothing and costs 43 KB of shared memory per tile in
+// flight (five warps per SM).  Here every lane loads its column of those 95 fields straight from HBM (field-major tiles:
+// each field is one coalesced 256 B segment per warp; the lower triangle is never read: 1.26x less read traffic), steps,
+// and stores all 161 fields straight back.  Shared memory holds only a 22 KB scratch per warp (Z, x', y), so eight warps
+// -- every register of the SM at 255 per thread -- hide each other's load latency and dependent FP64 chains.
+// Same arguments and semantics as kf_step_kernel (dense / sparse tile lists, per-slot dt, actions, pos_out, compacting
+// destination); replay (n_ticks > 1) stays on the staged kernel.
+#pragma once
+#include "te_kernels.cuh"
+
+namespace te {
+
+constexpr int AV_SCRATCH_FIELDS = 12 + 72 + 3;   // x' | Z (6 x 12) | y[3..5]
+constexpr int AV_SCRATCH_PREV = 12 + 72;
+__host__ __device__ constexpr size_t av_direct_smem_bytes(int warps) { return (size_t)warps * AV_SCRATCH_FIELDS * TILE * 8; }
+
+template <int WARPS, int ZF = 2>
+__global__ void __launch_bounds__(WARPS * 32, 1) kf_step_av_direct_kernel(const StepArgs a) {
+  using LY = Layout<ANGULAR_VELOCITIES>;
+  constexpr int N = 12, M = 6;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sc = reinterpret_cast<double*>(smem_raw) + (size_t)warp * AV_SCRATCH_FIELDS * TILE + lane;
+  const int n_work = a.d_nwork ? *a.d_nwork : a.n_tiles;
+  const int gw = blockIdx.x * WARPS + warp, GW = gridDim.x * WARPS;
+  for (int w = gw; w < n_work; w += GW) {
+    const int tile = a.tile_list ? a.tile_list[w] : a.tile_begin + w;
+    const int slot = tile * TILE + lane;
+    const bool valid = slot < a.n_slots;
+    int act = ACT_NONE, cls = 0, dst = -1;
+    double dt = a.dt;
+    if (valid) {
+      act = a.action ? (int)a.action[slot] : a.default_action;
+      if (a.dt_slot) dt = a.dt_slot[slot];
+      cls = (int)a.cls[slot];
+      if (a.dst_tiles) {
+        if (a.dst_alive[slot]) dst = a.dst_pos[slot];
+        else act = ACT_NONE;   // erased at the end of this tick: its step is unobservable
+      }
+    }
+    // (an L2 prefetch of the warp's next tile -- cp.async.bulk.prefetch.L2 of the field ranges the step reads -- was
+    //  measured SLOWER: 0.83 -> 0.71 of the HBM peak; eight warps per SM already keep enough loads in flight)
+    const double* in = a.tiles + (size_t)tile * LY::TILE_DOUBLES + lane;
+    double* out = a.dst_tiles ? (dst >= 0 ? a.dst_tiles + (size_t)(dst / TILE) * LY::TILE_DOUBLES + (dst % TILE) : nullptr)
+                              : a.tiles + (size_t)tile * LY::TILE_DOUBLES + lane;
+    if (act != ACT_NONE) {
+      double meas[7];
+      if (act == ACT_UPDATE) {
+        const double* mp = a.meas + (size_t)slot * a.meas_stride;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) meas[k] = __ldg(mp + k);
+      }
+      step_lane_av_sym<AV_SCRATCH_PREV, true, ZF>(in, out, sc, act, dt, meas, a.Qtab + (size_t)cls * N * N, a.Rtab + (size_t)cls * M * M);
+      if (a.clear_action) a.action[slot] = 0;
+      if (a.pos_out) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a.pos_out[(size_t)slot * 3 + k] = sc[(LY::F_X + k) * TILE];
+      }
+    } else if (valid) {
+      if (a.dst_tiles && dst >= 0) {   // compacting tick: an untouched survivor still moves to its new slot
+#pragma unroll 8
+        for (int f = 0; f < LY::NF; ++f) __stcs(out + (size_t)f * TILE, __ldcs(in + (size_t)f * TILE));
+      }
+      if (a.pos_out) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a.pos_out[(size_t)slot * 3 + k] = in[(LY::F_X + k) * TILE];
+      }
+    }
+    if (a.clear_action && lane == 0) a.tile_flag[tile] = 0;
+  }
+}
+
+}  // namespace te

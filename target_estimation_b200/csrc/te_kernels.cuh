@@ -5,6 +5,7 @@
 #pragma once
 #include "te_device.cuh"
 #include "te_quartic.h"
+#include "te_av_sym.cuh"
 
 namespace te {
 
@@ -63,7 +64,8 @@ template <int TYPE> __host__ __device__ constexpr size_t step_smem_bytes(int war
   return 1024 + (size_t)warps * stages * stage_doubles<TYPE>() * 8;
 }
 
-template <int TYPE, int WARPS, int STAGES, bool MULTI = false>
+// IMPL = 1 (AV only): step_lane_av_sym, the register-resident symmetric-covariance step of te_av_sym.cuh
+template <int TYPE, int WARPS, int STAGES, bool MULTI = false, int IMPL = 0>
 __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_kernel(const StepArgs a) {
   using MT = Model<TYPE>;
   using LY = Layout<TYPE>;
@@ -242,7 +244,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_kernel(const StepArgs a
         }
       }
       if (act != ACT_NONE) {
-        step_lane<TYPE>(st, lane, act, dt, meas, a.Qtab + (size_t)cls * MT::N * MT::N, a.Rtab + (size_t)cls * MT::M * MT::M);
+        if constexpr (IMPL == 1) step_lane_av_sym<LY::F_PREV, false>(st + lane, st + lane, st + lane, act, dt, meas, a.Qtab + (size_t)cls * MT::N * MT::N, a.Rtab + (size_t)cls * MT::M * MT::M);
+        else step_lane<TYPE>(st, lane, act, dt, meas, a.Qtab + (size_t)cls * MT::N * MT::N, a.Rtab + (size_t)cls * MT::M * MT::M);
         if (a.clear_action) a.action[slot] = 0;
       }
     }

@@ -19,6 +19,7 @@
 #include "../../include/te_pool.h"
 #include "te_kernels.cuh"
 #include "te_split.cuh"
+#include "te_direct.cuh"
 
 namespace {
 
@@ -95,6 +96,7 @@ struct te_pool {
   bool own_stream = false;
   int n_sm = 148;
   int variant = 0;
+  bool all_sym = true;   // every registered class has bitwise-symmetric Q, R, P0 (symmetric-covariance kernels are legal)
   long long n = 0;   // live targets
   Buf buf[2];
   int cur = 0;
@@ -271,9 +273,9 @@ template <class T> T* to_dev(te_pool* p, const T* host, size_t n) {
 }
 
 // ---- step kernel launch -----------------------------------------------------------------
-template <int TYPE, int WARPS, int STAGES, bool MULTI = false>
+template <int TYPE, int WARPS, int STAGES, bool MULTI = false, int IMPL = 0>
 void launch_step_t(te_pool* p, const te::StepArgs& a, int n_work_hint) {
-  auto kern = te::kf_step_kernel<TYPE, WARPS, STAGES, MULTI>;
+  auto kern = te::kf_step_kernel<TYPE, WARPS, STAGES, MULTI, IMPL>;
   const size_t smem = te::step_smem_bytes<TYPE>(WARPS, STAGES);
   static thread_local int configured_dev = -1;
   static bool configured[64] = {false};
@@ -313,13 +315,27 @@ void launch_step_multi(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   }
 }
 
+template <int WARPS, int ZF = 2>
+void launch_av_direct(te_pool* p, const te::StepArgs& a, int n_work_hint) {
+  auto kern = te::kf_step_av_direct_kernel<WARPS, ZF>;
+  const size_t smem = te::av_direct_smem_bytes(WARPS);
+  static bool configured[64] = {false};
+  if (!configured[p->device & 63]) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[p->device & 63] = true;
+  }
+  int grid = std::min(p->n_sm, std::max(1, cdiv(n_work_hint, WARPS)));
+  kern<<<grid, WARPS * 32, smem, p->stream>>>(a);
+  CK(cudaGetLastError());
+}
+
 // variant -> (warps, stages) per model.  Stage bytes: UV 13056, UA 25344, AV 43008, AR 90624.
 void launch_step(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   const int v = p->variant;
   if (a.dst_tiles) {
     // compacting tick: separate instantiations of the default split configurations, so that the in-place kernels carry
     // none of its code (the AV kernel at 128 registers lost 6 % to a few extra runtime branches)
-    if (p->model == te::ANGULAR_VELOCITIES) return launch_split_k<te::ANGULAR_VELOCITIES, 1, 2, 2, true>(p, a, n_work_hint);
+    if (p->model == te::ANGULAR_VELOCITIES && !(v == 0 && p->all_sym)) return launch_split_k<te::ANGULAR_VELOCITIES, 1, 2, 2, true>(p, a, n_work_hint);
     if (p->model == te::ANGULAR_RATES) return launch_split_k<te::ANGULAR_RATES, 1, 2, 1, true>(p, a, n_work_hint);
   }
   switch (p->model) {
@@ -334,7 +350,15 @@ void launch_step(te_pool* p, const te::StepArgs& a, int n_work_hint) {
       else launch_step_t<te::UNIFORM_ACCELERATION, 4, 2>(p, a, n_work_hint);
       break;
     case te::ANGULAR_VELOCITIES:
-      if (v == 1) launch_step_t<te::ANGULAR_VELOCITIES, 5, 1>(p, a, n_work_hint);
+      // default: the direct symmetric-covariance kernel (te_direct.cuh) when every class is symmetric, else the row-split
+      // kernel; variant 10 forces the row-split kernel
+      if (v == 0 && p->all_sym) launch_av_direct<8>(p, a, n_work_hint);
+      else if (v == 1) launch_step_t<te::ANGULAR_VELOCITIES, 5, 1>(p, a, n_work_hint);
+      else if (v == 5) launch_step_t<te::ANGULAR_VELOCITIES, 5, 1, false, 1>(p, a, n_work_hint);
+      else if (v == 6) launch_av_direct<8>(p, a, n_work_hint);
+      else if (v == 7) launch_av_direct<6>(p, a, n_work_hint);
+      else if (v == 8) launch_av_direct<8, 4>(p, a, n_work_hint);
+      else if (v == 9) launch_av_direct<8, 12>(p, a, n_work_hint);
       else if (v == 2) launch_split_t<te::ANGULAR_VELOCITIES, 1, 2, 1>(p, a, n_work_hint);
       else if (v == 3) launch_split_t<te::ANGULAR_VELOCITIES, 1, 1, 3>(p, a, n_work_hint);
       else if (v == 4) launch_split_t<te::ANGULAR_VELOCITIES, 1, 3, 1>(p, a, n_work_hint);
@@ -635,6 +659,13 @@ int te_pool_register_class(te_pool* p, const double* Q, const double* R, const d
     p->hQ.emplace_back(Q, Q + nn);
     p->hR.emplace_back(R, R + mm);
     p->hP0.emplace_back(P0, P0 + nn);
+    auto sym = [](const double* A, int n) {
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < i; ++j)
+          if (std::memcmp(&A[i * n + j], &A[j * n + i], 8) != 0) return false;
+      return true;
+    };
+    if (!sym(Q, p->N) || !sym(R, p->M) || !sym(P0, p->N)) p->all_sym = false;
     upload_classes(p);
     return (int)p->hQ.size() - 1;
   });

@@ -64,6 +64,35 @@ def test_step_parity_variants(model, variant):
     assert w["x"] <= 1.0 and w["P"] <= 1.0, w
 
 
+@pytest.mark.parametrize("variant", [5, 6, 7, 10])
+def test_step_parity_av_kernels(variant):
+    """AV: the staged (5) and direct (6, 7; 0 = default) symmetric-covariance kernels and the forced row-split kernel (10)"""
+    w = _run("angular_velocities", 200, 60, variant=variant, check_every=20)
+    assert w["x"] <= 1.0 and w["P"] <= 1.0, w
+
+
+def test_av_asymmetric_class_takes_general_kernel():
+    """a class whose Q is not bitwise symmetric must not run the symmetric-covariance kernel (which carries the upper
+    triangle only): the pool falls back to the row-split kernel, which keeps the full matrix -- the asymmetry of Q must
+    survive in P.  (No parity claim here: every kernel factors S by Cholesky, i.e. assumes the covariances are
+    symmetric, which any valid Q / R / P0 is.)"""
+    import target_estimation_b200 as te
+    mtype, _, Q, R, P0 = te.load_model("angular_velocities")
+    Qa = Q.copy(); Qa[6, 9] += 1e-9; Qa[9, 6] -= 1e-9
+    n, ticks = 64, 10
+    meas, action, scale = synth.make_streams(n, ticks, DT, accel=False, angular=True)
+    ids = np.arange(n, dtype=np.uint32)
+    pools = []
+    for q in (Qa, Q):
+        pool = te.TargetPool(mtype); pool.register_class(q, R, P0); pool.add(ids, meas[0])
+        for k in range(ticks):
+            pool.step_dense_host(DT, meas[k], action[k])
+        pools.append(pool.read_state()["P"])
+        pool.close()
+    assert np.abs(pools[0][:, 6, 9] - pools[0][:, 9, 6]).min() > 1e-9        # general kernel: P(v, w) keeps Q's asymmetry
+    assert np.array_equal(pools[1], pools[1].transpose(0, 2, 1))            # symmetric kernel: both halves identical
+
+
 def test_step_parity_xyz_stride():
     w = _run("uniform_acceleration", 130, 60, dense_stride=3)
     assert w["x"] <= 1.0 and w["P"] <= 1.0, w
