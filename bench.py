@@ -35,7 +35,7 @@ DT = 1.0 / 250.0
 METRIC = "kf_predict_update_target_steps_per_sec"
 UNIT = "target-steps/s"
 # dominant kernel per model with the default variant (te_pool.cu launch_step)
-KERNEL_NAME = {"uniform_velocity": "te::kf_step_kernel", "uniform_acceleration": "te::kf_step_kernel",
+KERNEL_NAME = {"uniform_velocity": "te::kf_step_kin_direct_kernel", "uniform_acceleration": "te::kf_step_kin_direct_kernel",
                "angular_velocities": "te::kf_step_av_direct_kernel", "angular_rates": "te::kf_step_split_kernel"}
 MODEL_SHORT = {"uniform_velocity": "UV", "uniform_acceleration": "UA", "angular_velocities": "AV", "angular_rates": "AR"}
 

@@ -12,6 +12,7 @@
 // destination); replay (n_ticks > 1) stays on the staged kernel.
 #pragma once
 #include "te_kernels.cuh"
+#include "te_kin_sym.cuh"
 
 namespace te {
 
@@ -61,6 +62,57 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_av_direct_kernel(const 
 #pragma unroll
         for (int k = 0; k < 3; ++k) a.pos_out[(size_t)slot * 3 + k] = sc[(LY::F_X + k) * TILE];
       }
+    } else if (valid) {
+      if (a.dst_tiles && dst >= 0) {   // compacting tick: an untouched survivor still moves to its new slot
+#pragma unroll 8
+        for (int f = 0; f < LY::NF; ++f) __stcs(out + (size_t)f * TILE, __ldcs(in + (size_t)f * TILE));
+      }
+      if (a.pos_out) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a.pos_out[(size_t)slot * 3 + k] = in[(LY::F_X + k) * TILE];
+      }
+    }
+    if (a.clear_action && lane == 0) a.tile_flag[tile] = 0;
+  }
+}
+
+// The same for the linear models (UV / UA): no shared memory at all, everything lives in registers.
+template <int TYPE, int WARPS, int MIN_CTAS>
+__global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) kf_step_kin_direct_kernel(const StepArgs a) {
+  using MT = Model<TYPE>;
+  using LY = Layout<TYPE>;
+  constexpr int N = MT::N, M = MT::M;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_work = a.d_nwork ? *a.d_nwork : a.n_tiles;
+  const int gw = blockIdx.x * WARPS + warp, GW = gridDim.x * WARPS;
+  for (int w = gw; w < n_work; w += GW) {
+    const int tile = a.tile_list ? a.tile_list[w] : a.tile_begin + w;
+    const int slot = tile * TILE + lane;
+    const bool valid = slot < a.n_slots;
+    int act = ACT_NONE, cls = 0, dst = -1;
+    double dt = a.dt;
+    if (valid) {
+      act = a.action ? (int)a.action[slot] : a.default_action;
+      if (a.dt_slot) dt = a.dt_slot[slot];
+      cls = (int)a.cls[slot];
+      if (a.dst_tiles) {
+        if (a.dst_alive[slot]) dst = a.dst_pos[slot];
+        else act = ACT_NONE;   // erased at the end of this tick: its step is unobservable
+      }
+    }
+    const double* in = a.tiles + (size_t)tile * LY::TILE_DOUBLES + lane;
+    double* out = a.dst_tiles ? (dst >= 0 ? a.dst_tiles + (size_t)(dst / TILE) * LY::TILE_DOUBLES + (dst % TILE) : nullptr)
+                              : a.tiles + (size_t)tile * LY::TILE_DOUBLES + lane;
+    if (act != ACT_NONE) {
+      double meas[3];
+      if (act == ACT_UPDATE) {
+        const double* mp = a.meas + (size_t)slot * a.meas_stride;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) meas[k] = __ldg(mp + k);
+      }
+      step_lane_kin_sym<TYPE>(in, out, act, dt, meas, a.Qtab + (size_t)cls * N * N, a.Rtab + (size_t)cls * M * M,
+                              a.pos_out ? a.pos_out + (size_t)slot * 3 : nullptr);
+      if (a.clear_action) a.action[slot] = 0;
     } else if (valid) {
       if (a.dst_tiles && dst >= 0) {   // compacting tick: an untouched survivor still moves to its new slot
 #pragma unroll 8

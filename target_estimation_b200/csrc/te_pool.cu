@@ -329,6 +329,14 @@ void launch_av_direct(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   CK(cudaGetLastError());
 }
 
+template <int TYPE, int WARPS, int CTAS>
+void launch_kin_direct(te_pool* p, const te::StepArgs& a, int n_work_hint) {
+  auto kern = te::kf_step_kin_direct_kernel<TYPE, WARPS, CTAS>;
+  int grid = std::min(p->n_sm * CTAS, std::max(1, cdiv(n_work_hint, WARPS)));
+  kern<<<grid, WARPS * 32, 0, p->stream>>>(a);
+  CK(cudaGetLastError());
+}
+
 // variant -> (warps, stages) per model.  Stage bytes: UV 13056, UA 25344, AV 43008, AR 90624.
 void launch_step(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   const int v = p->variant;
@@ -340,12 +348,20 @@ void launch_step(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   }
   switch (p->model) {
     case te::UNIFORM_VELOCITY:
-      if (v == 1) launch_step_t<te::UNIFORM_VELOCITY, 16, 1>(p, a, n_work_hint);
+      // default (symmetric classes): the direct symmetric-covariance kernel of te_direct.cuh; variant 10 (or an asymmetric
+      // class) = the TMA-staged full-matrix kernel
+      if (v == 5) launch_kin_direct<te::UNIFORM_VELOCITY, 4, 4>(p, a, n_work_hint);
+      else if (v == 6 || (v == 0 && p->all_sym)) launch_kin_direct<te::UNIFORM_VELOCITY, 8, 1>(p, a, n_work_hint);
+      else if (v == 7) launch_kin_direct<te::UNIFORM_VELOCITY, 4, 3>(p, a, n_work_hint);
+      else if (v == 1) launch_step_t<te::UNIFORM_VELOCITY, 16, 1>(p, a, n_work_hint);
       else if (v == 2) launch_step_t<te::UNIFORM_VELOCITY, 4, 4>(p, a, n_work_hint);
       else launch_step_t<te::UNIFORM_VELOCITY, 8, 2>(p, a, n_work_hint);
       break;
     case te::UNIFORM_ACCELERATION:
-      if (v == 1) launch_step_t<te::UNIFORM_ACCELERATION, 8, 1>(p, a, n_work_hint);
+      if (v == 5 || (v == 0 && p->all_sym)) launch_kin_direct<te::UNIFORM_ACCELERATION, 8, 1>(p, a, n_work_hint);
+      else if (v == 6) launch_kin_direct<te::UNIFORM_ACCELERATION, 4, 3>(p, a, n_work_hint);
+      else if (v == 7) launch_kin_direct<te::UNIFORM_ACCELERATION, 5, 2>(p, a, n_work_hint);
+      else if (v == 1) launch_step_t<te::UNIFORM_ACCELERATION, 8, 1>(p, a, n_work_hint);
       else if (v == 2) launch_step_t<te::UNIFORM_ACCELERATION, 2, 4>(p, a, n_work_hint);
       else launch_step_t<te::UNIFORM_ACCELERATION, 4, 2>(p, a, n_work_hint);
       break;

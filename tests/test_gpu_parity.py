@@ -64,6 +64,15 @@ def test_step_parity_variants(model, variant):
     assert w["x"] <= 1.0 and w["P"] <= 1.0, w
 
 
+@pytest.mark.parametrize("model", ["uniform_velocity", "uniform_acceleration"])
+@pytest.mark.parametrize("variant", [5, 6, 7, 10])
+def test_step_parity_kinematic_kernels(model, variant):
+    """UV / UA: the direct symmetric-covariance kernel in its launch shapes (5, 6, 7; 0 = default) and the forced
+    TMA-staged full-matrix kernel (10)"""
+    w = _run(model, 200, 60, variant=variant, check_every=20)
+    assert w["x"] <= 1.0 and w["P"] <= 1.0, w
+
+
 @pytest.mark.parametrize("variant", [5, 6, 7, 10])
 def test_step_parity_av_kernels(variant):
     """AV: the staged (5) and direct (6, 7; 0 = default) symmetric-covariance kernels and the forced row-split kernel (10)"""
