@@ -35,7 +35,7 @@ template <int N> struct SymP {
 // from / to HBM (DIRECT = true: x is copied from the scratch to out at the end).
 template <int PREV_S, bool DIRECT, int ZF = 2>
 __device__ __forceinline__ void step_lane_av_sym(const double* in, double* out, double* sc, int action, double dt, const double* meas,
-                                                 const double* __restrict__ Q, const double* __restrict__ R) {
+                                                 const double* __restrict__ Q, const double* __restrict__ R, bool packed = false) {
   using LY = Layout<ANGULAR_VELOCITIES>;
   constexpr int N = 12, M = 6;
   // Register budget: the 78 covariance entries stay in registers from the load to the store; everything else is kept
@@ -272,7 +272,8 @@ __device__ __forceinline__ void step_lane_av_sym(const double* in, double* out, 
 #pragma unroll
   for (int i = 0; i < N; ++i)
 #pragma unroll
-    for (int j = 0; j < N; ++j) out[(LY::F_P + i * N + j) * TILE] = P(i, j);
+    for (int j = 0; j < N; ++j)
+      if (i <= j || !packed) out[(LY::F_P + i * N + j) * TILE] = P(i, j);   // packed: the pool mirrors the upper triangle on demand
   if (DIRECT) {
 #pragma unroll
     for (int i = 0; i < N; ++i) out[(LY::F_X + i) * TILE] = sc[(LY::F_X + i) * TILE];

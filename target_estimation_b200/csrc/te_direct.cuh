@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_av_direct_kernel(const 
 #pragma unroll
         for (int k = 0; k < 7; ++k) meas[k] = __ldg(mp + k);
       }
-      step_lane_av_sym<AV_SCRATCH_PREV, true, ZF>(in, out, sc, act, dt, meas, a.Qtab + (size_t)cls * N * N, a.Rtab + (size_t)cls * M * M);
+      step_lane_av_sym<AV_SCRATCH_PREV, true, ZF>(in, out, sc, act, dt, meas, a.Qtab + (size_t)cls * N * N, a.Rtab + (size_t)cls * M * M, a.packed != 0);
       if (a.clear_action) a.action[slot] = 0;
       if (a.pos_out) {
 #pragma unroll
@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_av_direct_kernel(const 
   }
 }
 
-// The same for the linear models (UV / UA): no shared memory at all, everything lives in registers.
+// The same for the linear models (UV / UA): no shared memory at all, everything lives in registers.  n_ticks > 1 = replay
+// launch (te_pool_step_dense_ticks): the target stays in registers for all its ticks.
 template <int TYPE, int WARPS, int MIN_CTAS>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) kf_step_kin_direct_kernel(const StepArgs a) {
   using MT = Model<TYPE>;
@@ -103,6 +104,31 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) kf_step_kin_direct_kerne
     const double* in = a.tiles + (size_t)tile * LY::TILE_DOUBLES + lane;
     double* out = a.dst_tiles ? (dst >= 0 ? a.dst_tiles + (size_t)(dst / TILE) * LY::TILE_DOUBLES + (dst % TILE) : nullptr)
                               : a.tiles + (size_t)tile * LY::TILE_DOUBLES + lane;
+    const double* __restrict__ Q = a.Qtab + (size_t)cls * N * N;
+    const double* __restrict__ R = a.Rtab + (size_t)cls * M * M;
+    if (a.n_ticks > 1) {
+      if (!valid) continue;
+      // a lane whose actions are all ACT_NONE still goes through load / store: cheaper than a second pass to find out
+      KinSym<TYPE> ks;
+      ks.load(in);
+      for (int tick = 0; tick < a.n_ticks; ++tick) {
+        const int at = a.action ? (int)a.action[(size_t)tick * a.action_tick_stride + slot] : a.default_action;
+        if (at == ACT_NONE) continue;
+        double meas[3] = {0.0, 0.0, 0.0};
+        if (at == ACT_UPDATE) {
+          const double* mp = a.meas + (size_t)tick * a.meas_tick_stride + (size_t)slot * a.meas_stride;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) meas[k] = __ldg(mp + k);
+        }
+        ks.tick(at, dt, meas, Q, R);
+      }
+      ks.store(out, a.packed != 0);
+      if (a.pos_out) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a.pos_out[(size_t)slot * 3 + k] = ks.x[k];
+      }
+      continue;
+    }
     if (act != ACT_NONE) {
       double meas[3];
       if (act == ACT_UPDATE) {
@@ -110,8 +136,14 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) kf_step_kin_direct_kerne
 #pragma unroll
         for (int k = 0; k < 3; ++k) meas[k] = __ldg(mp + k);
       }
-      step_lane_kin_sym<TYPE>(in, out, act, dt, meas, a.Qtab + (size_t)cls * N * N, a.Rtab + (size_t)cls * M * M,
-                              a.pos_out ? a.pos_out + (size_t)slot * 3 : nullptr);
+      KinSym<TYPE> ks;
+      ks.load(in);
+      ks.tick(act, dt, meas, Q, R);
+      ks.store(out, a.packed != 0);
+      if (a.pos_out) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a.pos_out[(size_t)slot * 3 + k] = ks.x[k];
+      }
       if (a.clear_action) a.action[slot] = 0;
     } else if (valid) {
       if (a.dst_tiles && dst >= 0) {   // compacting tick: an untouched survivor still moves to its new slot

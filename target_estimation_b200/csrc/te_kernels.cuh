@@ -52,6 +52,7 @@ struct StepArgs {
   double* dst_tiles;
   const int* dst_alive;     // [n_slots] 1 = survives
   const int* dst_pos;       // [n_slots] exclusive scan of dst_alive
+  int packed;               // direct symmetric kernels: write the upper triangle of P only (pool flag lower_stale)
   int cls_c;                // class held in Qc / Rc, -1 = none
   double Rc[36];
   double Qc[324];
@@ -485,7 +486,7 @@ __global__ void fill_dt_kernel(double* dt_slot, int n, double v) {
 // read-back gathers -------------------------------------------------------------------
 template <int TYPE>
 __global__ void gather_state_kernel(const double* __restrict__ tiles, const ColdArrays cold, const int* __restrict__ slots, long long n,
-                                    double* x, double* P, double* t, long long* n_meas, double* prev, double* mpose) {
+                                    double* x, double* P, double* t, long long* n_meas, double* prev, double* mpose, int lower_stale) {
   using MT = Model<TYPE>;
   using LY = Layout<TYPE>;
   long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -494,7 +495,14 @@ __global__ void gather_state_kernel(const double* __restrict__ tiles, const Cold
   if (s < 0) return;
   const double* rec = tiles + (size_t)(s / TILE) * LY::TILE_DOUBLES + (s % TILE);
   if (x) for (int i = 0; i < MT::N; ++i) x[k * MT::N + i] = rec[(LY::F_X + i) * TILE];
-  if (P) for (int e = 0; e < MT::N * MT::N; ++e) P[k * MT::N * MT::N + e] = rec[(LY::F_P + e) * TILE];
+  if (P) {
+    for (int i = 0; i < MT::N; ++i)
+      for (int j = 0; j < MT::N; ++j) {
+        // lower_stale: the packed symmetric kernels maintain the upper triangle only -- P(i, j) = P(j, i) for i > j
+        const int e = (lower_stale && i > j) ? j * MT::N + i : i * MT::N + j;
+        P[k * MT::N * MT::N + i * MT::N + j] = rec[(LY::F_P + e) * TILE];
+      }
+  }
   if (t) t[k] = rec[LY::F_T * TILE];
   if (n_meas) n_meas[k] = reinterpret_cast<const long long*>(rec)[LY::F_NMEAS * TILE];
   if (prev) for (int e = 0; e < 3; ++e) prev[k * 3 + e] = (MT::NPREV ? rec[(LY::F_PREV + (MT::NPREV ? e : 0)) * TILE] : 0.0);
@@ -563,6 +571,18 @@ __global__ void collect_erased_kernel(const int* __restrict__ alive, const int* 
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_slots || alive[s]) return;
   erased[s - pos[s]] = ids[s];
+}
+
+// lower triangle <- upper triangle (before a full-matrix kernel runs on a pool whose last steps were packed)
+template <int TYPE>
+__global__ void mirror_lower_kernel(double* __restrict__ tiles, int n_slots) {
+  using MT = Model<TYPE>;
+  using LY = Layout<TYPE>;
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  double* rec = tiles + (size_t)(s / TILE) * LY::TILE_DOUBLES + (s % TILE);
+  for (int i = 1; i < MT::N; ++i)
+    for (int j = 0; j < i; ++j) rec[(LY::F_P + i * MT::N + j) * TILE] = rec[(LY::F_P + j * MT::N + i) * TILE];
 }
 
 // compacting tick: the cold arrays of the survivors move to their destination slots (the tile fields are moved by the step

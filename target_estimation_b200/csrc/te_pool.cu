@@ -97,6 +97,10 @@ struct te_pool {
   int n_sm = 148;
   int variant = 0;
   bool all_sym = true;   // every registered class has bitwise-symmetric Q, R, P0 (symmetric-covariance kernels are legal)
+  // The direct symmetric kernels maintain the UPPER triangle of every covariance only ("packed": 36 of UA's 92 fields are
+  // neither read nor written per step).  lower_stale = the lower triangles in HBM are out of date; whoever needs the full
+  // matrix (a full-matrix kernel, a state read-back) mirrors it first / on the fly.
+  bool lower_stale = false;
   long long n = 0;   // live targets
   Buf buf[2];
   int cur = 0;
@@ -306,7 +310,19 @@ void launch_split_k(te_pool* p, const te::StepArgs& a, int n_work_hint) {
 template <int TYPE, int CS, int STAGES, int CTAS>
 void launch_split_t(te_pool* p, const te::StepArgs& a, int n_work_hint) { launch_split_k<TYPE, CS, STAGES, CTAS, false>(p, a, n_work_hint); }
 
-void launch_step_multi(te_pool* p, const te::StepArgs& a, int n_work_hint) {
+bool uses_direct(const te_pool* p);
+void ensure_full(te_pool* p);
+template <int TYPE, int WARPS, int CTAS> void launch_kin_direct(te_pool* p, const te::StepArgs& a, int n_work_hint);
+void launch_step_multi(te_pool* p, const te::StepArgs& a_in, int n_work_hint) {
+  te::StepArgs a = a_in;
+  if (uses_direct(p) && p->model != te::ANGULAR_VELOCITIES) {   // UV / UA: the direct kernel keeps the target in registers for all ticks
+    a.packed = (p->all_sym && p->variant != 12) ? 1 : 0;
+    if (a.packed) p->lower_stale = true;
+    if (p->model == te::UNIFORM_VELOCITY) launch_kin_direct<te::UNIFORM_VELOCITY, 8, 1>(p, a, n_work_hint);
+    else launch_kin_direct<te::UNIFORM_ACCELERATION, 8, 1>(p, a, n_work_hint);
+    return;
+  }
+  ensure_full(p);
   switch (p->model) {
     case te::UNIFORM_VELOCITY: launch_step_t<te::UNIFORM_VELOCITY, 8, 2, true>(p, a, n_work_hint); break;
     case te::UNIFORM_ACCELERATION: launch_step_t<te::UNIFORM_ACCELERATION, 4, 2, true>(p, a, n_work_hint); break;
@@ -337,44 +353,82 @@ void launch_kin_direct(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   CK(cudaGetLastError());
 }
 
-// variant -> (warps, stages) per model.  Stage bytes: UV 13056, UA 25344, AV 43008, AR 90624.
-void launch_step(te_pool* p, const te::StepArgs& a, int n_work_hint) {
+// does the current variant run a direct symmetric-covariance kernel (te_direct.cuh)?
+bool uses_direct(const te_pool* p) {
   const int v = p->variant;
+  const bool dflt = v == 0 && p->all_sym;
+  switch (p->model) {
+    case te::UNIFORM_VELOCITY:
+    case te::UNIFORM_ACCELERATION: return dflt || v == 5 || v == 6 || v == 7 || v == 12;
+    case te::ANGULAR_VELOCITIES: return dflt || (v >= 6 && v <= 9) || v == 12;
+    default: return false;
+  }
+}
+// full-matrix kernels (and anything else that reads both halves) first get the lower triangles back
+void ensure_full(te_pool* p) {
+  if (!p->lower_stale || p->n == 0) { p->lower_stale = false; return; }
+  double* tiles = p->buf[p->cur].tiles;
+  const int n = (int)p->n;
+  switch (p->model) {
+    case te::UNIFORM_VELOCITY: te::mirror_lower_kernel<te::UNIFORM_VELOCITY><<<cdiv(n, 128), 128, 0, p->stream>>>(tiles, n); break;
+    case te::UNIFORM_ACCELERATION: te::mirror_lower_kernel<te::UNIFORM_ACCELERATION><<<cdiv(n, 128), 128, 0, p->stream>>>(tiles, n); break;
+    case te::ANGULAR_VELOCITIES: te::mirror_lower_kernel<te::ANGULAR_VELOCITIES><<<cdiv(n, 128), 128, 0, p->stream>>>(tiles, n); break;
+    default: te::mirror_lower_kernel<te::ANGULAR_RATES><<<cdiv(n, 128), 128, 0, p->stream>>>(tiles, n); break;
+  }
+  CK(cudaGetLastError());
+  p->lower_stale = false;
+}
+
+// variant -> kernel.  0 = default: the direct symmetric-covariance kernels for UV / UA / AV when every class is symmetric
+// (packed: upper triangle only), else the full-matrix kernels; 10 = force the full-matrix kernel (TMA-staged / row-split);
+// 12 = direct kernel writing both halves; the others are launch shapes kept for experiments (tests cover all of them).
+// Stage bytes of the staged kernel: UV 13056, UA 25344, AV 43008, AR 90624.
+void launch_step(te_pool* p, const te::StepArgs& a_in, int n_work_hint) {
+  const int v = p->variant;
+  te::StepArgs a = a_in;
+  if (uses_direct(p)) {
+    a.packed = (p->all_sym && v != 12) ? 1 : 0;
+    if (a.packed) p->lower_stale = true;
+    switch (p->model) {
+      case te::UNIFORM_VELOCITY:
+        if (v == 5) launch_kin_direct<te::UNIFORM_VELOCITY, 4, 4>(p, a, n_work_hint);
+        else if (v == 7) launch_kin_direct<te::UNIFORM_VELOCITY, 4, 3>(p, a, n_work_hint);
+        else launch_kin_direct<te::UNIFORM_VELOCITY, 8, 1>(p, a, n_work_hint);
+        return;
+      case te::UNIFORM_ACCELERATION:
+        if (v == 6) launch_kin_direct<te::UNIFORM_ACCELERATION, 4, 3>(p, a, n_work_hint);
+        else if (v == 7) launch_kin_direct<te::UNIFORM_ACCELERATION, 5, 2>(p, a, n_work_hint);
+        else launch_kin_direct<te::UNIFORM_ACCELERATION, 8, 1>(p, a, n_work_hint);
+        return;
+      default:
+        if (v == 7) launch_av_direct<6>(p, a, n_work_hint);
+        else if (v == 8) launch_av_direct<8, 4>(p, a, n_work_hint);
+        else if (v == 9) launch_av_direct<8, 12>(p, a, n_work_hint);
+        else launch_av_direct<8>(p, a, n_work_hint);
+        return;
+    }
+  }
+  ensure_full(p);
   if (a.dst_tiles) {
     // compacting tick: separate instantiations of the default split configurations, so that the in-place kernels carry
     // none of its code (the AV kernel at 128 registers lost 6 % to a few extra runtime branches)
-    if (p->model == te::ANGULAR_VELOCITIES && !(v == 0 && p->all_sym)) return launch_split_k<te::ANGULAR_VELOCITIES, 1, 2, 2, true>(p, a, n_work_hint);
+    if (p->model == te::ANGULAR_VELOCITIES) return launch_split_k<te::ANGULAR_VELOCITIES, 1, 2, 2, true>(p, a, n_work_hint);
     if (p->model == te::ANGULAR_RATES) return launch_split_k<te::ANGULAR_RATES, 1, 2, 1, true>(p, a, n_work_hint);
   }
   switch (p->model) {
     case te::UNIFORM_VELOCITY:
-      // default (symmetric classes): the direct symmetric-covariance kernel of te_direct.cuh; variant 10 (or an asymmetric
-      // class) = the TMA-staged full-matrix kernel
-      if (v == 5) launch_kin_direct<te::UNIFORM_VELOCITY, 4, 4>(p, a, n_work_hint);
-      else if (v == 6 || (v == 0 && p->all_sym)) launch_kin_direct<te::UNIFORM_VELOCITY, 8, 1>(p, a, n_work_hint);
-      else if (v == 7) launch_kin_direct<te::UNIFORM_VELOCITY, 4, 3>(p, a, n_work_hint);
-      else if (v == 1) launch_step_t<te::UNIFORM_VELOCITY, 16, 1>(p, a, n_work_hint);
+      if (v == 1) launch_step_t<te::UNIFORM_VELOCITY, 16, 1>(p, a, n_work_hint);
       else if (v == 2) launch_step_t<te::UNIFORM_VELOCITY, 4, 4>(p, a, n_work_hint);
       else launch_step_t<te::UNIFORM_VELOCITY, 8, 2>(p, a, n_work_hint);
       break;
     case te::UNIFORM_ACCELERATION:
-      if (v == 5 || (v == 0 && p->all_sym)) launch_kin_direct<te::UNIFORM_ACCELERATION, 8, 1>(p, a, n_work_hint);
-      else if (v == 6) launch_kin_direct<te::UNIFORM_ACCELERATION, 4, 3>(p, a, n_work_hint);
-      else if (v == 7) launch_kin_direct<te::UNIFORM_ACCELERATION, 5, 2>(p, a, n_work_hint);
-      else if (v == 1) launch_step_t<te::UNIFORM_ACCELERATION, 8, 1>(p, a, n_work_hint);
+      if (v == 1) launch_step_t<te::UNIFORM_ACCELERATION, 8, 1>(p, a, n_work_hint);
       else if (v == 2) launch_step_t<te::UNIFORM_ACCELERATION, 2, 4>(p, a, n_work_hint);
       else launch_step_t<te::UNIFORM_ACCELERATION, 4, 2>(p, a, n_work_hint);
       break;
     case te::ANGULAR_VELOCITIES:
-      // default: the direct symmetric-covariance kernel (te_direct.cuh) when every class is symmetric, else the row-split
-      // kernel; variant 10 forces the row-split kernel
-      if (v == 0 && p->all_sym) launch_av_direct<8>(p, a, n_work_hint);
-      else if (v == 1) launch_step_t<te::ANGULAR_VELOCITIES, 5, 1>(p, a, n_work_hint);
+      if (v == 1) launch_step_t<te::ANGULAR_VELOCITIES, 5, 1>(p, a, n_work_hint);
       else if (v == 5) launch_step_t<te::ANGULAR_VELOCITIES, 5, 1, false, 1>(p, a, n_work_hint);
-      else if (v == 6) launch_av_direct<8>(p, a, n_work_hint);
-      else if (v == 7) launch_av_direct<6>(p, a, n_work_hint);
-      else if (v == 8) launch_av_direct<8, 4>(p, a, n_work_hint);
-      else if (v == 9) launch_av_direct<8, 12>(p, a, n_work_hint);
       else if (v == 2) launch_split_t<te::ANGULAR_VELOCITIES, 1, 2, 1>(p, a, n_work_hint);
       else if (v == 3) launch_split_t<te::ANGULAR_VELOCITIES, 1, 1, 3>(p, a, n_work_hint);
       else if (v == 4) launch_split_t<te::ANGULAR_VELOCITIES, 1, 3, 1>(p, a, n_work_hint);
@@ -1043,10 +1097,10 @@ int te_pool_read_state(te_pool* p, long long n, const uint32_t* ids, double* x, 
     Buf& b = p->buf[p->cur];
     const int g = cdiv(n, 128);
     switch (p->model) {
-      case te::UNIFORM_VELOCITY: te::gather_state_kernel<te::UNIFORM_VELOCITY><<<g, 128, 0, p->stream>>>(b.tiles, b.cold, slots, n, dx, dP, dt_, dn, dprev, dmp); break;
-      case te::UNIFORM_ACCELERATION: te::gather_state_kernel<te::UNIFORM_ACCELERATION><<<g, 128, 0, p->stream>>>(b.tiles, b.cold, slots, n, dx, dP, dt_, dn, dprev, dmp); break;
-      case te::ANGULAR_VELOCITIES: te::gather_state_kernel<te::ANGULAR_VELOCITIES><<<g, 128, 0, p->stream>>>(b.tiles, b.cold, slots, n, dx, dP, dt_, dn, dprev, dmp); break;
-      default: te::gather_state_kernel<te::ANGULAR_RATES><<<g, 128, 0, p->stream>>>(b.tiles, b.cold, slots, n, dx, dP, dt_, dn, dprev, dmp); break;
+      case te::UNIFORM_VELOCITY: te::gather_state_kernel<te::UNIFORM_VELOCITY><<<g, 128, 0, p->stream>>>(b.tiles, b.cold, slots, n, dx, dP, dt_, dn, dprev, dmp, p->lower_stale ? 1 : 0); break;
+      case te::UNIFORM_ACCELERATION: te::gather_state_kernel<te::UNIFORM_ACCELERATION><<<g, 128, 0, p->stream>>>(b.tiles, b.cold, slots, n, dx, dP, dt_, dn, dprev, dmp, p->lower_stale ? 1 : 0); break;
+      case te::ANGULAR_VELOCITIES: te::gather_state_kernel<te::ANGULAR_VELOCITIES><<<g, 128, 0, p->stream>>>(b.tiles, b.cold, slots, n, dx, dP, dt_, dn, dprev, dmp, p->lower_stale ? 1 : 0); break;
+      default: te::gather_state_kernel<te::ANGULAR_RATES><<<g, 128, 0, p->stream>>>(b.tiles, b.cold, slots, n, dx, dP, dt_, dn, dprev, dmp, p->lower_stale ? 1 : 0); break;
     }
     CK(cudaGetLastError());
     if (x) CK(cudaMemcpyAsync(x, dx, (size_t)n * N * 8, cudaMemcpyDeviceToHost, p->stream));
