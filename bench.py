@@ -296,6 +296,19 @@ def main():
     peak, peak_src = peaks()
     achieved = alg_bytes / (ms / K * 1e-3) / 1e9
     traffic, traffic_src = ncu_traffic(model, n)
+    # bytes the default kernel actually has to move: UV / UA / AV keep the covariance packed (upper triangle only is read
+    # and written, SURVEY.md 8(d) "symmetric-packed" clause), AR moves the full matrix
+    npv = 3 if M == 6 else 0
+    if model != "angular_rates" and args.variant in (-1, 0):
+        fields = N + N * (N + 1) // 2 + 2 + npv
+        L_upd = 2 * fields * 8 + 8 * (7 if M == 6 else 3) + 3
+        L_pred = 2 * fields * 8 + 3
+        layout_note = "packed covariance: state + upper triangle + t + n_meas%s in and out, measurement, action + class bytes" % (" + prev_rpy" if npv else "")
+    else:
+        L_upd, L_pred = B_upd, B_pred
+        layout_note = "full covariance (the SURVEY.md 8(d) figure)"
+    layout_bytes = sum(n_upd[k % n_sets] * L_upd + (n - n_upd[k % n_sets]) * L_pred for k in range(K)) / K
+    achieved_layout = layout_bytes / (ms / K * 1e-3) / 1e9
 
     # ---- e2e: host buffers through the C-ABI ---------------------------------------------------------
     e2e = None
@@ -406,6 +419,30 @@ def main():
         rms = r0.elapsed_time(r1)
         small["replay64"] = {"ticks_per_launch": T, "launches": Kr, "us_per_tick": 1e3 * rms / (Kr * T), "value": ns * Kr * T / (rms * 1e-3),
                              "unit": UNIT, "note": "te_pool_step_dense_ticks: 64 buffered ticks per launch (batched ingestion / catch-up)"}
+        # the per-tick launches again, captured once into a CUDA graph (100 ticks) and replayed: the host's launch cost per
+        # tick (Python + ctypes + cudaLaunchKernel, what the loop above is bound by) leaves the measurement
+        try:
+            g = torch.cuda.CUDAGraph()
+            Tg = 100
+            with torch.cuda.graph(g, stream=stream):
+                for k in range(Tg):
+                    sp.step_dense(DT, ms_[k % 2], stride, as_[k % 2])
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            Kg = 20
+            with torch.cuda.stream(stream):
+                g0.record(stream)
+                for _ in range(Kg):
+                    g.replay()
+                g1.record(stream)
+            torch.cuda.synchronize()
+            gms = g0.elapsed_time(g1)
+            small["cuda_graph"] = {"ticks_per_graph": Tg, "replays": Kg, "us_per_tick": 1e3 * gms / (Kg * Tg), "value": ns * Kg * Tg / (gms * 1e-3),
+                                   "unit": UNIT, "note": "same one-launch-per-tick kernels, 100 ticks captured in a CUDA graph"}
+        except Exception as e:   # capture unsupported in this environment: report, do not fail the bench
+            small["cuda_graph"] = {"error": str(e)[:200]}
         sp.close()
 
     cpu = None
@@ -425,7 +462,10 @@ def main():
                "config": make_config(model, n, world, args.variant, n_sets, stride),
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                             "peak_source": peak_src, "kernel": KERNEL_NAME.get(model, "te::kf_step_kernel") + "<%s>" % short, "alg_bytes_per_launch": alg_bytes,
-                            "alg_bytes_per_update_step": B_upd, "alg_bytes_per_predict_step": B_pred, "kernel_ms": ms / K},
+                            "alg_bytes_per_update_step": B_upd, "alg_bytes_per_predict_step": B_pred, "kernel_ms": ms / K,
+                            "layout": {"bytes_per_update_step": L_upd, "bytes_per_predict_step": L_pred, "bytes_per_launch": layout_bytes,
+                                       "achieved": achieved_layout, "frac": achieved_layout / peak, "note": layout_note +
+                                       "; `frac` above uses the contract's full-matrix bytes and can therefore exceed 1, this one is the HBM utilisation"}},
                "clocks": clocks, "gpu_launches": K, "e2e": e2e, "cpu_baseline": cpu, "c2_10k": small}
         if allgather:
             out["allgather"] = allgather

@@ -84,8 +84,15 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) kf_step_kin_direct_kerne
   using LY = Layout<TYPE>;
   constexpr int N = MT::N, M = MT::M;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_work = a.d_nwork ? *a.d_nwork : a.n_tiles;
+  // Programmatic dependent launch (the pool launches this kernel with programmatic stream serialization): the next tick's
+  // grid may be scheduled while this one runs, and this one may have been scheduled while the previous kernel on the
+  // stream was still running -- everything above griddepcontrol.wait touches only launch parameters; the wait returns
+  // once all earlier work on the stream has completed and flushed.  Hides the launch latency between the ticks of a
+  // small pool (BASELINE configs[1]: 10 000 targets, where a tick is a few microseconds).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int gw = blockIdx.x * WARPS + warp, GW = gridDim.x * WARPS;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int n_work = a.d_nwork ? *a.d_nwork : a.n_tiles;
   for (int w = gw; w < n_work; w += GW) {
     const int tile = a.tile_list ? a.tile_list[w] : a.tile_begin + w;
     const int slot = tile * TILE + lane;

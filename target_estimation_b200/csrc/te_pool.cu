@@ -346,11 +346,29 @@ void launch_av_direct(te_pool* p, const te::StepArgs& a, int n_work_hint) {
 }
 
 template <int TYPE, int WARPS, int CTAS>
-void launch_kin_direct(te_pool* p, const te::StepArgs& a, int n_work_hint) {
+void launch_kin_direct_k(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   auto kern = te::kf_step_kin_direct_kernel<TYPE, WARPS, CTAS>;
   int grid = std::min(p->n_sm * CTAS, std::max(1, cdiv(n_work_hint, WARPS)));
-  kern<<<grid, WARPS * 32, 0, p->stream>>>(a);
-  CK(cudaGetLastError());
+  // programmatic stream serialization: see the kernel's griddepcontrol.wait
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(WARPS * 32);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = p->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, kern, a));
+}
+// small pools (fewer tiles than the SMs have scheduler partitions) spread over more, smaller CTAs: one warp per partition has
+// the FP64 pipe to itself, which is what bounds a tick of a few hundred tiles
+template <int TYPE, int WARPS, int CTAS>
+void launch_kin_direct(te_pool* p, const te::StepArgs& a, int n_work_hint) {
+  if (WARPS == 8 && CTAS == 1 && n_work_hint <= 2 * p->n_sm) launch_kin_direct_k<TYPE, 2, 1>(p, a, n_work_hint);
+  else if (WARPS == 8 && CTAS == 1 && n_work_hint <= 4 * p->n_sm) launch_kin_direct_k<TYPE, 4, 1>(p, a, n_work_hint);
+  else launch_kin_direct_k<TYPE, WARPS, CTAS>(p, a, n_work_hint);
 }
 
 // does the current variant run a direct symmetric-covariance kernel (te_direct.cuh)?
