@@ -22,6 +22,9 @@ import argparse
 import json
 import os
 import sys
+
+# NCCL prints its version banner (and any NCCL_DEBUG output) to stdout by default: keep stdout for the one JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 import threading
 import time
 
@@ -89,6 +92,9 @@ class ClockSampler(threading.Thread):
         self.power = []
 
     def run(self):
+        if os.environ.get("TE_NO_SAMPLER"):   # debugging switch
+            self.reasons.add("sampler_disabled")
+            return
         try:
             import pynvml as nv
             nv.nvmlInit()

@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) kf_step_kin_direct_kerne
   using LY = Layout<TYPE>;
   constexpr int N = MT::N, M = MT::M;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // Programmatic dependent launch (the pool launches this kernel with programmatic stream serialization): the next tick's
+  // Programmatic dependent launch (small pools are launched with programmatic stream serialization; without the launch
+  // attribute the two griddepcontrol instructions are no-ops): the next tick's
   // grid may be scheduled while this one runs, and this one may have been scheduled while the previous kernel on the
   // stream was still running -- everything above griddepcontrol.wait touches only launch parameters; the wait returns
   // once all earlier work on the stream has completed and flushed.  Hides the launch latency between the ticks of a

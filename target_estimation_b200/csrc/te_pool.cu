@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
@@ -358,8 +359,12 @@ void launch_kin_direct_k(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
+  // Only for small pools, where a tick is a few microseconds and the launch latency matters.  For big pools it buys nothing,
+  // and in a process with an NCCL communicator it was measured to cost 37 % (4 Mi UA targets: 0.64 -> 0.86 ms per tick under
+  // torchrun, 0.63 either way in a plain process) -- the early-scheduled grid and the running one compete for the SMs.
+  static const bool no_pdl = std::getenv("TE_NO_PDL") != nullptr;   // debugging switch
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (no_pdl || n_work_hint > 4 * p->n_sm) ? 0 : 1;
   CK(cudaLaunchKernelEx(&cfg, kern, a));
 }
 // small pools (fewer tiles than the SMs have scheduler partitions) spread over more, smaller CTAs: one warp per partition has

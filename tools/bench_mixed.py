@@ -14,6 +14,9 @@ import json
 import os
 import sys
 
+# NCCL prints its version banner (and any NCCL_DEBUG output) to stdout by default: keep stdout for the one JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
