@@ -23,8 +23,6 @@ import json
 import os
 import sys
 
-# NCCL prints its version banner (and any NCCL_DEBUG output) to stdout by default: keep stdout for the one JSON line
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 import threading
 import time
 
@@ -79,12 +77,28 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+class stdout_to_stderr:
+    """NCCL prints its version banner to the process's stdout (file descriptor 1) when the communicator is created: point
+    fd 1 at stderr for that moment, so that stdout carries nothing but the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi style clock/throttle sampling through NVML during the timed region."""
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         super().__init__(daemon=True)
         self.index = index
+        self.uuid = uuid      # NVML indices ignore CUDA_VISIBLE_DEVICES: address the device by UUID when torch knows it
         self.stop_flag = False
         self.sm = []
         self.reasons = set()
@@ -98,7 +112,14 @@ class ClockSampler(threading.Thread):
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            h = None
+            if self.uuid:
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + self.uuid).encode())
+                except Exception:
+                    h = None
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
             self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
             names = {
                 nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
@@ -254,7 +275,10 @@ def main():
 
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
     model = args.model
     short = MODEL_SHORT[model]
     n = args.targets or default_targets(model)
@@ -282,7 +306,11 @@ def main():
     for k in range(W):
         tick(k)
     barrier()
-    sampler = ClockSampler(local_rank)
+    try:
+        dev_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        dev_uuid = None
+    sampler = ClockSampler(local_rank, dev_uuid)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

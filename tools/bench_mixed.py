@@ -14,8 +14,6 @@ import json
 import os
 import sys
 
-# NCCL prints its version banner (and any NCCL_DEBUG output) to stdout by default: keep stdout for the one JSON line
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np
 
@@ -39,7 +37,10 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)      # NCCL's version banner goes to fd 1: keep stdout for the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier(); torch.cuda.synchronize()
+        sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
     stream = torch.cuda.Stream()
     n = args.targets_per_gpu
     ids_all = (np.arange(n, dtype=np.int64) * world + rank)           # the ids this rank owns
