@@ -431,7 +431,15 @@ void launch_step(te_pool* p, const te::StepArgs& a_in, int n_work_hint) {
         return;
     }
   }
-  ensure_full(p);
+  // AR, variant 11: the row-split kernel in packed form (only the upper-triangle field ranges travel; te_split.cuh).  Not the
+  // default: it moves 44 % fewer bytes but is not faster (1.07e9 vs 1.09e9 steps/s) -- with the traffic gone the six main
+  // warps' work per tile is the bound, and they still compute full rows.
+  if (p->model == te::ANGULAR_RATES && v == 11 && p->all_sym) {
+    a.packed = 1;
+    p->lower_stale = true;
+  } else {
+    ensure_full(p);
+  }
   if (a.dst_tiles) {
     // compacting tick: separate instantiations of the default split configurations, so that the in-place kernels carry
     // none of its code (the AV kernel at 128 registers lost 6 % to a few extra runtime branches)

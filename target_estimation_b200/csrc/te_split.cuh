@@ -133,14 +133,28 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
     return a.tile_list ? a.tile_list[ww] : a.tile_begin + ww;
   };
   auto use_meas_tma = [&](int tile) -> bool { return a.meas_tma && (tile * TILE + TILE <= a.n_slots); };
+  // Packed covariance (AR, a.packed): only the field ranges the step needs travel -- x + covariance row 0, the upper parts
+  // of rows 1..N-2, the last diagonal entry + t / n_meas / prev_rpy: 194 of AR's 347 fields.  The lower triangle of the
+  // staged tile stays unwritten; a row owner reads P(g, c), c < g, from the mirrored field P(c, g) instead, and only the
+  // same ranges are stored back (each row's upper part comes from the warp that owns the row).
+  const bool packed = (TYPE == ANGULAR_RATES) && a.packed != 0;
+  auto seg_f0 = [&](int i) -> int { return i == 0 ? 0 : (i < N - 1 ? LY::F_P + i * (N + 1) : LY::F_P + N * N - 1); };
+  auto seg_nf = [&](int i) -> int { return i == 0 ? 2 * N : (i < N - 1 ? N - i : 1 + (LY::NF - (LY::F_P + N * N))); };
+  constexpr uint32_t PACKED_BYTES = (uint32_t)(N + N * (N + 1) / 2 + (LY::NF - (LY::F_P + N * N))) * TILE * 8u;
   auto issue = [&](int it) {
     const int tile = tile_of(it);
     const int s = it % STAGES;
     double* st = stage0 + (size_t)s * STAGE_DOUBLES;
+    const double* src = a.tiles + (size_t)tile * LY::TILE_DOUBLES;
+    if (packed) {
+      mbar_expect_tx(&bars[s], PACKED_BYTES);
+#pragma unroll 1
+      for (int i = 0; i < N; ++i) bulk_g2s(st + (size_t)seg_f0(i) * TILE, src + (size_t)seg_f0(i) * TILE, (uint32_t)seg_nf(i) * TILE * 8u, &bars[s]);
+      return;
+    }
     mbar_expect_tx(&bars[s], (uint32_t)LY::TILE_BYTES);   // measurements are read from global memory by the converters
     // the tile travels as several bulk copies on one mbarrier: a single 40-90 KB copy is served at ~18 B/clk, several
     // smaller ones overlap in the copy engine
-    const double* src = a.tiles + (size_t)tile * LY::TILE_DOUBLES;
 #pragma unroll 1
     for (int off = 0; off < LY::TILE_DOUBLES; off += BULK_CHUNK_DOUBLES) {
       const int nd = (LY::TILE_DOUBLES - off) < BULK_CHUNK_DOUBLES ? (LY::TILE_DOUBLES - off) : BULK_CHUNK_DOUBLES;
@@ -196,7 +210,13 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
       }
       if (producer) {
         if (any_d) {
-          bulk_s2g(a.tiles + (size_t)tile_d * LY::TILE_DOUBLES, std_, LY::TILE_BYTES);
+          double* dstt = a.tiles + (size_t)tile_d * LY::TILE_DOUBLES;
+          if (packed) {
+#pragma unroll 1
+            for (int i = 0; i < N; ++i) bulk_s2g(dstt + (size_t)seg_f0(i) * TILE, std_ + (size_t)seg_f0(i) * TILE, (uint32_t)seg_nf(i) * TILE * 8u);
+          } else {
+            bulk_s2g(dstt, std_, LY::TILE_BYTES);
+          }
           bulk_commit();
           if (a.clear_action) a.tile_flag[tile_d] = 0;
         }
@@ -336,7 +356,8 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
         const int g = q * RS + r;
         if (h == 0) __stcs(dr + (size_t)(LY::F_X + g) * TILE, stg[(LY::F_X + g) * TILE + lane]);
 #pragma unroll
-        for (int j = 0; j < NCOL; ++j) __stcs(dr + (size_t)(LY::F_P + g * N + colof(j)) * TILE, stg[(LY::F_P + g * N + colof(j)) * TILE + lane]);
+        for (int j = 0; j < NCOL; ++j)
+          if (!packed || colof(j) >= g) __stcs(dr + (size_t)(LY::F_P + g * N + colof(j)) * TILE, stg[(LY::F_P + g * N + colof(j)) * TILE + lane]);
       }
       if (w == 0) {
 #pragma unroll
@@ -373,7 +394,11 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
         const int g = q * RS + r;
         xr[q] = st[(LY::F_X + g) * TILE + lane];
 #pragma unroll
-        for (int j = 0; j < NCOL; ++j) Pr[q][j] = st[(LY::F_P + g * N + colof(j)) * TILE + lane];
+        for (int j = 0; j < NCOL; ++j) {
+          const int col = colof(j);
+          const int e = (packed && col < g) ? col * N + g : g * N + col;   // packed: lower-triangle entries from their mirror
+          Pr[q][j] = st[(LY::F_P + e) * TILE + lane];
+        }
       }
 
       // ---- phase A: predict of the own block ----

@@ -102,7 +102,7 @@ def test_av_asymmetric_class_takes_general_kernel():
     assert np.array_equal(pools[1], pools[1].transpose(0, 2, 1))            # symmetric kernel: both halves identical
 
 
-@pytest.mark.parametrize("model", ["uniform_velocity", "uniform_acceleration", "angular_velocities"])
+@pytest.mark.parametrize("model", MODELS)
 def test_packed_covariance_round_trips_through_full_matrix_kernels(model):
     """the default kernels keep only the upper triangle of P up to date (packed); switching to a full-matrix kernel
     (variant 10) mirrors it first, reading the state back mirrors on the fly, and the unpacked direct kernel (variant 12)
@@ -111,20 +111,22 @@ def test_packed_covariance_round_trips_through_full_matrix_kernels(model):
     mtype, _, Q, R, P0 = te.load_model(model)
     N, M = te.model_dims(mtype)
     n, ticks = 150, 90
-    meas, action, scale = synth.make_streams(n, ticks, DT, accel=model == "uniform_acceleration", angular=M == 6, seed=3)
+    meas, action, scale = synth.make_streams(n, ticks, DT, accel=model in ("uniform_acceleration", "angular_rates"), angular=M == 6, seed=3)
     ids = np.arange(n, dtype=np.uint32)
     mgr = orc.Manager()
     for k in range(n):
         mgr.init_full(mtype, k, DT, 0.0, Q, R, scale[k] * P0, meas[0, k])
     pool = te.TargetPool(mtype); pool.register_class(Q, R, P0); pool.add(ids, meas[0], p0_scale=scale)
     schedule = [0] * 20 + [10] * 15 + [0] * 15 + [12] * 10 + [1] * 10 + [0] * 20
+    if model == "angular_rates":      # its packed form is variant 11 (the default moves the full matrix)
+        schedule = [11 if v == 0 else v for v in schedule]
     for k in range(ticks):
         pool.set_variant(schedule[k])
         mgr.step_batch(ids, DT, meas[k], action[k]); pool.step_dense_host(DT, meas[k], action[k])
         if k % 5 == 4 or k == ticks - 1:
             ref, got = mgr.states(ids, N), pool.read_state()
             assert synth.compare_h2(got["x"], ref["x"]) <= 1.0 and synth.compare_h2(got["P"], ref["P"]) <= 1.0, k
-            if schedule[k] in (0, 12):
+            if schedule[k] in (0, 11) or (schedule[k] == 12 and model != "angular_rates"):
                 assert np.array_equal(got["P"], got["P"].transpose(0, 2, 1)), k     # read-back of a packed pool is exactly symmetric
     pool.close()
 
