@@ -21,6 +21,7 @@
 #include "te_kernels.cuh"
 #include "te_split.cuh"
 #include "te_direct.cuh"
+#include "te_ar_pair.cuh"
 
 namespace {
 
@@ -376,6 +377,20 @@ void launch_kin_direct(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   else launch_kin_direct_k<TYPE, WARPS, CTAS>(p, a, n_work_hint);
 }
 
+template <int WARPS>
+void launch_ar_pair(te_pool* p, const te::StepArgs& a, int n_work_hint) {
+  auto kern = te::kf_step_ar_pair_kernel<WARPS>;
+  const size_t smem = te::ar_pair_smem_bytes(WARPS);
+  static bool configured[64] = {false};
+  if (!configured[p->device & 63]) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[p->device & 63] = true;
+  }
+  int grid = std::min(p->n_sm, std::max(1, cdiv(n_work_hint, WARPS)));
+  kern<<<grid, WARPS * 32, smem, p->stream>>>(a);
+  CK(cudaGetLastError());
+}
+
 // does the current variant run a direct symmetric-covariance kernel (te_direct.cuh)?
 bool uses_direct(const te_pool* p) {
   const int v = p->variant;
@@ -384,7 +399,7 @@ bool uses_direct(const te_pool* p) {
     case te::UNIFORM_VELOCITY:
     case te::UNIFORM_ACCELERATION: return dflt || v == 5 || v == 6 || v == 7 || v == 12;
     case te::ANGULAR_VELOCITIES: return dflt || (v >= 6 && v <= 9) || v == 12;
-    default: return false;
+    default: return v == 12 || v == 13;   // AR: the two-lanes-per-target kernel (te_ar_pair.cuh); 13 = packed
   }
 }
 // full-matrix kernels (and anything else that reads both halves) first get the lower triangles back
@@ -412,7 +427,11 @@ void launch_step(te_pool* p, const te::StepArgs& a_in, int n_work_hint) {
   if (uses_direct(p)) {
     a.packed = (p->all_sym && v != 12) ? 1 : 0;
     if (a.packed) p->lower_stale = true;
+    else if (p->model == te::ANGULAR_RATES) ensure_full(p);   // (the other direct kernels never read the lower triangle)
     switch (p->model) {
+      case te::ANGULAR_RATES:
+        launch_ar_pair<8>(p, a, n_work_hint);
+        return;
       case te::UNIFORM_VELOCITY:
         if (v == 5) launch_kin_direct<te::UNIFORM_VELOCITY, 4, 4>(p, a, n_work_hint);
         else if (v == 7) launch_kin_direct<te::UNIFORM_VELOCITY, 4, 3>(p, a, n_work_hint);

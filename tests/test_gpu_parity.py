@@ -73,6 +73,14 @@ def test_step_parity_kinematic_kernels(model, variant):
     assert w["x"] <= 1.0 and w["P"] <= 1.0, w
 
 
+@pytest.mark.parametrize("variant", [11, 12, 13])
+def test_step_parity_ar_kernels(variant):
+    """AR: the row-split kernel in packed form (11) and the two-lanes-per-target kernel (te_ar_pair.cuh) writing both halves
+    (12) or the upper triangle only (13); pool size ragged against both the tile and the 16-target pass"""
+    w = _run("angular_rates", 200 + 9, 60, variant=variant, check_every=20)
+    assert w["x"] <= 1.0 and w["P"] <= 1.0, w
+
+
 @pytest.mark.parametrize("variant", [5, 6, 7, 10])
 def test_step_parity_av_kernels(variant):
     """AV: the staged (5) and direct (6, 7; 0 = default) symmetric-covariance kernels and the forced row-split kernel (10)"""
