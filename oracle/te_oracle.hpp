@@ -8,16 +8,19 @@
 // bench.py's cpu_baseline / --impl reference leg may build, link, import or run it.
 // The product (target_estimation_b200/) never includes or links anything from here.
 //
-// PARITY PINNED ONLY IN PART: the reference holds no golden vectors / known-answer tests for
-// this path (its only KF test asserts statistical convergence at 0.01/0.05 tolerance,
+// PARITY PINNED IN PART: the reference holds no golden vectors / known-answer tests for this
+// path (its only KF test asserts statistical convergence at 0.01/0.05 tolerance,
 // test/target_manager_test.cpp:179-189,223-233,268-281,321-340) and it cannot be built as a
 // whole here (Eigen 3, yaml-cpp, gtest, ROS absent; no network).  Pinned against reference
-// code: the Kalman-filter classes below, bit-identical to the reference's own src/kalman.cpp
-// compiled unmodified against an Eigen stand-in (oracle/_ref/libref_kalman.so,
-// oracle/eigen_standin/, tests/test_ref_kalman.py).  The models, geometry, manager and
-// intersection solver are UNPINNED by reference code; they are pinned only (a) against the
-// four convergence tests re-run verbatim with the libstdc++ RNG stream, (b) against
-// tests/golden/ anchors produced by an independent numpy restatement.
+// code: the Kalman filters, the four models, geometry helpers, TargetManager, the
+// IntersectionSolver's control flow, the moving-average filters, getId / toSec and the C-ABI
+// semantics below are bit-identical to the reference's own sources compiled unmodified
+// against stand-in headers for Eigen / yaml-cpp (oracle/_ref/*.so, oracle/eigen_standin/,
+// tests/test_ref_kalman.py, test_ref_models.py, test_ref_manager.py).  NOT pinned by
+// reference code: Eigen's own rounding, Eigen's polynomial root finder (restated here), and
+// the RosTargetManager tick / expiry logic (needs ROS types) -- those rest on (a) the four
+// convergence tests re-run verbatim with the libstdc++ RNG stream, (b) tests/golden/ anchors
+// produced by an independent numpy restatement, (c) the restatement's own unit tests.
 //
 // Every function cites the reference file:line it follows (paths relative to
 // /root/reference).  Arithmetic is evaluated in the reference's order, without FMA
