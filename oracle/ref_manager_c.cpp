@@ -10,6 +10,7 @@
 
 #include "target_estimation/intersection_solver.hpp"
 #include "target_estimation/target_manager.hpp"
+#include "target_estimation/target_manager_ros.hpp"
 #include "target_estimation/utils.hpp"
 
 namespace {
@@ -29,7 +30,8 @@ struct Quiet {   // the reference prints matrices / "does not exist" lines to st
   Quiet() : old(std::cout.rdbuf(sink.rdbuf())), olde(std::cerr.rdbuf(sink.rdbuf())) {}
   ~Quiet() { std::cout.rdbuf(old); std::cerr.rdbuf(olde); }
 };
-struct Mgr { TargetManager::Ptr m; };
+struct Mgr { TargetManager::Ptr m; std::shared_ptr<ros::NodeHandle::State> nh_state; };
+std::shared_ptr<ros::NodeHandle::State>& g_last_nh_state(void* h) { return static_cast<Mgr*>(h)->nh_state; }
 }  // namespace
 
 extern "C" {
@@ -104,6 +106,67 @@ int refs_pose(void* s, unsigned id, double t1, double pos_th, double ang_th, con
                                                                                    radius, p);
   std::memcpy(pose, p.data(), 56);
   return ok ? 1 : 0;
+}
+
+// ---- RosTargetManager (src/target_manager_ros.cpp) on the ROS stand-ins of oracle/eigen_standin ----
+// The handle is a Mgr too: refm_ids / refm_state / refm_pose ... work on it.
+void* refr_new(const char* type, const double* Q, int nq, const double* R, int nr, const double* P, int np) {
+  Quiet q;
+  try {
+    ros::NodeHandle nh;
+    nh.st_->lists["Q"].assign(Q, Q + nq);      // flat lists, as `rosparam load models/*.yaml` puts them on the server
+    nh.st_->lists["R"].assign(R, R + nr);
+    nh.st_->lists["P"].assign(P, P + np);
+    nh.st_->strings["type"] = type;
+    Mgr* h = new Mgr;
+    h->m.reset(new RosTargetManager(nh));
+    h->nh_state = nh.st_;
+    return h;
+  } catch (...) {
+    return nullptr;
+  }
+}
+static RosTargetManager* R_(void* h) { return static_cast<RosTargetManager*>(static_cast<Mgr*>(h)->m.get()); }
+void refr_set_expiration(void* h, double t) { R_(h)->setExpirationTime(t); }
+void refr_set_token(void* h, const char* s) { R_(h)->setTargetTokenName(s); }
+// deliver one TFMessage to the subscribed (private) callback: frames separated by '\n', stamps [n][2], poses [n][7]
+void refr_callback(void* h, int n, const char* frames, const unsigned* stamps, const double* poses, const char* frame_id) {
+  Quiet q;
+  std::shared_ptr<tf2_msgs::TFMessage> msg(new tf2_msgs::TFMessage);
+  std::istringstream is(frames);
+  std::string name;
+  for (int i = 0; i < n; ++i) {
+    std::getline(is, name);
+    geometry_msgs::TransformStamped t;
+    t.header.stamp.sec = stamps[2 * i];
+    t.header.stamp.nsec = stamps[2 * i + 1];
+    t.header.frame_id = frame_id ? frame_id : "";
+    t.child_frame_id = name;
+    t.transform.translation.x = poses[7 * i + 0]; t.transform.translation.y = poses[7 * i + 1]; t.transform.translation.z = poses[7 * i + 2];
+    t.transform.rotation.x = poses[7 * i + 3]; t.transform.rotation.y = poses[7 * i + 4]; t.transform.rotation.z = poses[7 * i + 5];
+    t.transform.rotation.w = poses[7 * i + 6];
+    msg->transforms.push_back(t);
+  }
+  // the NodeHandle copy inside the manager shares its state with the one the constructor received: find the callback there
+  RosTargetManager* r = R_(h);
+  (void)r;
+  g_last_nh_state(h)->callback(std::static_pointer_cast<const void>(std::shared_ptr<const tf2_msgs::TFMessage>(msg)));
+}
+// RosTargetManager::update(dt) with ros::Time::now() = (now_sec, now_nsec); returns the number of transforms broadcast
+int refr_update(void* h, double dt, unsigned now_sec, unsigned now_nsec) {
+  Quiet q;
+  ros::Time::clock() = ros::Time(now_sec, now_nsec);
+  tf::TransformBroadcaster::log().clear();
+  R_(h)->update(dt);
+  return (int)tf::TransformBroadcaster::log().size();
+}
+// k-th transform of the last update: child frame name (<= 63 chars), parent frame, origin xyz + rotation xyzw
+void refr_broadcast(int k, char* child, char* parent, double* pose7) {
+  const tf::StampedTransform& t = tf::TransformBroadcaster::log()[(size_t)k];
+  std::strncpy(child, t.child_frame_id.c_str(), 63); child[63] = 0;
+  std::strncpy(parent, t.frame_id.c_str(), 63); parent[63] = 0;
+  pose7[0] = t.origin.x_; pose7[1] = t.origin.y_; pose7[2] = t.origin.z_;
+  pose7[3] = t.rotation.x_; pose7[4] = t.rotation.y_; pose7[5] = t.rotation.z_; pose7[6] = t.rotation.w_;
 }
 
 // ---- utils.hpp ----

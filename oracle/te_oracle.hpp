@@ -13,12 +13,12 @@
 // test/target_manager_test.cpp:179-189,223-233,268-281,321-340) and it cannot be built as a
 // whole here (Eigen 3, yaml-cpp, gtest, ROS absent; no network).  Pinned against reference
 // code: the Kalman filters, the four models, geometry helpers, TargetManager, the
-// IntersectionSolver's control flow, the moving-average filters, getId / toSec and the C-ABI
-// semantics below are bit-identical to the reference's own sources compiled unmodified
-// against stand-in headers for Eigen / yaml-cpp (oracle/_ref/*.so, oracle/eigen_standin/,
-// tests/test_ref_kalman.py, test_ref_models.py, test_ref_manager.py).  NOT pinned by
-// reference code: Eigen's own rounding, Eigen's polynomial root finder (restated here), and
-// the RosTargetManager tick / expiry logic (needs ROS types) -- those rest on (a) the four
+// IntersectionSolver's control flow, the moving-average filters, getId / toSec, the C-ABI
+// semantics and the RosTargetManager tick / mailbox / expiry below are bit-identical to the
+// reference's own sources compiled unmodified against stand-in headers for Eigen / yaml-cpp /
+// roscpp / tf (oracle/_ref/*.so, oracle/eigen_standin/, tests/test_ref_kalman.py,
+// test_ref_models.py, test_ref_manager.py, test_ref_ros_tick.py).  NOT pinned by reference
+// code: Eigen's own rounding and Eigen's polynomial root finder (restated here) -- those rest on (a) the four
 // convergence tests re-run verbatim with the libstdc++ RNG stream, (b) tests/golden/ anchors
 // produced by an independent numpy restatement, (c) the restatement's own unit tests.
 //
