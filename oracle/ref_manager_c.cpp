@@ -8,6 +8,11 @@
 #include <iostream>
 #include <sstream>
 
+#include <chrono>
+#include <thread>
+#include <memory>
+#include <vector>
+
 #include "target_estimation/intersection_solver.hpp"
 #include "target_estimation/target_manager.hpp"
 #include "target_estimation/target_manager_ros.hpp"
@@ -167,6 +172,56 @@ void refr_broadcast(int k, char* child, char* parent, double* pose7) {
   std::strncpy(parent, t.frame_id.c_str(), 63); parent[63] = 0;
   pose7[0] = t.origin.x_; pose7[1] = t.origin.y_; pose7[2] = t.origin.z_;
   pose7[3] = t.rotation.x_; pose7[4] = t.rotation.y_; pose7[5] = t.rotation.z_; pose7[6] = t.rotation.w_;
+}
+
+// ---- CPU baseline timing on the reference's own TargetManager (bench.py cpu_baseline / --impl reference) ----
+// Same workload, arguments and return value as orc_bench_steps (oracle_c.cpp): n_targets of `type` (ids 0..n-1, id % threads
+// over one reference TargetManager per thread -- the reference serialises a manager behind one mutex, so more threads on ONE
+// manager would not help it), then n_ticks ticks of TargetManager::update(id, dt, meas) / update(id, dt) are timed.
+// NOTE: this is the reference's code on the stand-in Eigen of oracle/eigen_standin (heap-backed dynamic matrices, no
+// vectorisation), not on real Eigen: bench.py reports it beside the oracle port and says so.
+double refm_bench_steps(int type, const double* Q, int n, const double* R, int m, const double* P0, int n_targets, int n_ticks,
+                        int threads, double dt, const double* meas, double miss_prob, double* checksum) {
+  Quiet q;
+  if (threads < 1) threads = 1;
+  std::vector<std::unique_ptr<TargetManager>> mgrs;
+  for (int t = 0; t < threads; ++t) mgrs.emplace_back(new TargetManager());
+  const Eigen::MatrixXd Qm = fromColMajor(Q, n, n), Rm = fromColMajor(R, m, m), Pm = fromColMajor(P0, n, n);
+  const double zero6[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < n_targets; ++i)
+    mgrs[(size_t)(i % threads)]->init((TargetManager::target_t)type, (unsigned)i, dt, 0.0, Qm, Rm, Pm, fromVec<Eigen::Vector7d>(meas + 7 * (size_t)i, 7),
+                                      fromVec<Eigen::Vector6d>(zero6, 6), fromVec<Eigen::Vector6d>(zero6, 6));
+  std::vector<double> sums((size_t)threads, 0.0);
+  auto worker = [&](int t) {
+    TargetManager* mg = mgrs[(size_t)t].get();
+    uint64_t rng = 0x9E3779B97F4A7C15ull * (uint64_t)(t + 1);
+    Eigen::Vector7d mm;
+    for (int k = 0; k < n_ticks; ++k) {
+      for (int i = t; i < n_targets; i += threads) {
+        rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+        double u = (double)(rng >> 11) * (1.0 / 9007199254740992.0);
+        if (u < miss_prob) { mg->update((unsigned)i, dt); continue; }
+        const double* b = meas + 7 * (size_t)i;
+        mm(0) = b[0] + 0.01 * k * dt; mm(1) = b[1] - 0.02 * k * dt; mm(2) = b[2] + (u - 0.5) * 0.01;
+        mm(3) = b[3]; mm(4) = b[4]; mm(5) = b[5]; mm(6) = b[6];
+        mg->update((unsigned)i, dt, mm);
+      }
+    }
+    Eigen::Vector7d p;
+    for (int i = t; i < n_targets; i += threads) { mg->getTargetPose((unsigned)i, p); sums[(size_t)t] += p(0) + p(1) + p(2); }
+  };
+  auto t0 = std::chrono::steady_clock::now();
+  if (threads == 1) worker(0);
+  else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; ++t) th.emplace_back(worker, t);
+    for (auto& x : th) x.join();
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  double s = 0.0;
+  for (double v : sums) s += v;
+  if (checksum) *checksum = s;
+  return std::chrono::duration<double>(t1 - t0).count();
 }
 
 // ---- utils.hpp ----

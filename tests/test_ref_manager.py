@@ -217,3 +217,21 @@ def test_reference_c_abi_matches_oracle_c_abi_semantics():
         assert _same(o, last["target_manager_get_est_pose"])
         assert L.target_manager_get_n_measurements(ref, 555) == 0
     L.target_manager_delete(ref)
+
+
+@pytest.mark.parametrize("name", ["uniform_velocity", "uniform_acceleration", "angular_rates", "angular_velocities"])
+def test_cpu_baseline_loops_agree(name):
+    """bench.py's two CPU arms (orc_bench_steps on the port, refm_bench_steps on the reference's own sources) run the same
+    workload: the checksum over every target's final estimated position must be bit-identical, for 1 and 3 threads"""
+    L = _lib(); O = orc.lib()
+    y = orc.load_yaml(os.path.join(ROOT, "models", "model_%s_params.yaml" % name))
+    L.refm_bench_steps.restype = C.c_double; L.refm_bench_steps.argtypes = O.orc_bench_steps.argtypes
+    n_t = 60
+    rng = np.random.default_rng(5)
+    meas = np.zeros((n_t, 7)); meas[:, :3] = rng.uniform(-5, 5, (n_t, 3)); meas[:, 6] = 1.0
+    Qc, Rc, Pc = orc.colmajor(y["Q"]), orc.colmajor(y["R"]), orc.colmajor(y["P"])
+    for threads in (1, 3):
+        c1, c2 = C.c_double(), C.c_double()
+        a = (y["type"], orc.ptr(Qc), y["Q"].shape[0], orc.ptr(Rc), y["R"].shape[0], orc.ptr(Pc), n_t, 25, threads, DT, orc.ptr(meas), 0.05)
+        assert L.refm_bench_steps(*a, C.byref(c1)) > 0 and O.orc_bench_steps(*a, C.byref(c2)) > 0
+        assert c1.value == c2.value and np.isfinite(c1.value)
