@@ -133,6 +133,33 @@ long long te_pool_step_dense_expire(te_pool* p, double dt, const double* dev_mea
                                     int default_action, uint32_t stamp_sec, uint32_t stamp_nsec, uint32_t now_sec, uint32_t now_nsec,
                                     double timeout, uint32_t* erased_out, long long cap);
 
+/* ---- device-resident mailboxes: the node loop of RosTargetManager for pools too large for a host loop ---------------- */
+/* The reference keeps one Measurement mailbox per id in a std::map (include/target_estimation/target_manager_ros.hpp:74-134,
+ * 176) and walks it once per tick on the host (src/target_manager_ros.cpp:46-76).  Here every target's mailbox lives beside
+ * its slot on the device: the stored stamp and pose, last_meas_time_, and new_meas_ kept as the action byte of the next tick;
+ * the pose and action arrays ARE the step kernel's measurement block and action array.  Only mailboxes whose id has no
+ * target yet stay on the host (a handful per tick: ids seen for the first time), where the tick promotes them.
+ *
+ * te_pool_mailbox_ingest = RosTargetManager::measurementCallBack (src/target_manager_ros.cpp:26-39) for records whose frame
+ * names are already parsed to ids (the caller stops at the first unparsable frame, as the reference loop does): record k =
+ * (ids[k], sec[k], nsec[k], poses[k][7]), host arrays, applied in arrival order per id (Measurement::update).  Synchronous. */
+int te_pool_mailbox_ingest(te_pool* p, long long n, const uint32_t* ids, const uint32_t* sec, const uint32_t* nsec,
+                           const double* poses /*[n][7]*/);
+/* te_pool_mailbox_tick = RosTargetManager::update(dt) (src/target_manager_ros.cpp:41-76) without the broadcast: readable
+ * mailboxes of unknown ids become targets (class 0, p0 = the pose, t0 = t0_new, v0 = a0 = 0) and are updated with that pose,
+ * targets with a readable mailbox are updated (the flag is sticky), the others predicted; every mailbox with
+ * last_meas_time > 0 && now - last_meas_time >= timeout is erased with its target.  One stable rebuild (expired slots out,
+ * new ids merged in, ascending ids kept) + one step launch.  Expired targets are not stepped (unobservable).  erased_out:
+ * ascending erased ids (up to cap), target-less mailboxes included, as the reference erases those too; *n_added_out: targets
+ * created.  Targets added through te_pool_add_batch carry an empty mailbox (predicted until a record arrives).  Returns
+ * #erased.  Once a pool keeps mailboxes, te_pool_step_dense_expire is refused (it would leave them behind). */
+long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, uint32_t now_sec, uint32_t now_nsec, double timeout,
+                               uint32_t* erased_out, long long cap, long long* n_added_out);
+/* mailboxes alive = targets + target-less ones (measurements_.size() of the reference) */
+long long te_pool_mailbox_count(te_pool* p);
+/* device views of the mailboxes in slot order: stored pose [size][7], action byte of the next tick [size] (NULL before first use) */
+const double* te_pool_mailbox_dev_pose(te_pool* p);
+const uint8_t* te_pool_mailbox_dev_action(te_pool* p);
 /* ---- batched IntersectionSolver (src/intersection_solver.cpp) ---------------------------- */
 /* n_streams independent solver states (each = one reference IntersectionSolver object: two moving
  * average filters of filters_length samples + previous intersection pose). */

@@ -573,6 +573,99 @@ __global__ void collect_erased_kernel(const int* __restrict__ alive, const int* 
   erased[s - pos[s]] = ids[s];
 }
 
+// device-resident mailboxes ---------------------------------------------------------------
+// One Measurement (include/target_estimation/target_manager_ros.hpp:74-134) per slot: tr_'s stamp and pose, new_meas_ kept
+// directly as the action byte of the next tick (ACT_UPDATE = readable, ACT_PREDICT = not), last_meas_time_ = cold.last_meas.
+// pose [slot][7] and act [slot] ARE the dense step's measurement block and action array: the tick needs no staging pass.
+struct MailArrays {
+  uint32_t* sec;
+  uint32_t* nsec;
+  uint8_t* act;
+  double* pose;
+};
+// mailboxes promoted to targets by a tick (index = AddData index; pose = AddData::p0, act = ACT_UPDATE); sec == nullptr:
+// targets added outside the tick get an empty mailbox (stamp 0, nothing readable)
+struct MailAdd {
+  const uint32_t* sec;
+  const uint32_t* nsec;
+  const double* last;
+};
+
+// record k of a /tf message -> sort key = its slot (unknown ids: key n_slots, listed for the host, which keeps the
+// target-less mailboxes)
+__global__ void mb_lookup_kernel(const uint32_t* __restrict__ ids_sorted, int n_slots, const uint32_t* __restrict__ q, int n,
+                                 uint32_t* __restrict__ key, int* __restrict__ rec, int* __restrict__ unknown, int* counter) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int s = n_slots ? lower_bound_u32(ids_sorted, n_slots, q[k]) : 0;
+  const bool hit = s < n_slots && ids_sorted[s] == q[k];
+  key[k] = hit ? (uint32_t)s : (uint32_t)n_slots;
+  rec[k] = k;
+  if (!hit) unknown[atomicAdd(counter, 1)] = k;
+}
+// records sorted by (slot, arrival order): the first record of each slot's run applies the whole run in arrival order --
+// Measurement::update (target_manager_ros.hpp:96-115): a stamp newer than the stored one makes the mailbox readable and
+// becomes last_meas_time_, any other stamp makes it unreadable; stamp and pose are stored either way.
+__global__ void mb_apply_kernel(int n, int n_slots, const uint32_t* __restrict__ key, const int* __restrict__ rec, const uint32_t* __restrict__ sec,
+                                const uint32_t* __restrict__ nsec, const double* __restrict__ poses, MailArrays mb, double* last_meas) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t s = key[k];
+  if (s >= (uint32_t)n_slots || (k > 0 && key[k - 1] == s)) return;
+  uint32_t msec = mb.sec[s], mnsec = mb.nsec[s];
+  uint8_t act = mb.act[s];
+  double last = last_meas[s];
+  int r = 0;
+  for (int j = k; j < n && key[j] == s; ++j) {
+    r = rec[j];
+    const double cur = to_sec_rn(sec[r], nsec[r]);
+    const double prev = to_sec_rn(msec, mnsec);
+    if (cur > prev) { act = (uint8_t)ACT_UPDATE; last = cur; }
+    else act = (uint8_t)ACT_PREDICT;
+    msec = sec[r];
+    mnsec = nsec[r];
+  }
+  mb.sec[s] = msec;
+  mb.nsec[s] = mnsec;
+  mb.act[s] = act;
+  last_meas[s] = last;
+#pragma unroll
+  for (int e = 0; e < 7; ++e) mb.pose[(size_t)s * 7 + e] = poses[(size_t)r * 7 + e];
+}
+// mailboxes follow their slots through a compaction / merge (srcmap of rebuild_kernel); promoted ones are filled in
+__global__ void mb_move_kernel(int n_new, const int* __restrict__ srcmap, MailArrays o, MailArrays nw, MailAdd add, const double* __restrict__ add_p0,
+                               double* __restrict__ new_last_meas) {
+  int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n_new) return;
+  const int s = srcmap[d];
+  if (s >= 0) {
+    nw.sec[d] = o.sec[s];
+    nw.nsec[d] = o.nsec[s];
+    nw.act[d] = o.act[s];
+#pragma unroll
+    for (int e = 0; e < 7; ++e) nw.pose[(size_t)d * 7 + e] = o.pose[(size_t)s * 7 + e];
+  } else {
+    const int k = -1 - s;
+    nw.sec[d] = add.sec ? add.sec[k] : 0u;
+    nw.nsec[d] = add.sec ? add.nsec[k] : 0u;
+    nw.act[d] = (uint8_t)(add.sec ? ACT_UPDATE : ACT_PREDICT);
+    if (add.sec) new_last_meas[d] = add.last[k];
+#pragma unroll
+    for (int e = 0; e < 7; ++e) nw.pose[(size_t)d * 7 + e] = add_p0 ? add_p0[(size_t)k * 7 + e] : (e == 6 ? 1.0 : 0.0);
+  }
+}
+// empty mailboxes for slots [base, base + n) (targets appended outside the tick)
+__global__ void mb_clear_kernel(MailArrays mb, int base, int n) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int d = base + k;
+  mb.sec[d] = 0u;
+  mb.nsec[d] = 0u;
+  mb.act[d] = (uint8_t)ACT_PREDICT;
+#pragma unroll
+  for (int e = 0; e < 7; ++e) mb.pose[(size_t)d * 7 + e] = (e == 6 ? 1.0 : 0.0);
+}
+
 // lower triangle <- upper triangle (before a full-matrix kernel runs on a pool whose last steps were packed)
 template <int TYPE>
 __global__ void mirror_lower_kernel(double* __restrict__ tiles, int n_slots) {

@@ -6,12 +6,14 @@
 // target_manager.hpp:36).  Add / erase rebuild the pool by a stable gather into the second buffer
 // (stream compaction; ids stay sorted); the append fast path (all new ids larger than every
 // existing id) writes in place.  There is no CPU fallback: every entry point needs a CUDA device.
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <numeric>
 #include <stdexcept>
 #include <string>
@@ -89,6 +91,25 @@ struct Buf {   // one generation of the pool's per-slot storage
   size_t cap = 0;   // slots (multiple of 32)
 };
 
+struct MailBuf {   // one generation of the per-slot mailboxes (te_pool_mailbox_*)
+  te::MailArrays a{nullptr, nullptr, nullptr, nullptr};
+  size_t cap = 0;
+};
+
+// A mailbox whose id has no target yet (Measurement of target_manager_ros.hpp:74-134 on the host): the message carried a
+// stamp that is not newer than the initial one, or a newer record was followed by an older one before the tick.  Rare, so
+// these stay in a host map; the tick promotes the readable ones to targets and expires the others by the same predicate.
+struct HostMail {
+  uint32_t sec = 0, nsec = 0;
+  double last = 0.0;
+  bool fresh = true;   // Measurement(): new_meas_ = true
+  double pose[7] = {0, 0, 0, 0, 0, 0, 0};
+};
+inline double host_to_sec(uint32_t sec, uint32_t nsec) {   // utils.hpp:59-62, never contracted
+  volatile double ns = 1e-9 * (double)nsec;
+  return (double)sec + ns;
+}
+
 }  // namespace
 
 struct te_pool {
@@ -130,6 +151,12 @@ struct te_pool {
   uint32_t h_last_id = 0;
   bool h_last_valid = false;
   Arena arena;
+  // device-resident mailboxes (te_pool_mailbox_*): allocated on first use, then carried through every compaction
+  bool mb_on = false;
+  MailBuf mb[2];
+  int mb_cur = 0;
+  te::MailAdd mb_add{nullptr, nullptr, nullptr};   // set by the mailbox tick around its merge
+  std::map<uint32_t, HostMail> orphans;            // mailboxes without a target
   // chunk pipeline of te_pool_tick_host
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   std::vector<cudaEvent_t> events;
@@ -234,6 +261,54 @@ void ensure_other_capacity(te_pool* p, size_t slots) {
   alloc_buf(p, b, std::max(slots, p->buf[p->cur].cap));
   // the work arrays hold the live alive[] / pos[] of the running compaction: callers size them up-front
   if (p->wcap < slots) throw std::logic_error("work arrays not sized before compaction");
+}
+
+// ---- mailboxes -------------------------------------------------------------------------------
+void free_mail(MailBuf& m) {
+  cudaFree(m.a.sec); cudaFree(m.a.nsec); cudaFree(m.a.act); cudaFree(m.a.pose);
+  m = MailBuf();
+}
+void alloc_mail(MailBuf& m, size_t slots) {
+  slots = (slots + te::TILE - 1) / te::TILE * te::TILE;
+  if (slots == 0) slots = te::TILE;
+  CK(cudaMalloc(&m.a.sec, slots * sizeof(uint32_t)));
+  CK(cudaMalloc(&m.a.nsec, slots * sizeof(uint32_t)));
+  CK(cudaMalloc(&m.a.act, slots));
+  CK(cudaMalloc(&m.a.pose, slots * 7 * sizeof(double)));   // cudaMalloc is 256-byte aligned: TMA-loadable measurement block
+  m.cap = slots;
+}
+// the current generation holds `slots` mailboxes (grow by copy, like ensure_cur_capacity)
+void ensure_mail_cur(te_pool* p, size_t slots) {
+  MailBuf& m = p->mb[p->mb_cur];
+  if (slots <= m.cap && m.a.sec) return;
+  MailBuf nm;
+  alloc_mail(nm, std::max(slots, m.cap + m.cap / 2));
+  if (p->n > 0 && m.a.sec) {
+    CK(cudaMemcpyAsync(nm.a.sec, m.a.sec, p->n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, p->stream));
+    CK(cudaMemcpyAsync(nm.a.nsec, m.a.nsec, p->n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, p->stream));
+    CK(cudaMemcpyAsync(nm.a.act, m.a.act, p->n, cudaMemcpyDeviceToDevice, p->stream));
+    CK(cudaMemcpyAsync(nm.a.pose, m.a.pose, p->n * 7 * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+  }
+  CK(cudaStreamSynchronize(p->stream));
+  free_mail(m);
+  m = nm;
+}
+void ensure_mail_other(te_pool* p, size_t slots) {
+  MailBuf& m = p->mb[1 - p->mb_cur];
+  if (slots <= m.cap && m.a.sec) return;
+  CK(cudaStreamSynchronize(p->stream));
+  free_mail(m);
+  alloc_mail(m, std::max(slots, p->mb[p->mb_cur].cap));
+}
+// first use: every existing target gets an empty mailbox
+void enable_mail(te_pool* p) {
+  if (p->mb_on) return;
+  ensure_mail_cur(p, std::max<size_t>((size_t)p->n, te::TILE));
+  if (p->n > 0) {
+    te::mb_clear_kernel<<<cdiv(p->n, 256), 256, 0, p->stream>>>(p->mb[p->mb_cur].a, 0, (int)p->n);
+    CK(cudaGetLastError());
+  }
+  p->mb_on = true;
 }
 
 void sync_host_ids(te_pool* p) {
@@ -590,6 +665,15 @@ int compact_and_merge(te_pool* p, const te::AddData& ad, const uint32_t* d_add_i
     CK(cudaGetLastError());
   }
   if (n_new > 0) rebuild(p, n_new, ad);
+  if (p->mb_on) {   // the mailboxes follow their slots; promoted host mailboxes are filled in (after rebuild: it zeroes last_meas of new slots)
+    ensure_mail_other(p, (size_t)n_new);
+    if (n_new > 0) {
+      te::mb_move_kernel<<<cdiv(n_new, 256), 256, 0, p->stream>>>(n_new, p->srcmap, p->mb[p->mb_cur].a, p->mb[1 - p->mb_cur].a, p->mb_add, ad.p0,
+                                                                  p->buf[1 - p->cur].cold.last_meas);
+      CK(cudaGetLastError());
+    }
+    p->mb_cur = 1 - p->mb_cur;
+  }
   p->cur = 1 - p->cur;
   p->n = n_new;
   p->h_ids_valid = false;
@@ -706,6 +790,8 @@ void te_pool_destroy(te_pool* p) {
   cudaStreamSynchronize(p->stream);
   free_buf(p->buf[0]);
   free_buf(p->buf[1]);
+  free_mail(p->mb[0]);
+  free_mail(p->mb[1]);
   cudaFree(p->action); cudaFree(p->dt_slot); cudaFree(p->tile_flag); cudaFree(p->tile_list);
   cudaFree(p->alive); cudaFree(p->pos); cudaFree(p->srcmap); cudaFree(p->d_counters); cudaFree(p->cub_tmp);
   cudaFree(p->dQ); cudaFree(p->dR); cudaFree(p->dP0);
@@ -874,6 +960,11 @@ long long te_pool_add_batch(te_pool* p, long long n, const uint32_t* ids, const 
         ensure_cur_capacity(p, (size_t)(p->n + na));
       }
       init_append(p, (int)p->n, ad, na);
+      if (p->mb_on) {
+        ensure_mail_cur(p, (size_t)(p->n + na));
+        te::mb_clear_kernel<<<cdiv(na, 256), 256, 0, p->stream>>>(p->mb[p->mb_cur].a, (int)p->n, (int)na);
+        CK(cudaGetLastError());
+      }
       p->n += na;
       if (p->h_ids_valid) p->h_ids.insert(p->h_ids.end(), s_ids, s_ids + na);
       p->h_last_id = s_ids[na - 1];
@@ -1269,6 +1360,7 @@ long long te_pool_step_dense_expire(te_pool* p, double dt, const double* dev_mea
                                     double timeout, uint32_t* erased_out, long long cap) {
   return guarded_ll(p, [&]() -> long long {
     if (p->n == 0) return 0;
+    if (p->mb_on) throw std::logic_error("this pool keeps device mailboxes: its ticks go through te_pool_mailbox_tick");
     if (!(dt >= 0.0)) throw std::invalid_argument("dt must be >= 0 (assert of src/target_interface.cpp:150)");
     if (dev_meas) check_meas_stride(p, meas_stride);
     else if (dev_action || default_action == TE_ACT_UPDATE) throw std::invalid_argument("update tick without measurements");
@@ -1327,6 +1419,161 @@ long long te_pool_step_dense_expire(te_pool* p, double dt, const double* dev_mea
     return n_er;
   });
 }
+
+// ---- device-resident mailboxes: measurementCallBack + update(dt) of RosTargetManager ----------------
+int te_pool_mailbox_ingest(te_pool* p, long long n, const uint32_t* ids, const uint32_t* sec, const uint32_t* nsec, const double* poses) {
+  return guarded(p, [&] {
+    if (n <= 0) return 0;
+    if (!ids || !sec || !nsec || !poses) throw std::invalid_argument("null record arrays");
+    if (n > 0x7FFFFFFF) throw std::invalid_argument("too many records in one message");
+    enable_mail(p);
+    const int nr = (int)n;
+    auto to_orphan = [&](long long k) {   // Measurement::update on a host mailbox (created on first sight)
+      HostMail& m = p->orphans[ids[k]];
+      const double cur = host_to_sec(sec[k], nsec[k]), prev = host_to_sec(m.sec, m.nsec);
+      if (cur > prev) { m.fresh = true; m.last = cur; }
+      else m.fresh = false;
+      m.sec = sec[k];
+      m.nsec = nsec[k];
+      std::memcpy(m.pose, poses + 7 * k, sizeof(m.pose));
+    };
+    if (p->n == 0) {   // no targets yet: every record belongs to a target-less mailbox
+      for (long long k = 0; k < n; ++k) to_orphan(k);
+      return 0;
+    }
+    uint32_t* d_ids = to_dev(p, ids, (size_t)n);
+    uint32_t* d_sec = to_dev(p, sec, (size_t)n);
+    uint32_t* d_nsec = to_dev(p, nsec, (size_t)n);
+    double* d_pose = to_dev(p, poses, (size_t)n * 7);
+    uint32_t* key_in = p->arena.get_n<uint32_t>((size_t)n);
+    uint32_t* key_out = p->arena.get_n<uint32_t>((size_t)n);
+    int* rec_in = p->arena.get_n<int>((size_t)n);
+    int* rec_out = p->arena.get_n<int>((size_t)n);
+    int* unknown = p->arena.get_n<int>((size_t)n);
+    int* counter = p->arena.get_n<int>(1);
+    CK(cudaMemsetAsync(counter, 0, sizeof(int), p->stream));
+    Buf& b = p->buf[p->cur];
+    te::mb_lookup_kernel<<<cdiv(n, 256), 256, 0, p->stream>>>(b.cold.ids, (int)p->n, d_ids, nr, key_in, rec_in, unknown, counter);
+    CK(cudaGetLastError());
+    // stable sort by slot: the records of one id stay in arrival order (a message may name an id more than once, and several
+    // messages may be ingested between two ticks)
+    int bits = 1;
+    while (bits < 32 && (1ll << bits) <= p->n) ++bits;   // keys are slots < n, or n for unknown ids: 2^bits > n
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_in, key_out, rec_in, rec_out, nr, 0, bits, p->stream));
+    void* tmp = p->arena.get(tmp_bytes);
+    CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key_in, key_out, rec_in, rec_out, nr, 0, bits, p->stream));
+    te::mb_apply_kernel<<<cdiv(n, 256), 256, 0, p->stream>>>(nr, (int)p->n, key_out, rec_out, d_sec, d_nsec, d_pose, p->mb[p->mb_cur].a, b.cold.last_meas);
+    CK(cudaGetLastError());
+    int n_unknown = 0;
+    CK(cudaMemcpyAsync(&n_unknown, counter, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));   // also: the caller's record arrays are free again
+    if (n_unknown > 0) {
+      std::vector<int> list((size_t)n_unknown);
+      CK(cudaMemcpy(list.data(), unknown, (size_t)n_unknown * sizeof(int), cudaMemcpyDeviceToHost));
+      std::sort(list.begin(), list.end());   // arrival order
+      for (int k : list) to_orphan(k);
+    }
+    return 0;
+  });
+}
+
+long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, uint32_t now_sec, uint32_t now_nsec, double timeout, uint32_t* erased_out,
+                               long long cap, long long* n_added_out) {
+  return guarded_ll(p, [&]() -> long long {
+    if (!(dt >= 0.0)) throw std::invalid_argument("dt must be >= 0 (assert of src/target_interface.cpp:150)");
+    if (p->hQ.empty()) throw std::runtime_error("no model class registered");
+    enable_mail(p);
+    const double now = host_to_sec(now_sec, now_nsec);
+    // 1. target-less mailboxes, ascending id: readable -> init on first sight (src/target_manager_ros.cpp:54-58) unless the
+    //    same tick would erase it again (:67-72; init + update + erase is unobservable); unreadable -> stays, or expires
+    std::vector<uint32_t> add_ids, add_sec, add_nsec, host_erased;
+    std::vector<double> add_pose, add_last, add_t0;
+    for (auto it = p->orphans.begin(); it != p->orphans.end();) {
+      const HostMail& m = it->second;
+      const bool expired = m.last > 0.0 && (now - m.last) >= timeout;
+      if (expired) {
+        host_erased.push_back(it->first);
+        it = p->orphans.erase(it);
+      } else if (m.fresh) {
+        add_ids.push_back(it->first);
+        add_sec.push_back(m.sec);
+        add_nsec.push_back(m.nsec);
+        add_last.push_back(m.last);
+        add_t0.push_back(t0_new);
+        add_pose.insert(add_pose.end(), m.pose, m.pose + 7);
+        it = p->orphans.erase(it);
+      } else {
+        ++it;   // "Target(id) does not exist!" (src/target_manager.cpp:209)
+      }
+    }
+    const int n_add = (int)add_ids.size();
+    const int n_old = (int)p->n;
+    if (n_added_out) *n_added_out = n_add;
+    // 2. expiry flags of the existing targets, then ONE stable rebuild: survivors compacted, promoted mailboxes merged in by id
+    ensure_work(p, (size_t)n_old + (size_t)n_add);
+    uint32_t* d_erased = nullptr;
+    long long n_dev_erased = 0;
+    if (n_old > 0) {
+      te::expire_flags_kernel<<<cdiv(n_old, 256), 256, 0, p->stream>>>(p->buf[p->cur].cold.last_meas, n_old, now, timeout, p->alive);
+      CK(cudaGetLastError());
+      d_erased = p->arena.get_n<uint32_t>((size_t)n_old);
+    }
+    te::AddData ad{};
+    if (n_add > 0) {
+      ad.ids = to_dev(p, add_ids.data(), (size_t)n_add);
+      ad.t0 = to_dev(p, add_t0.data(), (size_t)n_add);
+      ad.p0 = to_dev(p, add_pose.data(), (size_t)n_add * 7);
+      p->mb_add.sec = to_dev(p, add_sec.data(), (size_t)n_add);
+      p->mb_add.nsec = to_dev(p, add_nsec.data(), (size_t)n_add);
+      p->mb_add.last = to_dev(p, add_last.data(), (size_t)n_add);
+    }
+    if (n_old > 0 || n_add > 0) {
+      int alive = 0;
+      try {
+        alive = compact_and_merge(p, ad, ad.ids, n_add, d_erased);
+      } catch (...) {
+        p->mb_add = te::MailAdd{nullptr, nullptr, nullptr};
+        throw;
+      }
+      n_dev_erased = n_old - alive;
+    }
+    p->mb_add = te::MailAdd{nullptr, nullptr, nullptr};
+    // 3. the step: update where the mailbox is readable (the flag is sticky: a silent target re-applies its last pose),
+    //    predict elsewhere (:59,:64).  The mailbox arrays are the kernel's measurement block and action array.
+    if (p->n > 0) {
+      te::StepArgs a = base_args(p);
+      const te::MailArrays& mb = p->mb[p->mb_cur].a;
+      a.dt = dt;
+      a.meas = mb.pose;
+      a.meas_stride = 7;
+      a.meas_tma = 1;
+      a.action = mb.act;
+      a.default_action = TE_ACT_PREDICT;
+      launch_step(p, a, a.n_tiles);
+      te::copy_meas_masked_kernel<<<cdiv(p->n, 256), 256, 0, p->stream>>>(p->buf[p->cur].cold.meas, mb.pose, mb.act, (int)p->n);
+      CK(cudaGetLastError());
+    }
+    // 4. erased ids of this tick, ascending: targets the device expired + target-less mailboxes the host expired
+    std::vector<uint32_t> dev_erased((size_t)n_dev_erased);
+    if (n_dev_erased > 0)
+      CK(cudaMemcpyAsync(dev_erased.data(), d_erased, (size_t)n_dev_erased * sizeof(uint32_t), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    const long long n_er = n_dev_erased + (long long)host_erased.size();
+    if (erased_out && cap > 0 && n_er > 0) {
+      std::vector<uint32_t> all((size_t)n_er);
+      std::merge(dev_erased.begin(), dev_erased.end(), host_erased.begin(), host_erased.end(), all.begin());
+      std::memcpy(erased_out, all.data(), (size_t)std::min(cap, n_er) * sizeof(uint32_t));
+    }
+    return n_er;
+  });
+}
+
+long long te_pool_mailbox_count(te_pool* p) { return p ? p->n + (long long)p->orphans.size() : -1; }
+
+const double* te_pool_mailbox_dev_pose(te_pool* p) { return (p && p->mb_on) ? p->mb[p->mb_cur].a.pose : nullptr; }
+const uint8_t* te_pool_mailbox_dev_action(te_pool* p) { return (p && p->mb_on) ? p->mb[p->mb_cur].a.act : nullptr; }
+
 
 // ---- batched IntersectionSolver -------------------------------------------------------------
 te_isolver* te_isolver_create(te_pool* p, long long n_streams, unsigned filters_length) {

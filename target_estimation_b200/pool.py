@@ -232,6 +232,28 @@ class TargetPool:
         return buf[:n].copy()
 
 
+    # -- device-resident mailboxes: the node loop of RosTargetManager (include/te_pool.h) -------
+    def mailbox_ingest(self, ids, sec, nsec, poses):
+        """one /tf message: records (id, stamp, pose7) in arrival order (measurementCallBack, src/target_manager_ros.cpp:26-39)"""
+        ids = _np(ids, np.uint32); sec = _np(sec, np.uint32); nsec = _np(nsec, np.uint32)
+        poses = _np(poses, np.float64, (ids.size, 7))
+        check(lib.te_pool_mailbox_ingest(self._h, ids.size, _ptr(ids), _ptr(sec), _ptr(nsec), _ptr(poses)))
+
+    def mailbox_tick(self, dt, t0_new, now, timeout):
+        """RosTargetManager::update(dt) (src/target_manager_ros.cpp:41-76); now = (sec, nsec).  Returns (erased ids, #added)."""
+        cap = int(lib.te_pool_mailbox_count(self._h))
+        buf = getattr(self, "_erase_buf", None)
+        if buf is None or buf.size < cap:
+            buf = self._erase_buf = np.empty(max(cap + cap // 4, 1), dtype=np.uint32)
+        added = C.c_longlong(0)
+        n = check(lib.te_pool_mailbox_tick(self._h, float(dt), float(t0_new), int(now[0]), int(now[1]), float(timeout), _ptr(buf), cap,
+                                           C.byref(added)))
+        return buf[:n].copy(), int(added.value)
+
+    def mailbox_count(self):
+        return int(lib.te_pool_mailbox_count(self._h))
+
+
 class IntersectionSolver:
     """Batched IntersectionSolver: n_streams independent reference solver objects (include/te_pool.h)."""
 
