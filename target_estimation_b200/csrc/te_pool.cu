@@ -10,6 +10,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -282,7 +283,7 @@ void ensure_mail_cur(te_pool* p, size_t slots) {
   MailBuf& m = p->mb[p->mb_cur];
   if (slots <= m.cap && m.a.sec) return;
   MailBuf nm;
-  alloc_mail(nm, std::max(slots, m.cap + m.cap / 2));
+  alloc_mail(nm, std::max({slots, m.cap + m.cap / 2, p->buf[p->cur].cap}));   // sized like the slot buffers: no per-tick regrowth
   if (p->n > 0 && m.a.sec) {
     CK(cudaMemcpyAsync(nm.a.sec, m.a.sec, p->n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, p->stream));
     CK(cudaMemcpyAsync(nm.a.nsec, m.a.nsec, p->n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, p->stream));
@@ -298,7 +299,7 @@ void ensure_mail_other(te_pool* p, size_t slots) {
   if (slots <= m.cap && m.a.sec) return;
   CK(cudaStreamSynchronize(p->stream));
   free_mail(m);
-  alloc_mail(m, std::max(slots, p->mb[p->mb_cur].cap));
+  alloc_mail(m, std::max({slots + slots / 8, p->mb[p->mb_cur].cap, p->buf[p->cur].cap, p->buf[1 - p->cur].cap}));
 }
 // first use: every existing target gets an empty mailbox
 void enable_mail(te_pool* p) {
@@ -1484,6 +1485,11 @@ long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, uint32_t no
     if (!(dt >= 0.0)) throw std::invalid_argument("dt must be >= 0 (assert of src/target_interface.cpp:150)");
     if (p->hQ.empty()) throw std::runtime_error("no model class registered");
     enable_mail(p);
+    static const bool dbg = std::getenv("TE_MB_DEBUG") != nullptr;
+    auto wall = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tw[6] = {0, 0, 0, 0, 0, 0};
+    auto mark = [&](int i) { if (dbg) { cudaStreamSynchronize(p->stream); tw[i] = wall(); } };
+    mark(0);
     const double now = host_to_sec(now_sec, now_nsec);
     // 1. target-less mailboxes, ascending id: readable -> init on first sight (src/target_manager_ros.cpp:54-58) unless the
     //    same tick would erase it again (:67-72; init + update + erase is unobservable); unreadable -> stays, or expires
@@ -1510,6 +1516,7 @@ long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, uint32_t no
     const int n_add = (int)add_ids.size();
     const int n_old = (int)p->n;
     if (n_added_out) *n_added_out = n_add;
+    mark(1);
     // 2. expiry flags of the existing targets, then ONE stable rebuild: survivors compacted, promoted mailboxes merged in by id
     ensure_work(p, (size_t)n_old + (size_t)n_add);
     uint32_t* d_erased = nullptr;
@@ -1539,6 +1546,7 @@ long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, uint32_t no
       n_dev_erased = n_old - alive;
     }
     p->mb_add = te::MailAdd{nullptr, nullptr, nullptr};
+    mark(2);
     // 3. the step: update where the mailbox is readable (the flag is sticky: a silent target re-applies its last pose),
     //    predict elsewhere (:59,:64).  The mailbox arrays are the kernel's measurement block and action array.
     if (p->n > 0) {
@@ -1554,6 +1562,7 @@ long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, uint32_t no
       te::copy_meas_masked_kernel<<<cdiv(p->n, 256), 256, 0, p->stream>>>(p->buf[p->cur].cold.meas, mb.pose, mb.act, (int)p->n);
       CK(cudaGetLastError());
     }
+    mark(3);
     // 4. erased ids of this tick, ascending: targets the device expired + target-less mailboxes the host expired
     std::vector<uint32_t> dev_erased((size_t)n_dev_erased);
     if (n_dev_erased > 0)
@@ -1565,6 +1574,9 @@ long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, uint32_t no
       std::merge(dev_erased.begin(), dev_erased.end(), host_erased.begin(), host_erased.end(), all.begin());
       std::memcpy(erased_out, all.data(), (size_t)std::min(cap, n_er) * sizeof(uint32_t));
     }
+    mark(4);
+    if (dbg) std::fprintf(stderr, "[te mailbox tick] host mailboxes %.3f ms, flags + rebuild %.3f ms, step %.3f ms, erase list %.3f ms (n %lld, +%d, -%lld)\n",
+                          tw[1] - tw[0], tw[2] - tw[1], tw[3] - tw[2], tw[4] - tw[3], p->n, n_add, n_er);
     return n_er;
   });
 }

@@ -116,6 +116,89 @@ def c3_churn(n=1 << 20, ticks=48, fused=False):
     return out
 
 
+def c3_mailbox(n=1 << 20, ticks=48, model="angular_rates"):
+    """C3 through the node loop itself: per tick ONE /tf message from pinned host memory (a record = id, stamp, pose7 for every
+    speaking id, 68 B each) -> te_pool_mailbox_ingest, then te_pool_mailbox_tick (first-sight init of the fresh ids, sticky
+    update / predict, expiry, one stable rebuild + one step launch).  Same churn as c3_churn: 1 % of the speaking ids fall
+    silent per tick and expire 8 ticks later, as many fresh ids appear.  Erase lists and the final id set are checked against a
+    host model of the reference's predicate."""
+    stream = torch.cuda.Stream()
+    mtype, _, Q, R, P0 = te.load_model(model)
+    pool = te.TargetPool(mtype, stream=stream.cuda_stream)
+    pool.register_class(Q, R, P0)
+    pool.reserve(int(n * 1.3))
+    rng = np.random.default_rng(2)
+    timeout = 8 * DT
+
+    def clock(tk):
+        ns_ = 1000 * 10 ** 9 + tk * 4000000
+        return ns_ // 10 ** 9, ns_ % 10 ** 9
+
+    def to_sec(tk):
+        s_, n_ = clock(tk)
+        return float(s_) + 1e-9 * float(n_)
+
+    ids = np.arange(n, dtype=np.int64)
+    silent_at = np.full(n, 1 << 30, dtype=np.int64)
+    last_tick = np.full(n, -1, dtype=np.int64)
+    next_id = n
+    sched = []
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    n_max = int(n * 1.05)
+    poses = np.zeros((n_max, 7)); poses[:, :3] = rng.uniform(-5, 5, (n_max, 3)); poses[:, 3:] = rpy_to_quat(rng.uniform(-0.4, 0.4, (n_max, 3)))
+    poses = pin(poses)
+    for k in range(ticks + 1):   # tick 0 populates the pool (untimed)
+        if k > 0:
+            old = np.nonzero(silent_at > k)[0]
+            quit_ = rng.choice(old, size=max(1, old.size // 100), replace=False)
+            silent_at[quit_] = k
+            fresh = np.arange(next_id, next_id + quit_.size, dtype=np.int64); next_id += quit_.size
+            ids = np.concatenate([ids, fresh]); silent_at = np.concatenate([silent_at, np.full(fresh.size, 1 << 30, dtype=np.int64)])
+            last_tick = np.concatenate([last_tick, np.full(fresh.size, -1, dtype=np.int64)])
+        speaks = silent_at > k
+        last_tick[speaks] = k
+        now_ = to_sec(k)
+        cand = np.nonzero(~speaks & (last_tick >= 0))[0]
+        expired = np.zeros(ids.size, dtype=bool)
+        if cand.size:
+            uniq = {int(t_): to_sec(int(t_)) for t_ in np.unique(last_tick[cand])}
+            lasts = np.array([uniq[int(t_)] for t_ in last_tick[cand]])
+            expired[cand] = (now_ - lasts) >= timeout
+        rec_ids = ids[speaks].astype(np.uint32)
+        sec, nsec = clock(k)
+        sched.append((pin(rec_ids), pin(np.full(rec_ids.size, sec, dtype=np.uint32)), pin(np.full(rec_ids.size, nsec, dtype=np.uint32)),
+                      ids[expired].astype(np.uint32), int(ids.size)))
+        ids, silent_at, last_tick = ids[~expired], silent_at[~expired], last_tick[~expired]
+    r_ids, r_sec, r_nsec, exp_ids, live = sched[0]
+    pool.mailbox_ingest(r_ids, r_sec, r_nsec, poses[:r_ids.size])
+    erased, added = pool.mailbox_tick(DT, 0.0, clock(0), timeout)
+    assert added == n and erased.size == 0
+    pool.sync()
+    n_erased = n_added = steps = records = 0
+    parts = {"ingest": 0.0, "tick": 0.0}
+    t0 = time.perf_counter()
+    for k in range(1, ticks + 1):
+        r_ids, r_sec, r_nsec, exp_ids, live = sched[k]
+        ta = time.perf_counter()
+        pool.mailbox_ingest(r_ids, r_sec, r_nsec, poses[:r_ids.size])
+        tb = time.perf_counter()
+        erased, added = pool.mailbox_tick(DT, k * DT, clock(k), timeout)
+        tc = time.perf_counter()
+        parts["ingest"] += tb - ta; parts["tick"] += tc - tb
+        assert np.array_equal(erased, exp_ids), k
+        steps += live - erased.size; n_erased += erased.size; n_added += added; records += r_ids.size
+    dt_wall = time.perf_counter() - t0
+    assert np.array_equal(pool.ids().astype(np.int64), ids)
+    out = {"model": model, "targets": n, "ticks": ticks, "erased": int(n_erased), "added": int(n_added), "records_per_tick": records / ticks,
+           "h2d_bytes_per_tick": 68 * records / ticks, "ms_per_tick": 1e3 * dt_wall / ticks, "target_steps_per_s": steps / dt_wall,
+           "ms_per_tick_parts": {k_: 1e3 * v / ticks for k_, v in parts.items()},
+           "note": "the node loop through te_pool_mailbox_ingest + te_pool_mailbox_tick: records come from pinned HOST memory every tick (ids, "
+                   "stamps, poses), mailboxes, first-sight init, sticky update / predict and expiry run on the device; every tick's erase "
+                   "list and the final id set are checked against a host model of the churn"}
+    pool.close()
+    return out
+
+
 def c4_intersect(model, n=1 << 20, ticks=20):
     stream = torch.cuda.Stream()
     v0 = np.zeros((n, 6)); v0[:, 0] = 1.0                       # every target flies along +x at 1 m/s ...
@@ -182,6 +265,9 @@ def replay(model="uniform_acceleration", n=4 << 20, T=16, launches=10):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "mailbox":
+        print(json.dumps({"c3_mailbox_angular_rates": c3_mailbox(), "c3_mailbox_uniform_acceleration": c3_mailbox(model="uniform_acceleration")}))
+        sys.exit(0)
     res = {"c3_churn_angular_rates": c3_churn(), "c3_churn_angular_rates_fused": c3_churn(fused=True), "c4_intersect_uniform_velocity": c4_intersect("uniform_velocity"),
            "c4_intersect_uniform_acceleration": c4_intersect("uniform_acceleration"),
            "replay16_uniform_acceleration_4Mi": replay()}
