@@ -192,7 +192,9 @@ class IntersectionSolver {
 // RosTargetManager without ROS (target_manager_ros.hpp:74-183, src/target_manager_ros.cpp:6-107): the /tf
 // mailbox per id, the per-tick init-on-first-sight / update / predict loop, expiry erase and the list of
 // filtered poses the node broadcasts.  ros::Time stamps are (sec, nsec) pairs; ros::Time::now() is passed in.
-// One tick = at most one add, one sparse step launch, one expiry compaction and one estimate gather.
+// The mailboxes are DEVICE resident (te_pool_mailbox_*): one /tf message = one ingest call (lookup, stable sort by slot,
+// Measurement::update per slot), one tick = one rebuild + one step launch + one estimate gather; host work per tick is
+// proportional to the ids that appear or expire, not to the number of targets.
 // ---------------------------------------------------------------------------------------------------
 struct StampedPose {
   uint32_t sec = 0, nsec = 0;
@@ -239,14 +241,17 @@ class TickTargetManager : public TargetManager {
   void setTargetTokenName(const std::string& token_name) { token_name_ = token_name; }
   void setExpirationTime(double t);
   double time() const { return t_; }
-  size_t mailboxCount() const { return measurements_.size(); }
+  size_t mailboxCount();   // measurements_.size() of the reference: device mailboxes + target-less ones + host ones
   bool publish = true;   // gather the filtered poses every tick (the TF broadcast of :78-87)
  private:
+  te_pool* tickPool();
+  void tickForeign(const double& dt, uint32_t now_sec, uint32_t now_nsec, std::vector<unsigned>& gone_out);
+  int cls_ = -1;   // model class of (Q_, R_, P_) in the pool of type_
   target_t type_;
   MatrixXd Q_, P_, R_;
   std::string token_name_;
   double t_;
-  std::map<unsigned, Measurement> measurements_;
+  std::map<unsigned, Measurement> measurements_;   // host mailboxes: only ids that live in a pool of another model type
   double expiration_time_;
   std::vector<unsigned> pub_ids_;
   std::vector<double> pub_poses_;

@@ -146,16 +146,20 @@ long long te_pool_step_dense_expire(te_pool* p, double dt, const double* dev_mea
 int te_pool_mailbox_ingest(te_pool* p, long long n, const uint32_t* ids, const uint32_t* sec, const uint32_t* nsec,
                            const double* poses /*[n][7]*/);
 /* te_pool_mailbox_tick = RosTargetManager::update(dt) (src/target_manager_ros.cpp:41-76) without the broadcast: readable
- * mailboxes of unknown ids become targets (class 0, p0 = the pose, t0 = t0_new, v0 = a0 = 0) and are updated with that pose,
+ * mailboxes of unknown ids become targets (class cls_new, p0 = the pose, t0 = t0_new, v0 = a0 = 0) and are updated with that pose,
  * targets with a readable mailbox are updated (the flag is sticky), the others predicted; every mailbox with
  * last_meas_time > 0 && now - last_meas_time >= timeout is erased with its target.  One stable rebuild (expired slots out,
  * new ids merged in, ascending ids kept) + one step launch.  Expired targets are not stepped (unobservable).  erased_out:
- * ascending erased ids (up to cap), target-less mailboxes included, as the reference erases those too; *n_added_out: targets
- * created.  Targets added through te_pool_add_batch carry an empty mailbox (predicted until a record arrives).  Returns
- * #erased.  Once a pool keeps mailboxes, te_pool_step_dense_expire is refused (it would leave them behind). */
-long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, uint32_t now_sec, uint32_t now_nsec, double timeout,
-                               uint32_t* erased_out, long long cap, long long* n_added_out);
-/* mailboxes alive = targets + target-less ones (measurements_.size() of the reference) */
+ * ascending erased ids (up to cap), target-less mailboxes included, as the reference erases those too; added_out / *n_added_out:
+ * ascending ids of the targets created (up to added_cap) and their number.  Returns #erased.
+ * Interplay with the by-hand calls, as in the reference: a target added through te_pool_add_batch has no mailbox until its
+ * first record -- the tick does not touch it (the reference's loop walks mailboxes, not targets) -- unless its id already had a
+ * target-less mailbox, which then feeds it; te_pool_erase_batch keeps the erased targets' mailboxes (they become target-less,
+ * so a still-readable one re-creates its target on the next tick).  Once a pool keeps mailboxes, te_pool_step_dense_expire is
+ * refused (it would leave them behind). */
+long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, int cls_new, uint32_t now_sec, uint32_t now_nsec, double timeout,
+                               uint32_t* erased_out, long long cap, uint32_t* added_out, long long added_cap, long long* n_added_out);
+/* mailboxes alive = slots that have one + target-less ones (measurements_.size() of the reference); a device reduction + sync */
 long long te_pool_mailbox_count(te_pool* p);
 /* device views of the mailboxes in slot order: stored pose [size][7], action byte of the next tick [size] (NULL before first use) */
 const double* te_pool_mailbox_dev_pose(te_pool* p);

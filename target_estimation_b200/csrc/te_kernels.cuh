@@ -584,7 +584,8 @@ struct MailArrays {
   double* pose;
 };
 // mailboxes promoted to targets by a tick (index = AddData index; pose = AddData::p0, act = ACT_UPDATE); sec == nullptr:
-// targets added outside the tick get an empty mailbox (stamp 0, nothing readable)
+// targets added outside the tick have NO mailbox (action ACT_NONE: the tick does not touch them, as the reference's loop over
+// its mailboxes does not; the first record creates it)
 struct MailAdd {
   const uint32_t* sec;
   const uint32_t* nsec;
@@ -648,22 +649,58 @@ __global__ void mb_move_kernel(int n_new, const int* __restrict__ srcmap, MailAr
     const int k = -1 - s;
     nw.sec[d] = add.sec ? add.sec[k] : 0u;
     nw.nsec[d] = add.sec ? add.nsec[k] : 0u;
-    nw.act[d] = (uint8_t)(add.sec ? ACT_UPDATE : ACT_PREDICT);
+    nw.act[d] = (uint8_t)(add.sec ? ACT_UPDATE : ACT_NONE);
     if (add.sec) new_last_meas[d] = add.last[k];
 #pragma unroll
     for (int e = 0; e < 7; ++e) nw.pose[(size_t)d * 7 + e] = add_p0 ? add_p0[(size_t)k * 7 + e] : (e == 6 ? 1.0 : 0.0);
   }
 }
-// empty mailboxes for slots [base, base + n) (targets appended outside the tick)
+// no mailbox yet for slots [base, base + n) (targets appended outside the tick)
 __global__ void mb_clear_kernel(MailArrays mb, int base, int n) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int d = base + k;
   mb.sec[d] = 0u;
   mb.nsec[d] = 0u;
-  mb.act[d] = (uint8_t)ACT_PREDICT;
+  mb.act[d] = (uint8_t)ACT_NONE;
 #pragma unroll
   for (int e = 0; e < 7; ++e) mb.pose[(size_t)d * 7 + e] = (e == 6 ? 1.0 : 0.0);
+}
+// number of slots that have a mailbox (action != ACT_NONE)
+__global__ void mb_count_kernel(const uint8_t* __restrict__ act, int n, int* counter) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned m = __ballot_sync(0xFFFFFFFFu, s < n && act[s] != (uint8_t)ACT_NONE);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(counter, __popc(m));
+}
+// mailboxes of listed slots -> packed records (sec, nsec, act, last, pose) for the host (a target erased by hand keeps its
+// mailbox in the reference: it moves to the host's target-less map)
+__global__ void mb_gather_kernel(int n, const int* __restrict__ slots, MailArrays mb, const double* __restrict__ last_meas, uint32_t* __restrict__ sec,
+                                 uint32_t* __restrict__ nsec, uint8_t* __restrict__ act, double* __restrict__ last, double* __restrict__ pose) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int s = slots[k];
+  if (s < 0) { act[k] = 0xFF; return; }
+  sec[k] = mb.sec[s];
+  nsec[k] = mb.nsec[s];
+  act[k] = mb.act[s];
+  last[k] = last_meas[s];
+#pragma unroll
+  for (int e = 0; e < 7; ++e) pose[(size_t)k * 7 + e] = mb.pose[(size_t)s * 7 + e];
+}
+// the reverse: host mailboxes attached to the slots of targets that were just created by hand
+__global__ void mb_scatter_kernel(int n, const int* __restrict__ slots, const uint32_t* __restrict__ sec, const uint32_t* __restrict__ nsec,
+                                  const uint8_t* __restrict__ act, const double* __restrict__ last, const double* __restrict__ pose, MailArrays mb,
+                                  double* __restrict__ last_meas) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int s = slots[k];
+  if (s < 0) return;
+  mb.sec[s] = sec[k];
+  mb.nsec[s] = nsec[k];
+  mb.act[s] = act[k];
+  last_meas[s] = last[k];
+#pragma unroll
+  for (int e = 0; e < 7; ++e) mb.pose[(size_t)s * 7 + e] = pose[(size_t)k * 7 + e];
 }
 
 // lower triangle <- upper triangle (before a full-matrix kernel runs on a pool whose last steps were packed)

@@ -689,6 +689,65 @@ int* lookup_slots(te_pool* p, const uint32_t* d_ids, long long n) {
   return slots;
 }
 
+// A target erased by hand keeps its mailbox in the reference (TargetManager::erase does not know the adapter's map,
+// src/target_manager.cpp:227-241): the mailboxes of the listed slots move to the host's target-less map before the compaction.
+void demote_mailboxes(te_pool* p, const uint32_t* ids, const int* d_slots, long long n) {
+  uint32_t* d_sec = p->arena.get_n<uint32_t>((size_t)n);
+  uint32_t* d_nsec = p->arena.get_n<uint32_t>((size_t)n);
+  uint8_t* d_act = p->arena.get_n<uint8_t>((size_t)n);
+  double* d_last = p->arena.get_n<double>((size_t)n);
+  double* d_pose = p->arena.get_n<double>((size_t)n * 7);
+  te::mb_gather_kernel<<<cdiv(n, 256), 256, 0, p->stream>>>((int)n, d_slots, p->mb[p->mb_cur].a, p->buf[p->cur].cold.last_meas, d_sec, d_nsec, d_act,
+                                                            d_last, d_pose);
+  CK(cudaGetLastError());
+  std::vector<uint32_t> sec((size_t)n), nsec((size_t)n);
+  std::vector<uint8_t> act((size_t)n);
+  std::vector<double> last((size_t)n), pose((size_t)n * 7);
+  CK(cudaMemcpyAsync(sec.data(), d_sec, (size_t)n * 4, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaMemcpyAsync(nsec.data(), d_nsec, (size_t)n * 4, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaMemcpyAsync(act.data(), d_act, (size_t)n, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaMemcpyAsync(last.data(), d_last, (size_t)n * 8, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaMemcpyAsync(pose.data(), d_pose, (size_t)n * 56, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  for (long long k = 0; k < n; ++k) {
+    if (act[(size_t)k] == 0xFF || act[(size_t)k] == (uint8_t)TE_ACT_NONE) continue;   // unknown id / target without a mailbox
+    HostMail& m = p->orphans[ids[k]];
+    m.sec = sec[(size_t)k];
+    m.nsec = nsec[(size_t)k];
+    m.last = last[(size_t)k];
+    m.fresh = act[(size_t)k] == (uint8_t)TE_ACT_UPDATE;
+    std::memcpy(m.pose, &pose[(size_t)k * 7], sizeof(m.pose));
+  }
+}
+// ... and a target created by hand for an id that already has a (target-less) mailbox is fed by it from the next tick on
+void attach_mailboxes(te_pool* p, const uint32_t* ids, long long n) {
+  std::vector<uint32_t> a_ids, sec, nsec;
+  std::vector<uint8_t> act;
+  std::vector<double> last, pose;
+  for (long long k = 0; k < n; ++k) {
+    auto it = p->orphans.find(ids[k]);
+    if (it == p->orphans.end()) continue;
+    const HostMail& m = it->second;
+    a_ids.push_back(ids[k]);
+    sec.push_back(m.sec);
+    nsec.push_back(m.nsec);
+    act.push_back((uint8_t)(m.fresh ? TE_ACT_UPDATE : TE_ACT_PREDICT));
+    last.push_back(m.last);
+    pose.insert(pose.end(), m.pose, m.pose + 7);
+    p->orphans.erase(it);
+  }
+  const long long na = (long long)a_ids.size();
+  if (na == 0) return;
+  uint32_t* d_ids = to_dev(p, a_ids.data(), (size_t)na);
+  int* slots = lookup_slots(p, d_ids, na);
+  te::mb_scatter_kernel<<<cdiv(na, 256), 256, 0, p->stream>>>((int)na, slots, to_dev(p, sec.data(), (size_t)na), to_dev(p, nsec.data(), (size_t)na),
+                                                              to_dev(p, act.data(), (size_t)na), to_dev(p, last.data(), (size_t)na),
+                                                              to_dev(p, pose.data(), (size_t)na * 7), p->mb[p->mb_cur].a,
+                                                              p->buf[p->cur].cold.last_meas);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(p->stream));   // the host vectors above go out of scope
+}
+
 template <class F> int guarded(te_pool* p, F&& f) {
   try {
     if (!p) throw std::invalid_argument("null pool");
@@ -980,6 +1039,7 @@ long long te_pool_add_batch(te_pool* p, long long n, const uint32_t* ids, const 
       p->h_ids.swap(merged);
       p->h_ids_valid = true;
     }
+    if (p->mb_on && !p->orphans.empty()) attach_mailboxes(p, s_ids, na);
     CK(cudaStreamSynchronize(p->stream));   // host payload vectors go out of scope
     return na;
   });
@@ -992,6 +1052,7 @@ long long te_pool_erase_batch(te_pool* p, long long n, const uint32_t* ids) {
     ensure_work(p, (size_t)p->n);
     uint32_t* d_ids = to_dev(p, ids, n);
     int* slots = lookup_slots(p, d_ids, n);
+    if (p->mb_on) demote_mailboxes(p, ids, slots, n);
     te::fill_i32_kernel<<<cdiv(p->n, 256), 256, 0, p->stream>>>(p->alive, (int)p->n, 1);
     te::clear_listed_kernel<<<cdiv(n, 256), 256, 0, p->stream>>>(p->alive, slots, n);
     CK(cudaGetLastError());
@@ -1479,11 +1540,12 @@ int te_pool_mailbox_ingest(te_pool* p, long long n, const uint32_t* ids, const u
   });
 }
 
-long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, uint32_t now_sec, uint32_t now_nsec, double timeout, uint32_t* erased_out,
-                               long long cap, long long* n_added_out) {
+long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, int cls_new, uint32_t now_sec, uint32_t now_nsec, double timeout,
+                               uint32_t* erased_out, long long cap, uint32_t* added_out, long long added_cap, long long* n_added_out) {
   return guarded_ll(p, [&]() -> long long {
     if (!(dt >= 0.0)) throw std::invalid_argument("dt must be >= 0 (assert of src/target_interface.cpp:150)");
     if (p->hQ.empty()) throw std::runtime_error("no model class registered");
+    if (cls_new < 0 || cls_new >= (int)p->hQ.size()) throw std::invalid_argument("unknown model class for the new targets");
     enable_mail(p);
     static const bool dbg = std::getenv("TE_MB_DEBUG") != nullptr;
     auto wall = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -1516,6 +1578,7 @@ long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, uint32_t no
     const int n_add = (int)add_ids.size();
     const int n_old = (int)p->n;
     if (n_added_out) *n_added_out = n_add;
+    if (added_out && added_cap > 0 && n_add > 0) std::memcpy(added_out, add_ids.data(), (size_t)std::min<long long>(added_cap, n_add) * sizeof(uint32_t));
     mark(1);
     // 2. expiry flags of the existing targets, then ONE stable rebuild: survivors compacted, promoted mailboxes merged in by id
     ensure_work(p, (size_t)n_old + (size_t)n_add);
@@ -1527,8 +1590,13 @@ long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, uint32_t no
       d_erased = p->arena.get_n<uint32_t>((size_t)n_old);
     }
     te::AddData ad{};
+    std::vector<uint16_t> add_cls;
     if (n_add > 0) {
       ad.ids = to_dev(p, add_ids.data(), (size_t)n_add);
+      if (cls_new != 0) {
+        add_cls.assign((size_t)n_add, (uint16_t)cls_new);
+        ad.cls = to_dev(p, add_cls.data(), (size_t)n_add);
+      }
       ad.t0 = to_dev(p, add_t0.data(), (size_t)n_add);
       ad.p0 = to_dev(p, add_pose.data(), (size_t)n_add * 7);
       p->mb_add.sec = to_dev(p, add_sec.data(), (size_t)n_add);
@@ -1581,7 +1649,20 @@ long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, uint32_t no
   });
 }
 
-long long te_pool_mailbox_count(te_pool* p) { return p ? p->n + (long long)p->orphans.size() : -1; }
+long long te_pool_mailbox_count(te_pool* p) {
+  return guarded_ll(p, [&]() -> long long {
+    long long n = (long long)p->orphans.size();
+    if (!p->mb_on || p->n == 0) return n;
+    int* counter = p->arena.get_n<int>(1);
+    CK(cudaMemsetAsync(counter, 0, sizeof(int), p->stream));
+    te::mb_count_kernel<<<cdiv(p->n, 256), 256, 0, p->stream>>>(p->mb[p->mb_cur].a.act, (int)p->n, counter);
+    CK(cudaGetLastError());
+    int c = 0;
+    CK(cudaMemcpyAsync(&c, counter, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return n + c;
+  });
+}
 
 const double* te_pool_mailbox_dev_pose(te_pool* p) { return (p && p->mb_on) ? p->mb[p->mb_cur].a.pose : nullptr; }
 const uint8_t* te_pool_mailbox_dev_action(te_pool* p) { return (p && p->mb_on) ? p->mb[p->mb_cur].a.act : nullptr; }

@@ -1,6 +1,8 @@
 // tick_manager.cpp -- RosTargetManager's tick / mailbox / expiry semantics without ROS
 // (/root/reference/include/target_estimation/target_manager_ros.hpp:74-134, src/target_manager_ros.cpp:6-107),
 // driving the device pool with one batch per tick instead of one call per id.
+#include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <stdexcept>
 
@@ -41,51 +43,87 @@ void TickTargetManager::setExpirationTime(double t) {
   expiration_time_ = t;
 }
 
+// The mailboxes live on the device, beside the slots of the pool of type_ (te_pool_mailbox_*, include/te_pool.h).  Only ids
+// the manager knows under ANOTHER model type (created by hand through TargetManager::init) cannot be fed from that pool:
+// they keep a host Measurement in measurements_ and go through the by-id loop of tickForeign().
+te_pool* TickTargetManager::tickPool() {
+  te_pool* pool = poolOf((int)type_, true);
+  if (cls_ < 0) cls_ = registerClass((int)type_, Q_, R_, P_);
+  return pool;
+}
+
 void TickTargetManager::measurementCallBack(long long n, const char* const* frames, const uint32_t* sec, const uint32_t* nsec,
                                             const double* poses) {   // :26-39
   std::lock_guard<std::recursive_mutex> lg(target_lock_);
+  // frame names -> ids; the loop ends at the first frame that carries the token but does not parse (e.g. the node's own
+  // "<token>_filt_<id>" output frames); frames without the token are skipped
+  std::vector<unsigned> ids;
+  std::vector<uint32_t> s, ns;
+  std::vector<double> p;
+  ids.reserve((size_t)n); s.reserve((size_t)n); ns.reserve((size_t)n); p.reserve((size_t)n * 7);
   for (long long i = 0; i < n; ++i) {
     const std::string name(frames[i]);
     if (name.find(token_name_) != std::string::npos) {
       unsigned id;
-      if (!getId(name, id)) break;   // e.g. the node's own "<token>_filt_<id>" output frames
-      StampedPose tr;
-      tr.sec = sec[i];
-      tr.nsec = nsec[i];
-      std::memcpy(tr.pose.data(), poses + 7 * i, 7 * sizeof(double));
-      measurements_[id].update(tr);
+      if (!getId(name, id)) break;
+      ids.push_back(id);
+      s.push_back(sec[i]);
+      ns.push_back(nsec[i]);
+      p.insert(p.end(), poses + 7 * i, poses + 7 * i + 7);
     }
   }
+  measurementCallBackIds((long long)ids.size(), ids.data(), s.data(), ns.data(), p.data());
 }
 
 void TickTargetManager::measurementCallBackIds(long long n, const unsigned* ids, const uint32_t* sec, const uint32_t* nsec,
                                                const double* poses) {
   std::lock_guard<std::recursive_mutex> lg(target_lock_);
-  for (long long i = 0; i < n; ++i) {
-    StampedPose tr;
-    tr.sec = sec[i];
-    tr.nsec = nsec[i];
-    std::memcpy(tr.pose.data(), poses + 7 * i, 7 * sizeof(double));
-    measurements_[ids[i]].update(tr);
+  if (n <= 0) return;
+  flushLocked();
+  te_pool* pool = tickPool();
+  const bool foreign_possible = !measurements_.empty() || targets_.size() != (size_t)te_pool_size(pool);
+  if (!foreign_possible) {   // the whole message in one call: lookup, stable sort by slot, per-slot Measurement::update on the device
+    if (te_pool_mailbox_ingest(pool, n, ids, sec, nsec, poses) < 0) throw std::runtime_error(te_last_error());
+    return;
   }
+  std::vector<unsigned> d_ids;
+  std::vector<uint32_t> d_sec, d_nsec;
+  std::vector<double> d_pose;
+  for (long long i = 0; i < n; ++i) {
+    auto it = targets_.find(ids[i]);
+    const bool foreign = (it != targets_.end() && it->second != (uint8_t)type_) || measurements_.count(ids[i]);
+    if (foreign) {
+      StampedPose tr;
+      tr.sec = sec[i];
+      tr.nsec = nsec[i];
+      std::memcpy(tr.pose.data(), poses + 7 * i, 7 * sizeof(double));
+      measurements_[ids[i]].update(tr);
+    } else {
+      d_ids.push_back(ids[i]);
+      d_sec.push_back(sec[i]);
+      d_nsec.push_back(nsec[i]);
+      d_pose.insert(d_pose.end(), poses + 7 * i, poses + 7 * i + 7);
+    }
+  }
+  if (!d_ids.empty() && te_pool_mailbox_ingest(pool, (long long)d_ids.size(), d_ids.data(), d_sec.data(), d_nsec.data(), d_pose.data()) < 0)
+    throw std::runtime_error(te_last_error());
 }
 
-void TickTargetManager::tick(const double& dt, uint32_t now_sec, uint32_t now_nsec, std::vector<unsigned>* erased) {   // :41-92
-  std::lock_guard<std::recursive_mutex> lg(target_lock_);
-  if (!(dt >= 0.0)) throw std::invalid_argument("dt must be >= 0");
-  flushLocked();
+// by-id tick for the host mailboxes of measurements_ (ids living in a pool of another model type): the reference's loop
+// (:46-76) turned into one add, one sparse step launch and one expiry call
+void TickTargetManager::tickForeign(const double& dt, uint32_t now_sec, uint32_t now_nsec, std::vector<unsigned>& gone_out) {
   const size_t nm = measurements_.size();
-  // 1. walk the mailboxes in ascending id order (std::map) and turn the per-id decisions into batches
-  std::vector<unsigned> new_ids, step_ids, stamp_ids;
+  std::vector<unsigned> new_ids, step_ids;
   std::vector<double> new_p0, step_meas;
   std::vector<uint8_t> step_act;
-  std::vector<uint32_t> stamp_sec, stamp_nsec;
-  new_ids.reserve(16); step_ids.reserve(nm); step_meas.reserve(nm * 7); step_act.reserve(nm);
-  stamp_ids.reserve(nm); stamp_sec.reserve(nm); stamp_nsec.reserve(nm);
+  step_ids.reserve(nm); step_meas.reserve(nm * 7); step_act.reserve(nm);
+  const double now = toSec(now_sec, now_nsec);
+  std::vector<unsigned> expired;
   for (auto& kv : measurements_) {
     const unsigned id = kv.first;
     StampedPose tr;
     const bool known = targets_.count(id) != 0;
+    const double last = kv.second.getTime();
     if (kv.second.read(tr)) {
       if (!known) {   // target does not exist: create it from the measurement (:54-58), then update with the same one
         new_ids.push_back(id);
@@ -101,43 +139,58 @@ void TickTargetManager::tick(const double& dt, uint32_t now_sec, uint32_t now_ns
     } else if (!quiet) {
       std::printf("Target(%u) does not exist!\n", id);   // TargetManager::update(id,dt) on an unknown id (:209)
     }
-    if (kv.second.stampDirty() && (known || !new_ids.empty() && new_ids.back() == id)) {
-      // the device keeps the same last_meas_time_ for the expiry predicate: push accepted stamps that changed
-      stamp_ids.push_back(id);
-      stamp_sec.push_back(kv.second.acceptedSec());
-      stamp_nsec.push_back(kv.second.acceptedNsec());
-      kv.second.clearStampDirty();
-    }
+    if (last > 0.0 && (now - last) >= expiration_time_) expired.push_back(id);   // :67
   }
-  // 2. init on first sight: p0 = the measurement, t0 = t_, v0 = a0 = 0 (:57)
-  if (!new_ids.empty()) {
+  if (!new_ids.empty()) {   // init on first sight: p0 = the measurement, t0 = t_, v0 = a0 = 0 (:57)
     std::vector<double> t0(new_ids.size(), t_);
     const bool q = quiet;
-    quiet = true;   // one message per tick instead of one per target
+    quiet = true;
     initBatch(type_, Q_, R_, P_, (long long)new_ids.size(), new_ids.data(), dt, t0.data(), new_p0.data());
     quiet = q;
   }
-  // 3. one launch: update where a (possibly stale) measurement is readable, predict elsewhere (:59,:64)
   if (!step_ids.empty()) updateBatch((long long)step_ids.size(), step_ids.data(), dt, step_meas.data(), step_act.data());
-  // 4. expiry: last_meas_time > 0 && (now - last_meas_time) >= expiration_time_, evaluated on the device (:67-72)
-  te_pool* pool = poolOf((int)type_, false);
-  std::vector<uint32_t> gone;
-  if (pool && te_pool_size(pool) > 0) {
-    if (!stamp_ids.empty() &&
-        te_pool_set_stamps(pool, (long long)stamp_ids.size(), stamp_ids.data(), stamp_sec.data(), stamp_nsec.data()) < 0)
-      throw std::runtime_error(te_last_error());
-    gone.resize((size_t)te_pool_size(pool));
-    long long n_gone = te_pool_expire(pool, now_sec, now_nsec, expiration_time_, gone.data(), (long long)gone.size());
-    if (n_gone < 0) throw std::runtime_error(te_last_error());
-    gone.resize((size_t)n_gone);
-    for (uint32_t id : gone) {
-      if (!quiet) std::printf("Timeout for target %u\n", id);
-      measurements_.erase(id);
-      targets_.erase(id);
+  for (unsigned id : expired) {   // :69-71: the mailbox and the target go
+    if (!quiet) std::printf("Timeout for target %u\n", id);
+    measurements_.erase(id);
+    const bool q = quiet;
+    quiet = true;
+    erase(id);
+    quiet = q;
+    gone_out.push_back(id);
+  }
+  flushLocked();
+}
+
+void TickTargetManager::tick(const double& dt, uint32_t now_sec, uint32_t now_nsec, std::vector<unsigned>* erased) {   // :41-92
+  std::lock_guard<std::recursive_mutex> lg(target_lock_);
+  if (!(dt >= 0.0)) throw std::invalid_argument("dt must be >= 0");
+  flushLocked();
+  te_pool* pool = tickPool();
+  // 1. the device tick: first-sight init, sticky update / predict, expiry -- one rebuild + one step launch (:46-76)
+  const long long cap = std::max<long long>(te_pool_mailbox_count(pool), 1);
+  std::vector<uint32_t> gone((size_t)cap), born((size_t)cap);
+  long long n_born = 0;
+  const long long n_gone = te_pool_mailbox_tick(pool, dt, t_, cls_, now_sec, now_nsec, expiration_time_, gone.data(), cap, born.data(), cap, &n_born);
+  if (n_gone < 0) throw std::runtime_error(te_last_error());
+  gone.resize((size_t)n_gone);
+  born.resize((size_t)std::min(n_born, cap));
+  for (uint32_t id : born) targets_.emplace_hint(targets_.end(), id, (uint8_t)type_);
+  for (uint32_t id : gone) {
+    if (!quiet) std::printf("Timeout for target %u\n", id);
+    targets_.erase(id);   // (a target-less mailbox that expired has no entry here)
+  }
+  // 2. host mailboxes of ids living under another model type, if any
+  if (!measurements_.empty()) {
+    std::vector<unsigned> gone2;
+    tickForeign(dt, now_sec, now_nsec, gone2);
+    if (!gone2.empty()) {
+      std::vector<uint32_t> all(gone.size() + gone2.size());
+      std::merge(gone.begin(), gone.end(), gone2.begin(), gone2.end(), all.begin());
+      gone.swap(all);
     }
   }
   if (erased) erased->assign(gone.begin(), gone.end());
-  // 5. the filtered poses the node broadcasts (:76-87)
+  // 3. the filtered poses the node broadcasts (:76-87)
   pub_ids_.clear();
   pub_poses_.clear();
   if (publish) {
@@ -146,6 +199,14 @@ void TickTargetManager::tick(const double& dt, uint32_t now_sec, uint32_t now_ns
     if (!pub_ids_.empty()) getEstimatesBatch((long long)pub_ids_.size(), pub_ids_.data(), nullptr, pub_poses_.data(), nullptr, nullptr, nullptr);
   }
   t_ = t_ + dt;   // :89
+}
+
+size_t TickTargetManager::mailboxCount() {
+  std::lock_guard<std::recursive_mutex> lg(target_lock_);
+  te_pool* pool = poolOf((int)type_, false);
+  const long long n = pool ? te_pool_mailbox_count(pool) : 0;
+  if (n < 0) throw std::runtime_error(te_last_error());
+  return (size_t)n + measurements_.size();
 }
 
 }  // namespace target_estimation_b200

@@ -239,15 +239,19 @@ class TargetPool:
         poses = _np(poses, np.float64, (ids.size, 7))
         check(lib.te_pool_mailbox_ingest(self._h, ids.size, _ptr(ids), _ptr(sec), _ptr(nsec), _ptr(poses)))
 
-    def mailbox_tick(self, dt, t0_new, now, timeout):
-        """RosTargetManager::update(dt) (src/target_manager_ros.cpp:41-76); now = (sec, nsec).  Returns (erased ids, #added)."""
+    def mailbox_tick(self, dt, t0_new, now, timeout, cls_new=0, want_added=False):
+        """RosTargetManager::update(dt) (src/target_manager_ros.cpp:41-76); now = (sec, nsec).  Returns (erased ids, #added), or
+        (erased ids, added ids) with want_added."""
         cap = int(lib.te_pool_mailbox_count(self._h))
         buf = getattr(self, "_erase_buf", None)
         if buf is None or buf.size < cap:
             buf = self._erase_buf = np.empty(max(cap + cap // 4, 1), dtype=np.uint32)
         added = C.c_longlong(0)
-        n = check(lib.te_pool_mailbox_tick(self._h, float(dt), float(t0_new), int(now[0]), int(now[1]), float(timeout), _ptr(buf), cap,
-                                           C.byref(added)))
+        abuf = np.empty(max(cap, 1), dtype=np.uint32) if want_added else None
+        n = check(lib.te_pool_mailbox_tick(self._h, float(dt), float(t0_new), int(cls_new), int(now[0]), int(now[1]), float(timeout), _ptr(buf), cap,
+                                           _ptr(abuf), cap if want_added else 0, C.byref(added)))
+        if want_added:
+            return buf[:n].copy(), abuf[:int(added.value)].copy()
         return buf[:n].copy(), int(added.value)
 
     def mailbox_count(self):

@@ -144,45 +144,43 @@ def test_mailbox_quirks_match_oracle_tick():
     pool.close(); L.orc_manager_delete(h)
 
 
-def test_mailbox_pool_survives_direct_add_erase_and_expire():
-    """the mailboxes follow their slots through the other compaction paths (te_pool_erase_batch, te_pool_add_batch merge and
-    append); directly added targets carry an empty mailbox and are predicted"""
+def test_mailboxes_and_by_hand_calls_interplay_like_the_reference():
+    """TargetManager::erase / init by hand on a manager whose mailboxes live on the device: an erased target keeps its mailbox
+    (still readable -> the next tick re-creates the target from the stored pose); a target created by hand has no mailbox and
+    is not touched by the tick; one created by hand for an id that already has a target-less mailbox is fed by it (here an
+    unreadable one: predicted every tick).  The mailboxes follow their slots through te_pool_erase_batch and both
+    te_pool_add_batch paths (merge, append)."""
     import target_estimation_b200 as te
     pool, L, h, N = _pair("uniform_velocity")
-    ref = orc.Manager()
     mtype, _, Q, R, P0 = te.load_model("uniform_velocity")
+    ref = orc.Manager.__new__(orc.Manager); ref.L = L; ref.h = h      # the by-hand API of the oracle's tick manager
+    L.orc_tick_set_expiration(h, 1000.0)
     rng = np.random.default_rng(1)
     pose = lambda n: np.hstack([rng.normal(size=(n, 3)), np.tile([0, 0, 0, 1.0], (n, 1))])
     ids = np.arange(100, 400, 3, dtype=np.uint32)
-    now = 50 * 10**9
     p0 = pose(ids.size)
-    pool.mailbox_ingest(ids, np.full(ids.size, 50), np.zeros(ids.size), p0)
-    pool.mailbox_tick(DT, 0.0, (50, 0), 1000.0)
-    for j, i in enumerate(ids):
-        ref.init_full(mtype, int(i), DT, 0.0, Q, R, P0, p0[j]); ref.update_meas(int(i), DT, p0[j])
-    # direct erase of a few, direct add in the middle of the id range and beyond the end
+    _deliver(pool, L, h, np.concatenate([ids, [5000]]), [(50, 0)] * ids.size + [(0, 0)], np.concatenate([p0, pose(1)]))
+    _tick(pool, L, h, 0, 0.0, 50 * 10**9, 1000.0)
+    assert len(pool) == ids.size and pool.mailbox_count() == ids.size + 1
     gone = ids[5:20]
     assert pool.erase(gone) == gone.size
     for g in gone:
-        ref.erase(int(g))
+        assert ref.erase(int(g))
+    assert pool.mailbox_count() == ids.size + 1 == L.orc_tick_mailboxes(h)
     mid = np.array([101, 251, 252, 5000, 5001], dtype=np.uint32); pm = pose(mid.size)
     assert pool.add(mid, pm, t0=np.full(mid.size, DT)) == mid.size
     for j, i in enumerate(mid):
         ref.init_full(mtype, int(i), DT, DT, Q, R, P0, pm[j])
-    keep = np.array([i for i in ids if i not in set(gone.tolist())], dtype=np.uint32)
-    for k in range(1, 6):
-        # the mailbox targets re-apply their stored pose (sticky flag); the directly added ones are predicted
-        pool.mailbox_tick(DT, k * DT, (50, k * 4_000_000), 1000.0)
-        for j, i in enumerate(ids):
-            if i in keep:
-                ref.update_meas(int(i), DT, p0[j])
-        for i in mid:
-            ref.update(int(i), DT)
-    live = pool.ids()
-    assert np.array_equal(live, ref.ids())
-    got, want = pool.read_state(), ref.states(live, N)
-    assert synth.compare_h2(got["x"], want["x"]) <= 1.0 and synth.compare_h2(got["P"], want["P"]) <= 1.0
-    assert np.array_equal(got["n_meas"], want["n_meas"]) and np.array_equal(got["t"], want["t"])
+    t_tick = DT
+    for k in range(1, 7):
+        if k == 4:   # a record for a by-hand target creates its mailbox
+            _deliver(pool, L, h, [251], [(50, k * 4_000_000)], pose(1))
+        erased, added = _tick(pool, L, h, k, t_tick, 50 * 10**9 + k * 4_000_000, 1000.0)
+        assert added == (gone.size if k == 1 else 0) and erased.size == 0
+        t_tick = t_tick + DT
+        _compare_states(pool, L, h, N)
+    got = pool.read_state(mid)
+    assert got["n_meas"].tolist() == [0, 3, 0, 0, 0] and got["t"][0] == DT and got["t"][3] > 6 * DT    # 5000 predicted, 101 untouched
     with pytest.raises(te.TeError):
         pool.step_dense_expire(DT, None, 7, None, te.ACT_PREDICT, (50, 0), (50, 0), 1.0)
-    pool.close(); L.orc_manager_delete(h)
+    pool.close(); L.orc_manager_delete(h); ref.h = None
