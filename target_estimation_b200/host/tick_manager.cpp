@@ -33,8 +33,9 @@ void Measurement::update(const StampedPose& tr) {   // target_manager_ros.hpp:96
 TickTargetManager::TickTargetManager(target_t type, const MatrixXd& Q, const MatrixXd& R, const MatrixXd& P, int device)
     : TargetManager(device), type_(type), Q_(Q), P_(P), R_(R), token_name_("target"), t_(0.0), expiration_time_(1000.0) {}   // :6-24
 
+// (a manager built from a model file also carries it as its default model, like TargetManager(file): by-hand init(id, ...) works)
 TickTargetManager::TickTargetManager(const std::string& yaml_file, int device)
-    : TargetManager(device), type_(UNIFORM_VELOCITY), token_name_("target"), t_(0.0), expiration_time_(1000.0) {
+    : TargetManager(yaml_file, device), type_(UNIFORM_VELOCITY), token_name_("target"), t_(0.0), expiration_time_(1000.0) {
   if (!loadYamlFile(yaml_file, Q_, R_, P_, type_)) throw std::runtime_error("Can not load the Cov Matrices!");   // :19-23
 }
 

@@ -80,3 +80,53 @@ def test_tick_semantics(name):
         assert synth.compare_h2(st["x"][None], x[None]) <= 1.0 and synth.compare_h2(st["P"][None], P[None]) <= 1.0
         assert st["t"] == t.value and mgr.get_n_measurements(int(i)) == nm.value
     mgr.close()
+
+
+def test_tick_manager_by_hand_erase_and_init_like_the_reference():
+    """target_manager_erase / target_manager_init on a tick manager: the erased target's mailbox survives (sticky, readable ->
+    the target is re-created on the next tick from the stored pose, with t0 = the manager clock); a target created by hand is
+    not stepped by the tick until its first /tf record."""
+    from target_estimation_b200.manager import TickManagerC
+    path = os.path.join(ROOT, "models", "model_uniform_acceleration_params.yaml")
+    y = orc.load_yaml(path)
+    N = y["Q"].shape[0]
+    L = orc.lib()
+    h = L.orc_tick_new(y["type"], orc.ptr(orc.colmajor(y["Q"])), N, orc.ptr(orc.colmajor(y["R"])), y["R"].shape[0], orc.ptr(orc.colmajor(y["P"])))
+    ref = orc.Manager.__new__(orc.Manager); ref.L = L; ref.h = h
+    mgr = TickManagerC(path)
+    rng = np.random.default_rng(9)
+    ids = np.array([3, 8, 21, 34, 55], dtype=np.uint32)
+    pose = lambda n: np.hstack([rng.normal(size=(n, 3)), np.tile([0, 0, 0, 1.0], (n, 1))])
+
+    def deliver(which, k):
+        st = np.tile(np.array(_stamp(k), dtype=np.uint32), (len(which), 1)); ps = pose(len(which))
+        w = np.ascontiguousarray(which, dtype=np.uint32)
+        L.orc_tick_callback_ids(h, w.size, orc.ptr(w), orc.ptr(np.ascontiguousarray(st)), orc.ptr(ps))
+        mgr.callback_ids(w, st[:, 0].copy(), st[:, 1].copy(), ps)
+
+    for k in range(12):
+        if k < 3 or k == 9:
+            deliver(ids if k < 3 else [13], k)
+        if k == 4:      # by hand: erase 8 and 34 (their mailboxes stay), create 13 (no mailbox until k = 9)
+            for i in (8, 34):
+                assert mgr.erase(i) and ref.erase(i)
+            p13 = pose(1)[0]
+            mgr.init(13, DT, p13, 0.25)
+            ref.init_full(y["type"], 13, DT, 0.25, y["Q"], y["R"], y["P"], p13)
+        sec, nsec = _stamp(k)
+        er_ref = np.zeros(64, dtype=np.uint32)
+        n_er = L.orc_tick_update(h, DT, sec, nsec, orc.ptr(er_ref), 64)
+        er = mgr.tick(DT, sec, nsec)
+        assert n_er == er.size == 0
+        ref_ids = np.zeros(64, dtype=np.uint32)
+        n_ref = L.orc_get_ids(h, orc.ptr(ref_ids), 64)
+        assert np.array_equal(mgr.ids(), ref_ids[:n_ref]), k
+        assert mgr.mailboxes() == L.orc_tick_mailboxes(h), k
+        for i in ref_ids[:n_ref]:
+            x = np.zeros(N); P = np.zeros((N, N)); t = C.c_double(); nm = C.c_longlong()
+            L.orc_get_state(h, int(i), orc.ptr(x), orc.ptr(P), C.byref(t), C.byref(nm), None)
+            st = mgr.state(int(i))
+            assert synth.compare_h2(st["x"][None], x[None]) <= 1.0 and synth.compare_h2(st["P"][None], P[None]) <= 1.0, (k, i)
+            assert st["t"] == t.value and mgr.get_n_measurements(int(i)) == nm.value, (k, i)
+    assert mgr.ids().tolist() == [3, 8, 13, 21, 34, 55] and mgr.get_n_measurements(8) == 8 and mgr.get_n_measurements(13) == 3
+    mgr.close(); ref.h = None; L.orc_manager_delete(h)
