@@ -666,6 +666,60 @@ __global__ void mb_clear_kernel(MailArrays mb, int base, int n) {
 #pragma unroll
   for (int e = 0; e < 7; ++e) mb.pose[(size_t)d * 7 + e] = (e == 6 ? 1.0 : 0.0);
 }
+// ---- fused mailbox tick: the step kernel itself moves the survivors (StepArgs::dst_*), so the merge only needs the
+// destination of every old slot and of every new id ----
+// new id k -> its slot in the merged order (k + #surviving old ids below it); pos = exclusive scan of alive (unmodified)
+__global__ void merge_new_dst_kernel(int n_add, const uint32_t* __restrict__ add_ids, const uint32_t* __restrict__ old_ids, int n_old,
+                                     const int* __restrict__ pos, int total_alive, int* __restrict__ new_dst) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_add) return;
+  int e = lower_bound_u32(old_ids, n_old, add_ids[k]);
+  new_dst[k] = k + ((e < n_old) ? pos[e] : total_alive);
+}
+// surviving old slot s -> pos[s] + #new ids below its id (in place; run after merge_new_dst_kernel / collect_erased_kernel)
+__global__ void merge_old_dst_kernel(int n_old, const int* __restrict__ alive, int* __restrict__ pos, const uint32_t* __restrict__ old_ids,
+                                     const uint32_t* __restrict__ add_ids, int n_add) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_old || !alive[s]) return;
+  pos[s] += lower_bound_u32(add_ids, n_add, old_ids[s]);
+}
+// mailboxes of the survivors -> their destination slots
+__global__ void mb_compact_kernel(int n_old, const int* __restrict__ alive, const int* __restrict__ pos, MailArrays o, MailArrays nw) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_old || !alive[s]) return;
+  const int d = pos[s];
+  nw.sec[d] = o.sec[s];
+  nw.nsec[d] = o.nsec[s];
+  nw.act[d] = o.act[s];
+#pragma unroll
+  for (int e = 0; e < 7; ++e) nw.pose[(size_t)d * 7 + e] = o.pose[(size_t)s * 7 + e];
+}
+// promoted mailboxes: init the target in its merged slot (TargetManager::init, v0 = a0 = 0), fill its mailbox, and put it on
+// the sparse work list of the follow-up launch that applies its first update (src/target_manager_ros.cpp:54-59)
+template <int TYPE>
+__global__ void init_promoted_kernel(int n_add, const int* __restrict__ new_dst, double* tiles, ColdArrays cold, AddData ad, MailAdd add, MailArrays mb,
+                                     const double* P0tab, uint8_t* act_slot, uint8_t* tile_flag, int* tile_list, int* counters) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_add) return;
+  const int d = new_dst[k];
+  init_slot<TYPE>(tiles, cold, d, ad, (long long)k, P0tab);
+  cold.last_meas[d] = add.last[k];
+  mb.sec[d] = add.sec[k];
+  mb.nsec[d] = add.nsec[k];
+  mb.act[d] = (uint8_t)ACT_UPDATE;
+#pragma unroll
+  for (int e = 0; e < 7; ++e) {
+    const double v = ad.p0[(size_t)k * 7 + e];
+    mb.pose[(size_t)d * 7 + e] = v;
+    cold.meas[(size_t)d * 7 + e] = v;   // measured_pose_ after the first update
+  }
+  act_slot[d] = (uint8_t)ACT_UPDATE;
+  const int tile = d / TILE;
+  unsigned* w = reinterpret_cast<unsigned*>(tile_flag) + (tile >> 2);
+  const unsigned bit = 1u << ((tile & 3) * 8);
+  const unsigned old = atomicOr(w, bit);
+  if (!(old & bit)) tile_list[atomicAdd(&counters[0], 1)] = tile;
+}
 // number of slots that have a mailbox (action != ACT_NONE)
 __global__ void mb_count_kernel(const uint8_t* __restrict__ act, int n, int* counter) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;

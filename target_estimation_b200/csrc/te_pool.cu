@@ -626,6 +626,21 @@ void init_append(te_pool* p, int base, const te::AddData& ad, long long n) {
   }
 }
 
+template <int TYPE>
+void init_promoted_t(te_pool* p, int n_add, const int* new_dst, const Buf& nb, const te::AddData& ad, const te::MailArrays& mb) {
+  te::init_promoted_kernel<TYPE><<<cdiv(n_add, 128), 128, 0, p->stream>>>(n_add, new_dst, nb.tiles, nb.cold, ad, p->mb_add, mb, p->dP0, p->action,
+                                                                          p->tile_flag, p->tile_list, p->d_counters);
+  CK(cudaGetLastError());
+}
+void init_promoted(te_pool* p, int n_add, const int* new_dst, const Buf& nb, const te::AddData& ad, const te::MailArrays& mb) {
+  switch (p->model) {
+    case te::UNIFORM_VELOCITY: init_promoted_t<te::UNIFORM_VELOCITY>(p, n_add, new_dst, nb, ad, mb); break;
+    case te::UNIFORM_ACCELERATION: init_promoted_t<te::UNIFORM_ACCELERATION>(p, n_add, new_dst, nb, ad, mb); break;
+    case te::ANGULAR_VELOCITIES: init_promoted_t<te::ANGULAR_VELOCITIES>(p, n_add, new_dst, nb, ad, mb); break;
+    default: init_promoted_t<te::ANGULAR_RATES>(p, n_add, new_dst, nb, ad, mb); break;
+  }
+}
+
 // after a compaction: the largest surviving id (4 bytes; the callers synchronise the stream before they return)
 void fetch_last_id(te_pool* p) {
   p->h_last_valid = false;
@@ -1603,32 +1618,116 @@ long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, int cls_new
       p->mb_add.nsec = to_dev(p, add_nsec.data(), (size_t)n_add);
       p->mb_add.last = to_dev(p, add_last.data(), (size_t)n_add);
     }
-    if (n_old > 0 || n_add > 0) {
-      int alive = 0;
-      try {
-        alive = compact_and_merge(p, ad, ad.ids, n_add, d_erased);
-      } catch (...) {
-        p->mb_add = te::MailAdd{nullptr, nullptr, nullptr};
-        throw;
+    const bool unfused_env = std::getenv("TE_MB_UNFUSED") != nullptr;   // debugging / test switch: the rebuild-then-step form
+    const bool fused = !unfused_env && n_old > 0;
+    if (!fused) {
+      // reference form: stable rebuild (survivors gathered, new ids merged in and initialised), then the step in place
+      if (n_old > 0 || n_add > 0) {
+        int alive = 0;
+        try {
+          alive = compact_and_merge(p, ad, ad.ids, n_add, d_erased);
+        } catch (...) {
+          p->mb_add = te::MailAdd{nullptr, nullptr, nullptr};
+          throw;
+        }
+        n_dev_erased = n_old - alive;
       }
-      n_dev_erased = n_old - alive;
-    }
-    p->mb_add = te::MailAdd{nullptr, nullptr, nullptr};
-    mark(2);
-    // 3. the step: update where the mailbox is readable (the flag is sticky: a silent target re-applies its last pose),
-    //    predict elsewhere (:59,:64).  The mailbox arrays are the kernel's measurement block and action array.
-    if (p->n > 0) {
+      p->mb_add = te::MailAdd{nullptr, nullptr, nullptr};
+      mark(2);
+      // 3. the step: update where the mailbox is readable (the flag is sticky: a silent target re-applies its last pose),
+      //    predict elsewhere (:59,:64).  The mailbox arrays are the kernel's measurement block and action array.
+      if (p->n > 0) {
+        te::StepArgs a = base_args(p);
+        const te::MailArrays& mb = p->mb[p->mb_cur].a;
+        a.dt = dt;
+        a.meas = mb.pose;
+        a.meas_stride = 7;
+        a.meas_tma = 1;
+        a.action = mb.act;
+        a.default_action = TE_ACT_PREDICT;
+        launch_step(p, a, a.n_tiles);
+        te::copy_meas_masked_kernel<<<cdiv(p->n, 256), 256, 0, p->stream>>>(p->buf[p->cur].cold.meas, mb.pose, mb.act, (int)p->n);
+        CK(cudaGetLastError());
+      }
+    } else {
+      // fused form (same results bit for bit): the step kernel reads every tile in place and writes the survivors' columns
+      // straight to their slots in the merged order (StepArgs::dst_*), so the state crosses HBM once per tick; the promoted
+      // mailboxes are initialised in their slots afterwards and get their first update from a sparse follow-up launch
+      Buf& ob = p->buf[p->cur];
+      const te::MailArrays omb = p->mb[p->mb_cur].a;
+      size_t tmp = p->cub_bytes;
+      CK(cub::DeviceScan::ExclusiveSum(p->cub_tmp, tmp, p->alive, p->pos, n_old, p->stream));
+      int last_pos = 0, last_alive = 0;
+      CK(cudaMemcpyAsync(&last_pos, p->pos + n_old - 1, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+      CK(cudaMemcpyAsync(&last_alive, p->alive + n_old - 1, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+      CK(cudaStreamSynchronize(p->stream));
+      const int n_alive = last_pos + last_alive;
+      n_dev_erased = n_old - n_alive;
       te::StepArgs a = base_args(p);
-      const te::MailArrays& mb = p->mb[p->mb_cur].a;
       a.dt = dt;
-      a.meas = mb.pose;
+      a.meas = omb.pose;
       a.meas_stride = 7;
       a.meas_tma = 1;
-      a.action = mb.act;
+      a.action = omb.act;
       a.default_action = TE_ACT_PREDICT;
-      launch_step(p, a, a.n_tiles);
-      te::copy_meas_masked_kernel<<<cdiv(p->n, 256), 256, 0, p->stream>>>(p->buf[p->cur].cold.meas, mb.pose, mb.act, (int)p->n);
+      te::copy_meas_masked_kernel<<<cdiv(n_old, 256), 256, 0, p->stream>>>(ob.cold.meas, omb.pose, omb.act, n_old);   // measured_pose_
       CK(cudaGetLastError());
+      if (n_dev_erased == 0 && n_add == 0) {
+        launch_step(p, a, a.n_tiles);   // nothing moves: the ordinary in-place step
+        p->mb_add = te::MailAdd{nullptr, nullptr, nullptr};
+        mark(2);
+      } else {
+        const int n_new = n_alive + n_add;
+        if (n_dev_erased > 0) {
+          te::collect_erased_kernel<<<cdiv(n_old, 256), 256, 0, p->stream>>>(p->alive, p->pos, ob.cold.ids, n_old, d_erased);
+          CK(cudaGetLastError());
+        }
+        ensure_other_capacity(p, (size_t)n_new);
+        ensure_mail_other(p, (size_t)n_new);
+        Buf& nb = p->buf[1 - p->cur];
+        const te::MailArrays nmb = p->mb[1 - p->mb_cur].a;
+        int* new_dst = nullptr;
+        if (n_add > 0) {
+          new_dst = p->arena.get_n<int>((size_t)n_add);
+          te::merge_new_dst_kernel<<<cdiv(n_add, 256), 256, 0, p->stream>>>(n_add, ad.ids, ob.cold.ids, n_old, p->pos, n_alive, new_dst);
+          te::merge_old_dst_kernel<<<cdiv(n_old, 256), 256, 0, p->stream>>>(n_old, p->alive, p->pos, ob.cold.ids, ad.ids, n_add);
+          CK(cudaGetLastError());
+        }
+        te::compact_cold_kernel<<<cdiv(n_old, 256), 256, 0, p->stream>>>(n_old, p->alive, p->pos, ob.cold, nb.cold);
+        te::mb_compact_kernel<<<cdiv(n_old, 256), 256, 0, p->stream>>>(n_old, p->alive, p->pos, omb, nmb);
+        CK(cudaGetLastError());
+        if (n_alive > 0) {
+          a.dst_tiles = nb.tiles;
+          a.dst_alive = p->alive;
+          a.dst_pos = p->pos;
+          launch_step(p, a, a.n_tiles);
+        }
+        if (n_add > 0) {
+          CK(cudaMemsetAsync(p->d_counters, 0, 2 * sizeof(int), p->stream));
+          init_promoted(p, n_add, new_dst, nb, ad, nmb);
+        }
+        p->mb_add = te::MailAdd{nullptr, nullptr, nullptr};
+        p->cur = 1 - p->cur;
+        p->mb_cur = 1 - p->mb_cur;
+        p->n = n_new;
+        p->h_ids_valid = false;
+        mark(2);
+        if (n_add > 0) {   // first update of the new targets with the pose that created them: only their tiles, only their lanes
+          te::StepArgs b = base_args(p);
+          b.tile_list = p->tile_list;
+          b.d_nwork = p->d_counters;
+          b.dt = dt;
+          b.meas = nmb.pose;
+          b.meas_stride = 7;
+          b.meas_tma = 1;
+          b.action = p->action;
+          b.default_action = TE_ACT_NONE;
+          b.clear_action = 1;
+          b.tile_flag = p->tile_flag;
+          launch_step(p, b, std::min(n_add, b.n_tiles));
+        }
+        fetch_last_id(p);
+      }
     }
     mark(3);
     // 4. erased ids of this tick, ascending: targets the device expired + target-less mailboxes the host expired
@@ -1643,7 +1742,7 @@ long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, int cls_new
       std::memcpy(erased_out, all.data(), (size_t)std::min(cap, n_er) * sizeof(uint32_t));
     }
     mark(4);
-    if (dbg) std::fprintf(stderr, "[te mailbox tick] host mailboxes %.3f ms, flags + rebuild %.3f ms, step %.3f ms, erase list %.3f ms (n %lld, +%d, -%lld)\n",
+    if (dbg) std::fprintf(stderr, "[te mailbox tick] host mailboxes %.3f ms, flags + merge (fused: + step) %.3f ms, step (fused: first update of the new targets) %.3f ms, erase list %.3f ms (n %lld, +%d, -%lld)\n",
                           tw[1] - tw[0], tw[2] - tw[1], tw[3] - tw[2], tw[4] - tw[3], p->n, n_add, n_er);
     return n_er;
   });

@@ -184,3 +184,47 @@ def test_mailboxes_and_by_hand_calls_interplay_like_the_reference():
     with pytest.raises(te.TeError):
         pool.step_dense_expire(DT, None, 7, None, te.ACT_PREDICT, (50, 0), (50, 0), 1.0)
     pool.close(); L.orc_manager_delete(h); ref.h = None
+
+
+@pytest.mark.parametrize("name", ["uniform_velocity", "uniform_acceleration", "angular_velocities", "angular_rates"])
+def test_fused_mailbox_tick_is_bit_identical_to_rebuild_then_step(name, monkeypatch):
+    """the default tick lets the step kernel move the survivors to their merged slots and gives the new targets their first
+    update in a sparse follow-up launch; TE_MB_UNFUSED=1 selects rebuild-then-step.  Same ids, same erase lists, same bits."""
+    import target_estimation_b200 as te
+    mtype, _, Q, R, P0 = te.load_model(name)
+    results = []
+    for unfused in (False, True):
+        if unfused:
+            monkeypatch.setenv("TE_MB_UNFUSED", "1")
+        else:
+            monkeypatch.delenv("TE_MB_UNFUSED", raising=False)
+        pool = te.TargetPool(mtype); pool.register_class(Q, R, P0)
+        rng = np.random.default_rng(11)
+        universe = rng.choice(100000, size=3000, replace=False).astype(np.uint32)
+        streams, _, _ = synth.make_streams(universe.size, 30, DT, accel=True, angular=name.startswith("angular"), seed=5)
+        live = list(range(900)); nxt = 900
+        log = []
+        for k in range(30):
+            now = 1000 * 10**9 + k * 4_000_000
+            gone = set(j for j in live if rng.random() < 0.02)
+            live = [j for j in live if j not in gone] + list(range(nxt, nxt + 40)); nxt += 40
+            speak = np.array([j for j in live if rng.random() < 0.95])
+            if k % 4 == 1:
+                speak = speak[:0]                    # a tick without any message: nothing appears, maybe something expires
+            st = np.tile([now // 10**9, now % 10**9], (speak.size, 1)).astype(np.uint32)
+            if speak.size:
+                pool.mailbox_ingest(universe[speak], st[:, 0].copy(), st[:, 1].copy(), streams[k, speak])
+            erased, added = pool.mailbox_tick(DT, k * DT, (now // 10**9, now % 10**9), 6 * DT, want_added=True)
+            log.append((erased.copy(), added.copy()))
+        results.append((pool.ids(), pool.read_state(), log))
+        pool.close()
+    (ids_a, st_a, log_a), (ids_b, st_b, log_b) = results
+    assert np.array_equal(ids_a, ids_b) and ids_a.size > 1000
+    for (ea, aa), (eb, ab) in zip(log_a, log_b):
+        assert np.array_equal(ea, eb) and np.array_equal(aa, ab)
+    assert sum(e.size for e, _ in log_a) > 100
+    N = Q.shape[0]
+    iu = np.triu_indices(N)
+    for key in ("x", "t", "n_meas", "prev_rpy", "measured_pose"):
+        assert np.array_equal(st_a[key], st_b[key]), key
+    assert np.array_equal(st_a["P"][:, iu[0], iu[1]], st_b["P"][:, iu[0], iu[1]])   # (the packed kernels keep the upper triangle)
