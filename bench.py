@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--targets", type=int, default=0, help="targets per GPU (default: 4Mi for UV/UA, 1Mi for AV/AR)")
     ap.add_argument("--variant", type=int, default=-1)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ref-abi", action="store_true", help="skip the e2e figure through libtarget_c.so")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-small", action="store_true")
     ap.add_argument("--allgather", action="store_true", help="also time the optional all-gather of estimates (N>1)")
@@ -431,6 +432,44 @@ def main():
             e2e["xyz_only"] = {"value": n * world * Ke / (float(t3.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * (3 * 8 + 1),
                                "d2h_bytes_per_step": n * 24, "ms_per_step": float(t3.item()) / Ke,
                                "api": "te_pool_tick_host with meas_stride 3 (positions only)"}
+
+        # the same tick through the REFERENCE-FACING C-ABI (include/target_manager_c.h, libtarget_c.so): a TargetManager built from the
+        # model file, one target_manager_update_batch(ids, dt, meas, action) per step from pinned host arrays and one
+        # target_manager_get_est_pose read-back (a sync point); rank 0 only, a few steps (the manager keeps a host registry per id)
+        if rank == 0 and not args.no_ref_abi and stride == 7:
+            try:
+                from target_estimation_b200.manager import TargetManagerC, clib
+                import ctypes as C
+                mpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "models", "model_%s_params.yaml" % model)
+                mg = TargetManagerC(mpath, device=torch.cuda.current_device())
+                r_ids = torch.from_numpy(np.arange(n, dtype=np.int32)).pin_memory()
+                ids_np = r_ids.numpy().view(np.uint32)
+                p0 = h_meas[0].numpy()
+                chunk = 1 << 20
+                for c0 in range(0, n, chunk):
+                    mg.init_batch(ids_np[c0:c0 + chunk], DT, p0[c0:c0 + chunk])
+                pose = np.zeros(7)
+
+                def tick_abi(k):
+                    rc = clib.target_manager_update_batch(mg.h, n, ids_np.ctypes.data_as(C.c_void_p), DT, C.c_void_p(h_meas[k % 2].data_ptr()),
+                                                          C.c_void_p(h_act[k % 2].data_ptr()))
+                    if rc != n:
+                        raise RuntimeError("target_manager_update_batch applied %d of %d" % (rc, n))
+                    mg.get_est_pose(int(ids_np[k % n]), pose)
+                for k in range(2):
+                    tick_abi(k)
+                Ka = 5
+                t0 = time.perf_counter()
+                for k in range(Ka):
+                    tick_abi(k)
+                ta = (time.perf_counter() - t0) * 1e3
+                e2e["reference_abi"] = {"value": n * Ka / (ta * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * (4 + 7 * 8 + 1), "d2h_bytes_per_step": 56,
+                                        "ms_per_step": ta / Ka, "n_gpus": 1,
+                                        "api": "libtarget_c.so: target_manager_update_batch(n, ids, dt, meas[n][7], action[n]) + target_manager_get_est_pose(id), "
+                                               "pinned host arrays, one sparse-by-id launch per step (ids are looked up on the device)"}
+                mg.close()
+            except Exception as e:   # report, do not fail the headline
+                e2e["reference_abi"] = {"error": str(e)[:300]}
 
     # ---- optional all-gather of estimate records (off the hot path) -----------------------------------
     allgather = None
