@@ -127,6 +127,19 @@ class TargetManager {
   void flush();
   bool quiet = false;   // suppress the reference's stdout messages ("does not exist", "already exists", ...)
 
+  // sampled logging -----------------------------------------------------------------------------
+  // The reference's log() (src/target_manager.cpp:119-123 -> src/target_interface.cpp:50-55, under LOGGER_ON) publishes, per
+  // target, measured_pose_, pose_internal_, twist_, acceleration_ and P_ through rt_logger (:32-40); its tests dump time / pose /
+  // twist series with writeTxtFile (utils.hpp:78-120) for matlab/plot_*.m.  Here log() appends ONE batched read-back of those five
+  // quantities for the watched ids to an in-memory series, and writeLog() dumps them in writeTxtFile's format.
+  void watch(long long n, const unsigned* ids, size_t max_samples = 1 << 20);   // n = 0: stop logging and drop the series
+  size_t logSamples() const { return log_t_.size(); }
+  // one sample k of watched id j: [t | measured_pose 7 | pose_internal 6 | twist 6 | acceleration 6] = 26 doubles, then P (N*N)
+  bool logSample(size_t k, size_t j, double* row26, double* P, int* n_state) const;
+  // <folder>time_<id>, meas_pose_<id>, est_pose_<id> (x y z roll pitch yaw), est_twist_<id>, est_acc_<id>, cov_diag_<id>:
+  // one row per sample, values separated by a blank, default ostream precision (what writeTxtFile writes).  Returns #files.
+  int writeLog(const std::string& folder) const;
+
   // access for the proxies / solver
   struct Slot { int type; };
   bool typeOf(unsigned id, int& type);
@@ -153,7 +166,17 @@ class TargetManager {
   MatrixXd default_Q_, default_P_, default_R_;
   target_t default_type_ = UNIFORM_VELOCITY;
   bool default_values_loaded_ = false;
+  // sampled logging: watched ids, per-sample tick time, per-sample-per-id rows
+  std::vector<unsigned> log_ids_;
+  size_t log_cap_ = 0;
+  std::vector<double> log_t_;                  // [samples] time of the first watched target that exists (else NaN)
+  std::vector<double> log_rows_;               // [samples][ids][26]
+  std::vector<double> log_P_;                  // [samples][ids][18*18] (n_state^2 used)
+  std::vector<int> log_n_;                     // [samples][ids] state size, 0 = id unknown at that sample
 };
+
+// utils.hpp:78-120: one value (vector) or one row (matrix) per line, "value " per column, default ostream formatting
+bool writeTxtFile(const std::string& filename, const double* values, size_t rows, size_t cols);
 
 // utils.hpp:206-265 (host copy used by nothing on the hot path; kept for API completeness)
 class MovingAvgFilter {

@@ -99,6 +99,19 @@ long long target_bag_read_tf(const char* path, const char* topic, target_tf_reco
  * stats_out (optional): ticks, messages, transforms, erased.  Returns the number of ticks, -1 on error. */
 long long target_tick_manager_replay_bag(const target_manager_c* self, const char* path, const char* topic, double frequency,
                                          long long extra_ticks, long long stats_out[4]);
+/* ---- sampled logging: the reference's log() under LOGGER_ON (src/target_interface.cpp:32-40,50-55) + writeTxtFile dumps ---- */
+/* watch n ids (n = 0: stop and drop the series); every target_manager_log() call then appends one batched read-back of
+ * measured_pose / pose_internal / twist / acceleration / P for the watched ids (at most max_samples samples) */
+void target_manager_watch(const target_manager_c* self, long long n, const unsigned int* ids, long long max_samples);
+long long target_manager_log_samples(const target_manager_c* self);
+/* sample k of watched id j: row26 = [t | measured_pose 7 | pose_internal 6 | twist 6 | acceleration 6], P row-major n*n (either may
+ * be NULL); returns the state size n, 0 if the id did not exist at that sample, -1 on a bad index */
+int target_manager_log_sample(const target_manager_c* self, long long k, long long j, double* row26, double* P);
+/* <folder>time_<id>, meas_pose_<id>, est_pose_<id>, est_twist_<id>, est_acc_<id>, cov_diag_<id> in the format of writeTxtFile
+ * (utils.hpp:78-120), the files matlab/plot_target_manager_test.m loads; returns the number of files written, -1 on error */
+int target_manager_write_log(const target_manager_c* self, const char* folder);
+/* writeTxtFile itself (utils.hpp:78-120): cols == 1 writes the vector form */
+int target_write_txt_file(const char* filename, const double* values, long long rows, long long cols);
 const char* target_manager_last_error(void);
 
 #ifdef __cplusplus

@@ -225,6 +225,21 @@ double refm_bench_steps(int type, const double* Q, int n, const double* R, int m
 }
 
 // ---- utils.hpp ----
+// writeTxtFile (utils.hpp:78-120), both overloads; values row-major
+void refu_write_txt_vec(const char* fn, const double* v, int n) {
+  Quiet q;
+  Eigen::VectorXd x(n);
+  for (int i = 0; i < n; ++i) x(i) = v[i];
+  writeTxtFile(std::string(fn), x);
+}
+void refu_write_txt_mat(const char* fn, const double* v, int r, int c) {
+  Quiet q;
+  Eigen::MatrixXd m(r, c);
+  for (int i = 0; i < r; ++i)
+    for (int j = 0; j < c; ++j) m(i, j) = v[i * c + j];
+  writeTxtFile(std::string(fn), m);
+}
+
 void* refu_mavg_new(unsigned n) { return new MovingAvgFilter(n); }
 void refu_mavg_delete(void* f) { delete static_cast<MovingAvgFilter*>(f); }
 double refu_mavg_update(void* f, double v) { return static_cast<MovingAvgFilter*>(f)->update(v); }

@@ -474,8 +474,111 @@ long long TargetManager::getNumberMeasurements(const unsigned int& id) {   // :2
   return nm;
 }
 
-void TargetManager::log() {   // :119-123 -- per-target rt_logger publish, compiled out without LOGGER_ON
-  flush();
+// ---- sampled logging (the reference's rt_logger publishers + writeTxtFile dumps) ----------------------------
+void TargetManager::watch(long long n, const unsigned* ids, size_t max_samples) {
+  std::lock_guard<std::recursive_mutex> lg(target_lock_);
+  log_ids_.assign(ids, ids + (n > 0 ? n : 0));
+  log_cap_ = max_samples;
+  log_t_.clear(); log_rows_.clear(); log_P_.clear(); log_n_.clear();
+}
+
+void TargetManager::log() {   // :119-123: every target publishes measurement / pose / twist / acceleration / covariance
+  std::lock_guard<std::recursive_mutex> lg(target_lock_);
+  flushLocked();
+  const size_t m = log_ids_.size();
+  if (m == 0 || log_t_.size() >= log_cap_) return;
+  const size_t base = log_t_.size();
+  log_rows_.resize((base + 1) * m * 26, 0.0);
+  log_P_.resize((base + 1) * m * 324, 0.0);
+  log_n_.resize((base + 1) * m, 0);
+  double t_sample = std::nan("");
+  // one batched read-back per pool that holds watched ids
+  for (int type = 0; type < 4; ++type) {
+    if (!pools_[type]) continue;
+    std::vector<uint32_t> sub;
+    std::vector<size_t> where;
+    for (size_t j = 0; j < m; ++j) {
+      auto it = targets_.find(log_ids_[j]);
+      if (it != targets_.end() && it->second == type) { sub.push_back(log_ids_[j]); where.push_back(j); }
+    }
+    if (sub.empty()) continue;
+    int N = 0, M = 0;
+    te_model_dims(type, &N, &M);
+    const long long k = (long long)sub.size();
+    std::vector<double> t((size_t)k), P((size_t)k * N * N), mp((size_t)k * 7), tw((size_t)k * 6), ac((size_t)k * 6), pi((size_t)k * 6);
+    ck(te_pool_read_state(pools_[type], k, sub.data(), nullptr, P.data(), t.data(), nullptr, nullptr, mp.data()));
+    ck(te_pool_read_estimates(pools_[type], k, sub.data(), nullptr, nullptr, tw.data(), ac.data(), pi.data(), nullptr));
+    for (long long q = 0; q < k; ++q) {
+      const size_t j = where[(size_t)q];
+      double* row = &log_rows_[(base * m + j) * 26];
+      row[0] = t[(size_t)q];
+      std::memcpy(row + 1, &mp[(size_t)q * 7], 7 * sizeof(double));
+      std::memcpy(row + 8, &pi[(size_t)q * 6], 6 * sizeof(double));
+      std::memcpy(row + 14, &tw[(size_t)q * 6], 6 * sizeof(double));
+      std::memcpy(row + 20, &ac[(size_t)q * 6], 6 * sizeof(double));
+      std::memcpy(&log_P_[(base * m + j) * 324], &P[(size_t)q * N * N], sizeof(double) * (size_t)N * N);
+      log_n_[base * m + j] = N;
+      if (std::isnan(t_sample)) t_sample = t[(size_t)q];
+    }
+  }
+  log_t_.push_back(t_sample);
+}
+
+bool TargetManager::logSample(size_t k, size_t j, double* row26, double* P, int* n_state) const {
+  const size_t m = log_ids_.size();
+  if (k >= log_t_.size() || j >= m) return false;
+  const int N = log_n_[k * m + j];
+  if (n_state) *n_state = N;
+  if (row26) std::memcpy(row26, &log_rows_[(k * m + j) * 26], 26 * sizeof(double));
+  if (P && N > 0) std::memcpy(P, &log_P_[(k * m + j) * 324], sizeof(double) * (size_t)N * N);
+  return N > 0;
+}
+
+bool writeTxtFile(const std::string& filename, const double* values, size_t rows, size_t cols) {   // utils.hpp:78-120
+  std::ofstream f(filename.c_str());
+  if (!f.is_open()) {
+    std::cerr << "Unable to open file : [" << filename << "]" << std::endl;
+    return false;
+  }
+  for (size_t r = 0; r < rows; ++r) {
+    if (cols == 1) {   // the VectorXd overload: "value\n"
+      f << values[r] << "\n";
+    } else {           // the MatrixXd overload: "value " per column, then "\n"
+      for (size_t c = 0; c < cols; ++c) f << values[r * cols + c] << " ";
+      f << "\n";
+    }
+  }
+  return true;
+}
+
+int TargetManager::writeLog(const std::string& folder) const {
+  const size_t m = log_ids_.size(), S = log_t_.size();
+  int files = 0;
+  for (size_t j = 0; j < m; ++j) {
+    std::vector<double> time, meas, pose, twist, acc, diag;
+    size_t n_diag = 0;
+    for (size_t k = 0; k < S; ++k) {
+      const int N = log_n_[k * m + j];
+      if (N == 0) continue;   // the id did not exist at that sample
+      const double* row = &log_rows_[(k * m + j) * 26];
+      time.push_back(row[0]);
+      meas.insert(meas.end(), row + 1, row + 8);
+      pose.insert(pose.end(), row + 8, row + 14);
+      twist.insert(twist.end(), row + 14, row + 20);
+      acc.insert(acc.end(), row + 20, row + 26);
+      n_diag = (size_t)N;
+      for (int d = 0; d < N; ++d) diag.push_back(log_P_[(k * m + j) * 324 + (size_t)d * N + d]);
+    }
+    if (time.empty()) continue;
+    const std::string id = std::to_string(log_ids_[j]);
+    files += writeTxtFile(folder + "time_" + id, time.data(), time.size(), 1);
+    files += writeTxtFile(folder + "meas_pose_" + id, meas.data(), time.size(), 7);
+    files += writeTxtFile(folder + "est_pose_" + id, pose.data(), time.size(), 6);
+    files += writeTxtFile(folder + "est_twist_" + id, twist.data(), time.size(), 6);
+    files += writeTxtFile(folder + "est_acc_" + id, acc.data(), time.size(), 6);
+    files += writeTxtFile(folder + "cov_diag_" + id, diag.data(), time.size(), n_diag);
+  }
+  return files;
 }
 
 std::vector<unsigned int> TargetManager::getAvailableTargets() {   // :125-133

@@ -88,6 +88,26 @@ bool target_manager_get_est_acceleration(const target_manager_c* self, const uns
 int target_manager_get_n_measurements(const target_manager_c* self, const unsigned int id) {
   return guard(0, [&] { return (int)M(self)->getNumberMeasurements(id); });   // long long -> int like the reference (:64)
 }
+void target_manager_watch(const target_manager_c* self, long long n, const unsigned int* ids, long long max_samples) {
+  guard(0, [&] { M(self)->watch(n, ids, max_samples > 0 ? (size_t)max_samples : (size_t)1 << 20); return 0; });
+}
+long long target_manager_log_samples(const target_manager_c* self) {
+  return guard(-1LL, [&] { return (long long)M(self)->logSamples(); });
+}
+int target_manager_log_sample(const target_manager_c* self, long long k, long long j, double* row26, double* P) {
+  return guard(-1, [&] {
+    int n = 0;
+    if (k < 0 || j < 0) return -1;
+    const bool ok = M(self)->logSample((size_t)k, (size_t)j, row26, P, &n);
+    return (ok || (size_t)k < M(self)->logSamples()) ? n : -1;
+  });
+}
+int target_manager_write_log(const target_manager_c* self, const char* folder) {
+  return guard(-1, [&] { return M(self)->writeLog(folder ? std::string(folder) : std::string("/tmp/")); });
+}
+int target_write_txt_file(const char* filename, const double* values, long long rows, long long cols) {
+  return guard(-1, [&] { return target_estimation_b200::writeTxtFile(std::string(filename), values, (size_t)rows, (size_t)cols) ? 1 : 0; });
+}
 void target_manager_log(const target_manager_c* self) {
   guard(0, [&] { M(self)->log(); return 0; });
 }

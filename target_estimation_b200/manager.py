@@ -33,6 +33,11 @@ _SIG = {
     "target_manager_get_state": (_i, [_p, _u, _p, _p, _p]),
     "target_manager_flush": (None, [_p]),
     "target_manager_last_error": (C.c_char_p, []),
+    "target_manager_watch": (None, [_p, _ll, _p, _ll]),
+    "target_manager_log_samples": (_ll, [_p]),
+    "target_manager_log_sample": (_i, [_p, _ll, _ll, _p, _p]),
+    "target_manager_write_log": (_i, [_p, C.c_char_p]),
+    "target_write_txt_file": (_i, [C.c_char_p, _p, _ll, _ll]),
     "target_tick_manager_new": (_p, [C.c_char_p, _i]),
     "target_tick_manager_set_expiration": (None, [_p, _d]),
     "target_tick_manager_set_token": (None, [_p, C.c_char_p]),
@@ -138,6 +143,35 @@ class TargetManagerC:
         if n == 0:
             return None
         return {"x": x[:n].copy(), "P": P[: n * n].reshape(n, n).copy(), "t": t.value}
+
+    # -- sampled logging (the reference's log() under LOGGER_ON + writeTxtFile dumps) ----------
+    def watch(self, ids, max_samples=1 << 20):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        self._watched = ids.copy()
+        clib.target_manager_watch(self.h, ids.size, _ptr(ids) if ids.size else None, max_samples)
+
+    def log(self):
+        clib.target_manager_log(self.h)
+
+    def log_samples(self):
+        return int(clib.target_manager_log_samples(self.h))
+
+    def log_sample(self, k, j):
+        """sample k of watched id j -> dict(t, measured_pose, pose_internal, twist, acceleration, P) or None if the id did not exist"""
+        row, P = np.zeros(26), np.zeros(18 * 18)
+        n = int(clib.target_manager_log_sample(self.h, k, j, _ptr(row), _ptr(P)))
+        if n < 0:
+            raise IndexError((k, j))
+        if n == 0:
+            return None
+        return {"t": row[0], "measured_pose": row[1:8].copy(), "pose_internal": row[8:14].copy(), "twist": row[14:20].copy(),
+                "acceleration": row[20:26].copy(), "P": P[: n * n].reshape(n, n).copy()}
+
+    def write_log(self, folder="/tmp/"):
+        n = int(clib.target_manager_write_log(self.h, folder.encode()))
+        if n < 0:
+            raise RuntimeError(clib.target_manager_last_error().decode())
+        return n
 
     def flush(self):
         clib.target_manager_flush(self.h)

@@ -163,3 +163,52 @@ def test_batched_extensions(name):
     st, rs = mgr.state(int(ids[j])), ref.state(int(ids[j]), N)
     assert synth.compare_h2(st["P"][None], rs["P"][None]) <= 1.0
     mgr.close()
+
+
+@pytest.mark.parametrize("name", ["uniform_acceleration", "angular_rates"])
+def test_sampled_logging_and_text_dumps(name, tmp_path):
+    """target_manager_watch / target_manager_log / target_manager_write_log: the five quantities the reference publishes per
+    target under LOGGER_ON (measured_pose_, pose_internal_, twist_, acceleration_, P_; src/target_interface.cpp:32-40) sampled
+    once per log() call, against the oracle's getters; dumps in writeTxtFile's format under the names matlab/plot_*.m load."""
+    from target_estimation_b200.manager import TargetManagerC
+    y = orc.load_yaml(_yaml(name)); N = y["Q"].shape[0]
+    mgr = TargetManagerC(_yaml(name)); ref = orc.Manager(_yaml(name))
+    ids = np.array([4, 9, 17], dtype=np.uint32)
+    ticks = 25
+    meas, action, _ = synth.make_streams(ids.size, ticks, DT, accel=True, angular=name.startswith("angular"), seed=3)
+    watched = np.array([9, 555, 4], dtype=np.uint32)      # 555 never exists; 4 is erased half way
+    mgr.watch(watched)
+    for j, i in enumerate(ids):
+        mgr.init(int(i), DT, meas[0, j], 0.0); ref.init_default(int(i), DT, meas[0, j], 0.0)
+    for k in range(ticks):
+        if k == 12:
+            assert mgr.erase(4) and ref.erase(4)
+        live = [(j, int(i)) for j, i in enumerate(ids) if not (i == 4 and k >= 12)]
+        for j, i in live:
+            if action[k, j] == 2:
+                mgr.update_meas(i, DT, meas[k, j]); ref.update_meas(i, DT, meas[k, j])
+            else:
+                mgr.update(i, DT); ref.update(i, DT)
+        mgr.log()
+        assert mgr.log_samples() == k + 1
+        for jw, i in enumerate(watched):
+            s = mgr.log_sample(k, jw)
+            if i == 555 or (i == 4 and k >= 12):
+                assert s is None
+                continue
+            st = ref.state(int(i), N)
+            assert s["t"] == st["t"]
+            assert np.array_equal(s["measured_pose"], ref.measured_pose(int(i))[1])
+            for key, want in (("pose_internal", ref.pose_internal(int(i))[1]), ("twist", ref.twist(int(i))[1]), ("acceleration", ref.acc(int(i))[1])):
+                assert np.abs(s[key] - want).max() <= 1e-9 * max(1.0, np.abs(want).max()), (k, i, key)
+            assert synth.compare_h2(s["P"][None], st["P"][None]) <= 1.0
+    folder = str(tmp_path) + "/"
+    assert mgr.write_log(folder) == 12                    # 6 files for each of the two ids that ever existed
+    t9 = np.loadtxt(folder + "time_9"); p9 = np.loadtxt(folder + "est_pose_9"); m4 = np.loadtxt(folder + "meas_pose_4")
+    assert t9.shape == (ticks,) and p9.shape == (ticks, 6) and m4.shape == (12, 7) and not os.path.exists(folder + "time_555")
+    assert np.loadtxt(folder + "cov_diag_9").shape == (ticks, N) and np.loadtxt(folder + "est_twist_9").shape == (ticks, 6)
+    assert np.allclose(p9[-1, :3], ref.pose_internal(9)[1][:3], rtol=1e-5, atol=1e-6)      # 6 significant digits in the text form
+    mgr.watch([])                                         # stop: the series is dropped
+    mgr.log()
+    assert mgr.log_samples() == 0
+    mgr.close()

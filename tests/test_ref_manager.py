@@ -235,3 +235,31 @@ def test_cpu_baseline_loops_agree(name):
         a = (y["type"], orc.ptr(Qc), y["Q"].shape[0], orc.ptr(Rc), y["R"].shape[0], orc.ptr(Pc), n_t, 25, threads, DT, orc.ptr(meas), 0.05)
         assert L.refm_bench_steps(*a, C.byref(c1)) > 0 and O.orc_bench_steps(*a, C.byref(c2)) > 0
         assert c1.value == c2.value and np.isfinite(c1.value)
+
+
+def test_write_txt_file_matches_reference_source(tmp_path):
+    """target_write_txt_file (host library; what TargetManager::writeLog uses) against the reference's own writeTxtFile
+    (utils.hpp:78-120, both overloads) byte for byte -- default ostream formatting of awkward values included.  No GPU: the
+    host library loads and this entry point does not touch CUDA."""
+    L = _lib()
+    so = os.path.join(ROOT, "target_estimation_b200", "lib", "libtarget_c.so")
+    if not os.path.exists(so):
+        pytest.skip("libtarget_c.so not built")
+    H = C.CDLL(so)
+    H.target_write_txt_file.restype = C.c_int
+    H.target_write_txt_file.argtypes = [C.c_char_p, C.c_void_p, C.c_longlong, C.c_longlong]
+    L.refu_write_txt_vec.argtypes = [C.c_char_p, C.c_void_p, C.c_int]
+    L.refu_write_txt_mat.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
+    rng = np.random.default_rng(6)
+    vals = np.concatenate([rng.normal(0, 1, 40), rng.normal(0, 1e-7, 10), rng.normal(0, 1e9, 10),
+                           [0.0, -0.0, 1.0, 1e-5, 123456.7, 1234567.8, 0.1 + 0.2, 1.0 / 3.0, np.inf, -np.inf, np.nan, 5e-324]])
+    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+    L.refu_write_txt_vec(a.encode(), vals.ctypes.data, vals.size)
+    assert H.target_write_txt_file(b.encode(), vals.ctypes.data, vals.size, 1) == 1
+    assert open(a, "rb").read() == open(b, "rb").read() and os.path.getsize(a) > 300
+    m = np.ascontiguousarray(vals.reshape(12, 6))
+    L.refu_write_txt_mat(a.encode(), m.ctypes.data, 12, 6)
+    assert H.target_write_txt_file(b.encode(), m.ctypes.data, 12, 6) == 1
+    assert open(a, "rb").read() == open(b, "rb").read()
+    assert open(b).read().splitlines()[0].endswith(" ")        # "value " per column, then the newline
+    assert H.target_write_txt_file(str(tmp_path / "no" / "dir").encode(), m.ctypes.data, 2, 6) == 0
