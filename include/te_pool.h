@@ -161,6 +161,8 @@ long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, int cls_new
                                uint32_t* erased_out, long long cap, uint32_t* added_out, long long added_cap, long long* n_added_out);
 /* mailboxes alive = slots that have one + target-less ones (measurements_.size() of the reference); a device reduction + sync */
 long long te_pool_mailbox_count(te_pool* p);
+/* cheap upper bound of the above (no device work): enough room for the erased / added lists of the next tick */
+long long te_pool_mailbox_bound(te_pool* p);
 /* device views of the mailboxes in slot order: stored pose [size][7], action byte of the next tick [size] (NULL before first use) */
 const double* te_pool_mailbox_dev_pose(te_pool* p);
 const uint8_t* te_pool_mailbox_dev_action(te_pool* p);

@@ -64,6 +64,7 @@ SIGNATURES = {
     "te_pool_mailbox_ingest": (_i, [_p, _ll, _p, _p, _p, _p]),
     "te_pool_mailbox_tick": (_ll, [_p, _d, _d, _i, _u32, _u32, _d, _p, _ll, _p, _ll, _p]),
     "te_pool_mailbox_count": (_ll, [_p]),
+    "te_pool_mailbox_bound": (_ll, [_p]),
     "te_pool_mailbox_dev_pose": (_p, [_p]),
     "te_pool_mailbox_dev_action": (_p, [_p]),
     "te_isolver_create": (_p, [_p, _ll, C.c_uint]),

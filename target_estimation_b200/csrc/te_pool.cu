@@ -110,6 +110,20 @@ inline double host_to_sec(uint32_t sec, uint32_t nsec) {   // utils.hpp:59-62, n
   volatile double ns = 1e-9 * (double)nsec;
   return (double)sec + ns;
 }
+// a /tf record whose id has no target: kept in arrival order until the next tick folds it into a mailbox (the common case --
+// an id seen for the first time, promoted by that tick -- then never touches the std::map)
+struct PendingRec {
+  uint32_t id, sec, nsec;
+  double pose[7];
+};
+inline void apply_record(HostMail& m, const PendingRec& r) {   // Measurement::update (target_manager_ros.hpp:96-115)
+  const double cur = host_to_sec(r.sec, r.nsec), prev = host_to_sec(m.sec, m.nsec);
+  if (cur > prev) { m.fresh = true; m.last = cur; }
+  else m.fresh = false;
+  m.sec = r.sec;
+  m.nsec = r.nsec;
+  std::memcpy(m.pose, r.pose, sizeof(m.pose));
+}
 
 }  // namespace
 
@@ -157,7 +171,8 @@ struct te_pool {
   MailBuf mb[2];
   int mb_cur = 0;
   te::MailAdd mb_add{nullptr, nullptr, nullptr};   // set by the mailbox tick around its merge
-  std::map<uint32_t, HostMail> orphans;            // mailboxes without a target
+  std::map<uint32_t, HostMail> orphans;            // mailboxes without a target that outlived a tick (unreadable ones)
+  std::vector<PendingRec> pending;                 // records of unknown ids since the last tick, arrival order
   // chunk pipeline of te_pool_tick_host
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   std::vector<cudaEvent_t> events;
@@ -704,6 +719,12 @@ int* lookup_slots(te_pool* p, const uint32_t* d_ids, long long n) {
   return slots;
 }
 
+// queued records of unknown ids -> their (host) mailboxes, in arrival order
+void fold_pending(te_pool* p) {
+  for (const PendingRec& r : p->pending) apply_record(p->orphans[r.id], r);
+  p->pending.clear();
+}
+
 // A target erased by hand keeps its mailbox in the reference (TargetManager::erase does not know the adapter's map,
 // src/target_manager.cpp:227-241): the mailboxes of the listed slots move to the host's target-less map before the compaction.
 void demote_mailboxes(te_pool* p, const uint32_t* ids, const int* d_slots, long long n) {
@@ -736,6 +757,7 @@ void demote_mailboxes(te_pool* p, const uint32_t* ids, const int* d_slots, long 
 }
 // ... and a target created by hand for an id that already has a (target-less) mailbox is fed by it from the next tick on
 void attach_mailboxes(te_pool* p, const uint32_t* ids, long long n) {
+  fold_pending(p);
   std::vector<uint32_t> a_ids, sec, nsec;
   std::vector<uint8_t> act;
   std::vector<double> last, pose;
@@ -1054,7 +1076,7 @@ long long te_pool_add_batch(te_pool* p, long long n, const uint32_t* ids, const 
       p->h_ids.swap(merged);
       p->h_ids_valid = true;
     }
-    if (p->mb_on && !p->orphans.empty()) attach_mailboxes(p, s_ids, na);
+    if (p->mb_on && (!p->orphans.empty() || !p->pending.empty())) attach_mailboxes(p, s_ids, na);
     CK(cudaStreamSynchronize(p->stream));   // host payload vectors go out of scope
     return na;
   });
@@ -1505,14 +1527,13 @@ int te_pool_mailbox_ingest(te_pool* p, long long n, const uint32_t* ids, const u
     if (n > 0x7FFFFFFF) throw std::invalid_argument("too many records in one message");
     enable_mail(p);
     const int nr = (int)n;
-    auto to_orphan = [&](long long k) {   // Measurement::update on a host mailbox (created on first sight)
-      HostMail& m = p->orphans[ids[k]];
-      const double cur = host_to_sec(sec[k], nsec[k]), prev = host_to_sec(m.sec, m.nsec);
-      if (cur > prev) { m.fresh = true; m.last = cur; }
-      else m.fresh = false;
-      m.sec = sec[k];
-      m.nsec = nsec[k];
-      std::memcpy(m.pose, poses + 7 * k, sizeof(m.pose));
+    auto to_orphan = [&](long long k) {   // unknown id: queued in arrival order, folded into a mailbox by the next tick
+      PendingRec r;
+      r.id = ids[k];
+      r.sec = sec[k];
+      r.nsec = nsec[k];
+      std::memcpy(r.pose, poses + 7 * k, sizeof(r.pose));
+      p->pending.push_back(r);
     };
     if (p->n == 0) {   // no targets yet: every record belongs to a target-less mailbox
       for (long long k = 0; k < n; ++k) to_orphan(k);
@@ -1572,22 +1593,39 @@ long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, int cls_new
     //    same tick would erase it again (:67-72; init + update + erase is unobservable); unreadable -> stays, or expires
     std::vector<uint32_t> add_ids, add_sec, add_nsec, host_erased;
     std::vector<double> add_pose, add_last, add_t0;
-    for (auto it = p->orphans.begin(); it != p->orphans.end();) {
-      const HostMail& m = it->second;
-      const bool expired = m.last > 0.0 && (now - m.last) >= timeout;
-      if (expired) {
-        host_erased.push_back(it->first);
-        it = p->orphans.erase(it);
-      } else if (m.fresh) {
-        add_ids.push_back(it->first);
-        add_sec.push_back(m.sec);
-        add_nsec.push_back(m.nsec);
-        add_last.push_back(m.last);
-        add_t0.push_back(t0_new);
-        add_pose.insert(add_pose.end(), m.pose, m.pose + 7);
-        it = p->orphans.erase(it);
-      } else {
-        ++it;   // "Target(id) does not exist!" (src/target_manager.cpp:209)
+    auto promote = [&](uint32_t id, const HostMail& m) {
+      add_ids.push_back(id);
+      add_sec.push_back(m.sec);
+      add_nsec.push_back(m.nsec);
+      add_last.push_back(m.last);
+      add_t0.push_back(t0_new);
+      add_pose.insert(add_pose.end(), m.pose, m.pose + 7);
+    };
+    bool fast = p->orphans.empty();   // common case: every queued record is the first sight of a new id, ids ascending
+    for (size_t k = 1; fast && k < p->pending.size(); ++k) fast = p->pending[k - 1].id < p->pending[k].id;
+    if (fast) {
+      for (const PendingRec& r : p->pending) {
+        HostMail m;   // Measurement(): readable, stamp 0
+        apply_record(m, r);
+        if (m.last > 0.0 && (now - m.last) >= timeout) host_erased.push_back(r.id);
+        else if (m.fresh) promote(r.id, m);
+        else p->orphans.emplace_hint(p->orphans.end(), r.id, m);   // "Target(id) does not exist!" (src/target_manager.cpp:209)
+      }
+      p->pending.clear();
+    } else {
+      fold_pending(p);
+      for (auto it = p->orphans.begin(); it != p->orphans.end();) {
+        const HostMail& m = it->second;
+        const bool expired = m.last > 0.0 && (now - m.last) >= timeout;
+        if (expired) {
+          host_erased.push_back(it->first);
+          it = p->orphans.erase(it);
+        } else if (m.fresh) {
+          promote(it->first, m);
+          it = p->orphans.erase(it);
+        } else {
+          ++it;
+        }
       }
     }
     const int n_add = (int)add_ids.size();
@@ -1750,6 +1788,7 @@ long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, int cls_new
 
 long long te_pool_mailbox_count(te_pool* p) {
   return guarded_ll(p, [&]() -> long long {
+    fold_pending(p);
     long long n = (long long)p->orphans.size();
     if (!p->mb_on || p->n == 0) return n;
     int* counter = p->arena.get_n<int>(1);
@@ -1762,6 +1801,8 @@ long long te_pool_mailbox_count(te_pool* p) {
     return n + c;
   });
 }
+
+long long te_pool_mailbox_bound(te_pool* p) { return p ? p->n + (long long)p->orphans.size() + (long long)p->pending.size() : -1; }
 
 const double* te_pool_mailbox_dev_pose(te_pool* p) { return (p && p->mb_on) ? p->mb[p->mb_cur].a.pose : nullptr; }
 const uint8_t* te_pool_mailbox_dev_action(te_pool* p) { return (p && p->mb_on) ? p->mb[p->mb_cur].a.act : nullptr; }

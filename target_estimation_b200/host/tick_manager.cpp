@@ -168,7 +168,7 @@ void TickTargetManager::tick(const double& dt, uint32_t now_sec, uint32_t now_ns
   flushLocked();
   te_pool* pool = tickPool();
   // 1. the device tick: first-sight init, sticky update / predict, expiry -- one rebuild + one step launch (:46-76)
-  const long long cap = std::max<long long>(te_pool_mailbox_count(pool), 1);
+  const long long cap = std::max<long long>(te_pool_mailbox_bound(pool), 1);
   std::vector<uint32_t> gone((size_t)cap), born((size_t)cap);
   long long n_born = 0;
   const long long n_gone = te_pool_mailbox_tick(pool, dt, t_, cls_, now_sec, now_nsec, expiration_time_, gone.data(), cap, born.data(), cap, &n_born);

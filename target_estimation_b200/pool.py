@@ -242,7 +242,7 @@ class TargetPool:
     def mailbox_tick(self, dt, t0_new, now, timeout, cls_new=0, want_added=False):
         """RosTargetManager::update(dt) (src/target_manager_ros.cpp:41-76); now = (sec, nsec).  Returns (erased ids, #added), or
         (erased ids, added ids) with want_added."""
-        cap = int(lib.te_pool_mailbox_count(self._h))
+        cap = int(lib.te_pool_mailbox_bound(self._h))
         buf = getattr(self, "_erase_buf", None)
         if buf is None or buf.size < cap:
             buf = self._erase_buf = np.empty(max(cap + cap // 4, 1), dtype=np.uint32)
