@@ -195,9 +195,21 @@ void TickTargetManager::tick(const double& dt, uint32_t now_sec, uint32_t now_ns
   pub_ids_.clear();
   pub_poses_.clear();
   if (publish) {
-    pub_ids_ = getAvailableTargets();
-    pub_poses_.resize(pub_ids_.size() * 7);
-    if (!pub_ids_.empty()) getEstimatesBatch((long long)pub_ids_.size(), pub_ids_.data(), nullptr, pub_poses_.data(), nullptr, nullptr, nullptr);
+    const long long n_pool = te_pool_size(pool);
+    if (measurements_.empty() && targets_.size() == (size_t)n_pool) {
+      // every target lives in the tick's pool: ids and poses of all slots in slot order = ascending ids, no per-id lookups
+      pub_ids_.resize((size_t)n_pool);
+      pub_poses_.resize((size_t)n_pool * 7);
+      if (n_pool > 0) {
+        if (te_pool_ids(pool, pub_ids_.data(), n_pool) < 0 ||
+            te_pool_read_estimates(pool, n_pool, nullptr, nullptr, pub_poses_.data(), nullptr, nullptr, nullptr, nullptr) < 0)
+          throw std::runtime_error(te_last_error());
+      }
+    } else {
+      pub_ids_ = getAvailableTargets();
+      pub_poses_.resize(pub_ids_.size() * 7);
+      if (!pub_ids_.empty()) getEstimatesBatch((long long)pub_ids_.size(), pub_ids_.data(), nullptr, pub_poses_.data(), nullptr, nullptr, nullptr);
+    }
   }
   t_ = t_ + dt;   // :89
 }
