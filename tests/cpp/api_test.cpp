@@ -92,13 +92,15 @@ int main(int argc, char** argv) {
     mp->init(type, 5, dt, 0.0, Q, R, P, pose_at(0.0, 0.0, 2.0));
     for (unsigned i = 1; i <= 250; ++i) {
       const double t = i * dt;
-      CHECK(mp->update(5, dt, pose_at(0.3 * t, 0.0, 2.0 - 0.5 * 9.81 * t * t)));
+      CHECK(mp->update(5, dt, pose_at(2.0 * t, 0.0, 2.0 - 0.5 * 9.81 * t * t)));
     }
     IntersectionSolver solver(mp, 10);
-    const double t1 = 250 * dt;                        // z(t1) = -2.9, falling; the sphere's top is reached 0.35 s later
-    const Vector3d origin{0.45, 0.0, -8.0};
+    const double t1 = 250 * dt;                        // z(t1) = -2.9, falling at 9 m/s, 2 m/s sideways
+    const Vector3d origin{2.8, 0.0, -8.0};
     const double d = solver.getIntersectionTimeWithSphere(5, t1, origin, 1.0);
-    CHECK(d > 0.1 && d < 1.0);
+    NEAR(d, 0.4062777585451441, 1e-6);                 // the oracle's value for this stream (tests/orc.py, same scenario)
+    // the reference returns the LOWEST real root: a sphere the backward-extended parabola also crosses gives a negative root -> -1
+    CHECK(solver.getIntersectionTimeWithSphere(5, t1, Vector3d{-3.2, 0.0, -8.0}, 4.0) == -1.0);
     CHECK(solver.getIntersectionTimeWithSphere(99, t1, origin, 1.0) == -1.0);   // unknown id
   }
 
