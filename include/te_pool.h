@@ -145,6 +145,10 @@ long long te_pool_step_dense_expire(te_pool* p, double dt, const double* dev_mea
  * (ids[k], sec[k], nsec[k], poses[k][7]), host arrays, applied in arrival order per id (Measurement::update).  Synchronous. */
 int te_pool_mailbox_ingest(te_pool* p, long long n, const uint32_t* ids, const uint32_t* sec, const uint32_t* nsec,
                            const double* poses /*[n][7]*/);
+/* The same for a message that is already in DEVICE memory (another CUDA stage, a NCCL receive buffer) on the pool's stream: the
+ * records are used in place; only the records of unknown ids (first sights) are read back for the host's queue. */
+int te_pool_mailbox_ingest_dev(te_pool* p, long long n, const uint32_t* dev_ids, const uint32_t* dev_sec, const uint32_t* dev_nsec,
+                               const double* dev_poses /*[n][7]*/);
 /* te_pool_mailbox_tick = RosTargetManager::update(dt) (src/target_manager_ros.cpp:41-76) without the broadcast: readable
  * mailboxes of unknown ids become targets (class cls_new, p0 = the pose, t0 = t0_new, v0 = a0 = 0) and are updated with that pose,
  * targets with a readable mailbox are updated (the flag is sticky), the others predicted; every mailbox with

@@ -604,6 +604,19 @@ __global__ void mb_lookup_kernel(const uint32_t* __restrict__ ids_sorted, int n_
   rec[k] = k;
   if (!hit) unknown[atomicAdd(counter, 1)] = k;
 }
+// device-resident messages: the records of unknown ids, packed for the host (which keeps the target-less mailboxes)
+__global__ void mb_pack_unknown_kernel(int n_unknown, const int* __restrict__ list, const uint32_t* __restrict__ ids, const uint32_t* __restrict__ sec,
+                                       const uint32_t* __restrict__ nsec, const double* __restrict__ poses, uint32_t* __restrict__ o_ids,
+                                       uint32_t* __restrict__ o_sec, uint32_t* __restrict__ o_nsec, double* __restrict__ o_pose) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_unknown) return;
+  const int r = list[k];
+  o_ids[k] = ids[r];
+  o_sec[k] = sec[r];
+  o_nsec[k] = nsec[r];
+#pragma unroll
+  for (int e = 0; e < 7; ++e) o_pose[(size_t)k * 7 + e] = poses[(size_t)r * 7 + e];
+}
 // records sorted by (slot, arrival order): the first record of each slot's run applies the whole run in arrival order --
 // Measurement::update (target_manager_ros.hpp:96-115): a stamp newer than the stored one makes the mailbox readable and
 // becomes last_meas_time_, any other stamp makes it unreadable; stamp and pose are stored either way.

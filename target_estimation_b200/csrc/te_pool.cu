@@ -1520,39 +1520,45 @@ long long te_pool_step_dense_expire(te_pool* p, double dt, const double* dev_mea
 }
 
 // ---- device-resident mailboxes: measurementCallBack + update(dt) of RosTargetManager ----------------
-int te_pool_mailbox_ingest(te_pool* p, long long n, const uint32_t* ids, const uint32_t* sec, const uint32_t* nsec, const double* poses) {
-  return guarded(p, [&] {
-    if (n <= 0) return 0;
-    if (!ids || !sec || !nsec || !poses) throw std::invalid_argument("null record arrays");
-    if (n > 0x7FFFFFFF) throw std::invalid_argument("too many records in one message");
-    enable_mail(p);
-    const int nr = (int)n;
-    auto to_orphan = [&](long long k) {   // unknown id: queued in arrival order, folded into a mailbox by the next tick
-      PendingRec r;
-      r.id = ids[k];
-      r.sec = sec[k];
-      r.nsec = nsec[k];
-      std::memcpy(r.pose, poses + 7 * k, sizeof(r.pose));
-      p->pending.push_back(r);
-    };
-    if (p->n == 0) {   // no targets yet: every record belongs to a target-less mailbox
-      for (long long k = 0; k < n; ++k) to_orphan(k);
-      return 0;
-    }
-    uint32_t* d_ids = to_dev(p, ids, (size_t)n);
-    uint32_t* d_sec = to_dev(p, sec, (size_t)n);
-    uint32_t* d_nsec = to_dev(p, nsec, (size_t)n);
-    double* d_pose = to_dev(p, poses, (size_t)n * 7);
-    uint32_t* key_in = p->arena.get_n<uint32_t>((size_t)n);
-    uint32_t* key_out = p->arena.get_n<uint32_t>((size_t)n);
-    int* rec_in = p->arena.get_n<int>((size_t)n);
-    int* rec_out = p->arena.get_n<int>((size_t)n);
-    int* unknown = p->arena.get_n<int>((size_t)n);
-    int* counter = p->arena.get_n<int>(1);
-    CK(cudaMemsetAsync(counter, 0, sizeof(int), p->stream));
-    Buf& b = p->buf[p->cur];
-    te::mb_lookup_kernel<<<cdiv(n, 256), 256, 0, p->stream>>>(b.cold.ids, (int)p->n, d_ids, nr, key_in, rec_in, unknown, counter);
-    CK(cudaGetLastError());
+namespace {
+// one /tf message into the mailboxes.  Host source (ids .. poses non-null): the arrays are staged here; device source (d_* given,
+// host pointers null): the records are used in place and the few records of unknown ids are read back for the host's queue.
+int mailbox_ingest_impl(te_pool* p, long long n, const uint32_t* ids, const uint32_t* sec, const uint32_t* nsec, const double* poses,
+                        const uint32_t* d_ids, const uint32_t* d_sec, const uint32_t* d_nsec, const double* d_pose) {
+  if (n <= 0) return 0;
+  if (n > 0x7FFFFFFF) throw std::invalid_argument("too many records in one message");
+  const bool host_src = ids != nullptr;
+  enable_mail(p);
+  const int nr = (int)n;
+  auto queue = [&](uint32_t id, uint32_t s, uint32_t ns, const double* pose) {   // unknown id: queued in arrival order for the next tick
+    PendingRec r;
+    r.id = id;
+    r.sec = s;
+    r.nsec = ns;
+    std::memcpy(r.pose, pose, sizeof(r.pose));
+    p->pending.push_back(r);
+  };
+  if (p->n == 0 && host_src) {   // no targets yet: every record belongs to a target-less mailbox
+    for (long long k = 0; k < n; ++k) queue(ids[k], sec[k], nsec[k], poses + 7 * k);
+    return 0;
+  }
+  if (host_src) {
+    d_ids = to_dev(p, ids, (size_t)n);
+    d_sec = to_dev(p, sec, (size_t)n);
+    d_nsec = to_dev(p, nsec, (size_t)n);
+    d_pose = to_dev(p, poses, (size_t)n * 7);
+  }
+  uint32_t* key_in = p->arena.get_n<uint32_t>((size_t)n);
+  uint32_t* key_out = p->arena.get_n<uint32_t>((size_t)n);
+  int* rec_in = p->arena.get_n<int>((size_t)n);
+  int* rec_out = p->arena.get_n<int>((size_t)n);
+  int* unknown = p->arena.get_n<int>((size_t)n);
+  int* counter = p->arena.get_n<int>(1);
+  CK(cudaMemsetAsync(counter, 0, sizeof(int), p->stream));
+  Buf& b = p->buf[p->cur];
+  te::mb_lookup_kernel<<<cdiv(n, 256), 256, 0, p->stream>>>(b.cold.ids, (int)p->n, d_ids, nr, key_in, rec_in, unknown, counter);
+  CK(cudaGetLastError());
+  if (p->n > 0) {
     // stable sort by slot: the records of one id stay in arrival order (a message may name an id more than once, and several
     // messages may be ingested between two ticks)
     int bits = 1;
@@ -1563,16 +1569,55 @@ int te_pool_mailbox_ingest(te_pool* p, long long n, const uint32_t* ids, const u
     CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key_in, key_out, rec_in, rec_out, nr, 0, bits, p->stream));
     te::mb_apply_kernel<<<cdiv(n, 256), 256, 0, p->stream>>>(nr, (int)p->n, key_out, rec_out, d_sec, d_nsec, d_pose, p->mb[p->mb_cur].a, b.cold.last_meas);
     CK(cudaGetLastError());
-    int n_unknown = 0;
-    CK(cudaMemcpyAsync(&n_unknown, counter, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
-    CK(cudaStreamSynchronize(p->stream));   // also: the caller's record arrays are free again
-    if (n_unknown > 0) {
-      std::vector<int> list((size_t)n_unknown);
-      CK(cudaMemcpy(list.data(), unknown, (size_t)n_unknown * sizeof(int), cudaMemcpyDeviceToHost));
-      std::sort(list.begin(), list.end());   // arrival order
-      for (int k : list) to_orphan(k);
-    }
+  }
+  int n_unknown = 0;
+  CK(cudaMemcpyAsync(&n_unknown, counter, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));   // also: a host caller's record arrays are free again
+  if (n_unknown == 0) return 0;
+  std::vector<int> list((size_t)n_unknown);
+  if (host_src) {
+    CK(cudaMemcpy(list.data(), unknown, (size_t)n_unknown * sizeof(int), cudaMemcpyDeviceToHost));
+    std::sort(list.begin(), list.end());   // arrival order
+    for (int k : list) queue(ids[k], sec[k], nsec[k], poses + 7 * (size_t)k);
     return 0;
+  }
+  // device source: pack the unknown records (device order), read them back, queue them in arrival order
+  uint32_t* o_ids = p->arena.get_n<uint32_t>((size_t)n_unknown);
+  uint32_t* o_sec = p->arena.get_n<uint32_t>((size_t)n_unknown);
+  uint32_t* o_nsec = p->arena.get_n<uint32_t>((size_t)n_unknown);
+  double* o_pose = p->arena.get_n<double>((size_t)n_unknown * 7);
+  te::mb_pack_unknown_kernel<<<cdiv(n_unknown, 256), 256, 0, p->stream>>>(n_unknown, unknown, d_ids, d_sec, d_nsec, d_pose, o_ids, o_sec, o_nsec, o_pose);
+  CK(cudaGetLastError());
+  std::vector<uint32_t> h_ids((size_t)n_unknown), h_sec((size_t)n_unknown), h_nsec((size_t)n_unknown);
+  std::vector<double> h_pose((size_t)n_unknown * 7);
+  CK(cudaMemcpyAsync(list.data(), unknown, (size_t)n_unknown * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaMemcpyAsync(h_ids.data(), o_ids, (size_t)n_unknown * 4, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaMemcpyAsync(h_sec.data(), o_sec, (size_t)n_unknown * 4, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaMemcpyAsync(h_nsec.data(), o_nsec, (size_t)n_unknown * 4, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaMemcpyAsync(h_pose.data(), o_pose, (size_t)n_unknown * 56, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaStreamSynchronize(p->stream));
+  std::vector<int> order((size_t)n_unknown);
+  std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(), [&](int a, int c) { return list[(size_t)a] < list[(size_t)c]; });
+  for (int k : order) queue(h_ids[(size_t)k], h_sec[(size_t)k], h_nsec[(size_t)k], &h_pose[(size_t)k * 7]);
+  return 0;
+}
+}  // namespace
+
+int te_pool_mailbox_ingest(te_pool* p, long long n, const uint32_t* ids, const uint32_t* sec, const uint32_t* nsec, const double* poses) {
+  return guarded(p, [&] {
+    if (n <= 0) return 0;
+    if (!ids || !sec || !nsec || !poses) throw std::invalid_argument("null record arrays");
+    return mailbox_ingest_impl(p, n, ids, sec, nsec, poses, nullptr, nullptr, nullptr, nullptr);
+  });
+}
+
+int te_pool_mailbox_ingest_dev(te_pool* p, long long n, const uint32_t* dev_ids, const uint32_t* dev_sec, const uint32_t* dev_nsec,
+                               const double* dev_poses) {
+  return guarded(p, [&] {
+    if (n <= 0) return 0;
+    if (!dev_ids || !dev_sec || !dev_nsec || !dev_poses) throw std::invalid_argument("null record arrays");
+    return mailbox_ingest_impl(p, n, nullptr, nullptr, nullptr, nullptr, dev_ids, dev_sec, dev_nsec, dev_poses);
   });
 }
 

@@ -239,6 +239,10 @@ class TargetPool:
         poses = _np(poses, np.float64, (ids.size, 7))
         check(lib.te_pool_mailbox_ingest(self._h, ids.size, _ptr(ids), _ptr(sec), _ptr(nsec), _ptr(poses)))
 
+    def mailbox_ingest_dev(self, n, dev_ids, dev_sec, dev_nsec, dev_poses):
+        """the same for a message already in device memory (torch CUDA tensors: int32/uint32 ids and stamps, float64 [n][7] poses)"""
+        check(lib.te_pool_mailbox_ingest_dev(self._h, int(n), _dev_ptr(dev_ids), _dev_ptr(dev_sec), _dev_ptr(dev_nsec), _dev_ptr(dev_poses)))
+
     def mailbox_tick(self, dt, t0_new, now, timeout, cls_new=0, want_added=False):
         """RosTargetManager::update(dt) (src/target_manager_ros.cpp:41-76); now = (sec, nsec).  Returns (erased ids, #added), or
         (erased ids, added ids) with want_added."""

@@ -228,3 +228,44 @@ def test_fused_mailbox_tick_is_bit_identical_to_rebuild_then_step(name, monkeypa
     for key in ("x", "t", "n_meas", "prev_rpy", "measured_pose"):
         assert np.array_equal(st_a[key], st_b[key]), key
     assert np.array_equal(st_a["P"][:, iu[0], iu[1]], st_b["P"][:, iu[0], iu[1]])   # (the packed kernels keep the upper triangle)
+
+
+def test_device_resident_messages_equal_host_messages():
+    """te_pool_mailbox_ingest_dev (records already in device memory, used in place; unknown ids read back for the host queue)
+    against te_pool_mailbox_ingest on the same shuffled, duplicated, partly stale messages: same ids, erase lists, bits."""
+    import torch
+    import target_estimation_b200 as te
+    mtype, _, Q, R, P0 = te.load_model("angular_rates")
+    results = []
+    for on_device in (False, True):
+        pool = te.TargetPool(mtype); pool.register_class(Q, R, P0)
+        rng = np.random.default_rng(21)
+        universe = rng.choice(50000, size=2500, replace=False).astype(np.uint32)
+        streams, _, _ = synth.make_streams(universe.size, 24, DT, accel=True, angular=True, seed=8)
+        live = list(range(600)); nxt = 600
+        log = []
+        for k in range(24):
+            now = 1000 * 10**9 + k * 4_000_000
+            gone = set(j for j in live if rng.random() < 0.03)
+            live = [j for j in live if j not in gone] + list(range(nxt, nxt + 30)); nxt += 30
+            speak = np.array([j for j in live if rng.random() < 0.9]); rng.shuffle(speak)
+            speak = np.concatenate([speak, speak[:5]])                      # five ids twice
+            st_ns = now - np.where(rng.random(speak.size) < 0.05, 12_000_000, 0)
+            sec = (st_ns // 10**9).astype(np.uint32); nsec = (st_ns % 10**9).astype(np.uint32)
+            ids = universe[speak]; poses = np.ascontiguousarray(streams[k, speak])
+            if on_device:
+                d = [torch.from_numpy(a.view(np.int32)).cuda() for a in (ids, sec, nsec)] + [torch.from_numpy(poses).cuda()]
+                torch.cuda.synchronize()
+                pool.mailbox_ingest_dev(ids.size, *d)
+            else:
+                pool.mailbox_ingest(ids, sec, nsec, poses)
+            log.append(pool.mailbox_tick(DT, k * DT, (now // 10**9, now % 10**9), 6 * DT, want_added=True))
+        results.append((pool.ids(), pool.read_state(), log, pool.mailbox_count()))
+        pool.close()
+    (ids_a, st_a, log_a, mc_a), (ids_b, st_b, log_b, mc_b) = results
+    assert np.array_equal(ids_a, ids_b) and ids_a.size > 500 and mc_a == mc_b
+    for (ea, aa), (eb, ab) in zip(log_a, log_b):
+        assert np.array_equal(ea, eb) and np.array_equal(aa, ab)
+    assert sum(e.size for e, _ in log_a) > 50
+    for key in ("x", "P", "t", "n_meas", "prev_rpy", "measured_pose"):
+        assert np.array_equal(st_a[key], st_b[key]), key
