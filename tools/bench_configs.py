@@ -116,7 +116,7 @@ def c3_churn(n=1 << 20, ticks=48, fused=False):
     return out
 
 
-def c3_mailbox(n=1 << 20, ticks=48, model="angular_rates"):
+def c3_mailbox(n=1 << 20, ticks=48, model="angular_rates", device_records=False):
     """C3 through the node loop itself: per tick ONE /tf message from pinned host memory (a record = id, stamp, pose7 for every
     speaking id, 68 B each) -> te_pool_mailbox_ingest, then te_pool_mailbox_tick (first-sight init of the fresh ids, sticky
     update / predict, expiry, one stable rebuild + one step launch).  Same churn as c3_churn: 1 % of the speaking ids fall
@@ -169,6 +169,11 @@ def c3_mailbox(n=1 << 20, ticks=48, model="angular_rates"):
         sched.append((pin(rec_ids), pin(np.full(rec_ids.size, sec, dtype=np.uint32)), pin(np.full(rec_ids.size, nsec, dtype=np.uint32)),
                       ids[expired].astype(np.uint32), int(ids.size)))
         ids, silent_at, last_tick = ids[~expired], silent_at[~expired], last_tick[~expired]
+    d_sched, d_poses = None, None
+    if device_records:   # the messages already sit in device memory (another CUDA stage / a receive buffer): te_pool_mailbox_ingest_dev
+        d_poses = torch.from_numpy(poses).cuda()
+        d_sched = [tuple(torch.from_numpy(a.view(np.int32)).cuda() for a in s_[:3]) for s_ in sched]
+        torch.cuda.synchronize()
     r_ids, r_sec, r_nsec, exp_ids, live = sched[0]
     pool.mailbox_ingest(r_ids, r_sec, r_nsec, poses[:r_ids.size])
     erased, added = pool.mailbox_tick(DT, 0.0, clock(0), timeout)
@@ -180,7 +185,10 @@ def c3_mailbox(n=1 << 20, ticks=48, model="angular_rates"):
     for k in range(1, ticks + 1):
         r_ids, r_sec, r_nsec, exp_ids, live = sched[k]
         ta = time.perf_counter()
-        pool.mailbox_ingest(r_ids, r_sec, r_nsec, poses[:r_ids.size])
+        if device_records:
+            pool.mailbox_ingest_dev(r_ids.size, d_sched[k][0], d_sched[k][1], d_sched[k][2], d_poses)
+        else:
+            pool.mailbox_ingest(r_ids, r_sec, r_nsec, poses[:r_ids.size])
         tb = time.perf_counter()
         erased, added = pool.mailbox_tick(DT, k * DT, clock(k), timeout)
         tc = time.perf_counter()
@@ -190,7 +198,8 @@ def c3_mailbox(n=1 << 20, ticks=48, model="angular_rates"):
     dt_wall = time.perf_counter() - t0
     assert np.array_equal(pool.ids().astype(np.int64), ids)
     out = {"model": model, "targets": n, "ticks": ticks, "erased": int(n_erased), "added": int(n_added), "records_per_tick": records / ticks,
-           "h2d_bytes_per_tick": 68 * records / ticks, "ms_per_tick": 1e3 * dt_wall / ticks, "target_steps_per_s": steps / dt_wall,
+           "h2d_bytes_per_tick": 0 if device_records else 68 * records / ticks, "records_in": "device memory" if device_records else "pinned host memory",
+           "ms_per_tick": 1e3 * dt_wall / ticks, "target_steps_per_s": steps / dt_wall,
            "ms_per_tick_parts": {k_: 1e3 * v / ticks for k_, v in parts.items()},
            "note": "the node loop through te_pool_mailbox_ingest + te_pool_mailbox_tick: records come from pinned HOST memory every tick (ids, "
                    "stamps, poses), mailboxes, first-sight init, sticky update / predict and expiry run on the device; every tick's erase "
@@ -266,7 +275,9 @@ def replay(model="uniform_acceleration", n=4 << 20, T=16, launches=10):
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "mailbox":
-        print(json.dumps({"c3_mailbox_angular_rates": c3_mailbox(), "c3_mailbox_uniform_acceleration": c3_mailbox(model="uniform_acceleration")}))
+        print(json.dumps({"c3_mailbox_angular_rates": c3_mailbox(), "c3_mailbox_uniform_acceleration": c3_mailbox(model="uniform_acceleration"),
+                          "c3_mailbox_angular_rates_device_records": c3_mailbox(device_records=True),
+                          "c3_mailbox_uniform_acceleration_device_records": c3_mailbox(model="uniform_acceleration", device_records=True)}))
         sys.exit(0)
     res = {"c3_churn_angular_rates": c3_churn(), "c3_churn_angular_rates_fused": c3_churn(fused=True), "c4_intersect_uniform_velocity": c4_intersect("uniform_velocity"),
            "c4_intersect_uniform_acceleration": c4_intersect("uniform_acceleration"),
