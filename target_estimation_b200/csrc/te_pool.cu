@@ -173,6 +173,8 @@ struct te_pool {
   te::MailAdd mb_add{nullptr, nullptr, nullptr};   // set by the mailbox tick around its merge
   std::map<uint32_t, HostMail> orphans;            // mailboxes without a target that outlived a tick (unreadable ones)
   std::vector<PendingRec> pending;                 // records of unknown ids since the last tick, arrival order
+  char* h_stage = nullptr;                         // pinned staging for the tick's add arrays / the ingest's read-backs (grow-only)
+  size_t h_stage_cap = 0;
   // chunk pipeline of te_pool_tick_host
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   std::vector<cudaEvent_t> events;
@@ -280,6 +282,18 @@ void ensure_other_capacity(te_pool* p, size_t slots) {
 }
 
 // ---- mailboxes -------------------------------------------------------------------------------
+char* pinned_stage(te_pool* p, size_t bytes) {
+  if (bytes > p->h_stage_cap) {
+    CK(cudaStreamSynchronize(p->stream));
+    if (p->h_stage) cudaFreeHost(p->h_stage);
+    p->h_stage = nullptr;
+    p->h_stage_cap = 0;
+    const size_t cap = bytes + bytes / 2 + 4096;
+    CK(cudaHostAlloc((void**)&p->h_stage, cap, cudaHostAllocDefault));
+    p->h_stage_cap = cap;
+  }
+  return p->h_stage;
+}
 void free_mail(MailBuf& m) {
   cudaFree(m.a.sec); cudaFree(m.a.nsec); cudaFree(m.a.act); cudaFree(m.a.pose);
   m = MailBuf();
@@ -889,6 +903,7 @@ void te_pool_destroy(te_pool* p) {
   free_buf(p->buf[1]);
   free_mail(p->mb[0]);
   free_mail(p->mb[1]);
+  if (p->h_stage) cudaFreeHost(p->h_stage);
   cudaFree(p->action); cudaFree(p->dt_slot); cudaFree(p->tile_flag); cudaFree(p->tile_list);
   cudaFree(p->alive); cudaFree(p->pos); cudaFree(p->srcmap); cudaFree(p->d_counters); cudaFree(p->cub_tmp);
   cudaFree(p->dQ); cudaFree(p->dR); cudaFree(p->dP0);
@@ -1574,32 +1589,43 @@ int mailbox_ingest_impl(te_pool* p, long long n, const uint32_t* ids, const uint
   CK(cudaMemcpyAsync(&n_unknown, counter, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
   CK(cudaStreamSynchronize(p->stream));   // also: a host caller's record arrays are free again
   if (n_unknown == 0) return 0;
-  std::vector<int> list((size_t)n_unknown);
   if (host_src) {
+    std::vector<int> list((size_t)n_unknown);
     CK(cudaMemcpy(list.data(), unknown, (size_t)n_unknown * sizeof(int), cudaMemcpyDeviceToHost));
     std::sort(list.begin(), list.end());   // arrival order
     for (int k : list) queue(ids[k], sec[k], nsec[k], poses + 7 * (size_t)k);
     return 0;
   }
-  // device source: pack the unknown records (device order), read them back, queue them in arrival order
-  uint32_t* o_ids = p->arena.get_n<uint32_t>((size_t)n_unknown);
-  uint32_t* o_sec = p->arena.get_n<uint32_t>((size_t)n_unknown);
-  uint32_t* o_nsec = p->arena.get_n<uint32_t>((size_t)n_unknown);
-  double* o_pose = p->arena.get_n<double>((size_t)n_unknown * 7);
+  // device source: pack the unknown records (device order) into one block [pose 7 | index | id | sec | nsec] x n_unknown, read it
+  // back in one copy to pinned memory, queue the records in arrival order
+  const size_t nu = (size_t)n_unknown;
+  char* d_blk = (char*)p->arena.get(nu * 72);
+  double* o_pose = (double*)d_blk;
+  int* o_idx = (int*)(o_pose + 7 * nu);
+  uint32_t* o_ids = (uint32_t*)(o_idx + nu);
+  uint32_t* o_sec = o_ids + nu;
+  uint32_t* o_nsec = o_sec + nu;
   te::mb_pack_unknown_kernel<<<cdiv(n_unknown, 256), 256, 0, p->stream>>>(n_unknown, unknown, d_ids, d_sec, d_nsec, d_pose, o_ids, o_sec, o_nsec, o_pose);
   CK(cudaGetLastError());
-  std::vector<uint32_t> h_ids((size_t)n_unknown), h_sec((size_t)n_unknown), h_nsec((size_t)n_unknown);
-  std::vector<double> h_pose((size_t)n_unknown * 7);
-  CK(cudaMemcpyAsync(list.data(), unknown, (size_t)n_unknown * sizeof(int), cudaMemcpyDeviceToHost, p->stream));
-  CK(cudaMemcpyAsync(h_ids.data(), o_ids, (size_t)n_unknown * 4, cudaMemcpyDeviceToHost, p->stream));
-  CK(cudaMemcpyAsync(h_sec.data(), o_sec, (size_t)n_unknown * 4, cudaMemcpyDeviceToHost, p->stream));
-  CK(cudaMemcpyAsync(h_nsec.data(), o_nsec, (size_t)n_unknown * 4, cudaMemcpyDeviceToHost, p->stream));
-  CK(cudaMemcpyAsync(h_pose.data(), o_pose, (size_t)n_unknown * 56, cudaMemcpyDeviceToHost, p->stream));
+  CK(cudaMemcpyAsync(o_idx, unknown, nu * sizeof(int), cudaMemcpyDeviceToDevice, p->stream));
+  char* h_blk = pinned_stage(p, nu * 72);
+  CK(cudaMemcpyAsync(h_blk, d_blk, nu * 72, cudaMemcpyDeviceToHost, p->stream));
   CK(cudaStreamSynchronize(p->stream));
-  std::vector<int> order((size_t)n_unknown);
-  std::iota(order.begin(), order.end(), 0);
-  std::sort(order.begin(), order.end(), [&](int a, int c) { return list[(size_t)a] < list[(size_t)c]; });
-  for (int k : order) queue(h_ids[(size_t)k], h_sec[(size_t)k], h_nsec[(size_t)k], &h_pose[(size_t)k * 7]);
+  const double* h_pose = (const double*)h_blk;
+  const int* h_idx = (const int*)(h_pose + 7 * nu);
+  const uint32_t* h_ids = (const uint32_t*)(h_idx + nu);
+  const uint32_t* h_sec = h_ids + nu;
+  const uint32_t* h_nsec = h_sec + nu;
+  bool in_order = true;
+  for (size_t k = 1; k < nu && in_order; ++k) in_order = h_idx[k - 1] < h_idx[k];
+  if (in_order) {
+    for (size_t k = 0; k < nu; ++k) queue(h_ids[k], h_sec[k], h_nsec[k], h_pose + 7 * k);
+  } else {
+    std::vector<int> order(nu);
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(), [&](int a, int c) { return h_idx[a] < h_idx[c]; });
+    for (int k : order) queue(h_ids[(size_t)k], h_sec[(size_t)k], h_nsec[(size_t)k], h_pose + 7 * (size_t)k);
+  }
   return 0;
 }
 }  // namespace
@@ -1636,15 +1662,26 @@ long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, int cls_new
     const double now = host_to_sec(now_sec, now_nsec);
     // 1. target-less mailboxes, ascending id: readable -> init on first sight (src/target_manager_ros.cpp:54-58) unless the
     //    same tick would erase it again (:67-72; init + update + erase is unobservable); unreadable -> stays, or expires
-    std::vector<uint32_t> add_ids, add_sec, add_nsec, host_erased;
-    std::vector<double> add_pose, add_last, add_t0;
+    // the add arrays are written straight into ONE pinned block [pose 7 | t0 | last | id | sec | nsec] x max_add and go to the
+    // device in one copy
+    std::vector<uint32_t> host_erased;
+    const size_t max_add = p->pending.size() + p->orphans.size();
+    char* stage = max_add ? pinned_stage(p, max_add * 84) : nullptr;
+    double* add_pose = (double*)stage;
+    double* add_t0 = add_pose + 7 * max_add;
+    double* add_last = add_t0 + max_add;
+    uint32_t* add_ids = (uint32_t*)(add_last + max_add);
+    uint32_t* add_sec = add_ids + max_add;
+    uint32_t* add_nsec = add_sec + max_add;
+    size_t n_promoted = 0;
     auto promote = [&](uint32_t id, const HostMail& m) {
-      add_ids.push_back(id);
-      add_sec.push_back(m.sec);
-      add_nsec.push_back(m.nsec);
-      add_last.push_back(m.last);
-      add_t0.push_back(t0_new);
-      add_pose.insert(add_pose.end(), m.pose, m.pose + 7);
+      const size_t k = n_promoted++;
+      add_ids[k] = id;
+      add_sec[k] = m.sec;
+      add_nsec[k] = m.nsec;
+      add_last[k] = m.last;
+      add_t0[k] = t0_new;
+      std::memcpy(add_pose + 7 * k, m.pose, 56);
     };
     bool fast = p->orphans.empty();   // common case: every queued record is the first sight of a new id, ids ascending
     for (size_t k = 1; fast && k < p->pending.size(); ++k) fast = p->pending[k - 1].id < p->pending[k].id;
@@ -1673,10 +1710,10 @@ long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, int cls_new
         }
       }
     }
-    const int n_add = (int)add_ids.size();
+    const int n_add = (int)n_promoted;
     const int n_old = (int)p->n;
     if (n_added_out) *n_added_out = n_add;
-    if (added_out && added_cap > 0 && n_add > 0) std::memcpy(added_out, add_ids.data(), (size_t)std::min<long long>(added_cap, n_add) * sizeof(uint32_t));
+    if (added_out && added_cap > 0 && n_add > 0) std::memcpy(added_out, add_ids, (size_t)std::min<long long>(added_cap, n_add) * sizeof(uint32_t));
     mark(1);
     // 2. expiry flags of the existing targets, then ONE stable rebuild: survivors compacted, promoted mailboxes merged in by id
     ensure_work(p, (size_t)n_old + (size_t)n_add);
@@ -1690,16 +1727,22 @@ long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, int cls_new
     te::AddData ad{};
     std::vector<uint16_t> add_cls;
     if (n_add > 0) {
-      ad.ids = to_dev(p, add_ids.data(), (size_t)n_add);
+      char* d_stage = (char*)p->arena.get(max_add * 84);
+      CK(cudaMemcpyAsync(d_stage, stage, max_add * 84, cudaMemcpyHostToDevice, p->stream));   // (pinned: the final sync of the tick covers it)
+      const double* d_pose0 = (const double*)d_stage;
+      const double* d_t0 = d_pose0 + 7 * max_add;
+      const double* d_last = d_t0 + max_add;
+      const uint32_t* d_aid = (const uint32_t*)(d_last + max_add);
+      ad.ids = d_aid;
       if (cls_new != 0) {
         add_cls.assign((size_t)n_add, (uint16_t)cls_new);
         ad.cls = to_dev(p, add_cls.data(), (size_t)n_add);
       }
-      ad.t0 = to_dev(p, add_t0.data(), (size_t)n_add);
-      ad.p0 = to_dev(p, add_pose.data(), (size_t)n_add * 7);
-      p->mb_add.sec = to_dev(p, add_sec.data(), (size_t)n_add);
-      p->mb_add.nsec = to_dev(p, add_nsec.data(), (size_t)n_add);
-      p->mb_add.last = to_dev(p, add_last.data(), (size_t)n_add);
+      ad.t0 = d_t0;
+      ad.p0 = d_pose0;
+      p->mb_add.sec = d_aid + max_add;
+      p->mb_add.nsec = d_aid + 2 * max_add;
+      p->mb_add.last = d_last;
     }
     const bool unfused_env = std::getenv("TE_MB_UNFUSED") != nullptr;   // debugging / test switch: the rebuild-then-step form
     const bool fused = !unfused_env && n_old > 0;
