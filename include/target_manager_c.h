@@ -70,6 +70,9 @@ void target_manager_flush(const target_manager_c* self);
 target_manager_c* target_tick_manager_new(const char* file, int device);
 void target_tick_manager_set_expiration(const target_manager_c* self, double timeout_s);
 void target_tick_manager_set_token(const target_manager_c* self, const char* token);
+/* gather the filtered poses after every tick (the TF broadcast of src/target_manager_ros.cpp:78-87; default on) or leave them on the
+ * device until a getter asks */
+void target_tick_manager_set_publish(const target_manager_c* self, int on);
 /* /tf callback: n transforms with child frame "<token>_<id>" (frames) or already-parsed ids */
 void target_tick_manager_callback_frames(const target_manager_c* self, long long n, const char* const* child_frame_ids,
                                          const unsigned int* sec, const unsigned int* nsec, const double* poses /*[n][7]*/);

@@ -4,6 +4,7 @@
 // itself runs in the CUDA layer (no computation of filter state happens on the host).
 #include "target_estimation_b200/target_manager.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -143,6 +144,63 @@ te_pool* TargetManager::poolOf(int type, bool create) {
     if (!pools_[type]) throw PoolError(te_last_error());
   }
   return pools_[type];
+}
+
+// ---- IdRegistry ------------------------------------------------------------------------------------------
+IdRegistry::iterator IdRegistry::find(unsigned id) {
+  auto it = std::lower_bound(v_.begin(), v_.end(), id, [](const value_type& a, unsigned key) { return a.first < key; });
+  return (it != v_.end() && it->first == id) ? it : v_.end();
+}
+uint8_t& IdRegistry::operator[](unsigned id) {
+  if (v_.empty() || v_.back().first < id) {   // ascending arrivals (track ids grow): append
+    v_.emplace_back(id, (uint8_t)0);
+    return v_.back().second;
+  }
+  auto it = std::lower_bound(v_.begin(), v_.end(), id, [](const value_type& a, unsigned key) { return a.first < key; });
+  if (it == v_.end() || it->first != id) it = v_.insert(it, value_type(id, (uint8_t)0));
+  return it->second;
+}
+size_t IdRegistry::erase(unsigned id) {
+  auto it = find(id);
+  if (it == v_.end()) return 0;
+  v_.erase(it);
+  return 1;
+}
+void IdRegistry::mergeSorted(const std::vector<value_type>& add) {
+  if (add.empty()) return;
+  if (v_.empty() || v_.back().first < add.front().first) {   // append-only batch
+    v_.insert(v_.end(), add.begin(), add.end());
+    return;
+  }
+  std::vector<value_type> out;
+  out.reserve(v_.size() + add.size());
+  size_t i = 0, j = 0;
+  while (i < v_.size() && j < add.size()) {
+    if (v_[i].first < add[j].first) out.push_back(v_[i++]);
+    else if (add[j].first < v_[i].first) out.push_back(add[j++]);
+    else { out.push_back(v_[i++]); ++j; }   // existing entry wins
+  }
+  out.insert(out.end(), v_.begin() + (long)i, v_.end());
+  out.insert(out.end(), add.begin() + (long)j, add.end());
+  v_.swap(out);
+}
+void IdRegistry::insertSorted(const uint32_t* ids, size_t n, uint8_t type) {
+  std::vector<value_type> add;
+  add.reserve(n);
+  for (size_t k = 0; k < n; ++k) add.emplace_back(ids[k], type);
+  mergeSorted(add);
+}
+void IdRegistry::eraseSorted(const uint32_t* ids, size_t n) {
+  if (n == 0 || v_.empty()) return;
+  size_t w = 0, j = 0;
+  auto first = std::lower_bound(v_.begin(), v_.end(), ids[0], [](const value_type& a, unsigned key) { return a.first < key; });
+  w = (size_t)(first - v_.begin());
+  for (size_t i = w; i < v_.size(); ++i) {
+    while (j < n && ids[j] < v_[i].first) ++j;
+    if (j < n && ids[j] == v_[i].first) continue;   // dropped
+    v_[w++] = v_[i];
+  }
+  v_.resize(w);
 }
 
 int TargetManager::registerClass(int type, const MatrixXd& Q, const MatrixXd& R, const MatrixXd& P0) {
@@ -366,13 +424,15 @@ bool TargetManager::erase(const unsigned int& id) {   // :227-241
 long long TargetManager::eraseBatch(long long n, const unsigned* ids) {
   std::lock_guard<std::recursive_mutex> lg(target_lock_);
   flushLocked();
-  std::vector<uint32_t> per[4];
+  std::vector<uint32_t> per[4], found;
   for (long long k = 0; k < n; ++k) {
     auto it = targets_.find(ids[k]);
     if (it == targets_.end()) continue;
     per[it->second].push_back(ids[k]);
-    targets_.erase(it);
+    found.push_back(ids[k]);
   }
+  std::sort(found.begin(), found.end());
+  targets_.eraseSorted(found.data(), found.size());
   long long erased = 0;
   for (int t = 0; t < 4; ++t) {
     if (per[t].empty()) continue;

@@ -179,6 +179,9 @@ target_manager_c* target_tick_manager_new(const char* file, int device) {
 void target_tick_manager_set_expiration(const target_manager_c* self, double timeout_s) {
   guard(0, [&] { T(self)->setExpirationTime(timeout_s); return 0; });
 }
+void target_tick_manager_set_publish(const target_manager_c* self, int on) {
+  guard(0, [&] { T(self)->publish = on != 0; return 0; });
+}
 void target_tick_manager_set_token(const target_manager_c* self, const char* token) {
   guard(0, [&] { T(self)->setTargetTokenName(token ? token : ""); return 0; });
 }

@@ -169,17 +169,20 @@ void TickTargetManager::tick(const double& dt, uint32_t now_sec, uint32_t now_ns
   te_pool* pool = tickPool();
   // 1. the device tick: first-sight init, sticky update / predict, expiry -- one rebuild + one step launch (:46-76)
   const long long cap = std::max<long long>(te_pool_mailbox_bound(pool), 1);
-  std::vector<uint32_t> gone((size_t)cap), born((size_t)cap);
-  long long n_born = 0;
-  const long long n_gone = te_pool_mailbox_tick(pool, dt, t_, cls_, now_sec, now_nsec, expiration_time_, gone.data(), cap, born.data(), cap, &n_born);
-  if (n_gone < 0) throw std::runtime_error(te_last_error());
-  gone.resize((size_t)n_gone);
-  born.resize((size_t)std::min(n_born, cap));
-  for (uint32_t id : born) targets_.emplace_hint(targets_.end(), id, (uint8_t)type_);
-  for (uint32_t id : gone) {
-    if (!quiet) std::printf("Timeout for target %u\n", id);
-    targets_.erase(id);   // (a target-less mailbox that expired has no entry here)
+  if ((long long)gone_buf_.size() < cap) {   // reused across ticks: sizing them per tick would zero 8 bytes per target per tick
+    gone_buf_.resize((size_t)(cap + cap / 4));
+    born_buf_.resize((size_t)(cap + cap / 4));
   }
+  long long n_born = 0;
+  const long long n_gone = te_pool_mailbox_tick(pool, dt, t_, cls_, now_sec, now_nsec, expiration_time_, gone_buf_.data(), cap, born_buf_.data(), cap,
+                                                &n_born);
+  if (n_gone < 0) throw std::runtime_error(te_last_error());
+  std::vector<uint32_t> gone(gone_buf_.begin(), gone_buf_.begin() + std::min(n_gone, cap));
+  std::vector<uint32_t> born(born_buf_.begin(), born_buf_.begin() + std::min(n_born, cap));
+  targets_.insertSorted(born.data(), born.size(), (uint8_t)type_);   // both lists are ascending: one linear pass each
+  targets_.eraseSorted(gone.data(), gone.size());                    // (a target-less mailbox that expired has no entry here)
+  if (!quiet)
+    for (uint32_t id : gone) std::printf("Timeout for target %u\n", id);
   // 2. host mailboxes of ids living under another model type, if any
   if (!measurements_.empty()) {
     std::vector<unsigned> gone2;

@@ -41,6 +41,7 @@ _SIG = {
     "target_tick_manager_new": (_p, [C.c_char_p, _i]),
     "target_tick_manager_set_expiration": (None, [_p, _d]),
     "target_tick_manager_set_token": (None, [_p, C.c_char_p]),
+    "target_tick_manager_set_publish": (None, [_p, _i]),
     "target_tick_manager_callback_frames": (None, [_p, _ll, _p, _p, _p, _p]),
     "target_tick_manager_callback_ids": (None, [_p, _ll, _p, _p, _p, _p]),
     "target_tick_manager_update": (_ll, [_p, _d, _u, _u, _p, _ll]),
@@ -202,6 +203,9 @@ class TickManagerC(TargetManagerC):
 
     def set_expiration(self, t):
         clib.target_tick_manager_set_expiration(self.h, float(t))
+
+    def set_publish(self, on):
+        clib.target_tick_manager_set_publish(self.h, 1 if on else 0)
 
     def set_token(self, s):
         clib.target_tick_manager_set_token(self.h, s.encode())

@@ -208,6 +208,54 @@ def c3_mailbox(n=1 << 20, ticks=48, model="angular_rates", device_records=False)
     return out
 
 
+def c3_tick_manager(n=1 << 20, ticks=24, model="angular_rates", publish=False):
+    """the same churn through the REFERENCE-FACING library (libtarget_c.so): target_tick_manager_callback_ids + target_tick_manager_update
+    (TickTargetManager: host registry of ids + the device mailboxes), optionally with the per-tick gather of every filtered pose
+    (what the node broadcasts).  Messages come from ordinary host arrays."""
+    from target_estimation_b200.manager import TickManagerC
+    mgr = TickManagerC(os.path.join(ROOT, "models", "model_%s_params.yaml" % model), device=torch.cuda.current_device())
+    timeout = 8 * DT
+    mgr.set_expiration(timeout); mgr.set_publish(publish)
+    rng = np.random.default_rng(2)
+
+    def clock(tk):
+        ns_ = 1000 * 10 ** 9 + tk * 4000000
+        return ns_ // 10 ** 9, ns_ % 10 ** 9
+    ids = np.arange(n, dtype=np.int64); silent_at = np.full(n, 1 << 30, dtype=np.int64); next_id = n
+    poses = np.zeros((int(n * 1.1), 7)); poses[:, :3] = rng.uniform(-5, 5, (poses.shape[0], 3)); poses[:, 6] = 1.0
+    msgs = []
+    for k in range(ticks + 1):
+        if k > 0:
+            old = np.nonzero(silent_at > k)[0]
+            quit_ = rng.choice(old, size=max(1, old.size // 100), replace=False)
+            silent_at[quit_] = k
+            fresh = np.arange(next_id, next_id + quit_.size, dtype=np.int64); next_id += quit_.size
+            ids = np.concatenate([ids, fresh]); silent_at = np.concatenate([silent_at, np.full(fresh.size, 1 << 30, dtype=np.int64)])
+        sec, nsec = clock(k)
+        r = ids[silent_at > k].astype(np.uint32)
+        msgs.append((r, np.full(r.size, sec, dtype=np.uint32), np.full(r.size, nsec, dtype=np.uint32)))
+    r, s_, ns_ = msgs[0]
+    mgr.callback_ids(r, s_, ns_, poses[:r.size]); mgr.tick(DT, *clock(0))
+    parts = {"callback": 0.0, "tick": 0.0}
+    n_erased = 0
+    t0 = time.perf_counter()
+    for k in range(1, ticks + 1):
+        r, s_, ns_ = msgs[k]
+        ta = time.perf_counter()
+        mgr.callback_ids(r, s_, ns_, poses[:r.size])
+        tb = time.perf_counter()
+        n_erased += mgr.tick(DT, *clock(k), cap=1 << 16).size
+        tc = time.perf_counter()
+        parts["callback"] += tb - ta; parts["tick"] += tc - tb
+    dt_wall = time.perf_counter() - t0
+    n_live = mgr.ids().size
+    out = {"model": model, "targets": n, "ticks": ticks, "erased": int(n_erased), "live_at_end": int(n_live), "publish": bool(publish),
+           "ms_per_tick": 1e3 * dt_wall / ticks, "ms_per_tick_parts": {k_: 1e3 * v / ticks for k_, v in parts.items()},
+           "note": "libtarget_c.so: target_tick_manager_callback_ids + target_tick_manager_update, pageable host arrays"}
+    mgr.close()
+    return out
+
+
 def c4_intersect(model, n=1 << 20, ticks=20):
     stream = torch.cuda.Stream()
     v0 = np.zeros((n, 6)); v0[:, 0] = 1.0                       # every target flies along +x at 1 m/s ...
@@ -274,6 +322,9 @@ def replay(model="uniform_acceleration", n=4 << 20, T=16, launches=10):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "tickmgr":
+        print(json.dumps({"c3_tick_manager_angular_rates": c3_tick_manager(), "c3_tick_manager_angular_rates_publish": c3_tick_manager(publish=True)}))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "mailbox":
         print(json.dumps({"c3_mailbox_angular_rates": c3_mailbox(), "c3_mailbox_uniform_acceleration": c3_mailbox(model="uniform_acceleration"),
                           "c3_mailbox_angular_rates_device_records": c3_mailbox(device_records=True),
