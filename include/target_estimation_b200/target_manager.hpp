@@ -284,6 +284,7 @@ class TickTargetManager : public TargetManager {
  public:
   TickTargetManager(target_t type, const MatrixXd& Q, const MatrixXd& R, const MatrixXd& P, int device = 0);
   explicit TickTargetManager(const std::string& yaml_file, int device = 0);
+  ~TickTargetManager() override;
   // /tf callback (src/target_manager_ros.cpp:26-39): frame "<token>_<id>"; a frame that contains the token but does
   // not parse BREAKS the loop (the rest of the message is dropped), like the reference
   void measurementCallBack(long long n, const char* const* child_frame_ids, const uint32_t* sec, const uint32_t* nsec, const double* poses);
@@ -312,6 +313,7 @@ class TickTargetManager : public TargetManager {
   std::vector<unsigned> pub_ids_;
   std::vector<double> pub_poses_;
   std::vector<uint32_t> gone_buf_, born_buf_;   // reusable output buffers of te_pool_mailbox_tick
+  void* pub_pinned_ = nullptr;                  // storage of pub_poses_ while it is page-locked
 };
 
 // utils.hpp:273-313

@@ -35,6 +35,9 @@ int te_device_count(void);
 int te_model_dims(int model, int* n, int* m);           /* state / measurement dims, asserts of src/types/*.cpp */
 size_t te_model_bytes_per_step(int model);                /* SURVEY.md 8(d) algorithmic bytes per target-step */
 
+/* page-lock / unlock a host buffer the caller owns (cudaHostRegister): read-backs into it then run at PCIe speed */
+int te_host_register(void* ptr, size_t bytes);
+int te_host_unregister(void* ptr);
 /* ---- pool lifecycle ---------------------------------------------------------------- */
 te_pool* te_pool_create(int model, int device, void* cuda_stream /* cudaStream_t or NULL = own stream */);
 void te_pool_destroy(te_pool* p);

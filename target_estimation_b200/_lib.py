@@ -61,6 +61,8 @@ SIGNATURES = {
     "te_pool_stamp_dense": (_i, [_p, _p, _i, _u32, _u32]),
     "te_pool_expire": (_ll, [_p, _u32, _u32, _d, _p, _ll]),
     "te_pool_step_dense_expire": (_ll, [_p, _d, _p, _i, _p, _i, _u32, _u32, _u32, _u32, _d, _p, _ll]),
+    "te_host_register": (_i, [_p, C.c_size_t]),
+    "te_host_unregister": (_i, [_p]),
     "te_pool_mailbox_ingest": (_i, [_p, _ll, _p, _p, _p, _p]),
     "te_pool_mailbox_ingest_dev": (_i, [_p, _ll, _p, _p, _p, _p]),
     "te_pool_mailbox_tick": (_ll, [_p, _d, _d, _i, _u32, _u32, _d, _p, _ll, _p, _ll, _p]),

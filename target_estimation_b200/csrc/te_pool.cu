@@ -837,6 +837,19 @@ int te_device_count(void) {
   return n;
 }
 
+int te_host_register(void* ptr, size_t bytes) {
+  if (!ptr || !bytes) return 0;
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); g_err = std::string("cudaHostRegister: ") + cudaGetErrorString(e); return -1; }
+  return 0;
+}
+int te_host_unregister(void* ptr) {
+  if (!ptr) return 0;
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) { cudaGetLastError(); g_err = std::string("cudaHostUnregister: ") + cudaGetErrorString(e); return -1; }
+  return 0;
+}
+
 int te_model_dims(int model, int* n, int* m) {
   if (model < 0 || model > 3) return -1;
   if (n) *n = te::model_n(model);
