@@ -276,7 +276,8 @@ void ensure_other_capacity(te_pool* p, size_t slots) {
   if (slots <= b.cap && b.tiles) return;
   CK(cudaStreamSynchronize(p->stream));
   free_buf(b);
-  alloc_buf(p, b, std::max(slots, p->buf[p->cur].cap));
+  // grow geometrically: a pool that gains a few targets per tick must not re-allocate gigabytes on every tick
+  alloc_buf(p, b, std::max(slots + slots / 4, p->buf[p->cur].cap));
   // the work arrays hold the live alive[] / pos[] of the running compaction: callers size them up-front
   if (p->wcap < slots) throw std::logic_error("work arrays not sized before compaction");
 }
