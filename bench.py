@@ -177,6 +177,9 @@ def _cpu_bench_fn(kind):
     return R.refm_bench_steps
 
 
+_TICK_RATE = {}   # (kind, model, threads) -> ticks per second of the last timed run: later runs skip the probe
+
+
 def cpu_run(model_name, threads, seconds, n_targets=10000, kind="port"):
     import ctypes as C
     from tests import orc
@@ -195,9 +198,12 @@ def cpu_run(model_name, threads, seconds, n_targets=10000, kind="port"):
 
     def run(ticks):
         return fn(mtype, orc.ptr(Qc), n, orc.ptr(Rc), m, orc.ptr(Pc), n_targets, ticks, threads, DT, orc.ptr(meas), 0.05, C.byref(chk))
-    t_probe = run(2)
-    ticks = max(2, int(seconds / max(t_probe / 2, 1e-9)))
+    key = (kind, model_name, threads)
+    if key not in _TICK_RATE:
+        _TICK_RATE[key] = 2.0 / max(run(2), 1e-9)
+    ticks = max(2, int(seconds * _TICK_RATE[key]))
     t = run(ticks)
+    _TICK_RATE[key] = ticks / max(t, 1e-9)
     return {"value": n_targets * ticks / t, "ticks": ticks, "targets": n_targets, "seconds": t, "threads": threads, "kind": kind}
 
 
@@ -232,7 +238,7 @@ def reference_arm(args, rank):
     from tests import orc
     cores = orc.lib().orc_hardware_threads()
     K = max(1, args.steps)
-    per_step = min(5.0, 150.0 / (K + args.warmup))   # bounded sample: the whole run stays within a few minutes
+    per_step = min(5.0, 100.0 / (K + args.warmup))   # bounded sample: the whole run stays within a few minutes
     for _ in range(args.warmup):
         cpu_best(args.model, cores, per_step / 4)
     vals, secs, kinds = [], 0.0, []
