@@ -641,13 +641,17 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
       }
 
       // ---- phase D: own block back into the stage (nobody reads the published entries after phase B) ----
+      // (compacting tick: the stage is never stored, so a stepped target's rows go from the registers straight to its destination
+      // slot below instead of through shared memory)
       if (active) {
+        if (!COMPACT) {
 #pragma unroll
-        for (int q = 0; q < RPT; ++q) {
-          const int g = q * RS + r;
-          if (h == 0) st[(LY::F_X + g) * TILE + lane] = xr[q];
+          for (int q = 0; q < RPT; ++q) {
+            const int g = q * RS + r;
+            if (h == 0) st[(LY::F_X + g) * TILE + lane] = xr[q];
 #pragma unroll
-          for (int j = 0; j < NCOL; ++j) st[(LY::F_P + g * N + colof(j)) * TILE + lane] = Pr[q][j];
+            for (int j = 0; j < NCOL; ++j) st[(LY::F_P + g * N + colof(j)) * TILE + lane] = Pr[q][j];
+          }
         }
         if (w == 0) {
           st[LY::F_T * TILE + lane] = st[LY::F_T * TILE + lane] + dt;   // updateTime
@@ -659,7 +663,22 @@ __global__ void __launch_bounds__((SPLIT_RS * CS + split_nt<TYPE>()) * 32, MIN_C
         }
       }
       if (a.pos_out && valid && w < 3) a.pos_out[(size_t)slot * 3 + w] = xr[0];
-      if (COMPACT) compact_out(st);
+      if (COMPACT && dst >= 0) {
+        double* dr = a.dst_tiles + (size_t)(dst / TILE) * LY::TILE_DOUBLES + (dst % TILE);
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) {
+          const int g = q * RS + r;
+          if (h == 0) __stcs(dr + (size_t)(LY::F_X + g) * TILE, active ? xr[q] : st[(LY::F_X + g) * TILE + lane]);
+#pragma unroll
+          for (int j = 0; j < NCOL; ++j)
+            if (!packed || colof(j) >= g)
+              __stcs(dr + (size_t)(LY::F_P + g * N + colof(j)) * TILE, active ? Pr[q][j] : st[(LY::F_P + g * N + colof(j)) * TILE + lane]);
+        }
+        if (w == 0) {   // t, n_meas (updated in the stage above), previous unwrapped angles
+#pragma unroll
+          for (int f = LY::F_P + N * N; f < LY::NF; ++f) __stcs(dr + (size_t)f * TILE, st[f * TILE + lane]);
+        }
+      }
       fence_proxy_async();   // generic-proxy writes of the stage -> visible to the producer's bulk store
       TE_MARK(10);
       __syncwarp();
