@@ -44,7 +44,7 @@ void te_pool_destroy(te_pool* p);
 int te_pool_set_stream(te_pool* p, void* cuda_stream);
 int te_pool_sync(te_pool* p);
 int te_pool_set_variant(te_pool* p, int variant);         /* kernel shape (warps x stages); tuning knob */
-int te_pool_reserve(te_pool* p, size_t n_targets);
+int te_pool_reserve(te_pool* p, size_t n_targets);   /* both buffer generations: no later tick pays for the allocation */
 long long te_pool_size(te_pool* p);
 size_t te_pool_device_bytes(te_pool* p);
 

@@ -966,6 +966,13 @@ int te_pool_reserve(te_pool* p, size_t n_targets) {
     } else {
       ensure_cur_capacity(p, n_targets);
     }
+    // the second generation too (every compaction -- erase, merge-add, expiry -- gathers into it): no tick pays for a
+    // multi-gigabyte allocation later
+    ensure_other_capacity(p, n_targets);
+    if (p->mb_on) {
+      ensure_mail_cur(p, n_targets);
+      ensure_mail_other(p, n_targets);
+    }
     return 0;
   });
 }
