@@ -225,7 +225,7 @@ def make_config(model, n, world, variant, n_sets=4, stride=7):
     N, M = tp.model_dims(tp.MODEL_TYPES[model])
     short = MODEL_SHORT[model]
     return {"workload": "BASELINE configs[1] (%s, FP64 predict+update per measurement tick) at %d targets per GPU" % (short, n),
-            "model": model, "targets_per_gpu": n, "targets_total": n * world, "dt": DT, "missed_measurement_prob": 0.05,
+            "motion_model": model, "targets_per_gpu": n, "targets_total": n * world, "dt": DT, "missed_measurement_prob": 0.05,
             "measurement_layout": "[n][7] pose, device resident, %d rotating sets" % n_sets,
             "l2": "inputs larger than L2: state %.0f MB + %.0f MB of measurements per tick vs 126 MB L2" % (
                 n * (N + N * N + 2) * 8 / 1e6, n * stride * 8 / 1e6),
