@@ -329,9 +329,11 @@ if __name__ == "__main__":
         print(json.dumps({"c3_tick_manager_angular_rates": c3_tick_manager(), "c3_tick_manager_angular_rates_publish": c3_tick_manager(publish=True)}))
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "mailbox":
-        print(json.dumps({"c3_mailbox_angular_rates": c3_mailbox(), "c3_mailbox_uniform_acceleration": c3_mailbox(model="uniform_acceleration"),
-                          "c3_mailbox_angular_rates_device_records": c3_mailbox(device_records=True),
-                          "c3_mailbox_uniform_acceleration_device_records": c3_mailbox(model="uniform_acceleration", device_records=True)}))
+        res = {}
+        for m_ in ("angular_rates", "uniform_acceleration", "angular_velocities", "uniform_velocity"):
+            res["c3_mailbox_" + m_] = c3_mailbox(model=m_)
+            res["c3_mailbox_" + m_ + "_device_records"] = c3_mailbox(model=m_, device_records=True)
+        print(json.dumps(res))
         sys.exit(0)
     res = {"c3_churn_angular_rates": c3_churn(), "c3_churn_angular_rates_fused": c3_churn(fused=True), "c4_intersect_uniform_velocity": c4_intersect("uniform_velocity"),
            "c4_intersect_uniform_acceleration": c4_intersect("uniform_acceleration"),
