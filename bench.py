@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--variant", type=int, default=-1)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ref-abi", action="store_true", help="skip the e2e figure through libtarget_c.so")
+    ap.add_argument("--no-node-loop", action="store_true", help="skip the secondary node-loop (mailbox churn) figure")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-small", action="store_true")
     ap.add_argument("--allgather", action="store_true", help="also time the optional all-gather of estimates (N>1)")
@@ -597,6 +598,21 @@ def main():
                "clocks": clocks, "gpu_launches": K, "e2e": e2e, "cpu_baseline": cpu, "c2_10k": small}
         if allgather:
             out["allgather"] = allgather
+        if world == 1 and not args.no_node_loop:
+            # BASELINE configs[2]-style secondary figure (NOT the headline): the reference's whole node loop -- /tf records from pinned
+            # host memory into the device-resident mailboxes, first-sight init, sticky update / predict, expiry with 1 % id churn per
+            # tick -- for this motion model at 1 Mi targets (tools/bench_configs.py c3_mailbox; erase lists checked against a host model)
+            # (in a process of its own: whatever happens there cannot take the headline line with it)
+            try:
+                import subprocess
+                tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "bench_configs.py")
+                env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local_rank)))
+                pr = subprocess.run([sys.executable, tool, "mailbox1", model], capture_output=True, text=True, timeout=180, env=env)
+                r = json.loads(pr.stdout.strip().splitlines()[-1])
+                out["node_loop"] = {k_: r[k_] for k_ in ("model", "targets", "ticks", "erased", "added", "records_per_tick", "h2d_bytes_per_tick",
+                                                         "ms_per_tick", "target_steps_per_s", "ms_per_tick_parts", "note")}
+            except Exception as e:   # secondary figure: report, never fail the headline
+                out["node_loop"] = {"error": ("%s: %s" % (type(e).__name__, e))[:300]}
         print(json.dumps(out), flush=True)
     pool.close()
     if world > 1:

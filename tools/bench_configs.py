@@ -325,6 +325,9 @@ def replay(model="uniform_acceleration", n=4 << 20, T=16, launches=10):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "mailbox1":   # one model, short: bench.py's secondary node-loop figure
+        print(json.dumps(c3_mailbox(ticks=24, model=sys.argv[2])))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "tickmgr":
         print(json.dumps({"c3_tick_manager_angular_rates": c3_tick_manager(), "c3_tick_manager_angular_rates_publish": c3_tick_manager(publish=True)}))
         sys.exit(0)
