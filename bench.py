@@ -40,6 +40,11 @@ UNIT = "target-steps/s"
 KERNEL_NAME = {"uniform_velocity": "te::kf_step_kin_direct_kernel", "uniform_acceleration": "te::kf_step_kin_direct_kernel",
                "angular_velocities": "te::kf_step_av_direct_kernel", "angular_rates": "te::kf_step_split_kernel"}
 MODEL_SHORT = {"uniform_velocity": "UV", "uniform_acceleration": "UA", "angular_velocities": "AV", "angular_rates": "AR"}
+MODEL_DIMS = {"uniform_velocity": (6, 3), "uniform_acceleration": (9, 3), "angular_velocities": (12, 6), "angular_rates": (18, 6)}   # (n, m)
+
+
+def model_yaml(model):
+    return os.path.join(ROOT, "models", "model_%s_params.yaml" % model)
 
 
 def parse():
@@ -55,6 +60,7 @@ def parse():
     ap.add_argument("--no-ref-abi", action="store_true", help="skip the e2e figure through libtarget_c.so")
     ap.add_argument("--no-node-loop", action="store_true", help="skip the secondary node-loop (mailbox churn) figure")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sampled oracle check of the benchmarked pool")
     ap.add_argument("--no-small", action="store_true")
     ap.add_argument("--allgather", action="store_true", help="also time the optional all-gather of estimates (N>1)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -184,8 +190,8 @@ _TICK_RATE = {}   # (kind, model, threads) -> ticks per second of the last timed
 def cpu_run(model_name, threads, seconds, n_targets=10000, kind="port"):
     import ctypes as C
     from tests import orc
-    import target_estimation_b200.pool as tp  # load_model only (pure python)
-    mtype, _, Q, R, P0 = tp.load_model(model_name)
+    y = orc.load_yaml(model_yaml(model_name))   # the oracle's own reader: the CPU arms never load the CUDA library
+    mtype, Q, R, P0 = y["type"], y["Q"], y["R"], y["P"]
     fn = _cpu_bench_fn(kind)
     if fn is None:
         return None
@@ -222,8 +228,7 @@ def default_targets(model):
 
 
 def make_config(model, n, world, variant, n_sets=4, stride=7):
-    import target_estimation_b200.pool as tp
-    N, M = tp.model_dims(tp.MODEL_TYPES[model])
+    N, M = MODEL_DIMS[model]
     short = MODEL_SHORT[model]
     return {"workload": "BASELINE configs[1] (%s, FP64 predict+update per measurement tick) at %d targets per GPU" % (short, n),
             "motion_model": model, "targets_per_gpu": n, "targets_total": n * world, "dt": DT, "missed_measurement_prob": 0.05,
@@ -275,7 +280,7 @@ def make_pool(te, torch, model_name, n, rank, world, stream, variant):
     pool.reserve(n)
     rng = np.random.default_rng(0x7A26E7 + rank)
     chunk = 1 << 20
-    p0_all = []
+    p0_all, scale_all = [], []
     for s in range(0, n, chunk):
         k = min(chunk, n - s)
         ids = (np.arange(s, s + k, dtype=np.int64) * world + rank).astype(np.uint32)   # owner(id) = id mod G
@@ -287,7 +292,8 @@ def make_pool(te, torch, model_name, n, rank, world, stream, variant):
         scale = rng.uniform(0.5, 2.0, k)                                                # anti-cohort P0 scale (H6)
         pool.add(ids, p0, p0_scale=scale)
         p0_all.append(p0)
-    return pool, mtype, np.concatenate(p0_all)
+        scale_all.append(scale)
+    return pool, mtype, np.concatenate(p0_all), np.concatenate(scale_all)
 
 
 def make_inputs(torch, p0, n_sets, stride, miss_prob, seed):
@@ -329,7 +335,7 @@ def main():
     n = args.targets or default_targets(model)
     K, W = args.steps, max(args.warmup, 3)
     stream = torch.cuda.Stream()
-    pool, mtype, p0 = make_pool(te, torch, model, n, rank, world, stream, args.variant)
+    pool, mtype, p0, p0_scale = make_pool(te, torch, model, n, rank, world, stream, args.variant)
     N, M = te.model_dims(mtype)
     stride = 7
     n_sets = 4
@@ -344,8 +350,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    history = []   # measurement / action set of every tick the pool has seen, in order (replayed by the oracle in parity_check)
+
     def tick(k):
         pool.step_dense(DT, meas[k % n_sets], stride, act[k % n_sets])
+        history.append(k % n_sets)
 
     # ---- resident-input throughput -----------------------------------------------------------------
     for k in range(W):
@@ -412,6 +421,7 @@ def main():
             check = te.lib.te_pool_tick_host(pool._h, DT, h_meas[k % 2].data_ptr(), stride, h_act[k % 2].data_ptr(), 2, h_out.data_ptr())
             if check < 0:
                 raise RuntimeError(te._lib.last_error())
+            history.append(k % 2)
         for k in range(3):
             tick_host(k)
         barrier()
@@ -437,6 +447,7 @@ def main():
             def tick_host3(k):
                 if te.lib.te_pool_tick_host(pool._h, DT, h3[k % 2].data_ptr(), 3, h_act[k % 2].data_ptr(), 2, h_out.data_ptr()) < 0:
                     raise RuntimeError(te._lib.last_error())
+                history.append(k % 2)
             for k in range(3):
                 tick_host3(k)
             barrier()
@@ -515,7 +526,7 @@ def main():
     small = None
     if rank == 0 and not args.no_small:
         ns = 10000
-        sp, _, p0s = make_pool(te, torch, model, ns, 0, 1, stream, args.variant)
+        sp, _, p0s, _ = make_pool(te, torch, model, ns, 0, 1, stream, args.variant)
         ms_, as_ = make_inputs(torch, p0s, 2, stride, 0.05, 99)
         for k in range(20):
             sp.step_dense(DT, ms_[k % 2], stride, as_[k % 2])
@@ -573,6 +584,39 @@ def main():
             small["cuda_graph"] = {"error": str(e)[:200]}
         sp.close()
 
+    # ---- parity_check: sampled targets of THIS pool after everything above, against the oracle replaying the same history ----
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from tests import orc, synth
+        rng = np.random.default_rng(5)
+        ns = min(n, 1024)
+        sample = np.unique(np.concatenate([np.arange(min(n, 32)), np.arange(max(0, n - 40), n), rng.choice(n, ns, replace=False)]))
+        ids_s = (sample.astype(np.int64) * world + rank).astype(np.uint32)
+        st = torch.from_numpy(sample).cuda()
+        meas_s = [m[st].cpu().numpy() for m in meas]
+        act_s = [a_[st].cpu().numpy() for a_ in act]
+        full = np.zeros((len(history), sample.size, 7))
+        full[:, :, 6] = 1.0
+        acts = np.zeros((len(history), sample.size), dtype=np.uint8)
+        for j, h in enumerate(history):
+            full[j, :, :stride] = meas_s[h]
+            acts[j] = act_s[h]
+        _, _, Qm, Rm, P0m = te.load_model(model)
+        ref = orc.ShardedManager()
+        ref.init_batch(mtype, ids_s, DT, Qm, Rm, P0m, p0[sample], p0_scale[sample])
+        ref.step_ticks(ids_s, DT, full, acts)
+        want = ref.states(ids_s, N)
+        got = pool.read_state(ids_s)
+        rx, rx6 = synth.compare_both(got["x"], want["x"])
+        rP, rP6 = synth.compare_both(got["P"], want["P"])
+        exact = bool(np.array_equal(got["n_meas"], want["n_meas"]) and np.array_equal(got["t"], want["t"]))
+        parity = {"n": int(sample.size), "ticks_replayed": len(history), "max_ratio": max(rx, rP), "max_ratio_x": rx, "max_ratio_P": rP,
+                  "max_ratio_floor1e-6": max(rx6, rP6), "t_and_n_meas_exact": exact, "pass": bool(max(rx, rP) <= 1.0 and exact),
+                  "bar": "|d| <= 1e-9 * max(|ref_ij|, 1e-4 * max|ref|) per state vector / covariance matrix (tests/synth.py compare_h2); "
+                         "max_ratio = worst |d| / bound over the sampled targets of the %d-target pool after every tick of this run "
+                         "(resident-input ticks, clock burst, e2e ticks), oracle = oracle/ port replaying the copied-back inputs" % n}
+        ref.close()
+
     cpu = None
     if rank == 0 and not args.no_cpu:
         from tests import orc
@@ -595,7 +639,7 @@ def main():
                             "layout": {"bytes_per_update_step": L_upd, "bytes_per_predict_step": L_pred, "bytes_per_launch": layout_bytes,
                                        "achieved": achieved_layout, "frac": achieved_layout / peak, "note": layout_note +
                                        "; `frac` above uses the contract's full-matrix bytes and can therefore exceed 1, this one is the HBM utilisation"}},
-               "clocks": clocks, "gpu_launches": K, "e2e": e2e, "cpu_baseline": cpu, "c2_10k": small}
+               "clocks": clocks, "gpu_launches": K, "e2e": e2e, "cpu_baseline": cpu, "parity_check": parity, "c2_10k": small}
         if allgather:
             out["allgather"] = allgather
         if world == 1 and not args.no_node_loop:

@@ -153,6 +153,8 @@ class TargetManager {
   long long initBatch(target_t type, const MatrixXd& Q, const MatrixXd& R, const MatrixXd& P0, long long n, const unsigned* ids, double dt0,
                       const double* t0, const double* p0, const double* v0 = nullptr, const double* a0 = nullptr,
                       const double* p0_scale = nullptr);
+  // (an id may appear more than once: the records are applied in order, as the reference's sequential update() calls would --
+  //  the batch is cut in front of every repeat and the pieces are launched one after the other)
   long long updateBatch(long long n, const unsigned* ids, double dt, const double* meas /*[n][7]*/, const unsigned char* action = nullptr);
   long long eraseBatch(long long n, const unsigned* ids);
   void getEstimatesBatch(long long n, const unsigned* ids, const double* t1, double* pose7, double* twist6, double* acc6,
@@ -189,6 +191,7 @@ class TargetManager {
   void flushLocked();
   int registerClass(int type, const MatrixXd& Q, const MatrixXd& R, const MatrixXd& P0);
   void queue(int type, unsigned id, double dt, const double* meas, int action);
+  long long updateBatchUnique(long long n, const unsigned* ids, double dt, const double* meas, const unsigned char* action);   // no id twice
 
   int device_;
   te_pool* pools_[4] = {nullptr, nullptr, nullptr, nullptr};

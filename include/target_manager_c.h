@@ -46,7 +46,8 @@ target_manager_c* target_manager_new_on_device(const char* file, int device);
 long long target_manager_init_batch(const target_manager_c* self, long long n, const unsigned int* ids, double dt0, const double* p0,
                                     const double* t0 /* [n] or NULL = 0 */);
 /* one tick: action[k] 2 = update(id,dt,meas[k]) / 1 = update(id,dt) / 0 = skip; action NULL = all 2.
- * Returns #applied (unknown ids are skipped like the reference's "does not exist"). */
+ * Returns #applied (unknown ids are skipped like the reference's "does not exist").  An id may be named more than once:
+ * its records are applied in order, like the reference's sequential update() calls (one launch per run of distinct ids). */
 long long target_manager_update_batch(const target_manager_c* self, long long n, const unsigned int* ids, double dt, const double* meas,
                                       const unsigned char* action);
 /* TargetManager::update(dt): predict every target */

@@ -44,6 +44,9 @@ void te_pool_destroy(te_pool* p);
 int te_pool_set_stream(te_pool* p, void* cuda_stream);
 int te_pool_sync(te_pool* p);
 int te_pool_set_variant(te_pool* p, int variant);         /* kernel shape (warps x stages); tuning knob */
+/* test hook: at most max_ctas CTAs per step launch (0 = no cap), so that a small pool walks the persistent loops of the step
+   kernels (grid-stride tiles, the TMA stage ring) as many times per CTA as a bench-size pool does on the whole machine */
+int te_pool_set_grid_cap(te_pool* p, int max_ctas);
 int te_pool_reserve(te_pool* p, size_t n_targets);   /* both buffer generations: no later tick pays for the allocation */
 long long te_pool_size(te_pool* p);
 size_t te_pool_device_bytes(te_pool* p);

@@ -36,6 +36,7 @@ SIGNATURES = {
     "te_pool_set_stream": (_i, [_p, _p]),
     "te_pool_sync": (_i, [_p]),
     "te_pool_set_variant": (_i, [_p, _i]),
+    "te_pool_set_grid_cap": (_i, [_p, _i]),
     "te_pool_reserve": (_i, [_p, _sz]),
     "te_pool_size": (_ll, [_p]),
     "te_pool_device_bytes": (_sz, [_p]),

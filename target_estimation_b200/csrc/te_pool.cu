@@ -134,6 +134,7 @@ struct te_pool {
   bool own_stream = false;
   int n_sm = 148;
   int variant = 0;
+  int grid_cap = 0;      // test hook (te_pool_set_grid_cap): upper bound on the CTAs of a step launch, 0 = none
   bool all_sym = true;   // every registered class has bitwise-symmetric Q, R, P0 (symmetric-covariance kernels are legal)
   // The direct symmetric kernels maintain the UPPER triangle of every covariance only ("packed": 36 of UA's 92 fields are
   // neither read nor written per step).  lower_stale = the lower triangles in HBM are out of date; whoever needs the full
@@ -385,6 +386,9 @@ template <class T> T* to_dev(te_pool* p, const T* host, size_t n) {
 }
 
 // ---- step kernel launch -----------------------------------------------------------------
+// te_pool_set_grid_cap: a small pool under a capped grid walks the same persistent loops (grid-stride tiles, the STAGES ring of
+// the split kernel with its mbarrier phase flips) that a bench-size pool walks on the full machine
+inline int capped(const te_pool* p, int grid) { return p->grid_cap > 0 ? std::min(grid, p->grid_cap) : grid; }
 template <int TYPE, int WARPS, int STAGES, bool MULTI = false, int IMPL = 0>
 void launch_step_t(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   auto kern = te::kf_step_kernel<TYPE, WARPS, STAGES, MULTI, IMPL>;
@@ -396,7 +400,7 @@ void launch_step_t(te_pool* p, const te::StepArgs& a, int n_work_hint) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[p->device & 63] = true;
   }
-  int grid = std::min(p->n_sm, std::max(1, cdiv(n_work_hint, WARPS)));
+  int grid = capped(p, std::min(p->n_sm, std::max(1, cdiv(n_work_hint, WARPS))));
   kern<<<grid, WARPS * 32, smem, p->stream>>>(a);
   CK(cudaGetLastError());
 }
@@ -411,7 +415,7 @@ void launch_split_k(te_pool* p, const te::StepArgs& a, int n_work_hint) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[p->device & 63] = true;
   }
-  int grid = std::min(p->n_sm * CTAS, std::max(1, n_work_hint));
+  int grid = capped(p, std::min(p->n_sm * CTAS, std::max(1, n_work_hint)));
   kern<<<grid, (te::SPLIT_RS * CS + te::split_nt<TYPE>()) * 32, smem, p->stream>>>(a);
   CK(cudaGetLastError());
 }
@@ -448,7 +452,7 @@ void launch_av_direct(te_pool* p, const te::StepArgs& a, int n_work_hint) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[p->device & 63] = true;
   }
-  int grid = std::min(p->n_sm, std::max(1, cdiv(n_work_hint, WARPS)));
+  int grid = capped(p, std::min(p->n_sm, std::max(1, cdiv(n_work_hint, WARPS))));
   kern<<<grid, WARPS * 32, smem, p->stream>>>(a);
   CK(cudaGetLastError());
 }
@@ -456,7 +460,7 @@ void launch_av_direct(te_pool* p, const te::StepArgs& a, int n_work_hint) {
 template <int TYPE, int WARPS, int CTAS>
 void launch_kin_direct_k(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   auto kern = te::kf_step_kin_direct_kernel<TYPE, WARPS, CTAS>;
-  int grid = std::min(p->n_sm * CTAS, std::max(1, cdiv(n_work_hint, WARPS)));
+  int grid = capped(p, std::min(p->n_sm * CTAS, std::max(1, cdiv(n_work_hint, WARPS))));
   // programmatic stream serialization: see the kernel's griddepcontrol.wait
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
@@ -492,7 +496,7 @@ void launch_ar_pair(te_pool* p, const te::StepArgs& a, int n_work_hint) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[p->device & 63] = true;
   }
-  int grid = std::min(p->n_sm, std::max(1, cdiv(n_work_hint, WARPS)));
+  int grid = capped(p, std::min(p->n_sm, std::max(1, cdiv(n_work_hint, WARPS))));
   kern<<<grid, WARPS * 32, smem, p->stream>>>(a);
   CK(cudaGetLastError());
 }
@@ -899,6 +903,7 @@ te_pool* te_pool_create(int model, int device, void* cuda_stream) {
     }
     CK(cudaMalloc(&p->d_counters, 4 * sizeof(int)));
     CK(cudaMemsetAsync(p->d_counters, 0, 4 * sizeof(int), p->stream));
+    if (const char* cap = std::getenv("TE_GRID_CAP")) p->grid_cap = std::max(0, std::atoi(cap));   // test hook, see te_pool_set_grid_cap
     return p;
   } catch (const std::exception& e) {
     g_err = e.what();
@@ -958,6 +963,12 @@ int te_pool_set_variant(te_pool* p, int variant) {
   return 0;
 }
 
+int te_pool_set_grid_cap(te_pool* p, int max_ctas) {
+  if (!p || max_ctas < 0) return -1;
+  p->grid_cap = max_ctas;
+  return 0;
+}
+
 int te_pool_reserve(te_pool* p, size_t n_targets) {
   return guarded(p, [&] {
     if (!p->buf[p->cur].tiles) {
@@ -966,6 +977,7 @@ int te_pool_reserve(te_pool* p, size_t n_targets) {
     } else {
       ensure_cur_capacity(p, n_targets);
     }
+    ensure_work(p, std::max(n_targets, p->buf[p->cur].cap));   // (a flipped buffer can be larger than the work arrays)
     // the second generation too (every compaction -- erase, merge-add, expiry -- gathers into it): no tick pays for a
     // multi-gigabyte allocation later
     ensure_other_capacity(p, n_targets);
@@ -1177,9 +1189,8 @@ int te_pool_step_dense(te_pool* p, double dt, const double* dev_meas, int meas_s
       check_meas_stride(p, meas_stride);
       a.meas_tma = ((uintptr_t)dev_meas % 16 == 0) ? 1 : 0;
     } else if (dev_action || default_action == TE_ACT_UPDATE) {
-      if (default_action == TE_ACT_UPDATE || dev_action) {
-        if (!dev_meas && default_action == TE_ACT_UPDATE) throw std::invalid_argument("update tick without measurements");
-      }
+      // (an action array may name ACT_UPDATE for any slot: without measurements the kernel would read a null pointer)
+      throw std::invalid_argument("update tick without measurements");
     }
     launch_step(p, a, a.n_tiles);
     return 0;

@@ -11,6 +11,7 @@
 #include <iostream>
 #include <sstream>
 #include <stdexcept>
+#include <unordered_set>
 
 namespace target_estimation_b200 {
 
@@ -375,6 +376,28 @@ long long TargetManager::updateBatch(long long n, const unsigned* ids, double dt
   std::lock_guard<std::recursive_mutex> lg(target_lock_);
   if (n <= 0) return 0;
   flushLocked();
+  // te_pool_step_ids applies one op per id per launch.  A batch that names an id again stands for the reference's sequential
+  // update() calls, which apply every record in order: cut the batch in front of each repeat and launch the pieces one after
+  // the other (strictly ascending ids -- the usual batch -- cannot repeat and skip the hash set).
+  bool ascending = true;
+  for (long long k = 1; k < n && ascending; ++k) ascending = ids[k - 1] < ids[k];
+  if (ascending) return updateBatchUnique(n, ids, dt, meas, action);
+  long long applied = 0, start = 0;
+  std::unordered_set<unsigned> seen;
+  seen.reserve((size_t)std::min<long long>(n, 1 << 22));
+  for (long long k = 0; k < n; ++k) {
+    if (!seen.insert(ids[k]).second) {
+      applied += updateBatchUnique(k - start, ids + start, dt, meas ? meas + 7 * (size_t)start : nullptr, action ? action + start : nullptr);
+      start = k;
+      seen.clear();
+      seen.insert(ids[k]);
+    }
+  }
+  return applied + updateBatchUnique(n - start, ids + start, dt, meas ? meas + 7 * (size_t)start : nullptr, action ? action + start : nullptr);
+}
+
+long long TargetManager::updateBatchUnique(long long n, const unsigned* ids, double dt, const double* meas, const unsigned char* action) {
+  if (n <= 0) return 0;
   int n_pools = 0, only = -1;
   for (int t = 0; t < 4; ++t)
     if (pools_[t] && te_pool_size(pools_[t]) > 0) { ++n_pools; only = t; }

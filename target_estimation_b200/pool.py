@@ -91,6 +91,9 @@ class TargetPool:
     def set_variant(self, v):
         check(lib.te_pool_set_variant(self._h, int(v)))
 
+    def set_grid_cap(self, max_ctas):
+        check(lib.te_pool_set_grid_cap(self._h, int(max_ctas)))
+
     def set_stream(self, stream_ptr):
         check(lib.te_pool_set_stream(self._h, stream_ptr))
 

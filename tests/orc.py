@@ -47,6 +47,10 @@ def lib():
         L.orc_get_pose_internal.restype = _i; L.orc_get_pose_internal.argtypes = [_p, _u, _p]
         L.orc_get_period_estimate.restype = _d; L.orc_get_period_estimate.argtypes = [_p, _u]
         L.orc_step_batch.argtypes = [_p, _i, _p, _d, _p, _p]
+        L.orc_step_batch_mt.argtypes = [_p, _i, _i, _p, _d, _p, _p]
+        L.orc_step_ticks_mt.argtypes = [_p, _i, _i, _p, _i, _d, _p, _p]
+        L.orc_init_batch_mt.argtypes = [_p, _i, _i, _i, _p, _d, _p, _p, _i, _p, _i, _p, _p, _p]
+        L.orc_get_states_mt.argtypes = [_p, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p]
         L.orc_run_stream.argtypes = [_p, _u, _i, _d, _p, _p, _i, _p, _p, _p, _p]
         L.orc_reftest_streams.argtypes = [_d, _i, _i, _p, _p]
         L.orc_libstdcxx_normal.argtypes = [_d, _d, _i, _p]
@@ -179,6 +183,55 @@ class Manager:
     def measured_pose(self, id_): return self._get(self.L.orc_get_measured_pose, id_, 7)
     def pose_internal(self, id_): return self._get(self.L.orc_get_pose_internal, id_, 6)
     def n_measurements(self, id_): return int(self.L.orc_get_n_measurements(self.h, id_))
+
+
+class ShardedManager:
+    """T oracle TargetManagers, id k in manager k % T, stepped by T host threads (orc_*_mt): the same per-target arithmetic as
+    Manager, fast enough for parity runs at bench scale.  One (Q, R, P0) for all targets, optional per-target P0 scale."""
+
+    def __init__(self, threads=None):
+        self.L = lib()
+        self.T = int(threads or min(32, max(1, self.L.orc_hardware_threads())))
+        self.hs = (C.c_void_p * self.T)(*[self.L.orc_manager_new(None) for _ in range(self.T)])
+
+    def close(self):
+        if getattr(self, "hs", None) is not None:
+            for h in self.hs:
+                self.L.orc_manager_delete(h)
+            self.hs = None
+
+    def __del__(self):
+        self.close()
+
+    def init_batch(self, type_, ids, dt0, Q, R, P0, p0, scale=None, t0=None):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        Qc, Rc, Pc = colmajor(Q), colmajor(R), colmajor(P0)
+        p0 = np.ascontiguousarray(p0, dtype=np.float64)
+        scale = np.ascontiguousarray(scale, dtype=np.float64) if scale is not None else None
+        t0 = np.ascontiguousarray(t0, dtype=np.float64) if t0 is not None else None
+        n = int(np.sqrt(Qc.size)); m = int(np.sqrt(Rc.size))
+        self.L.orc_init_batch_mt(self.hs, self.T, type_, ids.size, ptr(ids), dt0, ptr(t0), ptr(Qc), n, ptr(Rc), m, ptr(Pc), ptr(scale), ptr(p0))
+
+    def step_batch(self, ids, dt, meas, action):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        meas = np.ascontiguousarray(meas, dtype=np.float64)
+        action = np.ascontiguousarray(action, dtype=np.uint8)
+        self.L.orc_step_batch_mt(self.hs, self.T, ids.size, ptr(ids), dt, ptr(meas), ptr(action))
+
+    def step_ticks(self, ids, dt, meas, action):
+        """meas [n_ticks][n][7], action [n_ticks][n]: all ticks in one call (no Python between ticks)"""
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        meas = np.ascontiguousarray(meas, dtype=np.float64)
+        action = np.ascontiguousarray(action, dtype=np.uint8)
+        self.L.orc_step_ticks_mt(self.hs, self.T, ids.size, ptr(ids), action.shape[0], dt, ptr(meas), ptr(action))
+
+    def states(self, ids, n):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        k = ids.size
+        xs = np.zeros((k, n)); Ps = np.zeros((k, n, n)); ts = np.zeros(k); nms = np.zeros(k, dtype=np.int64); prevs = np.zeros((k, 3))
+        found = np.zeros(k, dtype=np.uint8)
+        self.L.orc_get_states_mt(self.hs, self.T, k, ptr(ids), n, ptr(xs), ptr(Ps), ptr(ts), ptr(nms), ptr(prevs), ptr(found))
+        return {"x": xs, "P": Ps, "t": ts, "n_meas": nms, "prev_rpy": prevs, "found": found}
 
 
 def load_yaml(path):

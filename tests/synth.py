@@ -21,7 +21,7 @@ def rpy_to_quat(rpy):
     return q / np.linalg.norm(q, axis=-1, keepdims=True)
 
 
-def make_streams(n_targets, n_ticks, dt, seed=0x7A26E7, accel=True, angular=True, miss_prob=0.05, noise=0.01):
+def make_streams(n_targets, n_ticks, dt, seed=0x7A26E7, accel=True, angular=True, miss_prob=0.05, noise=0.01, pitch0=0.4, pitch_amp=0.15):
     """Returns meas [n_ticks, n_targets, 7], action [n_ticks, n_targets] (2 = update, 1 = predict),
     p0_scale [n_targets].  Attitude: roll / yaw = rpy0 + rate * t, free to wrap so that the unwrap logic is
     exercised; pitch = pitch0 + 0.15 sin(.) with |pitch0| <= 0.4, i.e. |pitch| <= 0.55 rad (the Euler-rate
@@ -39,12 +39,12 @@ def make_streams(n_targets, n_ticks, dt, seed=0x7A26E7, accel=True, angular=True
     meas = np.zeros((n_ticks, n_targets, 7))
     meas[..., :3] = pos
     if angular:
-        rpy0 = np.stack([rng.uniform(-3, 3, n_targets), rng.uniform(-0.4, 0.4, n_targets), rng.uniform(-3, 3, n_targets)], axis=-1)
+        rpy0 = np.stack([rng.uniform(-3, 3, n_targets), rng.uniform(-pitch0, pitch0, n_targets), rng.uniform(-3, 3, n_targets)], axis=-1)
         rate = np.stack([rng.uniform(-2, 2, n_targets), rng.uniform(-0.3, 0.3, n_targets), rng.uniform(-2, 2, n_targets)], axis=-1)
         tt = t[..., 0]
         rpy = rpy0[None] + rate[None] * t
         # pitch oscillates instead of growing: stays within +-0.55 rad
-        rpy[..., 1] = rpy0[None, :, 1] + 0.15 * np.sin(rate[None, :, 1] * 4 * tt)
+        rpy[..., 1] = rpy0[None, :, 1] + pitch_amp * np.sin(rate[None, :, 1] * 4 * tt)
         meas[..., 3:7] = rpy_to_quat(rpy)
     else:
         meas[..., 6] = 1.0
@@ -67,3 +67,10 @@ def compare_h2(got, ref, rtol=1e-9, floor=1e-4):
     bound = rtol * np.maximum(np.abs(flat_ref), scale * floor)
     bound = np.maximum(bound, 1e-300)
     return float((np.abs(flat_got - flat_ref) / bound).max())
+
+
+def compare_both(got, ref):
+    """(ratio under the working H2 floor 1e-4, ratio under SURVEY.md's strict floor 1e-6): the second is reported beside
+    the first so that the loosening is visible (entries between 1e-6 and 1e-4 of their matrix scale are sums of O(scale)
+    terms; their relative error is bounded by eps * scale * sqrt(steps) / |entry| in any evaluation order)"""
+    return compare_h2(got, ref), compare_h2(got, ref, floor=1e-6)

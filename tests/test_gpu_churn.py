@@ -44,14 +44,31 @@ def test_add_erase_order_and_state():
     pool.close()
 
 
-def test_expiry_bit_exact():
-    """SURVEY.md C3 sub-run: synthetic clock (sec, nsec) with epoch 1000 s, per tick 1 % of the live ids stop
+def test_reserve_after_merge_add():
+    """te_pool_reserve once a merge flipped the buffers (the flipped buffer can be larger than the work arrays)"""
+    import target_estimation_b200 as te
+    mtype, _, Q, R, P0 = te.load_model("uniform_velocity")
+    pool = te.TargetPool(mtype); pool.register_class(Q, R, P0)
+    p0 = np.tile([0, 0, 0, 0, 0, 0, 1.0], (100, 1))
+    assert pool.add(np.arange(100, dtype=np.uint32) * 2 + 1000, p0) == 100
+    assert pool.add(np.arange(100, dtype=np.uint32) * 2, p0) == 100          # below the existing ids: merge into the other buffer
+    pool.reserve(250)
+    assert pool.add(np.arange(50, dtype=np.uint32) * 2 + 1, p0[:50]) == 50
+    assert len(pool) == 250 and np.array_equal(pool.ids(), np.sort(pool.ids()))
+    pool.step_dense_host(DT, np.tile(p0[:1], (250, 1)))
+    assert np.array_equal(pool.read_state()["n_meas"], np.ones(250, dtype=np.int64))
+    pool.close()
+
+
+@pytest.mark.parametrize("n0,ticks", [(2048, 48), (16384, 24)])
+def test_expiry_bit_exact(n0, ticks):
+    """(16 384 targets = the sub-run size SURVEY.md 8(d) names)
+    SURVEY.md C3 sub-run: synthetic clock (sec, nsec) with epoch 1000 s, per tick 1 % of the live ids stop
     receiving measurements, expire after timeout = 8 dt by `last > 0 && now - last >= timeout`, and as many fresh ids
     appear.  The set and order of live ids and every tick's erase list must match the oracle exactly."""
     import target_estimation_b200 as te
     name = "angular_rates"
     mtype, _, Q, R, P0 = te.load_model(name)
-    n0, ticks = 2048, 48
     timeout = 8 * DT
     pool = te.TargetPool(mtype); pool.register_class(Q, R, P0)
     L = orc.lib()
@@ -77,8 +94,8 @@ def test_expiry_bit_exact():
         stamps = np.tile(np.array([sec, nsec], dtype=np.uint32), (ids.size, 1))
         # ---- oracle: /tf callback then the tick
         L.orc_tick_callback_ids(h, ids.size, orc.ptr(ids), orc.ptr(np.ascontiguousarray(stamps)), orc.ptr(np.ascontiguousarray(poses)))
-        erased_ref = np.zeros(8192, dtype=np.uint32)
-        n_er = L.orc_tick_update(h, DT, sec, nsec, orc.ptr(erased_ref), 8192)
+        erased_ref = np.zeros(1 << 16, dtype=np.uint32)
+        n_er = L.orc_tick_update(h, DT, sec, nsec, orc.ptr(erased_ref), erased_ref.size)
         # ---- device: the same tick expressed with the pool primitives
         have = set(pool.ids().tolist())
         new_mask = np.array([int(i) not in have for i in ids])
@@ -102,7 +119,7 @@ def test_expiry_bit_exact():
         ref_ids = np.zeros(max(L.orc_num_targets(h), 1), dtype=np.uint32)
         n_ref = L.orc_get_ids(h, orc.ptr(ref_ids), ref_ids.size)
         assert np.array_equal(pool.ids(), ref_ids[:n_ref]), k
-    assert next_id > n0 + 500 and len(pool) > 0
+    assert next_id > n0 + n0 // 100 * (ticks - 1) // 2 and len(pool) > 0
     # state parity of a sample of survivors after all the compaction
     live = pool.ids()
     sample = live[:: max(1, live.size // 64)]

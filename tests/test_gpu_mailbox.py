@@ -58,11 +58,16 @@ def _compare_states(pool, L, h, N, ids=None):
     assert np.array_equal(got["measured_pose"], mp)
 
 
+@pytest.mark.parametrize("grid_cap", [0, 2])
 @pytest.mark.parametrize("name", ["uniform_velocity", "uniform_acceleration", "angular_velocities", "angular_rates"])
-def test_mailbox_churn_matches_oracle_tick(name):
-    """a /tf message per tick for a changing set of ids in shuffled order: newcomers (merged anywhere in the id order), ids
+def test_mailbox_churn_matches_oracle_tick(name, grid_cap, monkeypatch):
+    """(grid_cap 2: the fused compacting tick on two CTAs -- every CTA of the split kernel takes ~12 tiles through its two-stage
+    ring, every warp of the direct kernels several tiles)
+    a /tf message per tick for a changing set of ids in shuffled order: newcomers (merged anywhere in the id order), ids
     falling silent (sticky re-application of their last pose, then expiry), stale stamps (stored, predict-only), an id named
     twice in one message, a second message before some ticks."""
+    if grid_cap:
+        monkeypatch.setenv("TE_GRID_CAP", str(grid_cap))     # read by te_pool_create
     pool, L, h, N = _pair(name)
     timeout = 8 * DT
     L.orc_tick_set_expiration(h, timeout)

@@ -166,6 +166,40 @@ def test_batched_extensions(name):
 
 
 @pytest.mark.parametrize("name", ["uniform_acceleration", "angular_rates"])
+def test_update_batch_with_repeated_ids(name):
+    """target_manager_update_batch with an id named several times in one batch = the reference's sequential update() calls:
+    every record applied, in order (the batch is cut in front of each repeat)."""
+    from target_estimation_b200.manager import TargetManagerC
+    y = orc.load_yaml(_yaml(name))
+    N = y["Q"].shape[0]
+    n, ticks = 64, 6
+    meas, action, _ = synth.make_streams(n, 4 * ticks, DT, accel=True, angular=y["R"].shape[0] == 6, seed=9)
+    ids = np.arange(n, dtype=np.uint32) * 2 + 3
+    mgr = TargetManagerC(_yaml(name)); ref = orc.Manager(_yaml(name))
+    assert mgr.init_batch(ids, DT, meas[0]) == n
+    for k in range(n):
+        ref.init_default(int(ids[k]), DT, meas[0, k], 0.0)
+    rng = np.random.default_rng(4)
+    for k in range(ticks):
+        # three records for a third of the ids, two for another third, shuffled into one batch
+        reps = np.where(np.arange(n) % 3 == 0, 3, np.where(np.arange(n) % 3 == 1, 2, 1))
+        rows = np.repeat(np.arange(n), reps)
+        occ = np.concatenate([np.arange(r) for r in reps])
+        order = rng.permutation(rows.size)
+        order = order[np.argsort(occ[order], kind="stable")] if k % 2 else order    # odd ticks: all first records, then the repeats
+        b_ids = ids[rows[order]]
+        b_meas = np.stack([meas[4 * k + occ[j], rows[j]] for j in order])
+        b_act = np.where(rng.random(order.size) < 0.2, 1, 2).astype(np.uint8)
+        assert mgr.update_batch(b_ids, DT, b_meas, b_act) == order.size
+        ref.step_batch(b_ids, DT, b_meas, b_act)
+    for j in range(n):
+        st, rs = mgr.state(int(ids[j])), ref.state(int(ids[j]), N)
+        assert mgr.get_n_measurements(int(ids[j])) == rs["n_meas"] and st["t"] == rs["t"]
+        assert synth.compare_h2(st["x"][None], rs["x"][None]) <= 1.0 and synth.compare_h2(st["P"][None], rs["P"][None]) <= 1.0
+    mgr.close()
+
+
+@pytest.mark.parametrize("name", ["uniform_acceleration", "angular_rates"])
 def test_sampled_logging_and_text_dumps(name, tmp_path):
     """target_manager_watch / target_manager_log / target_manager_write_log: the five quantities the reference publishes per
     target under LOGGER_ON (measured_pose_, pose_internal_, twist_, acceleration_, P_; src/target_interface.cpp:32-40) sampled
