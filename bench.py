@@ -62,7 +62,10 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the sampled oracle check of the benchmarked pool")
     ap.add_argument("--no-small", action="store_true")
-    ap.add_argument("--allgather", action="store_true", help="also time the optional all-gather of estimates (N>1)")
+    ap.add_argument("--allgather", action="store_true", help="(default at N>1; kept for compatibility)")
+    ap.add_argument("--no-allgather", action="store_true", help="skip the all-gather of estimate records at N>1")
+    ap.add_argument("--no-c5", action="store_true", help="skip BASELINE configs[4] (mixed models sharded by id, all-gather at N>1)")
+    ap.add_argument("--c5-targets", type=int, default=8 << 20, help="C5 targets per GPU (64 Mi over 8 GPUs)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -473,10 +476,10 @@ def main():
                 mg = TargetManagerC(mpath, device=torch.cuda.current_device())
                 r_ids = torch.from_numpy(np.arange(n, dtype=np.int32)).pin_memory()
                 ids_np = r_ids.numpy().view(np.uint32)
-                p0 = h_meas[0].numpy()
+                p0_abi = h_meas[0].numpy()
                 chunk = 1 << 20
                 for c0 in range(0, n, chunk):
-                    mg.init_batch(ids_np[c0:c0 + chunk], DT, p0[c0:c0 + chunk])
+                    mg.init_batch(ids_np[c0:c0 + chunk], DT, p0_abi[c0:c0 + chunk])
                 pose = np.zeros(7)
 
                 def tick_abi(k):
@@ -502,7 +505,7 @@ def main():
 
     # ---- optional all-gather of estimate records (off the hot path) -----------------------------------
     allgather = None
-    if args.allgather and world > 1:
+    if world > 1 and not args.no_allgather:
         rec = torch.empty((n, 13), dtype=torch.float64, device="cuda")
         out = torch.empty((world * n, 13), dtype=torch.float64, device="cuda")
         with torch.cuda.stream(stream):
@@ -521,6 +524,17 @@ def main():
         dist.all_reduce(ag, op=dist.ReduceOp.MAX)
         allgather = {"ms": float(ag.item()), "bytes_per_rank": n * 104, "records": "pose7|twist6 per target",
                      "bus_gbs": (world - 1) * n * 104 / (float(ag.item()) * 1e-3) / 1e9}
+
+    # ---- BASELINE configs[4]: mixed models sharded by id (+ the NCCL all-gather of [pose7 | twist6] records at N > 1), every rank ----
+    c5 = None
+    if not args.no_c5:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_mixed
+            c5 = bench_mixed.run_c5(rank, world, local_rank, stream, args.c5_targets, 16, 3, barrier=barrier)
+        except Exception as e:   # a collective inside may leave the other ranks waiting: report and let the watchdog decide
+            c5 = {"error": ("%s: %s" % (type(e).__name__, e))[:300]}
+        torch.cuda.synchronize()
 
     # ---- BASELINE configs[1] literally: 10k targets, L2-resident, launch-bound (reported, not the headline) ----
     small = None
@@ -642,21 +656,34 @@ def main():
                "clocks": clocks, "gpu_launches": K, "e2e": e2e, "cpu_baseline": cpu, "parity_check": parity, "c2_10k": small}
         if allgather:
             out["allgather"] = allgather
+        if c5 is not None:
+            out["c5"] = c5
         if world == 1 and not args.no_node_loop:
-            # BASELINE configs[2]-style secondary figure (NOT the headline): the reference's whole node loop -- /tf records from pinned
-            # host memory into the device-resident mailboxes, first-sight init, sticky update / predict, expiry with 1 % id churn per
-            # tick -- for this motion model at 1 Mi targets (tools/bench_configs.py c3_mailbox; erase lists checked against a host model)
-            # (in a process of its own: whatever happens there cannot take the headline line with it)
+            # Secondary figures (NOT the headline), all in ONE process of their own -- whatever happens there cannot take the headline
+            # line with it (tools/bench_configs.py benchline):
+            #   c3         BASELINE configs[2]: 1 Mi ANGULAR-RATES targets through the reference's node loop -- /tf records from pinned host
+            #              memory into the device-resident mailboxes, first-sight init, sticky update / predict, expiry, 1 % id churn per tick
+            #   node_loop  the same loop for the benchmarked motion model
+            #   c4_*       BASELINE configs[3]: 1 Mi uniform-velocity targets + one IntersectionSolver query per target per tick (reference
+            #              semantics: c4 == 0, every query returns -1) and the same on 1 Mi uniform-acceleration targets (quartic path)
             try:
                 import subprocess
                 tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "bench_configs.py")
                 env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local_rank)))
-                pr = subprocess.run([sys.executable, tool, "mailbox1", model], capture_output=True, text=True, timeout=180, env=env)
+                pr = subprocess.run([sys.executable, tool, "benchline", model], capture_output=True, text=True, timeout=420, env=env)
                 r = json.loads(pr.stdout.strip().splitlines()[-1])
-                out["node_loop"] = {k_: r[k_] for k_ in ("model", "targets", "ticks", "erased", "added", "records_per_tick", "h2d_bytes_per_tick",
-                                                         "ms_per_tick", "target_steps_per_s", "ms_per_tick_parts", "note")}
-            except Exception as e:   # secondary figure: report, never fail the headline
-                out["node_loop"] = {"error": ("%s: %s" % (type(e).__name__, e))[:300]}
+                keep = ("model", "targets", "ticks", "erased", "added", "records_per_tick", "h2d_bytes_per_tick", "ms_per_tick", "target_steps_per_s",
+                        "ms_per_tick_parts", "note", "error")
+                for key in ("c3", "node_loop"):
+                    if key in r:
+                        out[key] = {k_: r[key][k_] for k_ in keep if k_ in r[key]}
+                if "node_loop" not in out and "c3" in out:
+                    out["node_loop"] = out["c3"]
+                out["c4"] = {"uniform_velocity": r.get("c4_uniform_velocity"), "uniform_acceleration": r.get("c4_uniform_acceleration"),
+                             "note": "1 Mi targets, one query per target per tick, queries and results device resident; UV returns -1 for every query by "
+                                     "reference semantics (src/intersection_solver.cpp:72: c4 == 0), UA exercises the quartic path"}
+            except Exception as e:   # secondary figures: report, never fail the headline
+                out["c3"] = {"error": ("%s: %s" % (type(e).__name__, e))[:300]}
         print(json.dumps(out), flush=True)
     pool.close()
     if world > 1:

