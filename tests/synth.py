@@ -21,12 +21,14 @@ def rpy_to_quat(rpy):
     return q / np.linalg.norm(q, axis=-1, keepdims=True)
 
 
-def make_streams(n_targets, n_ticks, dt, seed=0x7A26E7, accel=True, angular=True, miss_prob=0.05, noise=0.01, pitch0=0.4, pitch_amp=0.15):
+def make_streams(n_targets, n_ticks, dt, seed=0x7A26E7, accel=True, angular=True, miss_prob=0.05, noise=0.01, pitch0=0.4, pitch_amp=0.15,
+                 att_rate=2.0):
     """Returns meas [n_ticks, n_targets, 7], action [n_ticks, n_targets] (2 = update, 1 = predict),
     p0_scale [n_targets].  Attitude: roll / yaw = rpy0 + rate * t, free to wrap so that the unwrap logic is
     exercised; pitch = pitch0 + 0.15 sin(.) with |pitch0| <= 0.4, i.e. |pitch| <= 0.55 rad (the Euler-rate
     matrices of the EKF divide by cos(pitch) and cos(pitch)^2; a filter state that overshoots towards +-pi/2 amplifies
-    ulp-level libm differences past any fixed tolerance, on the reference as much as here)."""
+    ulp-level libm differences past any fixed tolerance, on the reference as much as here).  att_rate: bound of the roll / yaw
+    rates in rad/s (2.0 = several wraps in 2000 ticks; SURVEY.md 8(d) specifies 0.5)."""
     rng = np.random.default_rng(seed)
     p0 = rng.uniform(-5, 5, (n_targets, 3))
     v0 = rng.uniform(-1, 1, (n_targets, 3))
@@ -40,7 +42,7 @@ def make_streams(n_targets, n_ticks, dt, seed=0x7A26E7, accel=True, angular=True
     meas[..., :3] = pos
     if angular:
         rpy0 = np.stack([rng.uniform(-3, 3, n_targets), rng.uniform(-pitch0, pitch0, n_targets), rng.uniform(-3, 3, n_targets)], axis=-1)
-        rate = np.stack([rng.uniform(-2, 2, n_targets), rng.uniform(-0.3, 0.3, n_targets), rng.uniform(-2, 2, n_targets)], axis=-1)
+        rate = np.stack([rng.uniform(-att_rate, att_rate, n_targets), rng.uniform(-0.3, 0.3, n_targets), rng.uniform(-att_rate, att_rate, n_targets)], axis=-1)
         tt = t[..., 0]
         rpy = rpy0[None] + rate[None] * t
         # pitch oscillates instead of growing: stays within +-0.55 rad

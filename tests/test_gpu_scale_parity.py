@@ -183,16 +183,24 @@ def test_compacting_step_vs_oracle(model, cap):
 # ---------------------------------------------------------------------------------------------------------------------
 # 4. SURVEY.md 8(d) parity protocol for the angular models at full size (UV / UA: tests/test_gpu_parity.py)
 #
-# Conditioning.  The angular-velocities EKF of the reference is not stable on every stream: on a few targets in a thousand its
-# pitch STATE drifts away from the measured pitch (<= 0.55 rad here) through +-pi/2, where J_rpy and J_w divide by cos(pitch)^2,
-# and from then on the filter amplifies rounding-level noise exponentially -- the oracle run twice, the second time with every
-# measurement quaternion moved by ONE ULP, differs from itself by 1e-2 relative on those targets after 600 ticks
-# (measured: 2 of 4096 at tick 600, 3 at tick 700).  No implementation with another libm / summation order can track
-# such a target to 1e-9, the reference compiled against another libm included.  The protocol therefore runs the perturbed
-# oracle beside the oracle: a target on which the oracle itself moves by more than 1e-12 relative (1e-3 of the bar) under the
-# one-ulp perturbation is ill-conditioned from that tick on; those are counted (bounded, reported) and excluded, every other target
-# must meet the 1e-9 bar.  t and n_meas stay exact for all targets.
+# Conditioning.  The angular-velocities EKF of the reference is not stable on every stream: its pitch STATE drifts away from the
+# measured pitch (<= 0.55 rad here) and, on fast-rotating targets, through +-pi/2, where J_rpy and J_w divide by cos(pitch)^2; from
+# then on the filter amplifies rounding-level noise exponentially.  Measured on the CPU oracle alone (the oracle run twice, the
+# second time with every measurement quaternion component moved by ONE ULP; 4096 targets, worst |d| / bar over the run):
+#     roll / yaw rates within +-2 rad/s (tests/synth.py default): after 2000 ticks 343 targets differ FROM THEMSELVES by more
+#         than the 1e-9 bar, 692 by more than 1e-2 of it;
+#     roll / yaw rates within +-0.5 rad/s (the rates SURVEY.md 8(d) specifies): none above 1e-1 of the bar, 38 above 1e-2.
+# No implementation with another libm / summation order can track an amplifying target to 1e-9, the reference compiled against
+# another libm included.  The protocol therefore runs the perturbed oracle beside the oracle and measures each target's
+# amplification a_i = worst |d| / bar of the oracle against itself under the one-ulp perturbation:
+#     well-conditioned (a_i <= 1e-2, i.e. one ulp of input moves the result by <= 1e-11 relative): the 1e-9 bar, no exception;
+#     the others: |d| <= 100 a_i bars -- the GPU's arithmetic (Cholesky instead of LU, libdevice instead of glibc) may drift by
+#         what a hundred one-ulp perturbations of the input do to the reference itself; counted, bounded, reported.
+# t and n_meas stay exact for all targets, everything stays finite.
 # ---------------------------------------------------------------------------------------------------------------------
+ILL = 1e-2
+
+
 def _run_conditioned(tag, model, n, ticks, every, ill_frac_max, **stream_kw):
     te, pool, ref, ids, meas, action, N, M = _setup(model, n, ticks, **stream_kw)
     import target_estimation_b200 as te_
@@ -201,35 +209,51 @@ def _run_conditioned(tag, model, n, ticks, every, ill_frac_max, **stream_kw):
     pert = orc.ShardedManager()
     pert.init_batch(mtype, ids, DT, Q, R, P0, meas[0], scale)
     meas_p = synth.perturb_quaternions(meas)
-    ill = np.zeros(n, dtype=bool)
-    worst = {"x": 0.0, "P": 0.0, "x_all": 0.0, "P_all": 0.0}
+    amp = np.zeros(n)       # a_i so far (sticky: an amplifying target stays one)
+    worst = {"x": 0.0, "P": 0.0, "x_all": 0.0, "P_all": 0.0, "rel_ill": 0.0}
+    fail = None
     for k in range(ticks):
         pool.step_dense_host(DT, meas[k], action[k])
         if k % every == every - 1:
             ref.step_ticks(ids, DT, meas[k - every + 1:k + 1], action[k - every + 1:k + 1])
             pert.step_ticks(ids, DT, meas_p[k - every + 1:k + 1], action[k - every + 1:k + 1])
             want, wp, got = ref.states(ids, N), pert.states(ids, N), pool.read_state(ids)
-            ill |= (synth.ratio_per_target(wp["x"], want["x"]) > 1e-3) | (synth.ratio_per_target(wp["P"], want["P"]) > 1e-3)
+            amp = np.maximum(amp, np.maximum(synth.ratio_per_target(wp["x"], want["x"]), synth.ratio_per_target(wp["P"], want["P"])))
+            ill = amp > ILL
             rx, rP = synth.ratio_per_target(got["x"], want["x"]), synth.ratio_per_target(got["P"], want["P"])
             worst["x_all"] = max(worst["x_all"], float(rx.max())); worst["P_all"] = max(worst["P_all"], float(rP.max()))
-            worst["x"] = max(worst["x"], float(rx[~ill].max())); worst["P"] = max(worst["P"], float(rP[~ill].max()))
+            if (~ill).any():
+                worst["x"] = max(worst["x"], float(rx[~ill].max())); worst["P"] = max(worst["P"], float(rP[~ill].max()))
+            if ill.any():
+                worst["rel_ill"] = max(worst["rel_ill"], float((np.maximum(rx, rP)[ill] / amp[ill]).max()))
             assert np.array_equal(got["n_meas"], want["n_meas"]) and np.array_equal(got["t"], want["t"]), k
             assert np.isfinite(got["x"]).all() and np.isfinite(got["P"]).all(), k
-            assert worst["x"] <= 1.0 and worst["P"] <= 1.0, (tag, k, int(ill.sum()), worst)
+            if fail is None and not (worst["x"] <= 1.0 and worst["P"] <= 1.0 and worst["rel_ill"] <= 100.0):
+                fail = (tag, k, int(ill.sum()), dict(worst))
     pitch = float(np.abs(ref.states(ids, N)["x"][:, 4]).max()) if model == "angular_velocities" else None
-    report.record(tag, targets=n, ticks=ticks, ill_conditioned=int(ill.sum()), max_state_pitch=pitch,
-                  x=worst["x"], P=worst["P"], x_incl_ill=worst["x_all"], P_incl_ill=worst["P_all"])
-    assert ill.sum() <= ill_frac_max * n, (tag, int(ill.sum()))
+    n_ill = int((amp > ILL).sum())
+    report.record(tag, targets=n, ticks=ticks, ill_conditioned=n_ill, amplification_hist={("%g" % t): int((amp > t).sum()) for t in (1e-3, 1e-2, 1e-1, 1.0)},
+                  max_state_pitch=pitch, x=worst["x"], P=worst["P"], ill_error_over_amplification=worst["rel_ill"],
+                  x_incl_ill=worst["x_all"], P_incl_ill=worst["P_all"], first_failure=str(fail) if fail else None)
     pool.close(); ref.close(); pert.close()
-    return int(ill.sum())
+    assert fail is None, fail
+    assert n_ill <= ill_frac_max * n, (tag, n_ill)
+    return n_ill
 
 
 def test_step_parity_4096x2000_angular_velocities():
-    _run_conditioned("step_parity_4096x2000[angular_velocities]", "angular_velocities", 4096, 2000, 100, 0.03)
+    """4096 targets x 2000 ticks, compared every 100 ticks, attitude rates as specified there (+-0.5 rad/s)"""
+    _run_conditioned("step_parity_4096x2000[angular_velocities]", "angular_velocities", 4096, 2000, 100, 0.03, att_rate=0.5)
+
+
+def test_step_parity_4096x2000_angular_velocities_fast_rotation():
+    """the same with the +-2 rad/s roll / yaw rates every other test uses (several wraps per target): on these the reference's EKF
+    itself amplifies one-ulp input noise past the bar on 8 % of the targets (CPU measurement above)"""
+    _run_conditioned("step_parity_4096x2000[angular_velocities,fast]", "angular_velocities", 4096, 2000, 100, 0.25)
 
 
 def test_step_parity_4096x2000_angular_rates():
-    """(linear filter: no ill-conditioned targets at all)"""
+    """(linear filter: no amplifying targets at all)"""
     assert _run_conditioned("step_parity_4096x2000[angular_rates]", "angular_rates", 4096, 2000, 100, 0.0) == 0
 
 
@@ -238,7 +262,7 @@ def test_step_parity_4096x2000_angular_rates():
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("pitch_max", [0.55, 0.8, 1.0, 1.2])
 def test_av_pitch_range(pitch_max):
-    """every well-conditioned target (see above) meets 1e-9 for every range; the report carries the number of ill-conditioned ones
+    """every well-conditioned target (see above) meets 1e-9 for every range; the report carries the number of amplifying ones
     per range -- the width of the region in which the reference's EKF is trackable at all"""
     _run_conditioned("av_pitch_range[%.2f]" % pitch_max, "angular_velocities", 2048, 600, 100, 0.25, seed=21, pitch0=pitch_max - 0.15, pitch_amp=0.15)
 
