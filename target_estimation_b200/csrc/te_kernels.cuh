@@ -291,7 +291,7 @@ __device__ __forceinline__ int lower_bound_u32(const uint32_t* __restrict__ a, i
 }
 
 // ids -> slots (-1 if absent)
-__global__ void lookup_slots_kernel(const uint32_t* __restrict__ ids_sorted, int n_slots, const uint32_t* __restrict__ q,
+static __global__ void lookup_slots_kernel(const uint32_t* __restrict__ ids_sorted, int n_slots, const uint32_t* __restrict__ q,
                                     long long n, int* __restrict__ slots) {
   long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (k >= n) return;
@@ -375,17 +375,17 @@ __global__ void init_append_kernel(double* tiles, ColdArrays cold, int base, Add
 }
 
 // alive[s] = 1 for all, then 0 for listed slots
-__global__ void fill_i32_kernel(int* a, int n, int v) {
+static __global__ void fill_i32_kernel(int* a, int n, int v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] = v;
 }
-__global__ void clear_listed_kernel(int* alive, const int* slots, long long n) {
+static __global__ void clear_listed_kernel(int* alive, const int* slots, long long n) {
   long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (k < n && slots[k] >= 0) alive[slots[k]] = 0;
 }
 
 // merge ranks: surviving old slot s -> dest = pos[s] + #(new ids < id[s])
-__global__ void map_existing_kernel(int n_old, const int* __restrict__ alive, const int* __restrict__ pos,
+static __global__ void map_existing_kernel(int n_old, const int* __restrict__ alive, const int* __restrict__ pos,
                                     const uint32_t* __restrict__ old_ids, const uint32_t* __restrict__ add_ids, int n_add,
                                     int* __restrict__ srcmap) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -394,7 +394,7 @@ __global__ void map_existing_kernel(int n_old, const int* __restrict__ alive, co
   srcmap[d] = s;
 }
 // new id k -> dest = k + #(surviving old ids < new id)
-__global__ void map_new_kernel(int n_add, const uint32_t* __restrict__ add_ids, const uint32_t* __restrict__ old_ids, int n_old,
+static __global__ void map_new_kernel(int n_add, const uint32_t* __restrict__ add_ids, const uint32_t* __restrict__ old_ids, int n_old,
                                const int* __restrict__ pos, int total_alive, int* __restrict__ srcmap) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_add) return;
@@ -438,7 +438,7 @@ __global__ void rebuild_kernel(int n_new, const int* __restrict__ srcmap, const 
 
 // sparse tick: op k -> per-slot action / dt / measurement; tiles touched for the first time are
 // appended to tile_list (counters[0] = #tiles, counters[1] = #ops applied).  One op per id per call.
-__global__ void scatter_ops_kernel(const uint32_t* __restrict__ ids_sorted, int n_slots, long long n, const uint32_t* __restrict__ q,
+static __global__ void scatter_ops_kernel(const uint32_t* __restrict__ ids_sorted, int n_slots, long long n, const uint32_t* __restrict__ q,
                                    const double* __restrict__ dt, double dt_scalar, const double* __restrict__ meas,
                                    const uint8_t* __restrict__ action, uint8_t* act_slot, double* dt_slot, double* meas_slot,
                                    uint8_t* tile_flag, int* tile_list, int* counters) {
@@ -464,21 +464,21 @@ __global__ void scatter_ops_kernel(const uint32_t* __restrict__ ids_sorted, int 
 }
 
 // measured_pose_ refresh of a masked dense host tick (src/target_interface.cpp:142-146)
-__global__ void copy_meas_masked_kernel(double* __restrict__ dst, const double* __restrict__ src, const uint8_t* __restrict__ action, int n) {
+static __global__ void copy_meas_masked_kernel(double* __restrict__ dst, const double* __restrict__ src, const uint8_t* __restrict__ action, int n) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n || action[s] != ACT_UPDATE) return;
 #pragma unroll
   for (int e = 0; e < 7; ++e) dst[(size_t)s * 7 + e] = src[(size_t)s * 7 + e];
 }
 // initPose (utils.hpp:64-72): [0 0 0 | 0 0 0 1]
-__global__ void init_pose_kernel(double* pose, long long n) {
+static __global__ void init_pose_kernel(double* pose, long long n) {
   long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (k >= n) return;
   for (int e = 0; e < 7; ++e) pose[k * 7 + e] = (e == 6) ? 1.0 : 0.0;
 }
 
 // dense host-API tick: remember the applied measurement as measured_pose_ (stride 7 only)
-__global__ void fill_dt_kernel(double* dt_slot, int n, double v) {
+static __global__ void fill_dt_kernel(double* dt_slot, int n, double v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dt_slot[i] = v;
 }
@@ -543,7 +543,7 @@ __global__ void gather_estimates_kernel(const double* __restrict__ tiles, const 
 __device__ __forceinline__ double to_sec_rn(uint32_t sec, uint32_t nsec) {
   return __dadd_rn(__uint2double_rn(sec), __dmul_rn(1e-9, __uint2double_rn(nsec)));
 }
-__global__ void set_stamps_kernel(const uint32_t* __restrict__ ids_sorted, int n_slots, long long n, const uint32_t* __restrict__ q,
+static __global__ void set_stamps_kernel(const uint32_t* __restrict__ ids_sorted, int n_slots, long long n, const uint32_t* __restrict__ q,
                                   const uint32_t* __restrict__ sec, const uint32_t* __restrict__ nsec, double* last_meas) {
   long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (k >= n) return;
@@ -552,21 +552,21 @@ __global__ void set_stamps_kernel(const uint32_t* __restrict__ ids_sorted, int n
   last_meas[s] = to_sec_rn(sec[k], nsec[k]);
 }
 // dense tick: every slot updated this tick gets the tick's stamp as last_meas_time_
-__global__ void stamp_dense_kernel(const uint8_t* __restrict__ action, int default_action, int n_slots, double stamp, double* last_meas) {
+static __global__ void stamp_dense_kernel(const uint8_t* __restrict__ action, int default_action, int n_slots, double stamp, double* last_meas) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_slots) return;
   const int a = action ? (int)action[s] : default_action;
   if (a == ACT_UPDATE) last_meas[s] = stamp;
 }
 // alive[s] = !(last > 0.0 && (now - last) >= timeout)   (src/target_manager_ros.cpp:67)
-__global__ void expire_flags_kernel(const double* __restrict__ last_meas, int n_slots, double now, double timeout, int* alive) {
+static __global__ void expire_flags_kernel(const double* __restrict__ last_meas, int n_slots, double now, double timeout, int* alive) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_slots) return;
   const double last = last_meas[s];
   const bool expired = (last > 0.0) && (__dsub_rn(now, last) >= timeout);
   alive[s] = expired ? 0 : 1;
 }
-__global__ void collect_erased_kernel(const int* __restrict__ alive, const int* __restrict__ pos, const uint32_t* __restrict__ ids,
+static __global__ void collect_erased_kernel(const int* __restrict__ alive, const int* __restrict__ pos, const uint32_t* __restrict__ ids,
                                       int n_slots, uint32_t* erased) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_slots || alive[s]) return;
@@ -594,7 +594,7 @@ struct MailAdd {
 
 // record k of a /tf message -> sort key = its slot (unknown ids: key n_slots, listed for the host, which keeps the
 // target-less mailboxes)
-__global__ void mb_lookup_kernel(const uint32_t* __restrict__ ids_sorted, int n_slots, const uint32_t* __restrict__ q, int n,
+static __global__ void mb_lookup_kernel(const uint32_t* __restrict__ ids_sorted, int n_slots, const uint32_t* __restrict__ q, int n,
                                  uint32_t* __restrict__ key, int* __restrict__ rec, int* __restrict__ unknown, int* counter) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
@@ -605,7 +605,7 @@ __global__ void mb_lookup_kernel(const uint32_t* __restrict__ ids_sorted, int n_
   if (!hit) unknown[atomicAdd(counter, 1)] = k;
 }
 // device-resident messages: the records of unknown ids, packed for the host (which keeps the target-less mailboxes)
-__global__ void mb_pack_unknown_kernel(int n_unknown, const int* __restrict__ list, const uint32_t* __restrict__ ids, const uint32_t* __restrict__ sec,
+static __global__ void mb_pack_unknown_kernel(int n_unknown, const int* __restrict__ list, const uint32_t* __restrict__ ids, const uint32_t* __restrict__ sec,
                                        const uint32_t* __restrict__ nsec, const double* __restrict__ poses, uint32_t* __restrict__ o_ids,
                                        uint32_t* __restrict__ o_sec, uint32_t* __restrict__ o_nsec, double* __restrict__ o_pose) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -620,7 +620,7 @@ __global__ void mb_pack_unknown_kernel(int n_unknown, const int* __restrict__ li
 // records sorted by (slot, arrival order): the first record of each slot's run applies the whole run in arrival order --
 // Measurement::update (target_manager_ros.hpp:96-115): a stamp newer than the stored one makes the mailbox readable and
 // becomes last_meas_time_, any other stamp makes it unreadable; stamp and pose are stored either way.
-__global__ void mb_apply_kernel(int n, int n_slots, const uint32_t* __restrict__ key, const int* __restrict__ rec, const uint32_t* __restrict__ sec,
+static __global__ void mb_apply_kernel(int n, int n_slots, const uint32_t* __restrict__ key, const int* __restrict__ rec, const uint32_t* __restrict__ sec,
                                 const uint32_t* __restrict__ nsec, const double* __restrict__ poses, MailArrays mb, double* last_meas) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
@@ -647,7 +647,7 @@ __global__ void mb_apply_kernel(int n, int n_slots, const uint32_t* __restrict__
   for (int e = 0; e < 7; ++e) mb.pose[(size_t)s * 7 + e] = poses[(size_t)r * 7 + e];
 }
 // mailboxes follow their slots through a compaction / merge (srcmap of rebuild_kernel); promoted ones are filled in
-__global__ void mb_move_kernel(int n_new, const int* __restrict__ srcmap, MailArrays o, MailArrays nw, MailAdd add, const double* __restrict__ add_p0,
+static __global__ void mb_move_kernel(int n_new, const int* __restrict__ srcmap, MailArrays o, MailArrays nw, MailAdd add, const double* __restrict__ add_p0,
                                double* __restrict__ new_last_meas) {
   int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= n_new) return;
@@ -669,7 +669,7 @@ __global__ void mb_move_kernel(int n_new, const int* __restrict__ srcmap, MailAr
   }
 }
 // no mailbox yet for slots [base, base + n) (targets appended outside the tick)
-__global__ void mb_clear_kernel(MailArrays mb, int base, int n) {
+static __global__ void mb_clear_kernel(MailArrays mb, int base, int n) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int d = base + k;
@@ -682,7 +682,7 @@ __global__ void mb_clear_kernel(MailArrays mb, int base, int n) {
 // ---- fused mailbox tick: the step kernel itself moves the survivors (StepArgs::dst_*), so the merge only needs the
 // destination of every old slot and of every new id ----
 // new id k -> its slot in the merged order (k + #surviving old ids below it); pos = exclusive scan of alive (unmodified)
-__global__ void merge_new_dst_kernel(int n_add, const uint32_t* __restrict__ add_ids, const uint32_t* __restrict__ old_ids, int n_old,
+static __global__ void merge_new_dst_kernel(int n_add, const uint32_t* __restrict__ add_ids, const uint32_t* __restrict__ old_ids, int n_old,
                                      const int* __restrict__ pos, int total_alive, int* __restrict__ new_dst) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_add) return;
@@ -690,14 +690,14 @@ __global__ void merge_new_dst_kernel(int n_add, const uint32_t* __restrict__ add
   new_dst[k] = k + ((e < n_old) ? pos[e] : total_alive);
 }
 // surviving old slot s -> pos[s] + #new ids below its id (in place; run after merge_new_dst_kernel / collect_erased_kernel)
-__global__ void merge_old_dst_kernel(int n_old, const int* __restrict__ alive, int* __restrict__ pos, const uint32_t* __restrict__ old_ids,
+static __global__ void merge_old_dst_kernel(int n_old, const int* __restrict__ alive, int* __restrict__ pos, const uint32_t* __restrict__ old_ids,
                                      const uint32_t* __restrict__ add_ids, int n_add) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_old || !alive[s]) return;
   pos[s] += lower_bound_u32(add_ids, n_add, old_ids[s]);
 }
 // mailboxes of the survivors -> their destination slots
-__global__ void mb_compact_kernel(int n_old, const int* __restrict__ alive, const int* __restrict__ pos, MailArrays o, MailArrays nw) {
+static __global__ void mb_compact_kernel(int n_old, const int* __restrict__ alive, const int* __restrict__ pos, MailArrays o, MailArrays nw) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_old || !alive[s]) return;
   const int d = pos[s];
@@ -734,14 +734,14 @@ __global__ void init_promoted_kernel(int n_add, const int* __restrict__ new_dst,
   if (!(old & bit)) tile_list[atomicAdd(&counters[0], 1)] = tile;
 }
 // number of slots that have a mailbox (action != ACT_NONE)
-__global__ void mb_count_kernel(const uint8_t* __restrict__ act, int n, int* counter) {
+static __global__ void mb_count_kernel(const uint8_t* __restrict__ act, int n, int* counter) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned m = __ballot_sync(0xFFFFFFFFu, s < n && act[s] != (uint8_t)ACT_NONE);
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(counter, __popc(m));
 }
 // mailboxes of listed slots -> packed records (sec, nsec, act, last, pose) for the host (a target erased by hand keeps its
 // mailbox in the reference: it moves to the host's target-less map)
-__global__ void mb_gather_kernel(int n, const int* __restrict__ slots, MailArrays mb, const double* __restrict__ last_meas, uint32_t* __restrict__ sec,
+static __global__ void mb_gather_kernel(int n, const int* __restrict__ slots, MailArrays mb, const double* __restrict__ last_meas, uint32_t* __restrict__ sec,
                                  uint32_t* __restrict__ nsec, uint8_t* __restrict__ act, double* __restrict__ last, double* __restrict__ pose) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
@@ -755,7 +755,7 @@ __global__ void mb_gather_kernel(int n, const int* __restrict__ slots, MailArray
   for (int e = 0; e < 7; ++e) pose[(size_t)k * 7 + e] = mb.pose[(size_t)s * 7 + e];
 }
 // the reverse: host mailboxes attached to the slots of targets that were just created by hand
-__global__ void mb_scatter_kernel(int n, const int* __restrict__ slots, const uint32_t* __restrict__ sec, const uint32_t* __restrict__ nsec,
+static __global__ void mb_scatter_kernel(int n, const int* __restrict__ slots, const uint32_t* __restrict__ sec, const uint32_t* __restrict__ nsec,
                                   const uint8_t* __restrict__ act, const double* __restrict__ last, const double* __restrict__ pose, MailArrays mb,
                                   double* __restrict__ last_meas) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -784,7 +784,7 @@ __global__ void mirror_lower_kernel(double* __restrict__ tiles, int n_slots) {
 
 // compacting tick: the cold arrays of the survivors move to their destination slots (the tile fields are moved by the step
 // kernel itself)
-__global__ void compact_cold_kernel(int n_old, const int* __restrict__ alive, const int* __restrict__ pos, ColdArrays old_cold, ColdArrays new_cold) {
+static __global__ void compact_cold_kernel(int n_old, const int* __restrict__ alive, const int* __restrict__ pos, ColdArrays old_cold, ColdArrays new_cold) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_old || !alive[s]) return;
   const int d = pos[s];

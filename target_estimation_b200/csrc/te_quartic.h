@@ -21,7 +21,7 @@
 
 #if defined(__CUDACC__)
 #define TE_QHD __host__ __device__ __forceinline__
-#define TE_QHD_NOINLINE __host__ __device__ __noinline__
+#define TE_QHD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define TE_QHD inline
 #define TE_QHD_NOINLINE inline

@@ -194,14 +194,16 @@ def test_compacting_step_vs_oracle(model, cap):
 # another libm included.  The protocol therefore runs the perturbed oracle beside the oracle and measures each target's
 # amplification a_i = worst |d| / bar of the oracle against itself under the one-ulp perturbation:
 #     well-conditioned (a_i <= 1e-2, i.e. one ulp of input moves the result by <= 1e-11 relative): the 1e-9 bar, no exception;
-#     the others: |d| <= 100 a_i bars -- the GPU's arithmetic (Cholesky instead of LU, libdevice instead of glibc) may drift by
-#         what a hundred one-ulp perturbations of the input do to the reference itself; counted, bounded, reported.
-# t and n_meas stay exact for all targets, everything stays finite.
+#     the others (the reference's own trajectory is not reproducible to the bar from one-ulp-different inputs; once a target
+#         amplifies exponentially the difference saturates at O(1), so no multiple of a_i bounds it): counted, bounded in number,
+#         reported with their worst ratio -- and excluded.
+# On the SURVEY.md 8(d) stream (+-0.5 rad/s) NOTHING is excluded: all 4096 targets meet the bar at every checkpoint (measured worst
+# ratio 0.06).  t and n_meas stay exact for all targets, everything stays finite.
 # ---------------------------------------------------------------------------------------------------------------------
 ILL = 1e-2
 
 
-def _run_conditioned(tag, model, n, ticks, every, ill_frac_max, **stream_kw):
+def _run_conditioned(tag, model, n, ticks, every, ill_frac_max, exclude=True, **stream_kw):
     te, pool, ref, ids, meas, action, N, M = _setup(model, n, ticks, **stream_kw)
     import target_estimation_b200 as te_
     mtype, _, Q, R, P0 = te_.load_model(model)
@@ -228,7 +230,8 @@ def _run_conditioned(tag, model, n, ticks, every, ill_frac_max, **stream_kw):
                 worst["rel_ill"] = max(worst["rel_ill"], float((np.maximum(rx, rP)[ill] / amp[ill]).max()))
             assert np.array_equal(got["n_meas"], want["n_meas"]) and np.array_equal(got["t"], want["t"]), k
             assert np.isfinite(got["x"]).all() and np.isfinite(got["P"]).all(), k
-            if fail is None and not (worst["x"] <= 1.0 and worst["P"] <= 1.0 and worst["rel_ill"] <= 100.0):
+            ok = (worst["x"] <= 1.0 and worst["P"] <= 1.0) if exclude else (worst["x_all"] <= 1.0 and worst["P_all"] <= 1.0)
+            if fail is None and not ok:
                 fail = (tag, k, int(ill.sum()), dict(worst))
     pitch = float(np.abs(ref.states(ids, N)["x"][:, 4]).max()) if model == "angular_velocities" else None
     n_ill = int((amp > ILL).sum())
@@ -243,7 +246,7 @@ def _run_conditioned(tag, model, n, ticks, every, ill_frac_max, **stream_kw):
 
 def test_step_parity_4096x2000_angular_velocities():
     """4096 targets x 2000 ticks, compared every 100 ticks, attitude rates as specified there (+-0.5 rad/s)"""
-    _run_conditioned("step_parity_4096x2000[angular_velocities]", "angular_velocities", 4096, 2000, 100, 0.03, att_rate=0.5)
+    _run_conditioned("step_parity_4096x2000[angular_velocities]", "angular_velocities", 4096, 2000, 100, 0.03, exclude=False, att_rate=0.5)
 
 
 def test_step_parity_4096x2000_angular_velocities_fast_rotation():
@@ -254,7 +257,7 @@ def test_step_parity_4096x2000_angular_velocities_fast_rotation():
 
 def test_step_parity_4096x2000_angular_rates():
     """(linear filter: no amplifying targets at all)"""
-    assert _run_conditioned("step_parity_4096x2000[angular_rates]", "angular_rates", 4096, 2000, 100, 0.0) == 0
+    assert _run_conditioned("step_parity_4096x2000[angular_rates]", "angular_rates", 4096, 2000, 100, 0.0, exclude=False) == 0
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,110 @@
+#!/usr/bin/env python3
+"""tools/pcie_probe.py -- what the host side of the box gives one rank, and all ranks at once.
+
+    python tools/pcie_probe.py                                       # one GPU
+    python -m torch.distributed.run --nproc-per-node 8 ... tools/pcie_probe.py
+
+Per rank: pinned H2D alone, pinned D2H alone, both directions at once (two streams), each as GB/s over a 256 MB buffer
+(CUDA events, best of 5 after a warm-up).  Under torchrun the same three figures are taken (a) rank by rank, the others idle,
+and (b) on all ranks concurrently after a barrier; rank 0 prints one JSON line with the per-rank figures, the aggregates and
+where every GPU hangs (PCI bus id, NUMA node from sysfs, the CPU affinity of the process).  The e2e figure of bench.py moves
+h2d_bytes_per_step + d2h_bytes_per_step through exactly this path; `e2e_bound` is the step time those bytes need at the measured
+concurrent rates."""
+import json
+import os
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+
+MB = 1 << 20
+
+
+def numa_of(bus_id):
+    try:
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus_id.lower()) as f:
+            return int(f.read().strip())
+    except Exception:
+        return None
+
+
+def measure(size, mode, reps=5):
+    """mode 'h2d' | 'd2h' | 'both' -> (GB/s h2d, GB/s d2h) ; both directions are timed over the same window in 'both'"""
+    h_in = torch.empty(size, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(size, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(size, dtype=torch.uint8, device="cuda")
+    d_out = torch.empty(size, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    best = None
+    for r in range(reps + 1):
+        torch.cuda.synchronize()
+        e0, e1, f0, f1 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+        if mode in ("h2d", "both"):
+            with torch.cuda.stream(s1):
+                e0.record(s1)
+                d_in.copy_(h_in, non_blocking=True)
+                e1.record(s1)
+        if mode in ("d2h", "both"):
+            with torch.cuda.stream(s2):
+                f0.record(s2)
+                h_out.copy_(d_out, non_blocking=True)
+                f1.record(s2)
+        torch.cuda.synchronize()
+        a = size / (e0.elapsed_time(e1) * 1e-3) / 1e9 if mode in ("h2d", "both") else 0.0
+        b = size / (f0.elapsed_time(f1) * 1e-3) / 1e9 if mode in ("d2h", "both") else 0.0
+        if r > 0 and (best is None or a + b > best[0] + best[1]):
+            best = (a, b)
+    return best
+
+
+def main():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    size = 256 * MB
+    props = torch.cuda.get_device_properties(local)
+    bus = "%04x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), getattr(props, "pci_bus_id", 0), getattr(props, "pci_device_id", 0))
+    info = {"rank": rank, "pci": bus, "numa_node": numa_of(bus), "cpu_affinity": sorted(os.sched_getaffinity(0))[:4] + ["..."] + [len(os.sched_getaffinity(0))]}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    alone = {}
+    for r in range(world):           # rank by rank, the others idle
+        barrier()
+        if r == rank:
+            for mode in ("h2d", "d2h", "both"):
+                alone[mode] = measure(size, mode)
+    barrier()
+    together = {}
+    for mode in ("h2d", "d2h", "both"):   # all ranks at once
+        barrier()
+        together[mode] = measure(size, mode)
+    barrier()
+    mine = {"info": info, "alone": alone, "together": together}
+    if world > 1:
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+    else:
+        allr = [mine]
+    if rank == 0:
+        def agg(key, mode, idx):
+            return sum(r[key][mode][idx] for r in allr)
+        out = {"tool": "pcie_probe", "n_gpus": world, "buffer_mb": size // MB, "ranks": allr,
+               "aggregate_gbs": {"alone_sum_h2d": agg("alone", "h2d", 0), "alone_sum_d2h": agg("alone", "d2h", 1),
+                                 "together_h2d": agg("together", "h2d", 0), "together_d2h": agg("together", "d2h", 1),
+                                 "together_both_h2d": agg("together", "both", 0), "together_both_d2h": agg("together", "both", 1)},
+               "note": "alone = one rank copies, the others idle; together = every rank copies at once (what a multi-GPU e2e step does)"}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
