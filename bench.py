@@ -413,57 +413,56 @@ def main():
     achieved_layout = layout_bytes / (ms / K * 1e-3) / 1e9
 
     # ---- e2e: host buffers through the C-ABI ---------------------------------------------------------
+    # Headline form: the pipelined host tick (te_pool_tick_host_async + te_pool_tick_host_wait(1): the copies of tick k + 1 run under
+    # the kernels and the read-back of tick k) with the measurement block the model reads -- [n][3] positions for the linear models
+    # (UV / UA use x y z of the pose only), [n][7] poses for the angular ones.  Every step moves its inputs from pinned host memory
+    # and every target's estimated position back to pinned host memory inside the timed region.  The synchronous call and the
+    # 56-byte pose form of the same tick are reported beside it.
     e2e = None
     if not args.no_e2e:
-        h_meas = [m.cpu().pin_memory() for m in meas[:2]]
         h_act = [a.cpu().pin_memory() for a in act[:2]]
-        h_out = torch.empty((n, 3), dtype=torch.float64).pin_memory()
-        Ke = max(3, min(K, 20))
+        h_out = [torch.empty((n, 3), dtype=torch.float64).pin_memory() for _ in range(2)]
+        Ke = max(5, min(K, 40))
 
-        def tick_host(k):
-            check = te.lib.te_pool_tick_host(pool._h, DT, h_meas[k % 2].data_ptr(), stride, h_act[k % 2].data_ptr(), 2, h_out.data_ptr())
-            if check < 0:
-                raise RuntimeError(te._lib.last_error())
-            history.append(k % 2)
-        for k in range(3):
-            tick_host(k)
-        barrier()
-        t0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for k in range(Ke):
-            tick_host(k)
-        e1.record(stream)
-        barrier()
-        wall = time.perf_counter() - t0
-        ems = max(e0.elapsed_time(e1), wall * 1e3)     # host-synchronous API: wall clock covers the copies
-        t_e = torch.tensor([ems], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        e2e = {"value": n * world * Ke / (float(t_e.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * (stride * 8 + 1),
-               "d2h_bytes_per_step": n * 24, "steps": Ke, "ms_per_step": float(t_e.item()) / Ke,
-               "api": "te_pool_tick_host (pinned host meas[n][7] + action[n] in, est. position [n][3] out)"}
-        if M == 3:
-            # the linear models only read x y z of the pose: a caller that hands over [n][3] positions moves 2.3x fewer bytes
-            h3 = [m[:, :3].contiguous().cpu().pin_memory() for m in meas[:2]]
-
-            def tick_host3(k):
-                if te.lib.te_pool_tick_host(pool._h, DT, h3[k % 2].data_ptr(), 3, h_act[k % 2].data_ptr(), 2, h_out.data_ptr()) < 0:
+        def run_e2e(h_in, st, pipelined):
+            def one(k):
+                fn = te.lib.te_pool_tick_host_async if pipelined else te.lib.te_pool_tick_host
+                if fn(pool._h, DT, h_in[k % 2].data_ptr(), st, h_act[k % 2].data_ptr(), 2, h_out[k % 2].data_ptr()) < 0:
+                    raise RuntimeError(te._lib.last_error())
+                if pipelined and te.lib.te_pool_tick_host_wait(pool._h, 1) < 0:      # results of tick k - 1 are in h_out[(k - 1) % 2] now
                     raise RuntimeError(te._lib.last_error())
                 history.append(k % 2)
             for k in range(3):
-                tick_host3(k)
+                one(k)
+            te.lib.te_pool_tick_host_wait(pool._h, 0)
             barrier()
             t0 = time.perf_counter()
             for k in range(Ke):
-                tick_host3(k)
+                one(k)
+            if te.lib.te_pool_tick_host_wait(pool._h, 0) < 0:
+                raise RuntimeError(te._lib.last_error())
+            wall = (time.perf_counter() - t0) * 1e3          # host-synchronous end: the wall clock covers every copy
             barrier()
-            t3 = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device="cuda")
+            t_e = torch.tensor([wall], dtype=torch.float64, device="cuda")
             if world > 1:
-                dist.all_reduce(t3, op=dist.ReduceOp.MAX)
-            e2e["xyz_only"] = {"value": n * world * Ke / (float(t3.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * (3 * 8 + 1),
-                               "d2h_bytes_per_step": n * 24, "ms_per_step": float(t3.item()) / Ke,
-                               "api": "te_pool_tick_host with meas_stride 3 (positions only)"}
+                dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+            w = float(t_e.item())
+            return {"value": n * world * Ke / (w * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * (st * 8 + 1), "d2h_bytes_per_step": n * 24,
+                    "steps": Ke, "ms_per_step": w / Ke}
+
+        h7 = [m.cpu().pin_memory() for m in meas[:2]]
+        h3 = [m[:, :3].contiguous().cpu().pin_memory() for m in meas[:2]] if M == 3 else None
+        if M == 3:
+            e2e = run_e2e(h3, 3, True)
+            e2e["api"] = "te_pool_tick_host_async + te_pool_tick_host_wait(1): pinned host meas[n][3] (x y z: all the linear models read of a pose) + action[n] in, est. position [n][3] out, two ticks in flight"
+            e2e["pose7_pipelined"] = dict(run_e2e(h7, 7, True), api="the same with the reference's 56-byte pose measurements meas[n][7]")
+            e2e["xyz_sync"] = dict(run_e2e(h3, 3, False), api="te_pool_tick_host (one tick at a time, returns when est_pos_out is complete), meas[n][3]")
+            e2e["pose7_sync"] = dict(run_e2e(h7, 7, False), api="te_pool_tick_host, meas[n][7] (the round-1 headline form)")
+        else:
+            e2e = run_e2e(h7, 7, True)
+            e2e["api"] = "te_pool_tick_host_async + te_pool_tick_host_wait(1): pinned host meas[n][7] + action[n] in, est. position [n][3] out, two ticks in flight"
+            e2e["pose7_sync"] = dict(run_e2e(h7, 7, False), api="te_pool_tick_host (one tick at a time), meas[n][7]")
+        h_meas = h7
 
         # the same tick through the REFERENCE-FACING C-ABI (include/target_manager_c.h, libtarget_c.so): a TargetManager built from the
         # model file, one target_manager_update_batch(ids, dt, meas, action) per step from pinned host arrays and one

@@ -14,6 +14,7 @@
 #pragma once
 #include <array>
 #include <cstdint>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -127,39 +128,39 @@ class TargetManager {
   virtual ~TargetManager();
 
   // reference API ---------------------------------------------------------------------------
-  void init(const unsigned int& id, const double& dt0, const double& t0, const Vector7d& p0, const Vector6d& v0 = Vector6d{},
-            const Vector6d& a0 = Vector6d{});
-  void init(const target_t& type, const unsigned int& id, const double& dt0, const double& t0, const MatrixXd& Q, const MatrixXd& R,
-            const MatrixXd& P0, const Vector7d& p0, const Vector6d& v0 = Vector6d{}, const Vector6d& a0 = Vector6d{});
+  virtual void init(const unsigned int& id, const double& dt0, const double& t0, const Vector7d& p0, const Vector6d& v0 = Vector6d{},
+                    const Vector6d& a0 = Vector6d{});
+  virtual void init(const target_t& type, const unsigned int& id, const double& dt0, const double& t0, const MatrixXd& Q, const MatrixXd& R,
+                    const MatrixXd& P0, const Vector7d& p0, const Vector6d& v0 = Vector6d{}, const Vector6d& a0 = Vector6d{});
   void init(const std::string& file, const unsigned int& id, const double& dt0, const double& t0, const Vector7d& p0,
             const Vector6d& v0 = Vector6d{}, const Vector6d& a0 = Vector6d{});
-  bool update(const unsigned int& id, const double& dt, const Vector7d& meas);
-  bool update(const unsigned int& id, const double& dt);
+  virtual bool update(const unsigned int& id, const double& dt, const Vector7d& meas);
+  virtual bool update(const unsigned int& id, const double& dt);
   virtual void update(const double& dt);
-  bool erase(const unsigned int& id);
-  TargetInterface::Ptr getTarget(const unsigned int& id);
-  bool getTargetPose(const unsigned int& id, Vector7d& pose);
-  bool getTargetTwist(const unsigned int& id, Vector6d& twist);
-  bool getTargetAcceleration(const unsigned int& id, Vector6d& acc);
-  long long getNumberMeasurements(const unsigned int& id);
-  void log();
-  std::vector<unsigned int> getAvailableTargets();
+  virtual bool erase(const unsigned int& id);
+  virtual TargetInterface::Ptr getTarget(const unsigned int& id);
+  virtual bool getTargetPose(const unsigned int& id, Vector7d& pose);
+  virtual bool getTargetTwist(const unsigned int& id, Vector6d& twist);
+  virtual bool getTargetAcceleration(const unsigned int& id, Vector6d& acc);
+  virtual long long getNumberMeasurements(const unsigned int& id);
+  virtual void log();
+  virtual std::vector<unsigned int> getAvailableTargets();
   bool selectTargetType(const std::string& type_str, target_t& type);
   bool loadYamlFile(const std::string& file, MatrixXd& Q, MatrixXd& R, MatrixXd& P, target_t& type);
 
   // batched extensions (one kernel launch per call) ---------------------------------------------
   long long initBatch(long long n, const unsigned* ids, double dt0, const double* t0, const double* p0 /*[n][7]*/,
                       const double* v0 = nullptr, const double* a0 = nullptr);
-  long long initBatch(target_t type, const MatrixXd& Q, const MatrixXd& R, const MatrixXd& P0, long long n, const unsigned* ids, double dt0,
-                      const double* t0, const double* p0, const double* v0 = nullptr, const double* a0 = nullptr,
-                      const double* p0_scale = nullptr);
+  virtual long long initBatch(target_t type, const MatrixXd& Q, const MatrixXd& R, const MatrixXd& P0, long long n, const unsigned* ids, double dt0,
+                              const double* t0, const double* p0, const double* v0 = nullptr, const double* a0 = nullptr,
+                              const double* p0_scale = nullptr);
   // (an id may appear more than once: the records are applied in order, as the reference's sequential update() calls would --
   //  the batch is cut in front of every repeat and the pieces are launched one after the other)
-  long long updateBatch(long long n, const unsigned* ids, double dt, const double* meas /*[n][7]*/, const unsigned char* action = nullptr);
-  long long eraseBatch(long long n, const unsigned* ids);
-  void getEstimatesBatch(long long n, const unsigned* ids, const double* t1, double* pose7, double* twist6, double* acc6,
-                         unsigned char* found);
-  void flush();
+  virtual long long updateBatch(long long n, const unsigned* ids, double dt, const double* meas /*[n][7]*/, const unsigned char* action = nullptr);
+  virtual long long eraseBatch(long long n, const unsigned* ids);
+  virtual void getEstimatesBatch(long long n, const unsigned* ids, const double* t1, double* pose7, double* twist6, double* acc6,
+                                 unsigned char* found);
+  virtual void flush();
   bool quiet = false;   // suppress the reference's stdout messages ("does not exist", "already exists", ...)
 
   // sampled logging -----------------------------------------------------------------------------
@@ -167,7 +168,7 @@ class TargetManager {
   // target, measured_pose_, pose_internal_, twist_, acceleration_ and P_ through rt_logger (:32-40); its tests dump time / pose /
   // twist series with writeTxtFile (utils.hpp:78-120) for matlab/plot_*.m.  Here log() appends ONE batched read-back of those five
   // quantities for the watched ids to an in-memory series, and writeLog() dumps them in writeTxtFile's format.
-  void watch(long long n, const unsigned* ids, size_t max_samples = 1 << 20);   // n = 0: stop logging and drop the series
+  virtual void watch(long long n, const unsigned* ids, size_t max_samples = 1 << 20);   // n = 0: stop logging and drop the series
   size_t logSamples() const { return log_t_.size(); }
   // one sample k of watched id j: [t | measured_pose 7 | pose_internal 6 | twist 6 | acceleration 6] = 26 doubles, then P (N*N)
   bool logSample(size_t k, size_t j, double* row26, double* P, int* n_state) const;
@@ -317,6 +318,78 @@ class TickTargetManager : public TargetManager {
   std::vector<double> pub_poses_;
   std::vector<uint32_t> gone_buf_, born_buf_;   // reusable output buffers of te_pool_mailbox_tick
   void* pub_pinned_ = nullptr;                  // storage of pub_poses_ while it is page-locked
+};
+
+// ---------------------------------------------------------------------------------------------------
+// One TargetManager per GPU of the box behind the TargetManager interface (BASELINE.json north_star: "targets shard by ID across
+// the 8 GPUs of one box with no collective on the hot path ... the TargetManager API stays as the host surface in C++").
+// owner(id) = id mod G; shard r is an ordinary TargetManager on device devices[r] with its own pools and streams.  Per-id calls
+// go to the owner (their launches coalesce per shard as in TargetManager).  The batched calls route their records to the owners
+// in one host pass -- every shard's worker thread picks its own records out of the caller's arrays into page-locked staging, in
+// the caller's order, and runs the shard's batched call -- so the G devices copy and step concurrently.  Results are the
+// reference's: an id lives in exactly one shard, its records are applied in call order.
+// The optional exchange of estimates is gatherEstimates(): [pose7 | twist6] records of every target, all shards,
+// gathered on every device over NCCL (te_group_*), then read back from the publishing shard's device.
+// ---------------------------------------------------------------------------------------------------
+class ShardWorkers;
+class ShardedTargetManager : public TargetManager {
+ public:
+  // devices NULL = devices 0 .. n_shards-1; a device may repeat (several shards on one GPU: a one-GPU box still runs the
+  // sharded host logic -- the estimate exchange then uses device copies, NCCL needs distinct devices)
+  ShardedTargetManager(const std::string& file, int n_shards, const int* devices = nullptr);
+  ~ShardedTargetManager() override;
+  int shards() const { return (int)shard_.size(); }
+  int owner(unsigned id) const { return (int)(id % (unsigned)shard_.size()); }
+  TargetManager& shard(int r) { return *shard_[(size_t)r]; }
+
+  void init(const unsigned int& id, const double& dt0, const double& t0, const Vector7d& p0, const Vector6d& v0 = Vector6d{},
+            const Vector6d& a0 = Vector6d{}) override;
+  void init(const target_t& type, const unsigned int& id, const double& dt0, const double& t0, const MatrixXd& Q, const MatrixXd& R,
+            const MatrixXd& P0, const Vector7d& p0, const Vector6d& v0 = Vector6d{}, const Vector6d& a0 = Vector6d{}) override;
+  bool update(const unsigned int& id, const double& dt, const Vector7d& meas) override;
+  bool update(const unsigned int& id, const double& dt) override;
+  void update(const double& dt) override;
+  bool erase(const unsigned int& id) override;
+  TargetInterface::Ptr getTarget(const unsigned int& id) override;
+  bool getTargetPose(const unsigned int& id, Vector7d& pose) override;
+  bool getTargetTwist(const unsigned int& id, Vector6d& twist) override;
+  bool getTargetAcceleration(const unsigned int& id, Vector6d& acc) override;
+  long long getNumberMeasurements(const unsigned int& id) override;
+  void log() override;
+  std::vector<unsigned int> getAvailableTargets() override;   // ascending ids over all shards
+  long long initBatch(target_t type, const MatrixXd& Q, const MatrixXd& R, const MatrixXd& P0, long long n, const unsigned* ids, double dt0,
+                      const double* t0, const double* p0, const double* v0 = nullptr, const double* a0 = nullptr,
+                      const double* p0_scale = nullptr) override;
+  using TargetManager::initBatch;
+  long long updateBatch(long long n, const unsigned* ids, double dt, const double* meas, const unsigned char* action = nullptr) override;
+  long long eraseBatch(long long n, const unsigned* ids) override;
+  void getEstimatesBatch(long long n, const unsigned* ids, const double* t1, double* pose7, double* twist6, double* acc6,
+                         unsigned char* found) override;
+  void flush() override;
+  void watch(long long n, const unsigned* ids, size_t max_samples = 1 << 20) override;   // forwarded to the owners
+
+  // The optional all-gather of estimates: ids (shard-major: shard 0's targets of model type 0 in ascending id, ...) and their
+  // [pose7 | twist6] records, exchanged between the devices over NCCL and read back from shard `publisher`'s device.  Either output
+  // may be NULL (exchange only).  Returns the number of records; lastGatherMs() = device time of the exchange(s).
+  long long gatherEstimates(std::vector<unsigned>* ids, std::vector<double>* records13, int publisher = 0);
+  double lastGatherMs() const { return gather_ms_; }
+  bool gatherUsesNccl();
+
+ private:
+  template <class F> void forEachShard(F&& f);   // f(r) on shard r's worker thread, all shards at once; rethrows the first error
+  std::vector<std::unique_ptr<TargetManager>> shard_;
+  std::vector<int> devices_;
+  std::unique_ptr<ShardWorkers> workers_;
+  te_group* group_ = nullptr;
+  double gather_ms_ = -1.0;
+  struct Stage {   // per shard, page-locked, grow-only
+    std::vector<unsigned> ids;
+    std::vector<long long> where;
+    double* meas = nullptr;
+    unsigned char* action = nullptr;
+    size_t cap = 0;
+  };
+  std::vector<Stage> stage_;
 };
 
 // utils.hpp:273-313

@@ -66,6 +66,21 @@ int target_manager_get_state(const target_manager_c* self, unsigned int id, doub
 /* pending per-id calls are coalesced into one launch per tick; force them out */
 void target_manager_flush(const target_manager_c* self);
 
+/* ---- all GPUs of the box behind one handle (BASELINE.json north_star: targets shard by id, no collective on the hot path) ----
+ * n_shards TargetManagers, shard r on CUDA device devices[r] (NULL = devices 0 .. n_shards-1), owner(id) = id mod n_shards.  The
+ * handle is a valid target_manager_c* for every function above: per-id calls go to the owner, the *_batch calls route their records
+ * to the owners on the host and run on all devices at once.  (IntersectionSolver objects attach to one shard's manager.) */
+target_manager_c* target_manager_new_sharded(const char* file, int n_shards, const int* devices);
+/* number of shards behind the handle (1 for a plain manager) */
+int target_manager_shards(const target_manager_c* self);
+/* The optional exchange of estimates: [pose7 | twist6] records (13 doubles) of every target of every shard, all-gathered between
+ * the devices over NCCL and read back from shard `publisher`'s device, shard-major; ids_out / records_out may be NULL (exchange
+ * only).  Returns the number of records (call with cap 0 to size the buffers), -1 on error.  On a plain manager: its own records. */
+long long target_manager_gather_estimates(const target_manager_c* self, unsigned int* ids_out, double* records_out, long long cap, int publisher);
+/* device time of the exchange inside the last gather (ms, max over the devices); 1 if it went over NCCL, 0 for device copies */
+double target_manager_last_gather_ms(const target_manager_c* self);
+int target_manager_gather_uses_nccl(const target_manager_c* self);
+
 /* ---- tick front-end: RosTargetManager semantics without ROS (src/target_manager_ros.cpp:26-92) ----
  * The handle is also a valid target_manager_c* for every function above. */
 target_manager_c* target_tick_manager_new(const char* file, int device);

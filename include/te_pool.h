@@ -95,6 +95,15 @@ int te_pool_step_dense_host(te_pool* p, double dt, const double* meas, int meas_
  * streams.  Synchronous: returns when est_pos_out is complete. */
 int te_pool_tick_host(te_pool* p, double dt, const double* meas, int meas_stride, const uint8_t* action, int default_action,
                       double* est_pos_out);
+/* The same, pipelined ACROSS ticks (batched ingestion of a recorded or buffered stream at PCIe speed in both directions): the call
+ * enqueues the tick and returns; up to two ticks are in flight, so the host->device copies of tick k + 1 run under the kernels and
+ * the device->host read-back of tick k.  meas / action / est_pos_out of a tick must stay valid (and should be page-locked) until
+ * that tick is done: te_pool_tick_host_wait(p, 0) waits for every tick issued, (p, 1) for all but the newest one -- the loop
+ * "async(k); wait(1); consume est_pos_out of tick k - 1" keeps the link busy in both directions.  A third call waits for the tick
+ * two back by itself.  Results are those of te_pool_tick_host tick by tick. */
+int te_pool_tick_host_async(te_pool* p, double dt, const double* meas, int meas_stride, const uint8_t* action, int default_action,
+                            double* est_pos_out);
+int te_pool_tick_host_wait(te_pool* p, int lag);
 /* Sparse tick by id (host buffers): op k applies action[k] with dt[k] (dt_scalar if dt NULL) and
  * meas[k][7] to ids[k]; unknown ids are skipped.  An id may appear once per call.  Returns #applied. */
 long long te_pool_step_ids(te_pool* p, long long n, const uint32_t* ids, const double* dt, double dt_scalar,
@@ -192,6 +201,32 @@ int te_isolver_query(te_isolver* s, long long n, const uint32_t* ids, const int3
  * dev_t1 NULL = each target's own time; dev_delta / dev_pose7 / dev_converged may be NULL.  Asynchronous. */
 int te_isolver_query_dense(te_isolver* s, const double* dev_t1, const double* dev_origin /*[size][3]*/, const double* dev_radius,
                            double pos_th, double ang_th, double* dev_delta, double* dev_pose7, uint8_t* dev_converged);
+
+/* ---- several pools on several devices of one box (targets shard by id: owner = id mod n, no collective on the hot path) ------ */
+/* A group = the devices of the shards, in shard order, + one NCCL communicator per device created in this process
+ * (ncclCommInitAll; libnccl.so.2 is loaded on first use).  Two shards on the SAME device (a one-GPU test of the sharded host
+ * logic) cannot form a NCCL clique: such a group moves the records with device-to-device copies instead. */
+typedef struct te_group te_group;
+te_group* te_group_create(int n, const int* devices);
+void te_group_destroy(te_group* g);
+int te_group_size(te_group* g);
+/* 1 = NCCL communicators, 0 = same-device copies (see above) */
+int te_group_uses_nccl(te_group* g);
+/* The optional all-gather of estimates to the publishing rank(s): every pool writes its [size][13] =
+ * pose7 | twist6 records (te_pool_estimates_dev) on its own stream, then every device receives the records -- and the ids -- of
+ * all shards, shard-major (shard 0's targets in ascending id, then shard 1's, ...): ncclAllGather when the shards hold equally
+ * many targets, else one ncclBroadcast per shard inside one NCCL group (ragged all-gather, nothing padded).  pools[r] = the
+ * pool of shard r (NULL = that shard has no target of this model).  counts_out[r] (optional) = records of shard r.  Asynchronous:
+ * ordered on each pool's stream; te_group_sync waits.  Returns the total number of records, -1 on error. */
+long long te_group_allgather_estimates(te_group* g, te_pool* const* pools, long long* counts_out);
+int te_group_sync(te_group* g);
+/* device views of the gathered records / ids on shard r's device (valid until the next gather) */
+const double* te_group_dev_records(te_group* g, int r);
+const uint32_t* te_group_dev_ids(te_group* g, int r);
+/* the gathered records / ids from shard `root`'s device into host buffers ([total][13] doubles, [total] ids; either may be NULL) */
+long long te_group_fetch(te_group* g, int root, double* records_out, uint32_t* ids_out, long long cap);
+/* device time of the last gather (ms, max over the devices; CUDA events around the collective on every device's stream) */
+double te_group_last_gather_ms(te_group* g);
 
 #ifdef __cplusplus
 }

@@ -75,6 +75,18 @@ SIGNATURES = {
     "te_isolver_destroy": (None, [_p]),
     "te_isolver_query": (_i, [_p, _ll, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "te_isolver_query_dense": (_i, [_p, _p, _p, _p, _d, _d, _p, _p, _p]),
+    "te_pool_tick_host_async": (_i, [_p, _d, _p, _i, _p, _i, _p]),
+    "te_pool_tick_host_wait": (_i, [_p, _i]),
+    "te_group_create": (_p, [_i, _p]),
+    "te_group_destroy": (None, [_p]),
+    "te_group_size": (_i, [_p]),
+    "te_group_uses_nccl": (_i, [_p]),
+    "te_group_allgather_estimates": (_ll, [_p, _p, _p]),
+    "te_group_sync": (_i, [_p]),
+    "te_group_dev_records": (_p, [_p, _i]),
+    "te_group_dev_ids": (_p, [_p, _i]),
+    "te_group_fetch": (_ll, [_p, _i, _p, _p, _ll]),
+    "te_group_last_gather_ms": (_d, [_p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -471,6 +471,8 @@ void te_pool_destroy(te_pool* p) {
   cudaGetDevice(&prev);
   cudaSetDevice(p->device);
   cudaStreamSynchronize(p->stream);
+  if (p->h2d_stream) cudaStreamSynchronize(p->h2d_stream);
+  if (p->d2h_stream) cudaStreamSynchronize(p->d2h_stream);
   free_buf(p->buf[0]);
   free_buf(p->buf[1]);
   free_mail(p->mb[0]);
@@ -480,7 +482,14 @@ void te_pool_destroy(te_pool* p) {
   cudaFree(p->alive); cudaFree(p->pos); cudaFree(p->srcmap); cudaFree(p->d_counters); cudaFree(p->cub_tmp);
   cudaFree(p->dQ); cudaFree(p->dR); cudaFree(p->dP0);
   p->arena.destroy();
-  for (cudaEvent_t e : p->events) cudaEventDestroy(e);
+  for (te_pool::TickSet& ts : p->tick_set) {
+    for (cudaEvent_t e : ts.ev) cudaEventDestroy(e);
+    if (ts.step_done) cudaEventDestroy(ts.step_done);
+    if (ts.d2h_done) cudaEventDestroy(ts.d2h_done);
+    cudaFree(ts.meas);
+    cudaFree(ts.act);
+    cudaFree(ts.pos);
+  }
   if (p->h2d_stream) cudaStreamDestroy(p->h2d_stream);
   if (p->d2h_stream) cudaStreamDestroy(p->d2h_stream);
   if (p->own_stream) cudaStreamDestroy(p->stream);

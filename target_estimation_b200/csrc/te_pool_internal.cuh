@@ -171,9 +171,19 @@ struct te_pool {
   std::vector<tehost::PendingRec> pending;                 // records of unknown ids since the last tick, arrival order
   char* h_stage = nullptr;                         // pinned staging for the tick's add arrays / the ingest's read-backs (grow-only)
   size_t h_stage_cap = 0;
-  // chunk pipeline of te_pool_tick_host
+  // chunk pipeline of te_pool_tick_host / te_pool_tick_host_async: two sets of device staging (measurements, actions, positions)
+  // so that the copies of tick k + 1 run under the kernels and read-backs of tick k
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
-  std::vector<cudaEvent_t> events;
+  struct TickSet {
+    double* meas = nullptr;
+    uint8_t* act = nullptr;
+    double* pos = nullptr;
+    size_t meas_cap = 0, act_cap = 0, pos_cap = 0;   // bytes
+    std::vector<cudaEvent_t> ev;                     // [2 * chunk] h2d done, [2 * chunk + 1] step done
+    cudaEvent_t step_done = nullptr, d2h_done = nullptr;
+    bool busy = false;
+  } tick_set[2];
+  long long ticks_issued = 0;
 };
 
 struct te_isolver {

@@ -340,64 +340,137 @@ int te_pool_step_dense_host(te_pool* p, double dt, const double* meas, int meas_
   });
 }
 
+namespace {
+
+void tick_set_reserve(te_pool* p, te_pool::TickSet& ts, size_t meas_bytes, size_t act_bytes, size_t pos_bytes) {
+  auto grow = [&](void** ptr, size_t& cap, size_t need) {
+    if (need <= cap) return;
+    CK(cudaStreamSynchronize(p->stream));
+    CK(cudaStreamSynchronize(p->h2d_stream));
+    CK(cudaStreamSynchronize(p->d2h_stream));
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    cap = 0;
+    const size_t c = need + need / 8 + 256;
+    CK(cudaMalloc(ptr, c));
+    cap = c;
+  };
+  grow((void**)&ts.meas, ts.meas_cap, meas_bytes);
+  grow((void**)&ts.act, ts.act_cap, act_bytes);
+  grow((void**)&ts.pos, ts.pos_cap, pos_bytes);
+  if (!ts.step_done) {
+    CK(cudaEventCreateWithFlags(&ts.step_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ts.d2h_done, cudaEventDisableTiming));
+  }
+}
+
+// one dense tick from host buffers, enqueued on the pool's three streams; nothing here waits on the host
+void tick_host_enqueue(te_pool* p, double dt, const double* meas, int meas_stride, const uint8_t* action, int default_action, double* est_pos_out) {
+  if (!(dt >= 0.0)) throw std::invalid_argument("dt must be >= 0");
+  if (meas) check_meas_stride(p, meas_stride);
+  else if (!action && default_action == TE_ACT_UPDATE) throw std::invalid_argument("update tick without measurements");
+  if (!p->h2d_stream) {
+    CK(cudaStreamCreateWithFlags(&p->h2d_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&p->d2h_stream, cudaStreamNonBlocking));
+  }
+  const long long n = p->n;
+  const int n_tiles = cdiv(n, te::TILE);
+  const int chunk_tiles = std::max(256, std::min(n_tiles, 8192));   // 262144 targets: 14.7 MB of pose measurements
+  const int n_chunks = cdiv(n_tiles, chunk_tiles);
+  te_pool::TickSet& ts = p->tick_set[p->ticks_issued & 1];
+  if (ts.busy) {   // the tick that used this set two ticks ago must have left it (its results are in the caller's buffer by then)
+    CK(cudaEventSynchronize(ts.d2h_done));
+    ts.busy = false;
+  }
+  tick_set_reserve(p, ts, meas ? (size_t)n * meas_stride * 8 : 0, action ? (size_t)n : 0, est_pos_out ? (size_t)n * 24 : 0);
+  while ((int)ts.ev.size() < 2 * n_chunks) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ts.ev.push_back(e);
+  }
+  double* d_meas = meas ? ts.meas : nullptr;
+  uint8_t* d_act = action ? ts.act : nullptr;
+  double* d_pos = est_pos_out ? ts.pos : nullptr;
+  // the copies of this tick may start as soon as the kernels that last read this set's staging are done (two ticks ago: already
+  // waited for above through d2h_done, which follows them) and whatever the caller queued on the pool's stream before this call
+  // that could touch the pool -- nothing reads the staging but the step kernels, so the copy stream needs no further wait
+  te::StepArgs a = base_args(p);
+  a.dt = dt;
+  a.meas = d_meas;
+  a.meas_stride = meas_stride;
+  a.meas_tma = d_meas ? 1 : 0;
+  a.action = d_act;
+  a.default_action = default_action;
+  a.pos_out = d_pos;
+  for (int c = 0; c < n_chunks; ++c) {
+    const long long s0 = (long long)c * chunk_tiles * te::TILE;
+    const long long s1 = std::min<long long>(n, s0 + (long long)chunk_tiles * te::TILE);
+    if (d_meas) CK(cudaMemcpyAsync(d_meas + s0 * meas_stride, meas + s0 * meas_stride, (size_t)(s1 - s0) * meas_stride * 8, cudaMemcpyHostToDevice, p->h2d_stream));
+    if (d_act) CK(cudaMemcpyAsync(d_act + s0, action + s0, (size_t)(s1 - s0), cudaMemcpyHostToDevice, p->h2d_stream));
+    CK(cudaEventRecord(ts.ev[2 * c], p->h2d_stream));
+    CK(cudaStreamWaitEvent(p->stream, ts.ev[2 * c], 0));
+    a.tile_begin = c * chunk_tiles;
+    a.n_tiles = std::min(chunk_tiles, n_tiles - c * chunk_tiles);
+    launch_step(p, a, a.n_tiles);
+    if (d_pos) {
+      CK(cudaEventRecord(ts.ev[2 * c + 1], p->stream));
+      CK(cudaStreamWaitEvent(p->d2h_stream, ts.ev[2 * c + 1], 0));
+      CK(cudaMemcpyAsync(est_pos_out + s0 * 3, d_pos + s0 * 3, (size_t)(s1 - s0) * 24, cudaMemcpyDeviceToHost, p->d2h_stream));
+    }
+  }
+  if (d_meas && meas_stride == 7) {   // measured_pose_ = meas for the updated slots (src/target_interface.cpp:142-146)
+    if (d_act) te::copy_meas_masked_kernel<<<cdiv(n, 256), 256, 0, p->stream>>>(p->buf[p->cur].cold.meas, d_meas, d_act, (int)n);
+    else if (default_action == TE_ACT_UPDATE)
+      CK(cudaMemcpyAsync(p->buf[p->cur].cold.meas, d_meas, (size_t)n * 56, cudaMemcpyDeviceToDevice, p->stream));
+    CK(cudaGetLastError());
+  }
+  // the tick has left this set when its kernels AND its read-backs are done
+  CK(cudaEventRecord(ts.step_done, p->stream));
+  CK(cudaStreamWaitEvent(p->d2h_stream, ts.step_done, 0));
+  CK(cudaEventRecord(ts.d2h_done, p->d2h_stream));
+  ts.busy = true;
+  ++p->ticks_issued;
+}
+
+void tick_host_wait(te_pool* p, int lag) {
+  // ticks are numbered by issue; tick i used set i & 1.  lag 0: everything done; lag 1: all but the newest tick done
+  for (int back = 1; back >= 0; --back) {
+    if (back < lag) continue;
+    const long long i = p->ticks_issued - 1 - back;
+    if (i < 0) continue;
+    te_pool::TickSet& ts = p->tick_set[i & 1];
+    if (ts.busy) {
+      CK(cudaEventSynchronize(ts.d2h_done));
+      ts.busy = false;
+    }
+  }
+}
+
+}  // namespace
+
 int te_pool_tick_host(te_pool* p, double dt, const double* meas, int meas_stride, const uint8_t* action, int default_action,
                       double* est_pos_out) {
   return guarded(p, [&] {
     if (p->n == 0) return 0;
-    if (!(dt >= 0.0)) throw std::invalid_argument("dt must be >= 0");
-    if (meas) check_meas_stride(p, meas_stride);
-    else if (!action && default_action == TE_ACT_UPDATE) throw std::invalid_argument("update tick without measurements");
-    if (!p->h2d_stream) {
-      CK(cudaStreamCreateWithFlags(&p->h2d_stream, cudaStreamNonBlocking));
-      CK(cudaStreamCreateWithFlags(&p->d2h_stream, cudaStreamNonBlocking));
-    }
-    const long long n = p->n;
-    const int n_tiles = cdiv(n, te::TILE);
-    const int chunk_tiles = std::max(256, std::min(n_tiles, 8192));   // 262144 targets: 14.7 MB of pose measurements
-    const int n_chunks = cdiv(n_tiles, chunk_tiles);
-    while ((int)p->events.size() < 2 * n_chunks + 1) {
-      cudaEvent_t e;
-      CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      p->events.push_back(e);
-    }
-    double* d_meas = meas ? p->arena.get_n<double>((size_t)n * meas_stride) : nullptr;
-    uint8_t* d_act = action ? p->arena.get_n<uint8_t>((size_t)n) : nullptr;
-    double* d_pos = est_pos_out ? p->arena.get_n<double>((size_t)n * 3) : nullptr;
-    // staging buffers may have been carved by earlier work on the pool stream
-    CK(cudaEventRecord(p->events[2 * n_chunks], p->stream));
-    CK(cudaStreamWaitEvent(p->h2d_stream, p->events[2 * n_chunks], 0));
-    te::StepArgs a = base_args(p);
-    a.dt = dt;
-    a.meas = d_meas;
-    a.meas_stride = meas_stride;
-    a.meas_tma = d_meas ? 1 : 0;
-    a.action = d_act;
-    a.default_action = default_action;
-    a.pos_out = d_pos;
-    for (int c = 0; c < n_chunks; ++c) {
-      const long long s0 = (long long)c * chunk_tiles * te::TILE;
-      const long long s1 = std::min<long long>(n, s0 + (long long)chunk_tiles * te::TILE);
-      if (d_meas) CK(cudaMemcpyAsync(d_meas + s0 * meas_stride, meas + s0 * meas_stride, (size_t)(s1 - s0) * meas_stride * 8, cudaMemcpyHostToDevice, p->h2d_stream));
-      if (d_act) CK(cudaMemcpyAsync(d_act + s0, action + s0, (size_t)(s1 - s0), cudaMemcpyHostToDevice, p->h2d_stream));
-      CK(cudaEventRecord(p->events[2 * c], p->h2d_stream));
-      CK(cudaStreamWaitEvent(p->stream, p->events[2 * c], 0));
-      a.tile_begin = c * chunk_tiles;
-      a.n_tiles = std::min(chunk_tiles, n_tiles - c * chunk_tiles);
-      launch_step(p, a, a.n_tiles);
-      if (d_pos) {
-        CK(cudaEventRecord(p->events[2 * c + 1], p->stream));
-        CK(cudaStreamWaitEvent(p->d2h_stream, p->events[2 * c + 1], 0));
-        CK(cudaMemcpyAsync(est_pos_out + s0 * 3, d_pos + s0 * 3, (size_t)(s1 - s0) * 24, cudaMemcpyDeviceToHost, p->d2h_stream));
-      }
-    }
-    if (d_meas && meas_stride == 7) {   // measured_pose_ = meas for the updated slots (src/target_interface.cpp:142-146)
-      if (d_act) te::copy_meas_masked_kernel<<<cdiv(n, 256), 256, 0, p->stream>>>(p->buf[p->cur].cold.meas, d_meas, d_act, (int)n);
-      else if (default_action == TE_ACT_UPDATE)
-        CK(cudaMemcpyAsync(p->buf[p->cur].cold.meas, d_meas, (size_t)n * 56, cudaMemcpyDeviceToDevice, p->stream));
-      CK(cudaGetLastError());
-    }
-    CK(cudaStreamSynchronize(p->d2h_stream));
-    CK(cudaStreamSynchronize(p->stream));
+    tick_host_enqueue(p, dt, meas, meas_stride, action, default_action, est_pos_out);
+    tick_host_wait(p, 0);
+    return 0;
+  });
+}
+
+int te_pool_tick_host_async(te_pool* p, double dt, const double* meas, int meas_stride, const uint8_t* action, int default_action,
+                            double* est_pos_out) {
+  return guarded(p, [&] {
+    if (p->n == 0) return 0;
+    tick_host_enqueue(p, dt, meas, meas_stride, action, default_action, est_pos_out);
+    return 0;
+  });
+}
+
+int te_pool_tick_host_wait(te_pool* p, int lag) {
+  return guarded(p, [&] {
+    if (lag < 0 || lag > 1) throw std::invalid_argument("lag must be 0 or 1");
+    tick_host_wait(p, lag);
     return 0;
   });
 }

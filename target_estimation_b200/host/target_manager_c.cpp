@@ -162,6 +162,61 @@ void target_manager_flush(const target_manager_c* self) {
 }
 const char* target_manager_last_error(void) { return g_err.c_str(); }
 
+// ---- all GPUs of the box behind one handle --------------------------------------------------------------
+target_manager_c* target_manager_new_sharded(const char* file, int n_shards, const int* devices) {
+  return guard((target_manager_c*)nullptr, [&]() -> target_manager_c* {
+    if (!file || !file[0]) throw std::invalid_argument("a model file is required");
+    TargetManager* m = new ShardedTargetManager(std::string(file), n_shards, devices);
+    return (target_manager_c*)m;
+  });
+}
+int target_manager_shards(const target_manager_c* self) {
+  return guard(-1, [&] {
+    ShardedTargetManager* s = dynamic_cast<ShardedTargetManager*>(M(self));
+    return s ? s->shards() : 1;
+  });
+}
+long long target_manager_gather_estimates(const target_manager_c* self, unsigned int* ids_out, double* records_out, long long cap, int publisher) {
+  return guard(-1LL, [&]() -> long long {
+    ShardedTargetManager* s = dynamic_cast<ShardedTargetManager*>(M(self));
+    std::vector<unsigned> ids;
+    std::vector<double> rec;
+    long long n = 0;
+    if (s) {
+      const bool want = cap > 0 && (ids_out || records_out);
+      n = s->gatherEstimates(want && ids_out ? &ids : nullptr, want && records_out ? &rec : nullptr, publisher);
+    } else {   // a plain manager: its own targets, ascending ids
+      ids = M(self)->getAvailableTargets();
+      n = (long long)ids.size();
+      if (cap > 0 && records_out) {
+        rec.resize((size_t)n * 13);
+        std::vector<double> po((size_t)n * 7), tw((size_t)n * 6);
+        M(self)->getEstimatesBatch(n, ids.data(), nullptr, po.data(), tw.data(), nullptr, nullptr);
+        for (long long k = 0; k < n; ++k) {
+          std::memcpy(&rec[13 * (size_t)k], &po[7 * (size_t)k], 56);
+          std::memcpy(&rec[13 * (size_t)k + 7], &tw[6 * (size_t)k], 48);
+        }
+      }
+    }
+    const long long k = n < cap ? n : cap;
+    if (ids_out && k > 0 && !ids.empty()) std::memcpy(ids_out, ids.data(), sizeof(unsigned) * (size_t)k);
+    if (records_out && k > 0 && !rec.empty()) std::memcpy(records_out, rec.data(), sizeof(double) * 13 * (size_t)k);
+    return n;
+  });
+}
+double target_manager_last_gather_ms(const target_manager_c* self) {
+  return guard(-1.0, [&] {
+    ShardedTargetManager* s = dynamic_cast<ShardedTargetManager*>(M(self));
+    return s ? s->lastGatherMs() : -1.0;
+  });
+}
+int target_manager_gather_uses_nccl(const target_manager_c* self) {
+  return guard(-1, [&] {
+    ShardedTargetManager* s = dynamic_cast<ShardedTargetManager*>(M(self));
+    return (s && s->gatherUsesNccl()) ? 1 : 0;
+  });
+}
+
 // ---- tick front-end ---------------------------------------------------------------------------------
 static TickTargetManager* T(const target_manager_c* self) {
   TickTargetManager* t = dynamic_cast<TickTargetManager*>(M(self));

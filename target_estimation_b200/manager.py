@@ -38,6 +38,11 @@ _SIG = {
     "target_manager_log_sample": (_i, [_p, _ll, _ll, _p, _p]),
     "target_manager_write_log": (_i, [_p, C.c_char_p]),
     "target_write_txt_file": (_i, [C.c_char_p, _p, _ll, _ll]),
+    "target_manager_new_sharded": (_p, [C.c_char_p, _i, _p]),
+    "target_manager_shards": (_i, [_p]),
+    "target_manager_gather_estimates": (_ll, [_p, _p, _p, _ll, _i]),
+    "target_manager_last_gather_ms": (_d, [_p]),
+    "target_manager_gather_uses_nccl": (_i, [_p]),
     "target_tick_manager_new": (_p, [C.c_char_p, _i]),
     "target_tick_manager_set_expiration": (None, [_p, _d]),
     "target_tick_manager_set_token": (None, [_p, C.c_char_p]),
@@ -176,6 +181,38 @@ class TargetManagerC:
 
     def flush(self):
         clib.target_manager_flush(self.h)
+
+
+class ShardedManagerC(TargetManagerC):
+    """target_manager_new_sharded: one TargetManager per device behind the same handle type (owner(id) = id mod n_shards)"""
+
+    def __init__(self, yaml_file, n_shards, devices=None):
+        dev = np.ascontiguousarray(devices, dtype=np.int32) if devices is not None else None
+        self.h = clib.target_manager_new_sharded(yaml_file.encode(), int(n_shards), _ptr(dev))
+        if not self.h:
+            raise RuntimeError("target_manager_new_sharded failed: %s" % clib.target_manager_last_error().decode())
+
+    def shards(self):
+        return int(clib.target_manager_shards(self.h))
+
+    def gather_estimates(self, publisher=0, fetch=True):
+        """the optional all-gather of [pose7 | twist6] records: (ids, records [n][13]) read back from the publisher's device, or
+        the record count only (fetch=False: exchange between the devices, nothing comes to the host)"""
+        n = int(clib.target_manager_gather_estimates(self.h, None, None, 0, publisher))
+        if n < 0:
+            raise RuntimeError(clib.target_manager_last_error().decode())
+        if not fetch:
+            return n
+        ids = np.zeros(max(n, 1), dtype=np.uint32); rec = np.zeros((max(n, 1), 13))
+        if int(clib.target_manager_gather_estimates(self.h, _ptr(ids), _ptr(rec), n, publisher)) < 0:
+            raise RuntimeError(clib.target_manager_last_error().decode())
+        return ids[:n], rec[:n]
+
+    def last_gather_ms(self):
+        return float(clib.target_manager_last_gather_ms(self.h))
+
+    def gather_uses_nccl(self):
+        return int(clib.target_manager_gather_uses_nccl(self.h)) == 1
 
 
 # target_tf_record of include/target_manager_c.h
