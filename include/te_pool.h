@@ -160,6 +160,15 @@ long long te_pool_step_dense_expire(te_pool* p, double dt, const double* dev_mea
  * (ids[k], sec[k], nsec[k], poses[k][7]), host arrays, applied in arrival order per id (Measurement::update).  Synchronous. */
 int te_pool_mailbox_ingest(te_pool* p, long long n, const uint32_t* ids, const uint32_t* sec, const uint32_t* nsec,
                            const double* poses /*[n][7]*/);
+/* The same in two halves, so that the copy of the NEXT message runs under the current tick (the /tf callback thread uploads a message
+ * as it arrives; the 71 MB of a million records take as long over PCIe as the tick of a million targets): te_pool_mailbox_prefetch
+ * starts the host->device copies on the pool's copy stream and returns at once; te_pool_mailbox_ingest_prefetched -- called after
+ * te_pool_mailbox_tick, or whenever the message should take effect -- waits for the copy on the device and applies it exactly as
+ * te_pool_mailbox_ingest would (lookup against the CURRENT slots, arrival order per id, first sights queued from the host arrays).
+ * The record arrays must stay valid (and should be page-locked) until te_pool_mailbox_ingest_prefetched returns.  One message
+ * can be in flight. */
+int te_pool_mailbox_prefetch(te_pool* p, long long n, const uint32_t* ids, const uint32_t* sec, const uint32_t* nsec, const double* poses /*[n][7]*/);
+int te_pool_mailbox_ingest_prefetched(te_pool* p);
 /* The same for a message that is already in DEVICE memory (another CUDA stage, a NCCL receive buffer) on the pool's stream: the
  * records are used in place; only the records of unknown ids (first sights) are read back for the host's queue. */
 int te_pool_mailbox_ingest_dev(te_pool* p, long long n, const uint32_t* dev_ids, const uint32_t* dev_sec, const uint32_t* dev_nsec,

@@ -66,6 +66,8 @@ SIGNATURES = {
     "te_host_unregister": (_i, [_p]),
     "te_pool_mailbox_ingest": (_i, [_p, _ll, _p, _p, _p, _p]),
     "te_pool_mailbox_ingest_dev": (_i, [_p, _ll, _p, _p, _p, _p]),
+    "te_pool_mailbox_prefetch": (_i, [_p, _ll, _p, _p, _p, _p]),
+    "te_pool_mailbox_ingest_prefetched": (_i, [_p]),
     "te_pool_mailbox_tick": (_ll, [_p, _d, _d, _i, _u32, _u32, _d, _p, _ll, _p, _ll, _p]),
     "te_pool_mailbox_count": (_ll, [_p]),
     "te_pool_mailbox_bound": (_ll, [_p]),

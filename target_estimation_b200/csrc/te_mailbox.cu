@@ -32,7 +32,7 @@ int mailbox_ingest_impl(te_pool* p, long long n, const uint32_t* ids, const uint
     for (long long k = 0; k < n; ++k) queue(ids[k], sec[k], nsec[k], poses + 7 * k);
     return 0;
   }
-  if (host_src) {
+  if (host_src && !d_ids) {
     d_ids = to_dev(p, ids, (size_t)n);
     d_sec = to_dev(p, sec, (size_t)n);
     d_nsec = to_dev(p, nsec, (size_t)n);
@@ -112,6 +112,62 @@ int te_pool_mailbox_ingest(te_pool* p, long long n, const uint32_t* ids, const u
     if (n <= 0) return 0;
     if (!ids || !sec || !nsec || !poses) throw std::invalid_argument("null record arrays");
     return mailbox_ingest_impl(p, n, ids, sec, nsec, poses, nullptr, nullptr, nullptr, nullptr);
+  });
+}
+
+/* the message starts its way to the device on the pool's copy stream and the call returns: the copy runs under whatever the pool's
+   stream is doing (the tick) */
+int te_pool_mailbox_prefetch(te_pool* p, long long n, const uint32_t* ids, const uint32_t* sec, const uint32_t* nsec, const double* poses) {
+  return guarded(p, [&] {
+    te_pool::Prefetch& pf = p->prefetch;
+    if (pf.pending) throw std::logic_error("a prefetched message is waiting: call te_pool_mailbox_ingest_prefetched first");
+    if (n < 0 || n > 0x7FFFFFFF) throw std::invalid_argument("bad record count");
+    if (n > 0 && (!ids || !sec || !nsec || !poses)) throw std::invalid_argument("null record array");
+    if (!p->h2d_stream) {
+      CK(cudaStreamCreateWithFlags(&p->h2d_stream, cudaStreamNonBlocking));
+      CK(cudaStreamCreateWithFlags(&p->d2h_stream, cudaStreamNonBlocking));
+    }
+    if (!pf.done) CK(cudaEventCreateWithFlags(&pf.done, cudaEventDisableTiming));
+    const size_t nn = (size_t)n, need = nn * 68 + 1024;
+    if (need > pf.cap) {   // (the previous message's consumers ran on the pool's stream)
+      CK(cudaStreamSynchronize(p->stream));
+      cudaFree(pf.dev);
+      pf.dev = nullptr;
+      pf.cap = 0;
+      const size_t cap = need + need / 8;
+      CK(cudaMalloc((void**)&pf.dev, cap));
+      pf.cap = cap;
+    } else {
+      // the kernels that read the previous message out of this staging must be done before the copy overwrites it
+      CK(cudaEventRecord(pf.done, p->stream));
+      CK(cudaStreamWaitEvent(p->h2d_stream, pf.done, 0));
+    }
+    pf.n = n; pf.ids = ids; pf.sec = sec; pf.nsec = nsec; pf.poses = poses;
+    if (n > 0) {
+      double* d_pose = (double*)pf.dev;
+      uint32_t* d_ids = (uint32_t*)(d_pose + 7 * nn);
+      CK(cudaMemcpyAsync(d_pose, poses, nn * 56, cudaMemcpyHostToDevice, p->h2d_stream));
+      CK(cudaMemcpyAsync(d_ids, ids, nn * 4, cudaMemcpyHostToDevice, p->h2d_stream));
+      CK(cudaMemcpyAsync(d_ids + nn, sec, nn * 4, cudaMemcpyHostToDevice, p->h2d_stream));
+      CK(cudaMemcpyAsync(d_ids + 2 * nn, nsec, nn * 4, cudaMemcpyHostToDevice, p->h2d_stream));
+    }
+    CK(cudaEventRecord(pf.done, p->h2d_stream));
+    pf.pending = true;
+    return 0;
+  });
+}
+
+int te_pool_mailbox_ingest_prefetched(te_pool* p) {
+  return guarded(p, [&] {
+    te_pool::Prefetch& pf = p->prefetch;
+    if (!pf.pending) throw std::logic_error("no prefetched message");
+    pf.pending = false;
+    CK(cudaStreamWaitEvent(p->stream, pf.done, 0));
+    if (pf.n == 0) return 0;
+    const size_t nn = (size_t)pf.n;
+    const double* d_pose = (const double*)pf.dev;
+    const uint32_t* d_ids = (const uint32_t*)(d_pose + 7 * nn);
+    return mailbox_ingest_impl(p, pf.n, pf.ids, pf.sec, pf.nsec, pf.poses, d_ids, d_ids + nn, d_ids + 2 * nn, d_pose);
   });
 }
 

@@ -482,6 +482,8 @@ void te_pool_destroy(te_pool* p) {
   cudaFree(p->alive); cudaFree(p->pos); cudaFree(p->srcmap); cudaFree(p->d_counters); cudaFree(p->cub_tmp);
   cudaFree(p->dQ); cudaFree(p->dR); cudaFree(p->dP0);
   p->arena.destroy();
+  cudaFree(p->prefetch.dev);
+  if (p->prefetch.done) cudaEventDestroy(p->prefetch.done);
   for (te_pool::TickSet& ts : p->tick_set) {
     for (cudaEvent_t e : ts.ev) cudaEventDestroy(e);
     if (ts.step_done) cudaEventDestroy(ts.step_done);

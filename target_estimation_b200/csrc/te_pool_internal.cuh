@@ -184,6 +184,16 @@ struct te_pool {
     bool busy = false;
   } tick_set[2];
   long long ticks_issued = 0;
+  // a /tf message on its way to the device under the running tick (te_pool_mailbox_prefetch)
+  struct Prefetch {
+    char* dev = nullptr;
+    size_t cap = 0;
+    long long n = 0;
+    const uint32_t *ids = nullptr, *sec = nullptr, *nsec = nullptr;
+    const double* poses = nullptr;
+    cudaEvent_t done = nullptr;
+    bool pending = false;
+  } prefetch;
 };
 
 struct te_isolver {

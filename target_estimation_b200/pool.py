@@ -242,6 +242,18 @@ class TargetPool:
         poses = _np(poses, np.float64, (ids.size, 7))
         check(lib.te_pool_mailbox_ingest(self._h, ids.size, _ptr(ids), _ptr(sec), _ptr(nsec), _ptr(poses)))
 
+    def mailbox_prefetch(self, ids, sec, nsec, poses):
+        """start the host->device copy of the NEXT message and return (it runs under the current tick); the arrays must stay alive
+        and unchanged until mailbox_ingest_prefetched() -- they are kept referenced here"""
+        ids = _np(ids, np.uint32); sec = _np(sec, np.uint32); nsec = _np(nsec, np.uint32)
+        poses = _np(poses, np.float64, (ids.size, 7))
+        self._prefetched = (ids, sec, nsec, poses)
+        check(lib.te_pool_mailbox_prefetch(self._h, ids.size, _ptr(ids), _ptr(sec), _ptr(nsec), _ptr(poses)))
+
+    def mailbox_ingest_prefetched(self):
+        check(lib.te_pool_mailbox_ingest_prefetched(self._h))
+        self._prefetched = None
+
     def mailbox_ingest_dev(self, n, dev_ids, dev_sec, dev_nsec, dev_poses):
         """the same for a message already in device memory (torch CUDA tensors: int32/uint32 ids and stamps, float64 [n][7] poses)"""
         check(lib.te_pool_mailbox_ingest_dev(self._h, int(n), _dev_ptr(dev_ids), _dev_ptr(dev_sec), _dev_ptr(dev_nsec), _dev_ptr(dev_poses)))

@@ -274,3 +274,51 @@ def test_device_resident_messages_equal_host_messages():
     assert sum(e.size for e, _ in log_a) > 50
     for key in ("x", "P", "t", "n_meas", "prev_rpy", "measured_pose"):
         assert np.array_equal(st_a[key], st_b[key]), key
+
+
+def test_prefetched_messages_equal_synchronous_ingest():
+    """te_pool_mailbox_prefetch + te_pool_mailbox_ingest_prefetched: message k + 1 starts its copy BEFORE tick k and takes effect AFTER
+    it (looked up against the slots tick k left behind) -- same ids, erase / add lists and bits as te_pool_mailbox_ingest called
+    after tick k; shuffled, duplicated, partly stale messages, first sights, an empty message."""
+    import target_estimation_b200 as te
+    mtype, _, Q, R, P0 = te.load_model("uniform_acceleration")
+    rng = np.random.default_rng(33)
+    universe = rng.choice(50000, size=2500, replace=False).astype(np.uint32)
+    ticks = 24
+    streams, _, _ = synth.make_streams(universe.size, ticks, DT, accel=True, angular=False, seed=9)
+    live = list(range(600)); nxt = 600
+    msgs = []
+    for k in range(ticks):
+        now = 1000 * 10**9 + k * 4_000_000
+        gone = set(j for j in live if rng.random() < 0.03)
+        live = [j for j in live if j not in gone] + list(range(nxt, nxt + 30)); nxt += 30
+        speak = np.array([j for j in live if rng.random() < 0.9]); rng.shuffle(speak)
+        speak = np.concatenate([speak, speak[:5]])
+        if k == 7:
+            speak = speak[:0]                                                  # an empty message
+        st_ns = now - np.where(rng.random(speak.size) < 0.05, 12_000_000, 0)
+        msgs.append((universe[speak], (st_ns // 10**9).astype(np.uint32), (st_ns % 10**9).astype(np.uint32), np.ascontiguousarray(streams[k, speak]), now))
+    results = []
+    for prefetch in (False, True):
+        pool = te.TargetPool(mtype); pool.register_class(Q, R, P0)
+        log = []
+        if prefetch:
+            pool.mailbox_prefetch(*msgs[0][:4])
+        for k in range(ticks):
+            ids, sec, nsec, poses, now = msgs[k]
+            if prefetch:
+                pool.mailbox_ingest_prefetched()
+                if k + 1 < ticks:
+                    pool.mailbox_prefetch(*msgs[k + 1][:4])                    # in flight during the tick below
+            else:
+                pool.mailbox_ingest(ids, sec, nsec, poses)
+            log.append(pool.mailbox_tick(DT, k * DT, (now // 10**9, now % 10**9), 6 * DT, want_added=True))
+        results.append((pool.ids(), pool.read_state(), log, pool.mailbox_count()))
+        pool.close()
+    (ids_a, st_a, log_a, mc_a), (ids_b, st_b, log_b, mc_b) = results
+    assert np.array_equal(ids_a, ids_b) and ids_a.size > 500 and mc_a == mc_b
+    for (ea, aa), (eb, ab) in zip(log_a, log_b):
+        assert np.array_equal(ea, eb) and np.array_equal(aa, ab)
+    assert sum(e.size for e, _ in log_a) > 50
+    for key in ("x", "P", "t", "n_meas", "measured_pose"):
+        assert np.array_equal(st_a[key], st_b[key]), key

@@ -273,22 +273,35 @@ def test_av_pitch_range(pitch_max):
 # ---------------------------------------------------------------------------------------------------------------------
 # 6. the host-buffer tick the bench's e2e figure times (te_pool_tick_host: chunked H2D / step / D2H pipeline over three streams)
 # ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("pipelined", [False, True], ids=["sync", "two_in_flight"])
 @pytest.mark.parametrize("stride", [7, 3])
-def test_tick_host_pipeline(stride):
+def test_tick_host_pipeline(stride, pipelined):
     """300 000 uniform-acceleration targets = two pipeline chunks (262 144 targets each) + a ragged tail; pose [n][7] and
-    xyz-only [n][3] measurements; state, covariance and the returned positions against the oracle"""
+    xyz-only [n][3] measurements; state, covariance and the returned positions against the oracle.  two_in_flight: the same ticks
+    through te_pool_tick_host_async / te_pool_tick_host_wait(1) (the copies of tick k + 1 under the kernels and read-back of tick
+    k), every tick's returned positions checked against the synchronous run's."""
     import ctypes as C
-    n, ticks = 300000 + 5, 5
+    n, ticks = 300000 + 5, 6
     te, pool, ref, ids, meas, action, N, M = _setup("uniform_acceleration", n, ticks, seed=31)
-    out = np.zeros((n, 3))
+    outs = [np.zeros((n, 3)) for _ in range(ticks)]
     worst = _worst()
+    ms = [np.ascontiguousarray(meas[k][:, :stride]) for k in range(ticks)]
+    acts = [np.ascontiguousarray(action[k]) for k in range(ticks)]
     for k in range(ticks):
-        m = np.ascontiguousarray(meas[k][:, :stride])
-        a = np.ascontiguousarray(action[k])
-        rc = te.lib.te_pool_tick_host(pool._h, DT, m.ctypes.data_as(C.c_void_p), stride, a.ctypes.data_as(C.c_void_p), 2, out.ctypes.data_as(C.c_void_p))
-        assert rc == 0
-    ref.step_ticks(ids, DT, meas, action)
-    _check(("tick_host", stride), pool, ref, ids, N, False, worst)
-    assert np.array_equal(out, pool.read_state(ids)["x"][:, :3])          # the D2H record of the last tick = the estimated positions
-    report.record("tick_host_pipeline[stride=%d]" % stride, targets=n, ticks=ticks, **worst)
+        fn = te.lib.te_pool_tick_host_async if pipelined else te.lib.te_pool_tick_host
+        rc = fn(pool._h, DT, ms[k].ctypes.data_as(C.c_void_p), stride, acts[k].ctypes.data_as(C.c_void_p), 2, outs[k].ctypes.data_as(C.c_void_p))
+        assert rc == 0, te._lib.last_error()
+        if pipelined:
+            assert te.lib.te_pool_tick_host_wait(pool._h, 1) == 0
+            if k > 0:
+                assert np.abs(outs[k - 1]).max() > 0          # tick k - 1 has landed while tick k is in flight
+    assert te.lib.te_pool_tick_host_wait(pool._h, 0) == 0
+    # the oracle tick by tick: the returned positions of EVERY tick are that tick's estimated positions
+    for k in range(ticks):
+        ref.step_ticks(ids, DT, meas[k:k + 1], action[k:k + 1])
+        want = ref.states(ids, N)["x"][:, :3]
+        assert synth.compare_h2(outs[k], want) <= 1.0, k
+    _check(("tick_host", stride, pipelined), pool, ref, ids, N, False, worst)
+    assert np.array_equal(outs[-1], pool.read_state(ids)["x"][:, :3])          # the D2H record of the last tick = the estimated positions
+    report.record("tick_host_pipeline[stride=%d,%s]" % (stride, "two_in_flight" if pipelined else "sync"), targets=n, ticks=ticks, **worst)
     pool.close(); ref.close()

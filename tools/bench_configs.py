@@ -116,7 +116,7 @@ def c3_churn(n=1 << 20, ticks=48, fused=False):
     return out
 
 
-def c3_mailbox(n=1 << 20, ticks=48, model="angular_rates", device_records=False):
+def c3_mailbox(n=1 << 20, ticks=48, model="angular_rates", device_records=False, prefetch=False):
     """C3 through the node loop itself: per tick ONE /tf message from pinned host memory (a record = id, stamp, pose7 for every
     speaking id, 68 B each) -> te_pool_mailbox_ingest, then te_pool_mailbox_tick (first-sight init of the fresh ids, sticky
     update / predict, expiry, one stable rebuild + one step launch).  Same churn as c3_churn: 1 % of the speaking ids fall
@@ -181,12 +181,20 @@ def c3_mailbox(n=1 << 20, ticks=48, model="angular_rates", device_records=False)
     pool.sync()
     n_erased = n_added = steps = records = 0
     parts = {"ingest": 0.0, "tick": 0.0}
+    if prefetch:   # message 1 is on its way before the clock starts, as message k + 1 is while tick k runs
+        pool.mailbox_prefetch(sched[1][0], sched[1][1], sched[1][2], poses[:sched[1][0].size])
+        pool.sync()
     t0 = time.perf_counter()
     for k in range(1, ticks + 1):
         r_ids, r_sec, r_nsec, exp_ids, live = sched[k]
         ta = time.perf_counter()
         if device_records:
             pool.mailbox_ingest_dev(r_ids.size, d_sched[k][0], d_sched[k][1], d_sched[k][2], d_poses)
+        elif prefetch:
+            pool.mailbox_ingest_prefetched()           # message k takes effect (its copy ran under tick k - 1)
+            if k < ticks:                              # message k + 1 starts its way to the device: runs under tick k
+                nx = sched[k + 1]
+                pool.mailbox_prefetch(nx[0], nx[1], nx[2], poses[:nx[0].size])
         else:
             pool.mailbox_ingest(r_ids, r_sec, r_nsec, poses[:r_ids.size])
         tb = time.perf_counter()
@@ -198,7 +206,7 @@ def c3_mailbox(n=1 << 20, ticks=48, model="angular_rates", device_records=False)
     dt_wall = time.perf_counter() - t0
     assert np.array_equal(pool.ids().astype(np.int64), ids)
     out = {"model": model, "targets": n, "ticks": ticks, "erased": int(n_erased), "added": int(n_added), "records_per_tick": records / ticks,
-           "h2d_bytes_per_tick": 0 if device_records else 68 * records / ticks, "records_in": "device memory" if device_records else "pinned host memory",
+           "h2d_bytes_per_tick": 0 if device_records else 68 * records / ticks, "records_in": "device memory" if device_records else ("pinned host memory, next message prefetched under the tick" if prefetch else "pinned host memory"),
            "ms_per_tick": 1e3 * dt_wall / ticks, "target_steps_per_s": steps / dt_wall,
            "ms_per_tick_parts": {k_: 1e3 * v / ticks for k_, v in parts.items()},
            "note": "the node loop through te_pool_mailbox_ingest + te_pool_mailbox_tick: records come from pinned HOST memory every tick (ids, "
@@ -337,9 +345,13 @@ if __name__ == "__main__":
             except Exception as e:   # noqa: BLE001
                 res[key] = {"error": ("%s: %s" % (type(e).__name__, e))[:300]}
             print(json.dumps({key: res[key]}), file=sys.stderr, flush=True)
-        leg("c3", lambda: c3_mailbox(ticks=24, model="angular_rates"))
+        # (te_pool_mailbox_prefetch / te_pool_mailbox_ingest_prefetched: the copy of message k + 1 runs under tick k; the figure of
+        #  the synchronous te_pool_mailbox_ingest rides along as *_sync)
+        leg("c3", lambda: c3_mailbox(ticks=24, model="angular_rates", prefetch=True))
+        leg("c3_sync", lambda: c3_mailbox(ticks=24, model="angular_rates"))
         if sys.argv[2] != "angular_rates":
-            leg("node_loop", lambda: c3_mailbox(ticks=24, model=sys.argv[2]))
+            leg("node_loop", lambda: c3_mailbox(ticks=24, model=sys.argv[2], prefetch=True))
+            leg("node_loop_sync", lambda: c3_mailbox(ticks=24, model=sys.argv[2]))
         leg("c4_uniform_velocity", lambda: c4_intersect("uniform_velocity"))
         leg("c4_uniform_acceleration", lambda: c4_intersect("uniform_acceleration"))
         print(json.dumps(res))
