@@ -146,10 +146,17 @@ int te_pool_mailbox_prefetch(te_pool* p, long long n, const uint32_t* ids, const
     if (n > 0) {
       double* d_pose = (double*)pf.dev;
       uint32_t* d_ids = (uint32_t*)(d_pose + 7 * nn);
-      CK(cudaMemcpyAsync(d_pose, poses, nn * 56, cudaMemcpyHostToDevice, p->h2d_stream));
-      CK(cudaMemcpyAsync(d_ids, ids, nn * 4, cudaMemcpyHostToDevice, p->h2d_stream));
-      CK(cudaMemcpyAsync(d_ids + nn, sec, nn * 4, cudaMemcpyHostToDevice, p->h2d_stream));
-      CK(cudaMemcpyAsync(d_ids + 2 * nn, nsec, nn * 4, cudaMemcpyHostToDevice, p->h2d_stream));
+      // in pieces of 2 MB: the device has ONE host-to-device copy engine, and the running tick's own small uploads (its add
+      // arrays) would otherwise queue behind the whole 71 MB message (measured: the tick grew from 2.0 to 3.2 ms)
+      auto piecewise = [&](void* dst, const void* src, size_t bytes) {
+        const size_t piece = (size_t)2 << 20;
+        for (size_t o = 0; o < bytes; o += piece)
+          CK(cudaMemcpyAsync((char*)dst + o, (const char*)src + o, std::min(piece, bytes - o), cudaMemcpyHostToDevice, p->h2d_stream));
+      };
+      piecewise(d_pose, poses, nn * 56);
+      piecewise(d_ids, ids, nn * 4);
+      piecewise(d_ids + nn, sec, nn * 4);
+      piecewise(d_ids + 2 * nn, nsec, nn * 4);
     }
     CK(cudaEventRecord(pf.done, p->h2d_stream));
     pf.pending = true;

@@ -375,7 +375,8 @@ void tick_host_enqueue(te_pool* p, double dt, const double* meas, int meas_strid
   }
   const long long n = p->n;
   const int n_tiles = cdiv(n, te::TILE);
-  const int chunk_tiles = std::max(256, std::min(n_tiles, 8192));   // 262144 targets: 14.7 MB of pose measurements
+  static const int chunk_env = std::getenv("TE_TICK_CHUNK_TILES") ? std::atoi(std::getenv("TE_TICK_CHUNK_TILES")) : 0;   // tuning knob
+  const int chunk_tiles = std::max(256, std::min(n_tiles, chunk_env > 0 ? chunk_env : 8192));   // 262144 targets: 14.7 MB of pose measurements
   const int n_chunks = cdiv(n_tiles, chunk_tiles);
   te_pool::TickSet& ts = p->tick_set[p->ticks_issued & 1];
   if (ts.busy) {   // the tick that used this set two ticks ago must have left it (its results are in the caller's buffer by then)
