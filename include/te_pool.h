@@ -160,13 +160,15 @@ long long te_pool_step_dense_expire(te_pool* p, double dt, const double* dev_mea
  * (ids[k], sec[k], nsec[k], poses[k][7]), host arrays, applied in arrival order per id (Measurement::update).  Synchronous. */
 int te_pool_mailbox_ingest(te_pool* p, long long n, const uint32_t* ids, const uint32_t* sec, const uint32_t* nsec,
                            const double* poses /*[n][7]*/);
-/* The same in two halves, so that the copy of the NEXT message runs under the current tick (the /tf callback thread uploads a message
- * as it arrives; the 71 MB of a million records take as long over PCIe as the tick of a million targets): te_pool_mailbox_prefetch
- * starts the host->device copies on the pool's copy stream and returns at once; te_pool_mailbox_ingest_prefetched -- called after
- * te_pool_mailbox_tick, or whenever the message should take effect -- waits for the copy on the device and applies it exactly as
- * te_pool_mailbox_ingest would (lookup against the CURRENT slots, arrival order per id, first sights queued from the host arrays).
- * The record arrays must stay valid (and should be page-locked) until te_pool_mailbox_ingest_prefetched returns.  One message
- * can be in flight. */
+/* The same in two halves, so that the copy of the NEXT message runs under the current tick (the /tf callback thread hands a message
+ * over as it arrives; the 71 MB of a million records take as long over PCIe as the tick of a million targets):
+ * te_pool_mailbox_prefetch registers the message and returns at once; its host->device copies enter the copy stream's queue as soon
+ * as the next te_pool_mailbox_tick has queued its own small uploads (the device serves ONE host-to-device queue in order) and then
+ * travel under that tick's kernels, ids and stamps first.  te_pool_mailbox_ingest_prefetched -- called after the tick, or whenever
+ * the message should take effect -- applies it exactly as te_pool_mailbox_ingest would (lookup against the CURRENT slots, arrival
+ * order per id, first sights queued from the host arrays); lookup and sort of the records already run under the tail of the copy.
+ * The record arrays must stay valid (and should be page-locked) until te_pool_mailbox_ingest_prefetched returns.  One message can
+ * be in flight. */
 int te_pool_mailbox_prefetch(te_pool* p, long long n, const uint32_t* ids, const uint32_t* sec, const uint32_t* nsec, const double* poses /*[n][7]*/);
 int te_pool_mailbox_ingest_prefetched(te_pool* p);
 /* The same for a message that is already in DEVICE memory (another CUDA stage, a NCCL receive buffer) on the pool's stream: the
@@ -236,6 +238,11 @@ const uint32_t* te_group_dev_ids(te_group* g, int r);
 long long te_group_fetch(te_group* g, int root, double* records_out, uint32_t* ids_out, long long cap);
 /* device time of the last gather (ms, max over the devices; CUDA events around the collective on every device's stream) */
 double te_group_last_gather_ms(te_group* g);
+
+/* ---- device micro-benchmarks behind the roofline statements (csrc/te_diag.cu; not on any product path) ---------------------- */
+/* FP64 FMA rate of `device` in TFLOP/s (dependent-chain kernel, 8 chains per thread, best of 5) and the rate of a plain streaming
+ * copy kernel in GB/s (read + write bytes, 1 GiB each way); either output may be NULL */
+int te_diag_device_peaks(int device, double* fp64_tflops_out, double* copy_gbs_out);
 
 #ifdef __cplusplus
 }

@@ -79,6 +79,7 @@ SIGNATURES = {
     "te_isolver_query_dense": (_i, [_p, _p, _p, _p, _d, _d, _p, _p, _p]),
     "te_pool_tick_host_async": (_i, [_p, _d, _p, _i, _p, _i, _p]),
     "te_pool_tick_host_wait": (_i, [_p, _i]),
+    "te_diag_device_peaks": (_i, [_i, _p, _p]),
     "te_group_create": (_p, [_i, _p]),
     "te_group_destroy": (None, [_p]),
     "te_group_size": (_i, [_p]),

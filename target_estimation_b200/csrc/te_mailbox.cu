@@ -14,7 +14,8 @@ namespace {
 // one /tf message into the mailboxes.  Host source (ids .. poses non-null): the arrays are staged here; device source (d_* given,
 // host pointers null): the records are used in place and the few records of unknown ids are read back for the host's queue.
 int mailbox_ingest_impl(te_pool* p, long long n, const uint32_t* ids, const uint32_t* sec, const uint32_t* nsec, const double* poses,
-                        const uint32_t* d_ids, const uint32_t* d_sec, const uint32_t* d_nsec, const double* d_pose) {
+                        const uint32_t* d_ids, const uint32_t* d_sec, const uint32_t* d_nsec, const double* d_pose,
+                        cudaEvent_t payload_ready = nullptr /* d_sec / d_nsec / d_pose are complete once this event has fired */) {
   if (n <= 0) return 0;
   if (n > 0x7FFFFFFF) throw std::invalid_argument("too many records in one message");
   const bool host_src = ids != nullptr;
@@ -57,6 +58,7 @@ int mailbox_ingest_impl(te_pool* p, long long n, const uint32_t* ids, const uint
     CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_in, key_out, rec_in, rec_out, nr, 0, bits, p->stream));
     void* tmp = p->arena.get(tmp_bytes);
     CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key_in, key_out, rec_in, rec_out, nr, 0, bits, p->stream));
+    if (payload_ready) CK(cudaStreamWaitEvent(p->stream, payload_ready, 0));   // lookup and sort ran under the tail of the copy
     te::mb_apply_kernel<<<cdiv(n, 256), 256, 0, p->stream>>>(nr, (int)p->n, key_out, rec_out, d_sec, d_nsec, d_pose, p->mb[p->mb_cur].a, b.cold.last_meas);
     CK(cudaGetLastError());
   }
@@ -105,6 +107,49 @@ int mailbox_ingest_impl(te_pool* p, long long n, const uint32_t* ids, const uint
 }
 }  // namespace
 
+namespace tehost {
+void prefetch_start(te_pool* p) {
+  te_pool::Prefetch& pf = p->prefetch;
+  if (!pf.pending || pf.started) return;
+  pf.started = true;
+  if (!p->h2d_stream) {
+    CK(cudaStreamCreateWithFlags(&p->h2d_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&p->d2h_stream, cudaStreamNonBlocking));
+  }
+  if (!pf.done) {
+    CK(cudaEventCreateWithFlags(&pf.done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&pf.keys_done, cudaEventDisableTiming));
+  }
+  const size_t nn = (size_t)pf.n, need = nn * 68 + 1024;
+  if (need > pf.cap) {   // (the previous message's consumers ran on the pool's stream)
+    CK(cudaStreamSynchronize(p->stream));
+    cudaFree(pf.dev);
+    pf.dev = nullptr;
+    pf.cap = 0;
+    const size_t cap = need + need / 8;
+    CK(cudaMalloc((void**)&pf.dev, cap));
+    pf.cap = cap;
+  } else {
+    // the kernels that read the previous message out of this staging must be done before the copies overwrite it
+    CK(cudaEventRecord(pf.done, p->stream));
+    CK(cudaStreamWaitEvent(p->h2d_stream, pf.done, 0));
+  }
+  if (nn > 0) {
+    // ids and stamps first: the lookup and the sort of the records need nothing else and run under the copy of the poses
+    uint32_t* d_ids = (uint32_t*)pf.dev;
+    double* d_pose = (double*)(pf.dev + ((nn * 12 + 255) & ~(size_t)255));
+    CK(cudaMemcpyAsync(d_ids, pf.ids, nn * 4, cudaMemcpyHostToDevice, p->h2d_stream));
+    CK(cudaEventRecord(pf.keys_done, p->h2d_stream));
+    CK(cudaMemcpyAsync(d_ids + nn, pf.sec, nn * 4, cudaMemcpyHostToDevice, p->h2d_stream));
+    CK(cudaMemcpyAsync(d_ids + 2 * nn, pf.nsec, nn * 4, cudaMemcpyHostToDevice, p->h2d_stream));
+    CK(cudaMemcpyAsync(d_pose, pf.poses, nn * 56, cudaMemcpyHostToDevice, p->h2d_stream));
+  } else {
+    CK(cudaEventRecord(pf.keys_done, p->h2d_stream));
+  }
+  CK(cudaEventRecord(pf.done, p->h2d_stream));
+}
+}  // namespace tehost
+
 extern "C" {
 
 int te_pool_mailbox_ingest(te_pool* p, long long n, const uint32_t* ids, const uint32_t* sec, const uint32_t* nsec, const double* poses) {
@@ -115,51 +160,17 @@ int te_pool_mailbox_ingest(te_pool* p, long long n, const uint32_t* ids, const u
   });
 }
 
-/* the message starts its way to the device on the pool's copy stream and the call returns: the copy runs under whatever the pool's
-   stream is doing (the tick) */
+/* the message is registered; its copies go into the copy stream's queue when the next tick has queued its own small uploads (or at
+   te_pool_mailbox_ingest_prefetched, whichever comes first) and run under whatever the pool's stream is doing */
 int te_pool_mailbox_prefetch(te_pool* p, long long n, const uint32_t* ids, const uint32_t* sec, const uint32_t* nsec, const double* poses) {
   return guarded(p, [&] {
     te_pool::Prefetch& pf = p->prefetch;
     if (pf.pending) throw std::logic_error("a prefetched message is waiting: call te_pool_mailbox_ingest_prefetched first");
     if (n < 0 || n > 0x7FFFFFFF) throw std::invalid_argument("bad record count");
     if (n > 0 && (!ids || !sec || !nsec || !poses)) throw std::invalid_argument("null record array");
-    if (!p->h2d_stream) {
-      CK(cudaStreamCreateWithFlags(&p->h2d_stream, cudaStreamNonBlocking));
-      CK(cudaStreamCreateWithFlags(&p->d2h_stream, cudaStreamNonBlocking));
-    }
-    if (!pf.done) CK(cudaEventCreateWithFlags(&pf.done, cudaEventDisableTiming));
-    const size_t nn = (size_t)n, need = nn * 68 + 1024;
-    if (need > pf.cap) {   // (the previous message's consumers ran on the pool's stream)
-      CK(cudaStreamSynchronize(p->stream));
-      cudaFree(pf.dev);
-      pf.dev = nullptr;
-      pf.cap = 0;
-      const size_t cap = need + need / 8;
-      CK(cudaMalloc((void**)&pf.dev, cap));
-      pf.cap = cap;
-    } else {
-      // the kernels that read the previous message out of this staging must be done before the copy overwrites it
-      CK(cudaEventRecord(pf.done, p->stream));
-      CK(cudaStreamWaitEvent(p->h2d_stream, pf.done, 0));
-    }
     pf.n = n; pf.ids = ids; pf.sec = sec; pf.nsec = nsec; pf.poses = poses;
-    if (n > 0) {
-      double* d_pose = (double*)pf.dev;
-      uint32_t* d_ids = (uint32_t*)(d_pose + 7 * nn);
-      // in pieces of 2 MB: the device has ONE host-to-device copy engine, and the running tick's own small uploads (its add
-      // arrays) would otherwise queue behind the whole 71 MB message (measured: the tick grew from 2.0 to 3.2 ms)
-      auto piecewise = [&](void* dst, const void* src, size_t bytes) {
-        const size_t piece = (size_t)2 << 20;
-        for (size_t o = 0; o < bytes; o += piece)
-          CK(cudaMemcpyAsync((char*)dst + o, (const char*)src + o, std::min(piece, bytes - o), cudaMemcpyHostToDevice, p->h2d_stream));
-      };
-      piecewise(d_pose, poses, nn * 56);
-      piecewise(d_ids, ids, nn * 4);
-      piecewise(d_ids + nn, sec, nn * 4);
-      piecewise(d_ids + 2 * nn, nsec, nn * 4);
-    }
-    CK(cudaEventRecord(pf.done, p->h2d_stream));
     pf.pending = true;
+    pf.started = false;
     return 0;
   });
 }
@@ -168,13 +179,15 @@ int te_pool_mailbox_ingest_prefetched(te_pool* p) {
   return guarded(p, [&] {
     te_pool::Prefetch& pf = p->prefetch;
     if (!pf.pending) throw std::logic_error("no prefetched message");
+    prefetch_start(p);
     pf.pending = false;
-    CK(cudaStreamWaitEvent(p->stream, pf.done, 0));
+    pf.started = false;
     if (pf.n == 0) return 0;
     const size_t nn = (size_t)pf.n;
-    const double* d_pose = (const double*)pf.dev;
-    const uint32_t* d_ids = (const uint32_t*)(d_pose + 7 * nn);
-    return mailbox_ingest_impl(p, pf.n, pf.ids, pf.sec, pf.nsec, pf.poses, d_ids, d_ids + nn, d_ids + 2 * nn, d_pose);
+    const uint32_t* d_ids = (const uint32_t*)pf.dev;
+    const double* d_pose = (const double*)(pf.dev + ((nn * 12 + 255) & ~(size_t)255));
+    CK(cudaStreamWaitEvent(p->stream, pf.keys_done, 0));
+    return mailbox_ingest_impl(p, pf.n, pf.ids, pf.sec, pf.nsec, pf.poses, d_ids, d_ids + nn, d_ids + 2 * nn, d_pose, pf.done);
   });
 }
 
@@ -284,6 +297,10 @@ long long te_pool_mailbox_tick(te_pool* p, double dt, double t0_new, int cls_new
       p->mb_add.nsec = d_aid + 2 * max_add;
       p->mb_add.last = d_last;
     }
+    // a registered /tf message (te_pool_mailbox_prefetch) starts its way to the device now: this tick's own small uploads are already
+    // in the copy engine's queue (the device has ONE host-to-device engine and serves its queue in order -- 71 MB ahead of them held
+    // the whole tick back by 1.2 ms), and the message then travels under the kernels of this tick
+    prefetch_start(p);
     const bool unfused_env = std::getenv("TE_MB_UNFUSED") != nullptr;   // debugging / test switch: the rebuild-then-step form
     const bool fused = !unfused_env && n_old > 0;
     if (!fused) {

@@ -191,8 +191,9 @@ struct te_pool {
     long long n = 0;
     const uint32_t *ids = nullptr, *sec = nullptr, *nsec = nullptr;
     const double* poses = nullptr;
-    cudaEvent_t done = nullptr;
-    bool pending = false;
+    cudaEvent_t keys_done = nullptr, done = nullptr;   // ids / stamps on the device; everything on the device
+    bool pending = false;   // a message is registered
+    bool started = false;   // its copies are in the copy stream's queue
   } prefetch;
 };
 
@@ -236,6 +237,8 @@ int* lookup_slots(te_pool* p, const uint32_t* d_ids, long long n);
 void fold_pending(te_pool* p);
 void demote_mailboxes(te_pool* p, const uint32_t* ids, const int* d_slots, long long n);
 void attach_mailboxes(te_pool* p, const uint32_t* ids, long long n);
+// ---- te_mailbox.cu ----
+void prefetch_start(te_pool* p);   // put the registered message's copies into the copy stream's queue (no-op if none / started)
 // ---- te_step.cu ----
 bool uses_direct(const te_pool* p);
 void ensure_full(te_pool* p);

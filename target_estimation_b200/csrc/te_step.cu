@@ -5,7 +5,6 @@
 #include "te_pool_internal.cuh"
 #include "te_split.cuh"
 #include "te_direct.cuh"
-#include "te_ar_pair.cuh"
 
 namespace tehost {
 
@@ -110,30 +109,12 @@ void launch_kin_direct(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   else launch_kin_direct_k<TYPE, WARPS, CTAS>(p, a, n_work_hint);
 }
 
-template <int WARPS>
-void launch_ar_pair(te_pool* p, const te::StepArgs& a, int n_work_hint) {
-  auto kern = te::kf_step_ar_pair_kernel<WARPS>;
-  const size_t smem = te::ar_pair_smem_bytes(WARPS);
-  static bool configured[64] = {false};
-  if (!configured[p->device & 63]) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[p->device & 63] = true;
-  }
-  int grid = capped(p, std::min(p->n_sm, std::max(1, cdiv(n_work_hint, WARPS))));
-  kern<<<grid, WARPS * 32, smem, p->stream>>>(a);
-  CK(cudaGetLastError());
-}
-
 // does the current variant run a direct symmetric-covariance kernel (te_direct.cuh)?
 bool uses_direct(const te_pool* p) {
+  // variant 0 = the defaults; 12 = the direct kernels writing both halves of the covariance (unpacked); 1 / 10 / 11 = staged forms
   const int v = p->variant;
-  const bool dflt = v == 0 && p->all_sym;
-  switch (p->model) {
-    case te::UNIFORM_VELOCITY:
-    case te::UNIFORM_ACCELERATION: return dflt || v == 5 || v == 6 || v == 7 || v == 12;
-    case te::ANGULAR_VELOCITIES: return dflt || (v >= 6 && v <= 9) || v == 12;
-    default: return v == 12 || v == 13;   // AR: the two-lanes-per-target kernel (te_ar_pair.cuh); 13 = packed
-  }
+  if (p->model == te::ANGULAR_RATES) return false;
+  return (v == 0 && p->all_sym) || v == 12;
 }
 // full-matrix kernels (and anything else that reads both halves) first get the lower triangles back
 void ensure_full(te_pool* p) {
@@ -154,39 +135,34 @@ void ensure_full(te_pool* p) {
 // (packed: upper triangle only), else the full-matrix kernels; 10 = force the full-matrix kernel (TMA-staged / row-split);
 // 12 = direct kernel writing both halves; the others are launch shapes kept for experiments (tests cover all of them).
 // Stage bytes of the staged kernel: UV 13056, UA 25344, AV 43008, AR 90624.
+// Kernel per model and variant.  Variants are what the tests switch between, not tuning shapes:
+//   0   default: UV / UA / AV direct symmetric-covariance kernels (packed; te_direct.cuh) while every class is bitwise symmetric,
+//       AR the warp-specialised row-split kernel on the full matrix (te_split.cuh)
+//   1   the TMA-staged one-warp-per-tile kernel on the full matrix (te_kernels.cuh; also what replay launches of AV / AR run)
+//   10  forced full-matrix kernels (UV / UA staged, AV row-split): what a pool with an asymmetric class runs
+//   11  AR row-split kernel moving the upper triangle only (44 % fewer bytes, not faster: DESIGN.md section 7)
+//   12  UV / UA / AV direct kernels writing both halves of the covariance
+// Shape experiments of round 1 (warps x stages sweeps, the AR / AV two-lanes-per-target kernels, thread-per-target AR) were
+// measured, lost, and are gone from the tree: DESIGN.md section 7 keeps their numbers.
 void launch_step(te_pool* p, const te::StepArgs& a_in, int n_work_hint) {
   const int v = p->variant;
   te::StepArgs a = a_in;
   if (uses_direct(p)) {
     a.packed = (p->all_sym && v != 12) ? 1 : 0;
     if (a.packed) p->lower_stale = true;
-    else if (p->model == te::ANGULAR_RATES) ensure_full(p);   // (the other direct kernels never read the lower triangle)
     switch (p->model) {
-      case te::ANGULAR_RATES:
-        launch_ar_pair<8>(p, a, n_work_hint);
-        return;
       case te::UNIFORM_VELOCITY:
         // measured, packed, 4 Mi targets: <4,3> (12 warps per SM) 1.17e10, <4,4> 1.11e10, <8,1> 1.09e10 steps/s
-        if (v == 5) launch_kin_direct<te::UNIFORM_VELOCITY, 4, 4>(p, a, n_work_hint);
-        else if (v == 6) launch_kin_direct<te::UNIFORM_VELOCITY, 8, 1>(p, a, n_work_hint);
-        else launch_kin_direct<te::UNIFORM_VELOCITY, 4, 3>(p, a, n_work_hint);
+        launch_kin_direct<te::UNIFORM_VELOCITY, 4, 3>(p, a, n_work_hint);
         return;
       case te::UNIFORM_ACCELERATION:
-        if (v == 6) launch_kin_direct<te::UNIFORM_ACCELERATION, 4, 3>(p, a, n_work_hint);
-        else if (v == 7) launch_kin_direct<te::UNIFORM_ACCELERATION, 5, 2>(p, a, n_work_hint);
-        else launch_kin_direct<te::UNIFORM_ACCELERATION, 8, 1>(p, a, n_work_hint);
+        launch_kin_direct<te::UNIFORM_ACCELERATION, 8, 1>(p, a, n_work_hint);
         return;
       default:
-        if (v == 7) launch_av_direct<6>(p, a, n_work_hint);
-        else if (v == 8) launch_av_direct<8, 4>(p, a, n_work_hint);
-        else if (v == 9) launch_av_direct<8, 12>(p, a, n_work_hint);
-        else launch_av_direct<8>(p, a, n_work_hint);
+        launch_av_direct<8>(p, a, n_work_hint);
         return;
     }
   }
-  // AR, variant 11: the row-split kernel in packed form (only the upper-triangle field ranges travel; te_split.cuh).  Not the
-  // default: it moves 44 % fewer bytes but is not faster (1.07e9 vs 1.09e9 steps/s) -- with the traffic gone the six main
-  // warps' work per tile is the bound, and they still compute full rows.
   if (p->model == te::ANGULAR_RATES && v == 11 && p->all_sym) {
     a.packed = 1;
     p->lower_stale = true;
@@ -200,29 +176,13 @@ void launch_step(te_pool* p, const te::StepArgs& a_in, int n_work_hint) {
     if (p->model == te::ANGULAR_RATES) return launch_split_k<te::ANGULAR_RATES, 1, 2, 1, true>(p, a, n_work_hint);
   }
   switch (p->model) {
-    case te::UNIFORM_VELOCITY:
-      if (v == 1) launch_step_t<te::UNIFORM_VELOCITY, 16, 1>(p, a, n_work_hint);
-      else if (v == 2) launch_step_t<te::UNIFORM_VELOCITY, 4, 4>(p, a, n_work_hint);
-      else launch_step_t<te::UNIFORM_VELOCITY, 8, 2>(p, a, n_work_hint);
-      break;
-    case te::UNIFORM_ACCELERATION:
-      if (v == 1) launch_step_t<te::UNIFORM_ACCELERATION, 8, 1>(p, a, n_work_hint);
-      else if (v == 2) launch_step_t<te::UNIFORM_ACCELERATION, 2, 4>(p, a, n_work_hint);
-      else launch_step_t<te::UNIFORM_ACCELERATION, 4, 2>(p, a, n_work_hint);
-      break;
+    case te::UNIFORM_VELOCITY: launch_step_t<te::UNIFORM_VELOCITY, 8, 2>(p, a, n_work_hint); break;
+    case te::UNIFORM_ACCELERATION: launch_step_t<te::UNIFORM_ACCELERATION, 4, 2>(p, a, n_work_hint); break;
     case te::ANGULAR_VELOCITIES:
       if (v == 1) launch_step_t<te::ANGULAR_VELOCITIES, 5, 1>(p, a, n_work_hint);
-      else if (v == 5) launch_step_t<te::ANGULAR_VELOCITIES, 5, 1, false, 1>(p, a, n_work_hint);
-      else if (v == 2) launch_split_t<te::ANGULAR_VELOCITIES, 1, 2, 1>(p, a, n_work_hint);
-      else if (v == 3) launch_split_t<te::ANGULAR_VELOCITIES, 1, 1, 3>(p, a, n_work_hint);
-      else if (v == 4) launch_split_t<te::ANGULAR_VELOCITIES, 1, 3, 1>(p, a, n_work_hint);
       else launch_split_t<te::ANGULAR_VELOCITIES, 1, 2, 2>(p, a, n_work_hint);
       break;
-    default:
-      if (v == 1) launch_step_t<te::ANGULAR_RATES, 2, 1>(p, a, n_work_hint);
-      else if (v == 2) launch_split_t<te::ANGULAR_RATES, 1, 1, 1>(p, a, n_work_hint);
-      else launch_split_t<te::ANGULAR_RATES, 1, 2, 1>(p, a, n_work_hint);
-      break;
+    default: launch_split_t<te::ANGULAR_RATES, 1, 2, 1>(p, a, n_work_hint); break;
   }
 }
 
@@ -365,7 +325,8 @@ void tick_set_reserve(te_pool* p, te_pool::TickSet& ts, size_t meas_bytes, size_
 }
 
 // one dense tick from host buffers, enqueued on the pool's three streams; nothing here waits on the host
-void tick_host_enqueue(te_pool* p, double dt, const double* meas, int meas_stride, const uint8_t* action, int default_action, double* est_pos_out) {
+void tick_host_enqueue(te_pool* p, double dt, const double* meas, int meas_stride, const uint8_t* action, int default_action, double* est_pos_out,
+                       bool pipelined) {
   if (!(dt >= 0.0)) throw std::invalid_argument("dt must be >= 0");
   if (meas) check_meas_stride(p, meas_stride);
   else if (!action && default_action == TE_ACT_UPDATE) throw std::invalid_argument("update tick without measurements");
@@ -375,8 +336,13 @@ void tick_host_enqueue(te_pool* p, double dt, const double* meas, int meas_strid
   }
   const long long n = p->n;
   const int n_tiles = cdiv(n, te::TILE);
-  static const int chunk_env = std::getenv("TE_TICK_CHUNK_TILES") ? std::atoi(std::getenv("TE_TICK_CHUNK_TILES")) : 0;   // tuning knob
-  const int chunk_tiles = std::max(256, std::min(n_tiles, chunk_env > 0 ? chunk_env : 8192));   // 262144 targets: 14.7 MB of pose measurements
+  // Chunk of the copy / step / read-back pipeline.  Measured (tools/e2e_probe.py, 4 Mi UA targets, xyz in / positions out, ms per
+  // tick, one tick at a time | two ticks in flight): 2048 tiles 4.09 | 4.05, 8192 tiles 3.14 | 3.03, 32768 tiles 2.99 | 2.61,
+  // 131072 tiles 4.31 | 2.47 -- many small copies in both directions at once cost the link a third of its rate; with two ticks in
+  // flight the overlap comes from the neighbouring tick, so the chunks can be the whole pool.
+  const char* chunk_str = std::getenv("TE_TICK_CHUNK_TILES");   // tuning / test knob, read per call
+  const int chunk_env = chunk_str ? std::atoi(chunk_str) : 0;
+  const int chunk_tiles = std::max(256, std::min(n_tiles, chunk_env > 0 ? chunk_env : (pipelined ? 131072 : 32768)));
   const int n_chunks = cdiv(n_tiles, chunk_tiles);
   te_pool::TickSet& ts = p->tick_set[p->ticks_issued & 1];
   if (ts.busy) {   // the tick that used this set two ticks ago must have left it (its results are in the caller's buffer by then)
@@ -453,7 +419,7 @@ int te_pool_tick_host(te_pool* p, double dt, const double* meas, int meas_stride
                       double* est_pos_out) {
   return guarded(p, [&] {
     if (p->n == 0) return 0;
-    tick_host_enqueue(p, dt, meas, meas_stride, action, default_action, est_pos_out);
+    tick_host_enqueue(p, dt, meas, meas_stride, action, default_action, est_pos_out, false);
     tick_host_wait(p, 0);
     return 0;
   });
@@ -463,7 +429,7 @@ int te_pool_tick_host_async(te_pool* p, double dt, const double* meas, int meas_
                             double* est_pos_out) {
   return guarded(p, [&] {
     if (p->n == 0) return 0;
-    tick_host_enqueue(p, dt, meas, meas_stride, action, default_action, est_pos_out);
+    tick_host_enqueue(p, dt, meas, meas_stride, action, default_action, est_pos_out, true);
     return 0;
   });
 }

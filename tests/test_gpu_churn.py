@@ -136,7 +136,7 @@ def test_expiry_bit_exact(n0, ticks):
 
 
 @pytest.mark.parametrize("name,variant", [("uniform_velocity", 0), ("uniform_acceleration", 0), ("angular_velocities", 0), ("angular_rates", 0),
-                                          ("uniform_acceleration", 10), ("angular_velocities", 10), ("angular_rates", 13)])
+                                          ("uniform_acceleration", 10), ("angular_velocities", 10), ("angular_rates", 11)])
 def test_fused_step_expire_is_bit_identical(name, variant):
     """te_pool_step_dense_expire (compaction fused into the step kernel: survivors' columns go straight to their compacted
     slots in the second buffer) == te_pool_step_dense + te_pool_stamp_dense + te_pool_expire, bit for bit: erased ids,
@@ -152,7 +152,7 @@ def test_fused_step_expire_is_bit_identical(name, variant):
     pools = []
     for _ in range(2):
         p = te.TargetPool(mtype); p.register_class(Q, R, P0)
-        p.set_variant(variant)      # 0: the default kernels; 10: the full-matrix kernels; 13: AR two-lane packed kernel
+        p.set_variant(variant)      # 0: the default kernels; 10: the full-matrix kernels; 11: AR row-split kernel, packed
         p.add(np.arange(n0, dtype=np.uint32), meas_all[0, :n0], p0_scale=scale[:n0])
         pools.append(p)
     rng = np.random.default_rng(23)

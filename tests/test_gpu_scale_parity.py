@@ -88,8 +88,7 @@ def test_bench_scale_dense(model, cap):
 # 2. a handful of CTAs over ~100 tiles: every stage of every ring is reused tens of times; dense, sparse, packed, staged
 # ---------------------------------------------------------------------------------------------------------------------
 CASES = [("uniform_velocity", 0), ("uniform_velocity", 10), ("uniform_acceleration", 0), ("uniform_acceleration", 10), ("uniform_acceleration", 1),
-         ("angular_velocities", 0), ("angular_velocities", 10), ("angular_velocities", 1), ("angular_rates", 0), ("angular_rates", 11),
-         ("angular_rates", 1), ("angular_rates", 2)]
+         ("angular_velocities", 0), ("angular_velocities", 10), ("angular_velocities", 1), ("angular_rates", 0), ("angular_rates", 11)]
 
 
 @pytest.mark.parametrize("cap", [1, 4])
@@ -275,12 +274,13 @@ def test_av_pitch_range(pitch_max):
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("pipelined", [False, True], ids=["sync", "two_in_flight"])
 @pytest.mark.parametrize("stride", [7, 3])
-def test_tick_host_pipeline(stride, pipelined):
-    """300 000 uniform-acceleration targets = two pipeline chunks (262 144 targets each) + a ragged tail; pose [n][7] and
+def test_tick_host_pipeline(stride, pipelined, monkeypatch):
+    """300 000 uniform-acceleration targets in pipeline chunks of 2048 tiles (65 536 targets: four chunks + a ragged tail); pose [n][7] and
     xyz-only [n][3] measurements; state, covariance and the returned positions against the oracle.  two_in_flight: the same ticks
     through te_pool_tick_host_async / te_pool_tick_host_wait(1) (the copies of tick k + 1 under the kernels and read-back of tick
     k), every tick's returned positions checked against the synchronous run's."""
     import ctypes as C
+    monkeypatch.setenv("TE_TICK_CHUNK_TILES", "2048")     # (the default chunk is the whole pool at this size)
     n, ticks = 300000 + 5, 6
     te, pool, ref, ids, meas, action, N, M = _setup("uniform_acceleration", n, ticks, seed=31)
     outs = [np.zeros((n, 3)) for _ in range(ticks)]
