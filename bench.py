@@ -494,6 +494,29 @@ def main():
                 for k in range(Ka):
                     tick_abi(k)
                 ta = (time.perf_counter() - t0) * 1e3
+                # the dense tick of the same library: records in target_manager_get_dense_ids order, no ids travel, every target's estimated
+                # position comes back (target_manager_update_dense_async / _wait: two ticks in flight, as the headline form)
+                h_in_abi = h3 if M == 3 else h7
+                st_abi = 3 if M == 3 else 7
+
+                def tick_dense(k):
+                    rc = clib.target_manager_update_dense_async(mg.h, DT, C.c_void_p(h_in_abi[k % 2].data_ptr()), st_abi, C.c_void_p(h_act[k % 2].data_ptr()),
+                                                                C.c_void_p(h_out[k % 2].data_ptr()))
+                    if rc != n or clib.target_manager_update_dense_wait(mg.h, 1) < 0:
+                        raise RuntimeError("target_manager_update_dense_async: %s" % clib.target_manager_last_error().decode())
+                for k in range(3):
+                    tick_dense(k)
+                clib.target_manager_update_dense_wait(mg.h, 0)
+                Kd = 20
+                t0 = time.perf_counter()
+                for k in range(Kd):
+                    tick_dense(k)
+                clib.target_manager_update_dense_wait(mg.h, 0)
+                td = (time.perf_counter() - t0) * 1e3
+                e2e["reference_abi_dense"] = {"value": n * Kd / (td * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * (st_abi * 8 + 1), "d2h_bytes_per_step": n * 24,
+                                              "ms_per_step": td / Kd, "n_gpus": 1,
+                                              "api": "libtarget_c.so: target_manager_update_dense_async(dt, meas[n][%d], action[n], est_pos_out[n][3]) + "
+                                                     "target_manager_update_dense_wait(1), pinned host arrays in target_manager_get_dense_ids order" % st_abi}
                 e2e["reference_abi"] = {"value": n * Ka / (ta * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * (4 + 7 * 8 + 1), "d2h_bytes_per_step": 56,
                                         "ms_per_step": ta / Ka, "n_gpus": 1,
                                         "api": "libtarget_c.so: target_manager_update_batch(n, ids, dt, meas[n][7], action[n]) + target_manager_get_est_pose(id), "

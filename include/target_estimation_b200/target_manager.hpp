@@ -161,6 +161,16 @@ class TargetManager {
   virtual void getEstimatesBatch(long long n, const unsigned* ids, const double* t1, double* pose7, double* twist6, double* acc6,
                                  unsigned char* found);
   virtual void flush();
+  // One dense tick from host arrays, record k = the k-th target in denseIds() order (a homogeneous manager: getAvailableTargets()
+  // order): no ids travel, nothing is looked up -- te_pool_tick_host: the copies, the step and the read-back of every target's
+  // estimated position (est_pos_out [n][3], may be NULL: what the node broadcasts per tick, src/target_manager_ros.cpp:78-87) are
+  // pipelined in chunks.  meas_stride 7 = poses, 3 = x y z (UV / UA).  action NULL = update(id, dt, meas) for every target.
+  // updateDenseAsync enqueues the tick and returns (two ticks may be in flight; buffers must stay valid until the tick is done);
+  // updateDenseWait(0) waits for all of them, (1) for all but the newest.  Returns the number of targets.
+  virtual long long updateDense(double dt, const double* meas, int meas_stride, const unsigned char* action, double* est_pos_out);
+  virtual long long updateDenseAsync(double dt, const double* meas, int meas_stride, const unsigned char* action, double* est_pos_out);
+  virtual void updateDenseWait(int lag);
+  virtual std::vector<unsigned int> denseIds();
   bool quiet = false;   // suppress the reference's stdout messages ("does not exist", "already exists", ...)
 
   // sampled logging -----------------------------------------------------------------------------
@@ -193,6 +203,7 @@ class TargetManager {
   int registerClass(int type, const MatrixXd& Q, const MatrixXd& R, const MatrixXd& P0);
   void queue(int type, unsigned id, double dt, const double* meas, int action);
   long long updateBatchUnique(long long n, const unsigned* ids, double dt, const double* meas, const unsigned char* action);   // no id twice
+  te_pool* densePool();   // the one non-empty pool of a homogeneous manager (throws otherwise)
 
   int device_;
   te_pool* pools_[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -366,6 +377,12 @@ class ShardedTargetManager : public TargetManager {
   void getEstimatesBatch(long long n, const unsigned* ids, const double* t1, double* pose7, double* twist6, double* acc6,
                          unsigned char* found) override;
   void flush() override;
+  // dense ticks: the records are SHARD-MAJOR (denseIds(): shard 0's targets in ascending id, then shard 1's, ...); every shard's
+  // slice is copied, stepped and read back by its own worker thread on its own device
+  long long updateDense(double dt, const double* meas, int meas_stride, const unsigned char* action, double* est_pos_out) override;
+  long long updateDenseAsync(double dt, const double* meas, int meas_stride, const unsigned char* action, double* est_pos_out) override;
+  void updateDenseWait(int lag) override;
+  std::vector<unsigned int> denseIds() override;
   void watch(long long n, const unsigned* ids, size_t max_samples = 1 << 20) override;   // forwarded to the owners
 
   // The optional all-gather of estimates: ids (shard-major: shard 0's targets of model type 0 in ascending id, ...) and their

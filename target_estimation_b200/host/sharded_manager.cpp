@@ -268,6 +268,42 @@ void ShardedTargetManager::getEstimatesBatch(long long n, const unsigned* ids, c
   });
 }
 
+// ---- dense ticks: shard-major records, every shard's slice on its own device at once ---------------------------------------------
+std::vector<unsigned int> ShardedTargetManager::denseIds() {
+  std::vector<unsigned int> all;
+  for (auto& s : shard_) {
+    std::vector<unsigned int> part = s->getAvailableTargets();
+    all.insert(all.end(), part.begin(), part.end());
+  }
+  return all;
+}
+
+long long ShardedTargetManager::updateDense(double dt, const double* meas, int meas_stride, const unsigned char* action, double* est_pos_out) {
+  std::vector<long long> off(shard_.size() + 1, 0);
+  for (size_t r = 0; r < shard_.size(); ++r) off[r + 1] = off[r] + (long long)shard_[r]->getAvailableTargets().size();
+  forEachShard([&](int r) {
+    const long long o = off[(size_t)r];
+    if (off[(size_t)r + 1] == o) return;
+    shard_[(size_t)r]->updateDense(dt, meas ? meas + o * meas_stride : nullptr, meas_stride, action ? action + o : nullptr, est_pos_out ? est_pos_out + 3 * o : nullptr);
+  });
+  return off.back();
+}
+
+long long ShardedTargetManager::updateDenseAsync(double dt, const double* meas, int meas_stride, const unsigned char* action, double* est_pos_out) {
+  // enqueueing costs microseconds per shard: one thread issues all of them, the devices then run concurrently
+  long long o = 0;
+  for (auto& s : shard_) {
+    const long long n = (long long)s->getAvailableTargets().size();
+    if (n > 0) s->updateDenseAsync(dt, meas ? meas + o * meas_stride : nullptr, meas_stride, action ? action + o : nullptr, est_pos_out ? est_pos_out + 3 * o : nullptr);
+    o += n;
+  }
+  return o;
+}
+
+void ShardedTargetManager::updateDenseWait(int lag) {
+  for (auto& s : shard_) s->updateDenseWait(lag);
+}
+
 // ---- the optional exchange of estimates ----------------------------------------------------------------------------------------
 bool ShardedTargetManager::gatherUsesNccl() {
   if (!group_) {

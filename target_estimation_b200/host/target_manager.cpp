@@ -430,6 +430,40 @@ long long TargetManager::updateBatchUnique(long long n, const unsigned* ids, dou
   return applied;
 }
 
+te_pool* TargetManager::densePool() {
+  int n_pools = 0, only = -1;
+  for (int t = 0; t < 4; ++t)
+    if (pools_[t] && te_pool_size(pools_[t]) > 0) { ++n_pools; only = t; }
+  if (n_pools != 1) throw std::invalid_argument("a dense tick needs a manager whose targets share one model type");
+  return pools_[only];
+}
+
+long long TargetManager::updateDense(double dt, const double* meas, int meas_stride, const unsigned char* action, double* est_pos_out) {
+  std::lock_guard<std::recursive_mutex> lg(target_lock_);
+  flushLocked();
+  if (targets_.empty()) return 0;
+  te_pool* p = densePool();
+  ck(te_pool_tick_host(p, dt, meas, meas_stride, action, TE_ACT_UPDATE, est_pos_out));
+  return te_pool_size(p);
+}
+
+long long TargetManager::updateDenseAsync(double dt, const double* meas, int meas_stride, const unsigned char* action, double* est_pos_out) {
+  std::lock_guard<std::recursive_mutex> lg(target_lock_);
+  flushLocked();
+  if (targets_.empty()) return 0;
+  te_pool* p = densePool();
+  ck(te_pool_tick_host_async(p, dt, meas, meas_stride, action, TE_ACT_UPDATE, est_pos_out));
+  return te_pool_size(p);
+}
+
+void TargetManager::updateDenseWait(int lag) {
+  std::lock_guard<std::recursive_mutex> lg(target_lock_);
+  for (int t = 0; t < 4; ++t)
+    if (pools_[t]) ck(te_pool_tick_host_wait(pools_[t], lag));
+}
+
+std::vector<unsigned int> TargetManager::denseIds() { return getAvailableTargets(); }
+
 bool TargetManager::erase(const unsigned int& id) {   // :227-241
   std::lock_guard<std::recursive_mutex> lg(target_lock_);
   auto it = targets_.find(id);

@@ -122,6 +122,25 @@ long long target_manager_update_batch(const target_manager_c* self, long long n,
                                       const unsigned char* action) {
   return guard(-1LL, [&] { return M(self)->updateBatch(n, ids, dt, meas, action); });
 }
+long long target_manager_update_dense(const target_manager_c* self, double dt, const double* meas, int meas_stride, const unsigned char* action,
+                                      double* est_pos_out) {
+  return guard(-1LL, [&] { return M(self)->updateDense(dt, meas, meas_stride, action, est_pos_out); });
+}
+long long target_manager_update_dense_async(const target_manager_c* self, double dt, const double* meas, int meas_stride,
+                                            const unsigned char* action, double* est_pos_out) {
+  return guard(-1LL, [&] { return M(self)->updateDenseAsync(dt, meas, meas_stride, action, est_pos_out); });
+}
+int target_manager_update_dense_wait(const target_manager_c* self, int lag) {
+  return guard(-1, [&] { M(self)->updateDenseWait(lag); return 0; });
+}
+long long target_manager_get_dense_ids(const target_manager_c* self, unsigned int* out, long long cap) {
+  return guard(-1LL, [&] {
+    auto ids = M(self)->denseIds();
+    const long long n = (long long)ids.size();
+    if (out && cap > 0) std::memcpy(out, ids.data(), sizeof(unsigned) * (size_t)(n < cap ? n : cap));
+    return n;
+  });
+}
 void target_manager_update_all(const target_manager_c* self, double dt) {
   guard(0, [&] { M(self)->update(dt); return 0; });
 }

@@ -26,6 +26,10 @@ _SIG = {
     "target_manager_init_batch": (_ll, [_p, _ll, _p, _d, _p, _p]),
     "target_manager_update_batch": (_ll, [_p, _ll, _p, _d, _p, _p]),
     "target_manager_update_all": (None, [_p, _d]),
+    "target_manager_update_dense": (_ll, [_p, _d, _p, _i, _p, _p]),
+    "target_manager_update_dense_async": (_ll, [_p, _d, _p, _i, _p, _p]),
+    "target_manager_update_dense_wait": (_i, [_p, _i]),
+    "target_manager_get_dense_ids": (_ll, [_p, _p, _ll]),
     "target_manager_erase_batch": (_ll, [_p, _ll, _p]),
     "target_manager_erase": (C.c_bool, [_p, _u]),
     "target_manager_get_estimates_batch": (_i, [_p, _ll, _p, _p, _p, _p, _p, _p]),
@@ -119,6 +123,27 @@ class TargetManagerC:
 
     def update_all(self, dt):
         clib.target_manager_update_all(self.h, dt)
+
+    def update_dense(self, dt, meas, action=None, est_pos_out=None, pipelined=False):
+        """record k = the k-th id of dense_ids(); meas [n][7] or [n][3]; the arrays must stay alive until the tick is done"""
+        meas = np.ascontiguousarray(meas, dtype=np.float64)
+        action = np.ascontiguousarray(action, dtype=np.uint8) if action is not None else None
+        fn = clib.target_manager_update_dense_async if pipelined else clib.target_manager_update_dense
+        n = int(fn(self.h, dt, _ptr(meas), meas.shape[1], _ptr(action), _ptr(est_pos_out)))
+        if n < 0:
+            raise RuntimeError(clib.target_manager_last_error().decode())
+        self._dense_keep = (meas, action, est_pos_out)
+        return n
+
+    def update_dense_wait(self, lag=0):
+        if clib.target_manager_update_dense_wait(self.h, lag) < 0:
+            raise RuntimeError(clib.target_manager_last_error().decode())
+
+    def dense_ids(self):
+        n = int(clib.target_manager_get_dense_ids(self.h, None, 0))
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        clib.target_manager_get_dense_ids(self.h, _ptr(out), n)
+        return out[:n]
 
     def erase(self, id_):
         return bool(clib.target_manager_erase(self.h, id_))

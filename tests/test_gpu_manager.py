@@ -246,3 +246,44 @@ def test_sampled_logging_and_text_dumps(name, tmp_path):
     mgr.log()
     assert mgr.log_samples() == 0
     mgr.close()
+
+
+@pytest.mark.parametrize("stride", [7, 3])
+def test_dense_tick_through_c_abi(stride):
+    """target_manager_update_dense(_async): record k = the k-th id of target_manager_get_dense_ids, no ids travel; state against the
+    oracle, the returned positions against the getters, the pipelined form against the synchronous one (bit-identical)"""
+    from target_estimation_b200.manager import TargetManagerC
+    name = "uniform_acceleration"
+    y = orc.load_yaml(_yaml(name))
+    n, ticks = 5000 + 3, 8
+    meas, action, _ = synth.make_streams(n, ticks, DT, accel=True, angular=False, seed=41)
+    ids = np.random.default_rng(4).permutation(np.arange(n, dtype=np.uint32) * 3 + 2)
+    order = np.argsort(ids)                       # dense order of a plain manager = ascending ids
+    ref = orc.ShardedManager()
+    ref.init_batch(y["type"], ids, DT, y["Q"], y["R"], y["P"], meas[0])
+    outs = {}
+    for pipelined in (False, True):
+        mgr = TargetManagerC(_yaml(name))
+        assert mgr.init_batch(ids, DT, meas[0]) == n
+        assert np.array_equal(mgr.dense_ids(), ids[order])
+        pos = [np.zeros((n, 3)) for _ in range(ticks)]
+        for k in range(ticks):
+            m = np.ascontiguousarray(meas[k][order][:, :stride])
+            a = np.ascontiguousarray(action[k][order])
+            assert mgr.update_dense(DT, m, a, pos[k], pipelined=pipelined) == n
+            if pipelined:
+                mgr.update_dense_wait(1)
+        mgr.update_dense_wait(0)
+        pose, _, _, found = mgr.get_estimates_batch(ids[order])
+        assert found.all() and np.array_equal(pose[:, :3], pos[-1])
+        outs[pipelined] = (pos, mgr.state(int(ids[5])))
+        mgr.close()
+    for k in range(ticks):
+        assert np.array_equal(outs[False][0][k], outs[True][0][k]), k
+        ref.step_batch(ids, DT, meas[k], action[k])
+        want = ref.states(ids[order], y["Q"].shape[0])["x"][:, :3]
+        assert synth.compare_h2(outs[False][0][k], want) <= 1.0, k
+    st = outs[True][1]
+    want = ref.states(ids[5:6], y["Q"].shape[0])
+    assert synth.compare_h2(st["x"][None], want["x"]) <= 1.0 and synth.compare_h2(st["P"][None], want["P"]) <= 1.0
+    ref.close()

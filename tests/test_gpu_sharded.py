@@ -96,6 +96,21 @@ def _run(name, n_shards, devices, n=5003, ticks=12):
     pc, tc, _, fc = one.get_estimates_batch(g_ids)
     assert fc.all() and np.array_equal(g_rec[:, :7], pc) and np.array_equal(g_rec[:, 7:], tc)
     assert mgr.last_gather_ms() >= 0.0
+    # dense tick: shard-major records (dense_ids order), every shard's slice on its own device; == the same tick through update_batch
+    d_ids = mgr.dense_ids()
+    assert np.array_equal(d_ids, g_ids)
+    row = {int(i): k for k, i in enumerate(ids)}
+    sel = np.array([row[int(i)] for i in d_ids])
+    pos = np.zeros((n, 3))
+    assert mgr.update_dense(DT, meas[5][sel], action[5][sel], pos) == n
+    one.update_batch(ids, DT, meas[5], action[5])
+    pd, _, _, _ = one.get_estimates_batch(d_ids)
+    assert np.array_equal(pos, pd[:, :3])
+    assert mgr.update_dense(DT, meas[6][sel], action[6][sel], pos, pipelined=True) == n
+    mgr.update_dense_wait(0)
+    one.update_batch(ids, DT, meas[6], action[6])
+    pd, _, _, _ = one.get_estimates_batch(d_ids)
+    assert np.array_equal(pos, pd[:, :3])
     # erase through the routed batch call, then the id lists agree again
     gone = ids[::4]
     assert mgr.erase_batch(gone) == gone.size
