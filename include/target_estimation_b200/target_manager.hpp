@@ -171,6 +171,7 @@ class TargetManager {
   virtual long long updateDenseAsync(double dt, const double* meas, int meas_stride, const unsigned char* action, double* est_pos_out);
   virtual void updateDenseWait(int lag);
   virtual std::vector<unsigned int> denseIds();
+  size_t size();   // number of targets (of this manager / shard)
   bool quiet = false;   // suppress the reference's stdout messages ("does not exist", "already exists", ...)
 
   // sampled logging -----------------------------------------------------------------------------

@@ -105,7 +105,9 @@ int te_pool_tick_host_async(te_pool* p, double dt, const double* meas, int meas_
                             double* est_pos_out);
 int te_pool_tick_host_wait(te_pool* p, int lag);
 /* Sparse tick by id (host buffers): op k applies action[k] with dt[k] (dt_scalar if dt NULL) and
- * meas[k][7] to ids[k]; unknown ids are skipped.  An id may appear once per call.  Returns #applied. */
+ * meas[k][7] to ids[k]; unknown ids are skipped.  An id may appear once per call: a repeated id is detected on the device
+ * before anything is stepped -- nothing is applied then and -2 is returned (the caller splits the batch, as TargetManager::
+ * updateBatch does).  Returns #applied. */
 long long te_pool_step_ids(te_pool* p, long long n, const uint32_t* ids, const double* dt, double dt_scalar,
                            const double* meas /*[n][7]*/, const uint8_t* action /*NULL = UPDATE*/);
 /* TargetManager::update(dt): predict every target (src/target_manager.cpp:220-225). */

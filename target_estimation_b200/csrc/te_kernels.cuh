@@ -441,13 +441,19 @@ __global__ void rebuild_kernel(int n_new, const int* __restrict__ srcmap, const 
 static __global__ void scatter_ops_kernel(const uint32_t* __restrict__ ids_sorted, int n_slots, long long n, const uint32_t* __restrict__ q,
                                    const double* __restrict__ dt, double dt_scalar, const double* __restrict__ meas,
                                    const uint8_t* __restrict__ action, uint8_t* act_slot, double* dt_slot, double* meas_slot,
-                                   uint8_t* tile_flag, int* tile_list, int* counters) {
+                                   uint8_t* tile_flag, int* tile_list, int* counters, int* claim) {
   long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (k >= n) return;
   int a = action ? (int)action[k] : ACT_UPDATE;
   if (a == ACT_NONE) return;
   int s = lower_bound_u32(ids_sorted, n_slots, q[k]);
   if (s >= n_slots || ids_sorted[s] != q[k]) return;
+  // one op per slot and launch: a second op on the same slot (an id named twice) would race with the first one's record --
+  // counted here, and the host then applies nothing and splits the batch (counters[2]; claim is zeroed per call)
+  if (atomicAdd(&claim[s], 1) > 0) {
+    atomicAdd(&counters[2], 1);
+    return;
+  }
   act_slot[s] = (uint8_t)a;
   dt_slot[s] = dt ? dt[k] : dt_scalar;
   if (a == ACT_UPDATE) {

@@ -459,10 +459,23 @@ long long te_pool_step_ids(te_pool* p, long long n, const uint32_t* ids, const d
       if (action) for (long long k = 0; k < n && !needs; ++k) needs = action[k] == TE_ACT_UPDATE;
       if (needs) throw std::invalid_argument("update ops without measurements");
     }
-    CK(cudaMemsetAsync(p->d_counters, 0, 2 * sizeof(int), p->stream));
+    CK(cudaMemsetAsync(p->d_counters, 0, 3 * sizeof(int), p->stream));
+    CK(cudaMemsetAsync(p->alive, 0, (size_t)p->n * sizeof(int), p->stream));   // per-slot claim counts of this call (alive[] is scratch between compactions)
     te::scatter_ops_kernel<<<cdiv(n, 256), 256, 0, p->stream>>>(b.cold.ids, (int)p->n, n, d_ids, d_dt, dt_scalar, d_meas, d_act, p->action,
-                                                                 p->dt_slot, b.cold.meas, p->tile_flag, p->tile_list, p->d_counters);
+                                                                 p->dt_slot, b.cold.meas, p->tile_flag, p->tile_list, p->d_counters, p->alive);
     CK(cudaGetLastError());
+    if (n > 1) {   // a repeated id?  (checked before anything is stepped)
+      int dups = 0;
+      CK(cudaMemcpyAsync(&dups, p->d_counters + 2, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+      CK(cudaStreamSynchronize(p->stream));
+      if (dups > 0) {
+        CK(cudaMemsetAsync(p->action, 0, (size_t)p->n, p->stream));
+        CK(cudaMemsetAsync(p->tile_flag, 0, (size_t)cdiv(p->n, te::TILE) + 4, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+        last_error() = "an id appears more than once in the batch: nothing applied";
+        return -2;
+      }
+    }
     te::StepArgs a = base_args(p);
     a.tile_list = p->tile_list;
     a.d_nwork = p->d_counters;

@@ -280,7 +280,7 @@ std::vector<unsigned int> ShardedTargetManager::denseIds() {
 
 long long ShardedTargetManager::updateDense(double dt, const double* meas, int meas_stride, const unsigned char* action, double* est_pos_out) {
   std::vector<long long> off(shard_.size() + 1, 0);
-  for (size_t r = 0; r < shard_.size(); ++r) off[r + 1] = off[r] + (long long)shard_[r]->getAvailableTargets().size();
+  for (size_t r = 0; r < shard_.size(); ++r) off[r + 1] = off[r] + (long long)shard_[r]->size();
   forEachShard([&](int r) {
     const long long o = off[(size_t)r];
     if (off[(size_t)r + 1] == o) return;
@@ -293,7 +293,7 @@ long long ShardedTargetManager::updateDenseAsync(double dt, const double* meas, 
   // enqueueing costs microseconds per shard: one thread issues all of them, the devices then run concurrently
   long long o = 0;
   for (auto& s : shard_) {
-    const long long n = (long long)s->getAvailableTargets().size();
+    const long long n = (long long)s->size();
     if (n > 0) s->updateDenseAsync(dt, meas ? meas + o * meas_stride : nullptr, meas_stride, action ? action + o : nullptr, est_pos_out ? est_pos_out + 3 * o : nullptr);
     o += n;
   }

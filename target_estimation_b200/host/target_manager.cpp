@@ -276,14 +276,33 @@ long long TargetManager::initBatch(target_t type, const MatrixXd& Q, const Matri
   // ids already known to the manager under ANY type are skipped ("already exists"); first occurrence wins
   std::vector<long long> keep;
   keep.reserve((size_t)n);
-  std::map<unsigned, uint8_t> fresh;
-  for (long long k = 0; k < n; ++k) {
-    if (targets_.count(ids[k]) || fresh.count(ids[k])) {
-      if (!quiet) std::cout << "Target(" << ids[k] << ") already exists!" << std::endl;
-      continue;
+  std::vector<std::pair<unsigned, uint8_t>> fresh;   // ascending (id, type) pairs for the registry
+  bool ascending = true;
+  for (long long k = 1; k < n && ascending; ++k) ascending = ids[k - 1] < ids[k];
+  if (ascending) {
+    // the usual batch (track ids grow): no id repeats inside it, and one walk along the sorted registry finds the known ones
+    fresh.reserve((size_t)n);
+    auto it = targets_.begin();
+    for (long long k = 0; k < n; ++k) {
+      while (it != targets_.end() && it->first < ids[k]) ++it;
+      if (it != targets_.end() && it->first == ids[k]) {
+        if (!quiet) std::cout << "Target(" << ids[k] << ") already exists!" << std::endl;
+        continue;
+      }
+      fresh.emplace_back(ids[k], (uint8_t)type);
+      keep.push_back(k);
     }
-    fresh[ids[k]] = (uint8_t)type;
-    keep.push_back(k);
+  } else {
+    std::map<unsigned, uint8_t> seen;
+    for (long long k = 0; k < n; ++k) {
+      if (targets_.count(ids[k]) || seen.count(ids[k])) {
+        if (!quiet) std::cout << "Target(" << ids[k] << ") already exists!" << std::endl;
+        continue;
+      }
+      seen[ids[k]] = (uint8_t)type;
+      keep.push_back(k);
+    }
+    fresh.assign(seen.begin(), seen.end());
   }
   if (keep.empty()) return 0;
   const long long na = (long long)keep.size();
@@ -382,6 +401,22 @@ long long TargetManager::updateBatch(long long n, const unsigned* ids, double dt
   bool ascending = true;
   for (long long k = 1; k < n && ascending; ++k) ascending = ids[k - 1] < ids[k];
   if (ascending) return updateBatchUnique(n, ids, dt, meas, action);
+  {
+    // ids in arbitrary order (a /tf message lists its targets as they come): a homogeneous manager hands the batch over as it is --
+    // the device finds a repeated id while it looks the ids up, before anything is stepped (te_pool_step_ids returns -2) -- and
+    // only then the batch is cut on the host (a hash set of four million ids costs 50 x the tick it guards)
+    int n_pools = 0, only = -1;
+    for (int t = 0; t < 4; ++t)
+      if (pools_[t] && te_pool_size(pools_[t]) > 0) { ++n_pools; only = t; }
+    if (n_pools == 0) return 0;
+    if (n_pools == 1) {
+      const long long rc = te_pool_step_ids(pools_[only], n, ids, nullptr, dt, meas, action);
+      if (rc != -2) {
+        ck(rc);
+        return rc;
+      }
+    }
+  }
   long long applied = 0, start = 0;
   std::unordered_set<unsigned> seen;
   seen.reserve((size_t)std::min<long long>(n, 1 << 22));
@@ -463,6 +498,11 @@ void TargetManager::updateDenseWait(int lag) {
 }
 
 std::vector<unsigned int> TargetManager::denseIds() { return getAvailableTargets(); }
+
+size_t TargetManager::size() {
+  std::lock_guard<std::recursive_mutex> lg(target_lock_);
+  return targets_.size();
+}
 
 bool TargetManager::erase(const unsigned int& id) {   // :227-241
   std::lock_guard<std::recursive_mutex> lg(target_lock_);

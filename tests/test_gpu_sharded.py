@@ -102,13 +102,14 @@ def _run(name, n_shards, devices, n=5003, ticks=12):
     row = {int(i): k for k, i in enumerate(ids)}
     sel = np.array([row[int(i)] for i in d_ids])
     pos = np.zeros((n, 3))
-    assert mgr.update_dense(DT, meas[5][sel], action[5][sel], pos) == n
-    one.update_batch(ids, DT, meas[5], action[5])
+    ka, kb = ticks - 2, ticks - 1
+    assert mgr.update_dense(DT, meas[ka][sel], action[ka][sel], pos) == n
+    one.update_batch(ids, DT, meas[ka], action[ka])
     pd, _, _, _ = one.get_estimates_batch(d_ids)
     assert np.array_equal(pos, pd[:, :3])
-    assert mgr.update_dense(DT, meas[6][sel], action[6][sel], pos, pipelined=True) == n
+    assert mgr.update_dense(DT, meas[kb][sel], action[kb][sel], pos, pipelined=True) == n
     mgr.update_dense_wait(0)
-    one.update_batch(ids, DT, meas[6], action[6])
+    one.update_batch(ids, DT, meas[kb], action[kb])
     pd, _, _, _ = one.get_estimates_batch(d_ids)
     assert np.array_equal(pos, pd[:, :3])
     # erase through the routed batch call, then the id lists agree again
