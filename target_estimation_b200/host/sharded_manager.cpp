@@ -85,6 +85,19 @@ class ShardWorkers {
 };
 
 namespace {
+// id mod G without a division per record (the routing passes look at every id of a batch; a hardware divide per id cost more than
+// the tick it feeds): a mask for powers of two, else Lemire's multiply-shift remainder, exact for 32-bit operands
+struct FastMod {
+  explicit FastMod(unsigned d) : d_(d), pow2_((d & (d - 1)) == 0), m_(~(unsigned long long)0 / d + 1) {}
+  unsigned operator()(unsigned a) const {
+    if (pow2_) return a & (d_ - 1);
+    const unsigned long long low = m_ * a;
+    return (unsigned)(((unsigned __int128)low * d_) >> 64);
+  }
+  unsigned d_;
+  bool pow2_;
+  unsigned long long m_;
+};
 // page-locked staging of one shard (the shard's batched calls copy from it at PCIe speed)
 void stageReserve(double*& meas, unsigned char*& action, size_t& cap, size_t n) {
   if (n <= cap) return;
@@ -178,12 +191,13 @@ long long ShardedTargetManager::initBatch(target_t type, const MatrixXd& Q, cons
                                           double dt0, const double* t0, const double* p0, const double* v0, const double* a0, const double* p0_scale) {
   if (n <= 0) return 0;
   const unsigned G = (unsigned)shard_.size();
+  const FastMod owner_of(G);
   std::atomic<long long> added{0};
   forEachShard([&](int r) {
     std::vector<unsigned> s_ids;
     std::vector<double> s_t0, s_p0, s_v0, s_a0, s_sc;
     for (long long k = 0; k < n; ++k) {
-      if (ids[k] % G != (unsigned)r) continue;
+      if (owner_of(ids[k]) != (unsigned)r) continue;
       s_ids.push_back(ids[k]);
       if (t0) s_t0.push_back(t0[k]);
       if (p0) s_p0.insert(s_p0.end(), p0 + 7 * k, p0 + 7 * k + 7);
@@ -201,18 +215,19 @@ long long ShardedTargetManager::initBatch(target_t type, const MatrixXd& Q, cons
 long long ShardedTargetManager::updateBatch(long long n, const unsigned* ids, double dt, const double* meas, const unsigned char* action) {
   if (n <= 0) return 0;
   const unsigned G = (unsigned)shard_.size();
+  const FastMod owner_of(G);
   if (G == 1) return shard_[0]->updateBatch(n, ids, dt, meas, action);
   std::atomic<long long> applied{0};
   forEachShard([&](int r) {
     Stage& st = stage_[(size_t)r];
     size_t cnt = 0;
-    for (long long k = 0; k < n; ++k) cnt += (ids[k] % G == (unsigned)r);
+    for (long long k = 0; k < n; ++k) cnt += (owner_of(ids[k]) == (unsigned)r);
     if (cnt == 0) return;
     st.ids.resize(cnt);
     stageReserve(st.meas, st.action, st.cap, cnt);
     size_t j = 0;
     for (long long k = 0; k < n; ++k) {   // the caller's order is kept: records of one id stay in sequence
-      if (ids[k] % G != (unsigned)r) continue;
+      if (owner_of(ids[k]) != (unsigned)r) continue;
       st.ids[j] = ids[k];
       if (meas) std::memcpy(st.meas + 7 * j, meas + 7 * (size_t)k, 56);
       st.action[j] = action ? action[k] : (unsigned char)TE_ACT_UPDATE;
@@ -226,11 +241,12 @@ long long ShardedTargetManager::updateBatch(long long n, const unsigned* ids, do
 long long ShardedTargetManager::eraseBatch(long long n, const unsigned* ids) {
   if (n <= 0) return 0;
   const unsigned G = (unsigned)shard_.size();
+  const FastMod owner_of(G);
   std::atomic<long long> erased{0};
   forEachShard([&](int r) {
     std::vector<unsigned> s_ids;
     for (long long k = 0; k < n; ++k)
-      if (ids[k] % G == (unsigned)r) s_ids.push_back(ids[k]);
+      if (owner_of(ids[k]) == (unsigned)r) s_ids.push_back(ids[k]);
     if (!s_ids.empty()) erased += shard_[(size_t)r]->eraseBatch((long long)s_ids.size(), s_ids.data());
   });
   return erased.load();
@@ -240,6 +256,7 @@ void ShardedTargetManager::getEstimatesBatch(long long n, const unsigned* ids, c
                                              unsigned char* found) {
   if (n <= 0) return;
   const unsigned G = (unsigned)shard_.size();
+  const FastMod owner_of(G);
   if (G == 1) return shard_[0]->getEstimatesBatch(n, ids, t1, pose7, twist6, acc6, found);
   forEachShard([&](int r) {
     Stage& st = stage_[(size_t)r];
@@ -247,7 +264,7 @@ void ShardedTargetManager::getEstimatesBatch(long long n, const unsigned* ids, c
     st.where.clear();
     std::vector<double> s_t1;
     for (long long k = 0; k < n; ++k) {
-      if (ids[k] % G != (unsigned)r) continue;
+      if (owner_of(ids[k]) != (unsigned)r) continue;
       st.ids.push_back(ids[k]);
       st.where.push_back(k);
       if (t1) s_t1.push_back(t1[k]);
