@@ -594,6 +594,42 @@ def main():
         rms = r0.elapsed_time(r1)
         small["replay64"] = {"ticks_per_launch": T, "launches": Kr, "us_per_tick": 1e3 * rms / (Kr * T), "value": ns * Kr * T / (rms * 1e-3),
                              "unit": UNIT, "note": "te_pool_step_dense_ticks: 64 buffered ticks per launch (batched ingestion / catch-up)"}
+        # live launch (te_pool_live_*): the same 10k targets held in registers by ONE resident launch, ticks released one by one.
+        # (a) closed loop through the host: release tick k (a 4-byte write on the copy stream), spin until the launch reports it
+        # applied, release the next -- the round trip a 250 Hz loop sees; (b) ticks released as fast as the host can write the
+        # gate, waited for at the end -- the rate at which the launch drains ticks that arrive faster than it can apply them
+        try:
+            Tl = 512
+            ml = torch.stack([ms_[k % 2][:, :3] for k in range(Tl)]).contiguous()
+            al = torch.stack([as_[k % 2] for k in range(Tl)]).contiguous()
+            pl = torch.zeros((Tl, ns, 3), dtype=torch.float64, device="cuda")
+            torch.cuda.synchronize()
+            L_ = te.lib
+            sp.live_begin(Tl, DT, ml, 3, al, 2, pl)
+            for k in range(32):
+                sp.live_release(k + 1); sp.live_wait(k + 1)
+            t0 = time.perf_counter()
+            for k in range(32, 32 + 200):
+                L_.te_pool_live_release(sp._h, k + 1)
+                L_.te_pool_live_wait(sp._h, k + 1)
+            closed = (time.perf_counter() - t0) / 200
+            t0 = time.perf_counter()
+            for k in range(232, Tl):
+                L_.te_pool_live_release(sp._h, k + 1)
+            L_.te_pool_live_wait(sp._h, Tl)
+            burst = (time.perf_counter() - t0) / (Tl - 232)
+            done = sp.live_end()
+            small["live"] = {"ticks": done, "closed_loop_us_per_tick": 1e6 * closed, "closed_loop_value": ns / closed,
+                             "released_ahead_us_per_tick": 1e6 * burst, "released_ahead_value": ns / burst, "unit": UNIT,
+                             "note": "te_pool_live_*: one resident launch, every target in registers between ticks, no launch per tick; closed loop = "
+                                     "host releases a tick, waits for the launch to report it applied (page-locked flag), releases the next; "
+                                     "released ahead = the host only writes the gate, the launch drains the ticks"}
+        except Exception as e:   # secondary figure: report, do not fail the bench
+            small["live"] = {"error": ("%s: %s" % (type(e).__name__, e))[:300]}
+            try:
+                sp.live_end()
+            except Exception:
+                pass
         # the per-tick launches again, captured once into a CUDA graph (100 ticks) and replayed: the host's launch cost per
         # tick (Python + ctypes + cudaLaunchKernel, what the loop above is bound by) leaves the measurement
         try:

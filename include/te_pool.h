@@ -85,6 +85,23 @@ int te_pool_step_dense(te_pool* p, double dt, const double* dev_meas, int meas_s
  * per tick (targets are independent: temporal blocking is exact).  For batched ingestion / catch-up / offline replay. */
 int te_pool_step_dense_ticks(te_pool* p, int n_ticks, double dt, const double* dev_meas, int meas_stride, const uint8_t* dev_action,
                              int default_action);
+/* Live launch: the 250 Hz loop over a SMALL pool (BASELINE configs[1]: 10 000 targets) without a kernel launch per tick.  One
+ * resident launch holds every target in registers (uniform-velocity / uniform-acceleration pools of at most 8 tiles per SM:
+ * 37 888 targets on a B200) and applies up to max_ticks ticks AS THEY ARE RELEASED: tick k reads dev_meas[k][size][meas_stride] and
+ * dev_action[k][size] (NULL = default_action) once te_pool_live_release / te_pool_live_push has released it, and writes every
+ * target's estimated position to dev_pos[k][size][3] (NULL = none).  Results are bit-identical to max_ticks calls of
+ * te_pool_step_dense.  te_pool_live_push copies one tick's host arrays into the rings and releases it (in order, on the pool's copy
+ * stream); te_pool_live_release(upto) releases ticks whose blocks the caller has written itself.  te_pool_live_wait(ticks) spins until
+ * `ticks` ticks have been applied (the last warp of a tick writes a page-locked flag) and returns the number applied;
+ * te_pool_live_end stops the launch (unreleased ticks are skipped), waits for it and returns the ticks applied.  While the launch
+ * runs the pool accepts no other call, and the process must not issue anything that waits for the whole device (cudaFree,
+ * cudaDeviceSynchronize, a legacy-default-stream operation): it would wait for the resident launch, which waits for the host. */
+int te_pool_live_begin(te_pool* p, int max_ticks, double dt, double* dev_meas, int meas_stride, uint8_t* dev_action, int default_action,
+                       double* dev_pos);
+int te_pool_live_release(te_pool* p, int upto);
+int te_pool_live_push(te_pool* p, const double* meas, const uint8_t* action);
+int te_pool_live_wait(te_pool* p, int ticks);
+int te_pool_live_end(te_pool* p);
 /* Same with HOST buffers: host->device copies are part of the call. */
 int te_pool_step_dense_host(te_pool* p, double dt, const double* meas, int meas_stride, const uint8_t* action,
                             int default_action);

@@ -80,6 +80,11 @@ SIGNATURES = {
     "te_pool_tick_host_async": (_i, [_p, _d, _p, _i, _p, _i, _p]),
     "te_pool_tick_host_wait": (_i, [_p, _i]),
     "te_diag_device_peaks": (_i, [_i, _p, _p]),
+    "te_pool_live_begin": (_i, [_p, _i, _d, _p, _i, _p, _i, _p]),
+    "te_pool_live_release": (_i, [_p, _i]),
+    "te_pool_live_push": (_i, [_p, _p, _p]),
+    "te_pool_live_wait": (_i, [_p, _i]),
+    "te_pool_live_end": (_i, [_p]),
     "te_group_create": (_p, [_i, _p]),
     "te_group_destroy": (None, [_p]),
     "te_group_size": (_i, [_p]),

@@ -114,11 +114,63 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) kf_step_kin_direct_kerne
                               : a.tiles + (size_t)tile * LY::TILE_DOUBLES + lane;
     const double* __restrict__ Q = a.Qtab + (size_t)cls * N * N;
     const double* __restrict__ R = a.Rtab + (size_t)cls * M * M;
-    if (a.n_ticks > 1) {
+    if (a.n_ticks > 1 || a.tick_gate) {
       if (!valid) continue;
       // a lane whose actions are all ACT_NONE still goes through load / store: cheaper than a second pass to find out
       KinSym<TYPE> ks;
       ks.load(in);
+      if (a.tick_gate) {
+        // live launch: the target stays in registers while its ticks arrive one by one -- a tick costs neither a launch nor a
+        // trip of the state through L2.  Lane 0 watches the gate (released-tick count; the measurement block of a released tick is
+        // complete), the warp applies the tick, publishes the positions and counts itself done.  Every warp owns ONE tile here
+        // (the host sizes the grid so), so no tile waits behind another one's ticks.
+        const unsigned m = __activemask();
+        const int first = __ffs(m) - 1;
+        int applied = 0;
+        for (int tick = 0; tick < a.n_ticks; ++tick) {
+          int go = 1;
+          if (lane == first) {
+            for (;;) {
+              int released, stop;
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(released) : "l"(a.tick_gate) : "memory");
+              if (released > tick) break;
+              asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(stop) : "l"(a.tick_gate + 1) : "memory");
+              if (stop) { go = 0; break; }
+              __nanosleep(40);
+            }
+          }
+          go = __shfl_sync(m, go, first);
+          if (!go) break;
+          const int at = a.action ? (int)__ldcg(a.action + (size_t)tick * a.action_tick_stride + slot) : a.default_action;
+          if (at != ACT_NONE) {
+            double meas[3] = {0.0, 0.0, 0.0};
+            if (at == ACT_UPDATE) {
+              const double* mp = a.meas + (size_t)tick * a.meas_tick_stride + (size_t)slot * a.meas_stride;
+#pragma unroll
+              for (int k = 0; k < 3; ++k) meas[k] = __ldcg(mp + k);   // (written while this kernel runs: not through the read-only path)
+            }
+            ks.tick(at, dt, meas, Q, R);
+          }
+          if (a.pos_out && a.pos_tick_stride > 0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) __stcg(a.pos_out + (size_t)tick * a.pos_tick_stride + (size_t)slot * 3 + k, ks.x[k]);
+          }
+          __threadfence();
+          __syncwarp(m);
+          if (lane == first && atomicAdd(a.tick_done + tick, 1) == a.tick_warps - 1 && a.tick_done_host) {
+            __threadfence_system();   // the last warp of the tick tells the host (one 4-byte write over PCIe per tick)
+            *reinterpret_cast<volatile int*>(a.tick_done_host) = tick + 1;
+          }
+          ++applied;
+        }
+        ks.store(out, a.packed != 0);
+        if (a.pos_out && a.pos_tick_stride == 0) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) a.pos_out[(size_t)slot * 3 + k] = ks.x[k];
+        }
+        (void)applied;
+        continue;
+      }
       for (int tick = 0; tick < a.n_ticks; ++tick) {
         const int at = a.action ? (int)a.action[(size_t)tick * a.action_tick_stride + slot] : a.default_action;
         if (at == ACT_NONE) continue;

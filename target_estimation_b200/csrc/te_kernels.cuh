@@ -52,6 +52,14 @@ struct StepArgs {
   double* dst_tiles;
   const int* dst_alive;     // [n_slots] 1 = survives
   const int* dst_pos;       // [n_slots] exclusive scan of dst_alive
+  // live launch (te_pool_live_*): a replay launch whose ticks are released one by one.  tick_gate[0] = number of ticks released so
+  // far, tick_gate[1] != 0 = stop (unreleased ticks are skipped); tick_done[k] counts the warps that have applied tick k;
+  // pos_tick_stride > 0: the positions after tick k go to pos_out + k * pos_tick_stride
+  const int* tick_gate;
+  int* tick_done;
+  int* tick_done_host;         // page-locked, device-mapped: the warp that completes tick k stores k + 1 here
+  int tick_warps;              // warps that count themselves done per tick (= tiles of the pool)
+  long long pos_tick_stride;   // doubles
   int packed;               // direct symmetric kernels: write the upper triangle of P only (pool flag lower_stale)
   int cls_c;                // class held in Qc / Rc, -1 = none
   double Rc[36];

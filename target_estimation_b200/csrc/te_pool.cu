@@ -482,6 +482,8 @@ void te_pool_destroy(te_pool* p) {
   cudaFree(p->alive); cudaFree(p->pos); cudaFree(p->srcmap); cudaFree(p->d_counters); cudaFree(p->cub_tmp);
   cudaFree(p->dQ); cudaFree(p->dR); cudaFree(p->dP0);
   p->arena.destroy();
+  cudaFree(p->live.d_gate);
+  if (p->live.h_ring) cudaFreeHost(p->live.h_ring);
   cudaFree(p->prefetch.dev);
   if (p->prefetch.done) cudaEventDestroy(p->prefetch.done);
   for (te_pool::TickSet& ts : p->tick_set) {

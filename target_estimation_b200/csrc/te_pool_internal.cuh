@@ -184,6 +184,16 @@ struct te_pool {
     bool busy = false;
   } tick_set[2];
   long long ticks_issued = 0;
+  // live launch (te_pool_live_*): one resident replay launch whose ticks are released one by one
+  struct Live {
+    bool active = false;
+    int max_ticks = 0, released = 0, stride = 0;
+    int* d_gate = nullptr;      // [0] released ticks, [1] stop, [2 ..] done counts per tick
+    size_t d_cap = 0;           // ints
+    int* h_ring = nullptr;      // page-locked: staging of the gate writes ([0 .. 255]) and the done flag the kernel writes ([256])
+    double* d_meas = nullptr;   // the caller's rings
+    uint8_t* d_action = nullptr;
+  } live;
   // a /tf message on its way to the device under the running tick (te_pool_mailbox_prefetch)
   struct Prefetch {
     char* dev = nullptr;
@@ -256,9 +266,14 @@ template <class T> T* to_dev(te_pool* p, const T* host, size_t n) {
 
 // ---- step kernel launch -----------------------------------------------------------------
 
+inline bool& live_call() {   // set by the te_pool_live_* entry points: every other call is refused while a live launch holds the pool
+  static thread_local bool f = false;
+  return f;
+}
 template <class F> int guarded(te_pool* p, F&& f) {
   try {
     if (!p) throw std::invalid_argument("null pool");
+    if (p->live.active && !live_call()) throw std::logic_error("the pool is held by a live launch: call te_pool_live_end first");
     DeviceGuard g(p->device);
     p->arena.reset();
     return f();
@@ -270,6 +285,7 @@ template <class F> int guarded(te_pool* p, F&& f) {
 template <class F> long long guarded_ll(te_pool* p, F&& f) {
   try {
     if (!p) throw std::invalid_argument("null pool");
+    if (p->live.active && !live_call()) throw std::logic_error("the pool is held by a live launch: call te_pool_live_end first");
     DeviceGuard g(p->device);
     p->arena.reset();
     return f();

@@ -262,6 +262,139 @@ int te_pool_step_dense_ticks(te_pool* p, int n_ticks, double dt, const double* d
   });
 }
 
+// ---- live launch: the 250 Hz loop over a small pool without a launch (or a trip of the state through L2) per tick ------------------
+namespace {
+struct LiveScope {
+  LiveScope() { live_call() = true; }
+  ~LiveScope() { live_call() = false; }
+};
+void live_gate_write(te_pool* p, int index, int value) {   // a 4-byte write into the gate block, on the copy stream (the pool's stream is busy)
+  te_pool::Live& lv = p->live;
+  static thread_local unsigned ring_pos = 0;
+  int* src = lv.h_ring + (ring_pos++ & 255);
+  *src = value;
+  CK(cudaMemcpyAsync(lv.d_gate + index, src, sizeof(int), cudaMemcpyHostToDevice, p->h2d_stream));
+}
+}  // namespace
+
+int te_pool_live_begin(te_pool* p, int max_ticks, double dt, double* dev_meas, int meas_stride, uint8_t* dev_action, int default_action,
+                       double* dev_pos) {
+  LiveScope ls;
+  return guarded(p, [&] {
+    te_pool::Live& lv = p->live;
+    if (lv.active) throw std::logic_error("a live launch is already running");
+    if (p->n == 0 || max_ticks <= 0) throw std::invalid_argument("empty pool or no ticks");
+    if (!(dt >= 0.0)) throw std::invalid_argument("dt must be >= 0");
+    if (!(uses_direct(p) && p->model != te::ANGULAR_VELOCITIES)) throw std::invalid_argument("live launches serve uniform-velocity / uniform-acceleration pools");
+    if (!dev_meas && (default_action == TE_ACT_UPDATE || dev_action)) throw std::invalid_argument("update ticks without measurements");
+    if (dev_meas) check_meas_stride(p, meas_stride);
+    const int n_tiles = cdiv(p->n, te::TILE);
+    if (n_tiles > p->n_sm * 8) throw std::invalid_argument("pool too large for a live launch: every warp of one resident grid holds one tile in registers");
+    if (p->grid_cap > 0) throw std::invalid_argument("live launches need the whole grid (te_pool_set_grid_cap is set)");
+    if (!p->h2d_stream) {
+      CK(cudaStreamCreateWithFlags(&p->h2d_stream, cudaStreamNonBlocking));
+      CK(cudaStreamCreateWithFlags(&p->d2h_stream, cudaStreamNonBlocking));
+    }
+    if (!lv.h_ring) CK(cudaHostAlloc((void**)&lv.h_ring, 257 * sizeof(int), cudaHostAllocMapped));
+    if ((size_t)max_ticks + 2 > lv.d_cap) {
+      cudaFree(lv.d_gate);
+      lv.d_gate = nullptr;
+      CK(cudaMalloc((void**)&lv.d_gate, ((size_t)max_ticks + 2) * sizeof(int)));
+      lv.d_cap = (size_t)max_ticks + 2;
+    }
+    CK(cudaMemsetAsync(lv.d_gate, 0, ((size_t)max_ticks + 2) * sizeof(int), p->stream));
+    lv.h_ring[256] = 0;
+    void* done_dev = nullptr;
+    CK(cudaHostGetDevicePointer(&done_dev, lv.h_ring + 256, 0));
+    te::StepArgs a = base_args(p);
+    a.dt = dt;
+    a.meas = dev_meas;
+    a.meas_stride = meas_stride;
+    a.meas_tma = 0;
+    a.action = dev_action;
+    a.default_action = default_action;
+    a.n_ticks = max_ticks;
+    a.meas_tick_stride = (long long)p->n * meas_stride;
+    a.action_tick_stride = p->n;
+    a.pos_out = dev_pos;
+    a.pos_tick_stride = dev_pos ? (long long)p->n * 3 : 0;
+    a.tick_gate = lv.d_gate;
+    a.tick_done = lv.d_gate + 2;
+    a.tick_done_host = (int*)done_dev;
+    a.tick_warps = n_tiles;
+    launch_step_multi(p, a, a.n_tiles);
+    lv.active = true;
+    lv.max_ticks = max_ticks;
+    lv.released = 0;
+    lv.stride = meas_stride;
+    lv.d_meas = dev_meas;
+    lv.d_action = dev_action;
+    return 0;
+  });
+}
+
+int te_pool_live_release(te_pool* p, int upto) {
+  LiveScope ls;
+  return guarded(p, [&] {
+    te_pool::Live& lv = p->live;
+    if (!lv.active) throw std::logic_error("no live launch");
+    if (upto > lv.max_ticks) throw std::invalid_argument("more ticks than the launch holds");
+    if (upto <= lv.released) return lv.released;
+    live_gate_write(p, 0, upto);
+    lv.released = upto;
+    return upto;
+  });
+}
+
+int te_pool_live_push(te_pool* p, const double* meas, const uint8_t* action) {
+  LiveScope ls;
+  return guarded(p, [&] {
+    te_pool::Live& lv = p->live;
+    if (!lv.active) throw std::logic_error("no live launch");
+    if (lv.released >= lv.max_ticks) throw std::invalid_argument("the launch holds no more ticks");
+    const int k = lv.released;
+    // the tick's block, then the gate, in order on the copy stream: the kernel sees a released tick only with its data complete
+    if (meas && lv.d_meas) CK(cudaMemcpyAsync(lv.d_meas + (size_t)k * p->n * lv.stride, meas, (size_t)p->n * lv.stride * 8, cudaMemcpyHostToDevice, p->h2d_stream));
+    if (action && lv.d_action) CK(cudaMemcpyAsync(lv.d_action + (size_t)k * p->n, action, (size_t)p->n, cudaMemcpyHostToDevice, p->h2d_stream));
+    live_gate_write(p, 0, k + 1);
+    lv.released = k + 1;
+    return k + 1;
+  });
+}
+
+int te_pool_live_wait(te_pool* p, int ticks) {
+  LiveScope ls;
+  return guarded(p, [&] {
+    te_pool::Live& lv = p->live;
+    if (!lv.active) throw std::logic_error("no live launch");
+    if (ticks > lv.released) throw std::invalid_argument("waiting for a tick that has not been released");
+    volatile int* done = lv.h_ring + 256;
+    const auto t0 = std::chrono::steady_clock::now();
+    long long spins = 0;
+    while (*done < ticks) {
+      if ((++spins & 0xFFFF) == 0) {
+        if (cudaStreamQuery(p->stream) != cudaErrorNotReady) break;   // the launch ended (an error, or all ticks done)
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) throw std::runtime_error("live tick timed out");
+      }
+    }
+    return (int)*done;
+  });
+}
+
+int te_pool_live_end(te_pool* p) {
+  LiveScope ls;
+  return guarded(p, [&] {
+    te_pool::Live& lv = p->live;
+    if (!lv.active) return 0;
+    live_gate_write(p, 1, 1);   // stop: ticks not released by now are skipped
+    CK(cudaStreamSynchronize(p->h2d_stream));
+    const cudaError_t e = cudaStreamSynchronize(p->stream);
+    lv.active = false;
+    if (e != cudaSuccess) throw CudaError(std::string("live launch: ") + cudaGetErrorString(e));
+    return (int)lv.h_ring[256];
+  });
+}
+
 int te_pool_step_dense_host(te_pool* p, double dt, const double* meas, int meas_stride, const uint8_t* action, int default_action) {
   return guarded(p, [&] {
     if (p->n == 0) return 0;

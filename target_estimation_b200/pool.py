@@ -144,6 +144,27 @@ class TargetPool:
         check(lib.te_pool_step_dense_ticks(self._h, int(n_ticks), float(dt), _dev_ptr(dev_meas), int(meas_stride), _dev_ptr(dev_action),
                                            int(default_action)))
 
+    # -- live launch: ticks released one by one into one resident launch (te_pool_live_*) --
+    def live_begin(self, max_ticks, dt, dev_meas=None, meas_stride=7, dev_action=None, default_action=ACT_UPDATE, dev_pos=None):
+        self._live_keep = (dev_meas, dev_action, dev_pos)
+        check(lib.te_pool_live_begin(self._h, int(max_ticks), dt, _dev_ptr(dev_meas), meas_stride, _dev_ptr(dev_action), default_action, _dev_ptr(dev_pos)))
+
+    def live_release(self, upto):
+        return check(lib.te_pool_live_release(self._h, int(upto)))
+
+    def live_push(self, meas, action=None):
+        meas = _np(meas, np.float64); action = _np(action, np.uint8) if action is not None else None
+        self._live_host = (meas, action)
+        return check(lib.te_pool_live_push(self._h, _ptr(meas), _ptr(action)))
+
+    def live_wait(self, ticks):
+        return check(lib.te_pool_live_wait(self._h, int(ticks)))
+
+    def live_end(self):
+        n = check(lib.te_pool_live_end(self._h))
+        self._live_keep = None
+        return n
+
     def step_dense_host(self, dt, meas=None, action=None, default_action=ACT_UPDATE, meas_ptr=None, meas_stride=7, action_ptr=None):
         """Host buffers (numpy) or raw host pointers (pinned torch tensors: pass data_ptr())."""
         if meas is not None:
