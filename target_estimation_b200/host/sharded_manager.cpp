@@ -217,23 +217,45 @@ long long ShardedTargetManager::updateBatch(long long n, const unsigned* ids, do
   const unsigned G = (unsigned)shard_.size();
   const FastMod owner_of(G);
   if (G == 1) return shard_[0]->updateBatch(n, ids, dt, meas, action);
-  std::atomic<long long> applied{0};
-  forEachShard([&](int r) {
+  // Routing = a parallel stable partition of the batch by owner, every access sequential.  Worker t takes the t-th contiguous chunk
+  // of the records: (1) it counts the owners in its chunk; the prefix sums give chunk t a place in every shard's staging behind the
+  // chunks before it; (2) it streams its chunk once more and appends every record to its owner's staging (G write streams per
+  // worker).  Inside a shard the records keep the caller's order (chunks are ordered, and so is each chunk), so the records of one
+  // id stay in sequence.  (3) every shard runs its batched call on its own staging.  (A pass per shard over the whole batch, each
+  // picking its own records out, gathered 56-byte records at a stride of G records: 300 ms for 33 M records on 8 shards.)
+  std::vector<size_t> count((size_t)G * G, 0);   // [chunk t][owner r]
+  auto chunk_lo = [&](unsigned t) { return (long long)((__int128)n * t / G); };
+  forEachShard([&](int t) {
+    size_t* c = &count[(size_t)t * G];
+    for (long long k = chunk_lo((unsigned)t), e = chunk_lo((unsigned)t + 1); k < e; ++k) ++c[owner_of(ids[k])];
+  });
+  std::vector<size_t> offset((size_t)G * G, 0), total(G, 0);
+  for (unsigned r = 0; r < G; ++r)
+    for (unsigned t = 0; t < G; ++t) {
+      offset[(size_t)t * G + r] = total[r];
+      total[r] += count[(size_t)t * G + r];
+    }
+  forEachShard([&](int r) {   // (each worker sizes its own shard's staging: page-locking is the slow part and runs in parallel)
     Stage& st = stage_[(size_t)r];
-    size_t cnt = 0;
-    for (long long k = 0; k < n; ++k) cnt += (owner_of(ids[k]) == (unsigned)r);
-    if (cnt == 0) return;
-    st.ids.resize(cnt);
-    stageReserve(st.meas, st.action, st.cap, cnt);
-    size_t j = 0;
-    for (long long k = 0; k < n; ++k) {   // the caller's order is kept: records of one id stay in sequence
-      if (owner_of(ids[k]) != (unsigned)r) continue;
+    st.ids.resize(total[(size_t)r]);
+    stageReserve(st.meas, st.action, st.cap, total[(size_t)r]);
+  });
+  forEachShard([&](int t) {
+    std::vector<size_t> at(offset.begin() + (long)t * G, offset.begin() + (long)(t + 1) * G);
+    for (long long k = chunk_lo((unsigned)t), e = chunk_lo((unsigned)t + 1); k < e; ++k) {
+      const unsigned r = owner_of(ids[k]);
+      Stage& st = stage_[r];
+      const size_t j = at[r]++;
       st.ids[j] = ids[k];
       if (meas) std::memcpy(st.meas + 7 * j, meas + 7 * (size_t)k, 56);
       st.action[j] = action ? action[k] : (unsigned char)TE_ACT_UPDATE;
-      ++j;
     }
-    applied += shard_[(size_t)r]->updateBatch((long long)cnt, st.ids.data(), dt, meas ? st.meas : nullptr, st.action);
+  });
+  std::atomic<long long> applied{0};
+  forEachShard([&](int r) {
+    Stage& st = stage_[(size_t)r];
+    if (total[(size_t)r] == 0) return;
+    applied += shard_[(size_t)r]->updateBatch((long long)total[(size_t)r], st.ids.data(), dt, meas ? st.meas : nullptr, st.action);
   });
   return applied.load();
 }
