@@ -21,6 +21,12 @@ def _cuda_available():
 
 
 def pytest_collection_modifyitems(config, items):
+    # no test may hang a GPU box: a per-test wall-clock limit (pytest-timeout; the slowest test -- 4096 x 2000 against two oracles --
+    # takes under a minute).  A thread-method timeout ends the whole process, and with it any resident kernel.
+    if config.pluginmanager.hasplugin("timeout"):
+        for it in items:
+            if "gpu" in it.keywords and it.get_closest_marker("timeout") is None:
+                it.add_marker(pytest.mark.timeout(420, method="thread"))
     # -m gpu on a box without a GPU must fail loudly, not skip: only auto-skip when no -m was given
     if config.getoption("-m"):
         return
