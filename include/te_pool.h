@@ -95,7 +95,8 @@ int te_pool_step_dense_ticks(te_pool* p, int n_ticks, double dt, const double* d
  * `ticks` ticks have been applied (the last warp of a tick writes a page-locked flag) and returns the number applied;
  * te_pool_live_end stops the launch (unreleased ticks are skipped), waits for it and returns the ticks applied.  While the launch
  * runs the pool accepts no other call, and the process must not issue anything that waits for the whole device (cudaFree,
- * cudaDeviceSynchronize, a legacy-default-stream operation): it would wait for the resident launch, which waits for the host. */
+ * cudaDeviceSynchronize, cudaStreamCreate -- measured --, a legacy-default-stream operation): it would wait for the resident
+ * launch, which waits for the host.  te_pool_destroy stops a launch that is still resident. */
 int te_pool_live_begin(te_pool* p, int max_ticks, double dt, double* dev_meas, int meas_stride, uint8_t* dev_action, int default_action,
                        double* dev_pos);
 int te_pool_live_release(te_pool* p, int upto);

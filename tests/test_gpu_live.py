@@ -33,14 +33,14 @@ def test_live_ticks_equal_sequential_ticks(model, n, stride):
     d_meas = torch.zeros((ticks + 5, n, stride), dtype=torch.float64, device="cuda")
     d_act = torch.zeros((ticks + 5, n), dtype=torch.uint8, device="cuda")
     d_pos = torch.zeros((ticks + 5, n, 3), dtype=torch.float64, device="cuda")
+    side = torch.cuda.Stream()          # (created BEFORE the launch: creating a stream waits for the device)
     torch.cuda.synchronize()
     live.live_begin(ticks + 5, DT, d_meas, stride, d_act, te.ACT_UPDATE, d_pos)
     with pytest.raises(te.TeError):
         live.step_dense(DT, d_meas[0], stride, d_act[0])          # the pool is held by the live launch
-    side = torch.cuda.Stream()
     snaps = {}
-    # (nothing that synchronises the whole device may run while the launch is resident -- a cudaFree would wait for it forever --
-    #  so the sequential pool takes its ticks afterwards)
+    # (nothing that synchronises the whole device may run while the launch is resident -- a cudaFree or a stream creation would
+    #  wait for it forever -- so the sequential pool takes its ticks afterwards)
     for k in range(ticks):
         assert live.live_push(np.ascontiguousarray(meas[k][:, :stride]), action[k]) == k + 1
         assert live.live_wait(k + 1) >= k + 1
