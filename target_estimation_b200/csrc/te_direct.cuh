@@ -127,16 +127,36 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) kf_step_kin_direct_kerne
         const unsigned m = __activemask();
         const int first = __ffs(m) - 1;
         int applied = 0;
+        int pub_released = 0, pub_stop = 0;
         for (int tick = 0; tick < a.n_ticks; ++tick) {
           int go = 1;
           if (lane == first) {
+            // Two sources open the gate: the copy engine (a pushed tick: its block and then the count travel in order on the copy
+            // stream) and the host itself (a released tick: one store to a page-locked word, no CUDA call).  The warp of tile 0
+            // reads both -- the host word across PCIe -- and republishes their maximum in device memory for everybody else.
             for (;;) {
               int released, stop;
-              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(released) : "l"(a.tick_gate) : "memory");
+              if (gw == 0) {
+                int hr, hs, dr, ds;
+                asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(hr) : "l"(a.tick_gate_host) : "memory");
+                asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(hs) : "l"(a.tick_gate_host + 1) : "memory");
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(dr) : "l"(a.tick_gate) : "memory");
+                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(ds) : "l"(a.tick_gate + 1) : "memory");
+                released = hr > dr ? hr : dr;
+                stop = hs | ds;
+                if (released > pub_released || stop != pub_stop) {
+                  if (stop != pub_stop) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(a.tick_gate_eff + 1), "r"(stop) : "memory");
+                  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.tick_gate_eff), "r"(released) : "memory");
+                  pub_released = released;
+                  pub_stop = stop;
+                }
+              } else {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(released) : "l"(a.tick_gate_eff) : "memory");
+                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(stop) : "l"(a.tick_gate_eff + 1) : "memory");
+              }
               if (released > tick) break;
-              asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(stop) : "l"(a.tick_gate + 1) : "memory");
               if (stop) { go = 0; break; }
-              __nanosleep(40);
+              __nanosleep(gw == 0 ? 20 : 40);
             }
           }
           go = __shfl_sync(m, go, first);

@@ -55,7 +55,9 @@ struct StepArgs {
   // live launch (te_pool_live_*): a replay launch whose ticks are released one by one.  tick_gate[0] = number of ticks released so
   // far, tick_gate[1] != 0 = stop (unreleased ticks are skipped); tick_done[k] counts the warps that have applied tick k;
   // pos_tick_stride > 0: the positions after tick k go to pos_out + k * pos_tick_stride
-  const int* tick_gate;
+  const int* tick_gate;        // device words written by the copy engine (te_pool_live_push): [0] released ticks, [1] stop
+  const int* tick_gate_host;   // page-locked, device-mapped words written by the host (te_pool_live_release / _end): [0] released, [1] stop
+  int* tick_gate_eff;          // device words every warp watches: [0] = max of the two sources, [1] stop; kept by the warp of tile 0
   int* tick_done;
   int* tick_done_host;         // page-locked, device-mapped: the warp that completes tick k stores k + 1 here
   int tick_warps;              // warps that count themselves done per tick (= tiles of the pool)

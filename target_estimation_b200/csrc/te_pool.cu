@@ -470,10 +470,8 @@ void te_pool_destroy(te_pool* p) {
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(p->device);
-  if (p->live.active && p->live.d_gate && p->h2d_stream) {   // a resident live launch waits for the host: tell it to stop
-    static const int one = 1;
-    cudaMemcpyAsync(p->live.d_gate + 1, &one, sizeof(int), cudaMemcpyHostToDevice, p->h2d_stream);
-    cudaStreamSynchronize(p->h2d_stream);
+  if (p->live.active && p->live.h_ring) {   // a resident live launch waits for the host: tell it to stop
+    __atomic_store_n(p->live.h_ring + 258, 1, __ATOMIC_RELEASE);
     p->live.active = false;
   }
   cudaStreamSynchronize(p->stream);

@@ -188,9 +188,9 @@ struct te_pool {
   struct Live {
     bool active = false;
     int max_ticks = 0, released = 0, stride = 0;
-    int* d_gate = nullptr;      // [0] released ticks, [1] stop, [2 ..] done counts per tick
+    int* d_gate = nullptr;      // [0] released ticks (copy engine), [1] stop, [2] / [3] the gate every warp watches, [4 ..] done counts per tick
     size_t d_cap = 0;           // ints
-    int* h_ring = nullptr;      // page-locked: staging of the gate writes ([0 .. 255]) and the done flag the kernel writes ([256])
+    int* h_ring = nullptr;      // page-locked, mapped: staging of the pushed gate writes [0 .. 255], done flag (kernel writes) [256], host gate [257], host stop [258]
     double* d_meas = nullptr;   // the caller's rings
     uint8_t* d_action = nullptr;
   } live;

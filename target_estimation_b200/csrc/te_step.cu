@@ -295,15 +295,15 @@ int te_pool_live_begin(te_pool* p, int max_ticks, double dt, double* dev_meas, i
       CK(cudaStreamCreateWithFlags(&p->h2d_stream, cudaStreamNonBlocking));
       CK(cudaStreamCreateWithFlags(&p->d2h_stream, cudaStreamNonBlocking));
     }
-    if (!lv.h_ring) CK(cudaHostAlloc((void**)&lv.h_ring, 257 * sizeof(int), cudaHostAllocMapped));
-    if ((size_t)max_ticks + 2 > lv.d_cap) {
+    if (!lv.h_ring) CK(cudaHostAlloc((void**)&lv.h_ring, 260 * sizeof(int), cudaHostAllocMapped));
+    if ((size_t)max_ticks + 4 > lv.d_cap) {
       cudaFree(lv.d_gate);
       lv.d_gate = nullptr;
-      CK(cudaMalloc((void**)&lv.d_gate, ((size_t)max_ticks + 2) * sizeof(int)));
-      lv.d_cap = (size_t)max_ticks + 2;
+      CK(cudaMalloc((void**)&lv.d_gate, ((size_t)max_ticks + 4) * sizeof(int)));
+      lv.d_cap = (size_t)max_ticks + 4;
     }
-    CK(cudaMemsetAsync(lv.d_gate, 0, ((size_t)max_ticks + 2) * sizeof(int), p->stream));
-    lv.h_ring[256] = 0;
+    CK(cudaMemsetAsync(lv.d_gate, 0, ((size_t)max_ticks + 4) * sizeof(int), p->stream));
+    lv.h_ring[256] = lv.h_ring[257] = lv.h_ring[258] = 0;
     void* done_dev = nullptr;
     CK(cudaHostGetDevicePointer(&done_dev, lv.h_ring + 256, 0));
     te::StepArgs a = base_args(p);
@@ -319,8 +319,10 @@ int te_pool_live_begin(te_pool* p, int max_ticks, double dt, double* dev_meas, i
     a.pos_out = dev_pos;
     a.pos_tick_stride = dev_pos ? (long long)p->n * 3 : 0;
     a.tick_gate = lv.d_gate;
-    a.tick_done = lv.d_gate + 2;
+    a.tick_gate_eff = lv.d_gate + 2;
+    a.tick_done = lv.d_gate + 4;
     a.tick_done_host = (int*)done_dev;
+    a.tick_gate_host = (int*)done_dev + 1;
     a.tick_warps = n_tiles;
     launch_step_multi(p, a, a.n_tiles);
     lv.active = true;
@@ -340,7 +342,9 @@ int te_pool_live_release(te_pool* p, int upto) {
     if (!lv.active) throw std::logic_error("no live launch");
     if (upto > lv.max_ticks) throw std::invalid_argument("more ticks than the launch holds");
     if (upto <= lv.released) return lv.released;
-    live_gate_write(p, 0, upto);
+    // the caller's blocks are complete (its contract): one store to the page-locked gate word, no CUDA call; the launch's
+    // gate-keeping warp reads it across PCIe
+    __atomic_store_n(lv.h_ring + 257, upto, __ATOMIC_RELEASE);
     lv.released = upto;
     return upto;
   });
@@ -386,8 +390,8 @@ int te_pool_live_end(te_pool* p) {
   return guarded(p, [&] {
     te_pool::Live& lv = p->live;
     if (!lv.active) return 0;
-    live_gate_write(p, 1, 1);   // stop: ticks not released by now are skipped
-    CK(cudaStreamSynchronize(p->h2d_stream));
+    CK(cudaStreamSynchronize(p->h2d_stream));               // pushed ticks have reached the device
+    __atomic_store_n(lv.h_ring + 258, 1, __ATOMIC_RELEASE);   // stop: ticks not released by now are skipped
     const cudaError_t e = cudaStreamSynchronize(p->stream);
     lv.active = false;
     if (e != cudaSuccess) throw CudaError(std::string("live launch: ") + cudaGetErrorString(e));
