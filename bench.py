@@ -614,16 +614,25 @@ def main():
                 L_.te_pool_live_wait(sp._h, k + 1)
             closed = (time.perf_counter() - t0) / 200
             t0 = time.perf_counter()
-            for k in range(232, Tl):
-                L_.te_pool_live_release(sp._h, k + 1)
+            L_.te_pool_live_release(sp._h, Tl)           # every remaining tick at once: the rate at which the launch drains its ring
             L_.te_pool_live_wait(sp._h, Tl)
             burst = (time.perf_counter() - t0) / (Tl - 232)
             done = sp.live_end()
+            # the same closed loop with one launch per tick: launch, wait for it, launch the next
+            for k in range(20):
+                sp.step_dense(DT, ms_[k % 2], stride, as_[k % 2]); sp.sync()
+            t0 = time.perf_counter()
+            for k in range(200):
+                sp.step_dense(DT, ms_[k % 2], stride, as_[k % 2]); sp.sync()
+            launch_loop = (time.perf_counter() - t0) / 200
             small["live"] = {"ticks": done, "closed_loop_us_per_tick": 1e6 * closed, "closed_loop_value": ns / closed,
-                             "released_ahead_us_per_tick": 1e6 * burst, "released_ahead_value": ns / burst, "unit": UNIT,
-                             "note": "te_pool_live_*: one resident launch, every target in registers between ticks, no launch per tick; closed loop = "
-                                     "host releases a tick, waits for the launch to report it applied (page-locked flag), releases the next; "
-                                     "released ahead = the host only writes the gate, the launch drains the ticks"}
+                             "closed_loop_one_launch_per_tick_us": 1e6 * launch_loop,
+                             "drain_us_per_tick": 1e6 * burst, "drain_value": ns / burst, "unit": UNIT,
+                             "note": "te_pool_live_*: one resident launch, every target in registers between ticks, ticks released by a store to a "
+                                     "page-locked word (no CUDA call per tick); closed loop = the host releases a tick, spins until the launch reports "
+                                     "it applied, releases the next (closed_loop_one_launch_per_tick_us: te_pool_step_dense + te_pool_sync per tick, "
+                                     "same Python loop); drain = all remaining ticks released at once: the launch's own rate per tick (gate, "
+                                     "measurement block, tick, positions, completion count)"}
         except Exception as e:   # secondary figure: report, do not fail the bench
             small["live"] = {"error": ("%s: %s" % (type(e).__name__, e))[:300]}
             try:

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) kf_step_kin_direct_kerne
               }
               if (released > tick) break;
               if (stop) { go = 0; break; }
-              __nanosleep(gw == 0 ? 20 : 40);
+              __nanosleep(20);
             }
           }
           go = __shfl_sync(m, go, first);
@@ -175,11 +175,16 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) kf_step_kin_direct_kerne
 #pragma unroll
             for (int k = 0; k < 3; ++k) __stcg(a.pos_out + (size_t)tick * a.pos_tick_stride + (size_t)slot * 3 + k, ks.x[k]);
           }
-          __threadfence();
+          // completion count: the warp barrier orders every lane's position stores before lane `first`'s acq_rel increment
+          // (release patterns are cumulative), so whoever sees the full count -- the last warp -- has every warp's stores behind it
           __syncwarp(m);
-          if (lane == first && atomicAdd(a.tick_done + tick, 1) == a.tick_warps - 1 && a.tick_done_host) {
-            __threadfence_system();   // the last warp of the tick tells the host (one 4-byte write over PCIe per tick)
-            *reinterpret_cast<volatile int*>(a.tick_done_host) = tick + 1;
+          if (lane == first) {
+            int before;
+            asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(before) : "l"(a.tick_done + tick) : "memory");
+            if (before == a.tick_warps - 1 && a.tick_done_host) {
+              __threadfence_system();   // the last warp of the tick tells the host (one 4-byte write over PCIe per tick)
+              *reinterpret_cast<volatile int*>(a.tick_done_host) = tick + 1;
+            }
           }
           ++applied;
         }
