@@ -126,74 +126,89 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) kf_step_kin_direct_kerne
         // (the host sizes the grid so), so no tile waits behind another one's ticks.
         const unsigned m = __activemask();
         const int first = __ffs(m) - 1;
-        int applied = 0;
         int pub_released = 0, pub_stop = 0;
-        for (int tick = 0; tick < a.n_ticks; ++tick) {
-          int go = 1;
-          if (lane == first) {
-            // Two sources open the gate: the copy engine (a pushed tick: its block and then the count travel in order on the copy
-            // stream) and the host itself (a released tick: one store to a page-locked word, no CUDA call).  The warp of tile 0
-            // reads both -- the host word across PCIe -- and republishes their maximum in device memory for everybody else.
-            for (;;) {
-              int released, stop;
-              if (gw == 0) {
-                int hr, hs, dr, ds;
-                asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(hr) : "l"(a.tick_gate_host) : "memory");
-                asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(hs) : "l"(a.tick_gate_host + 1) : "memory");
-                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(dr) : "l"(a.tick_gate) : "memory");
-                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(ds) : "l"(a.tick_gate + 1) : "memory");
-                released = hr > dr ? hr : dr;
-                stop = hs | ds;
-                if (released > pub_released || stop != pub_stop) {
-                  if (stop != pub_stop) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(a.tick_gate_eff + 1), "r"(stop) : "memory");
-                  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.tick_gate_eff), "r"(released) : "memory");
-                  pub_released = released;
-                  pub_stop = stop;
-                }
-              } else {
-                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(released) : "l"(a.tick_gate_eff) : "memory");
-                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(stop) : "l"(a.tick_gate_eff + 1) : "memory");
-              }
-              if (released > tick) break;
-              if (stop) { go = 0; break; }
-              __nanosleep(20);
-            }
+        int known = 0;          // lane `first`: ticks known to be released (a gate read shows all of them: a burst costs one read)
+        int pending = 0;        // lane `first`: the completion count of the previous tick is still in flight
+        int before = 0;
+        auto resolve = [&]() {  // lane `first`: the previous tick's count has come back -- the last warp of a tick tells the host
+          if (pending && before == a.tick_warps - 1 && a.tick_done_host) {
+            __threadfence_system();   // (one 4-byte write over PCIe per tick)
+            *reinterpret_cast<volatile int*>(a.tick_done_host) = pending;
           }
-          go = __shfl_sync(m, go, first);
-          if (!go) break;
-          const int at = a.action ? (int)__ldcg(a.action + (size_t)tick * a.action_tick_stride + slot) : a.default_action;
-          if (at != ACT_NONE) {
-            double meas[3] = {0.0, 0.0, 0.0};
+          pending = 0;
+        };
+        for (int tick = 0; tick < a.n_ticks; ++tick) {
+          int at = ACT_NONE;
+          double meas[3] = {0.0, 0.0, 0.0};
+          auto fetch = [&]() {   // the tick's inputs (written while this kernel runs: not through the read-only path)
+            at = a.action ? (int)__ldcg(a.action + (size_t)tick * a.action_tick_stride + slot) : a.default_action;
             if (at == ACT_UPDATE) {
               const double* mp = a.meas + (size_t)tick * a.meas_tick_stride + (size_t)slot * a.meas_stride;
 #pragma unroll
-              for (int k = 0; k < 3; ++k) meas[k] = __ldcg(mp + k);   // (written while this kernel runs: not through the read-only path)
+              for (int k = 0; k < 3; ++k) meas[k] = __ldcg(mp + k);
             }
-            ks.tick(at, dt, meas, Q, R);
+          };
+          // a tick already known to be released: its inputs are requested before the previous tick's count is waited for, so the
+          // two L2 round trips overlap
+          const int ahead = __shfl_sync(m, known > tick ? 1 : 0, first);
+          if (ahead) fetch();
+          if (lane == first) resolve();
+          if (!ahead) {
+            int go = 1;
+            if (lane == first) {
+              // Two sources open the gate: the copy engine (a pushed tick: its block and then the count travel in order on the copy
+              // stream) and the host itself (a released tick: one store to a page-locked word, no CUDA call).  The warp of tile 0
+              // reads both -- the host word across PCIe -- and republishes their maximum in device memory for everybody else.
+              for (;;) {
+                int released, stop;
+                if (gw == 0) {
+                  int hr, hs, dr, ds;
+                  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(hr) : "l"(a.tick_gate_host) : "memory");
+                  asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(hs) : "l"(a.tick_gate_host + 1) : "memory");
+                  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(dr) : "l"(a.tick_gate) : "memory");
+                  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(ds) : "l"(a.tick_gate + 1) : "memory");
+                  released = hr > dr ? hr : dr;
+                  stop = hs | ds;
+                  if (released > pub_released || stop != pub_stop) {
+                    if (stop != pub_stop) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(a.tick_gate_eff + 1), "r"(stop) : "memory");
+                    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.tick_gate_eff), "r"(released) : "memory");
+                    pub_released = released;
+                    pub_stop = stop;
+                  }
+                } else {
+                  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(released) : "l"(a.tick_gate_eff) : "memory");
+                  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(stop) : "l"(a.tick_gate_eff + 1) : "memory");
+                }
+                known = released;
+                if (released > tick) break;
+                if (stop) { go = 0; break; }
+                __nanosleep(20);
+              }
+            }
+            go = __shfl_sync(m, go, first);
+            if (!go) break;
+            fetch();
           }
+          if (at != ACT_NONE) ks.tick(at, dt, meas, Q, R);
           if (a.pos_out && a.pos_tick_stride > 0) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) __stcg(a.pos_out + (size_t)tick * a.pos_tick_stride + (size_t)slot * 3 + k, ks.x[k]);
           }
           // completion count: the warp barrier orders every lane's position stores before lane `first`'s acq_rel increment
-          // (release patterns are cumulative), so whoever sees the full count -- the last warp -- has every warp's stores behind it
+          // (release patterns are cumulative), so whoever sees the full count -- the last warp -- has every warp's stores behind it.
+          // The count comes back under the next tick's input loads (resolve above).
           __syncwarp(m);
           if (lane == first) {
-            int before;
             asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(before) : "l"(a.tick_done + tick) : "memory");
-            if (before == a.tick_warps - 1 && a.tick_done_host) {
-              __threadfence_system();   // the last warp of the tick tells the host (one 4-byte write over PCIe per tick)
-              *reinterpret_cast<volatile int*>(a.tick_done_host) = tick + 1;
-            }
+            pending = tick + 1;
           }
-          ++applied;
         }
+        if (lane == first) resolve();
         ks.store(out, a.packed != 0);
         if (a.pos_out && a.pos_tick_stride == 0) {
 #pragma unroll
           for (int k = 0; k < 3; ++k) a.pos_out[(size_t)slot * 3 + k] = ks.x[k];
         }
-        (void)applied;
         continue;
       }
       for (int tick = 0; tick < a.n_ticks; ++tick) {
