@@ -397,7 +397,8 @@ class ShardedTargetManager : public TargetManager {
   template <class F> void forEachShard(F&& f);   // f(r) on shard r's worker thread, all shards at once; rethrows the first error
   std::vector<std::unique_ptr<TargetManager>> shard_;
   std::vector<int> devices_;
-  std::unique_ptr<ShardWorkers> workers_;
+  std::unique_ptr<ShardWorkers> workers_;   // one thread per shard: the shards' batched calls
+  std::unique_ptr<ShardWorkers> routers_;   // the routing passes of a batch: as many threads as the host offers (at most 16)
   te_group* group_ = nullptr;
   double gather_ms_ = -1.0;
   struct Stage {   // per shard, page-locked, grow-only

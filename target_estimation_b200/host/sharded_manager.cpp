@@ -31,6 +31,7 @@ class ShardWorkers {
     cv_.notify_all();
     for (auto& t : th_) t.join();
   }
+  int size() const { return n_; }
   void run(const std::function<void(int)>& f) {
     {
       std::lock_guard<std::mutex> lg(m_);
@@ -126,11 +127,15 @@ ShardedTargetManager::ShardedTargetManager(const std::string& file, int n_shards
   }
   stage_.resize((size_t)n_shards);
   workers_.reset(new ShardWorkers(n_shards));
+  const unsigned hw = std::thread::hardware_concurrency();
+  const int n_route = (int)std::max<unsigned>((unsigned)n_shards, std::min<unsigned>(hw ? hw : 1u, 16u));
+  routers_.reset(new ShardWorkers(n_route));
   quiet = true;
 }
 
 ShardedTargetManager::~ShardedTargetManager() {
   workers_.reset();
+  routers_.reset();
   if (group_) te_group_destroy(group_);
   for (Stage& s : stage_) {
     if (s.meas) { te_host_unregister(s.meas); std::free(s.meas); }
@@ -217,21 +222,24 @@ long long ShardedTargetManager::updateBatch(long long n, const unsigned* ids, do
   const unsigned G = (unsigned)shard_.size();
   const FastMod owner_of(G);
   if (G == 1) return shard_[0]->updateBatch(n, ids, dt, meas, action);
-  // Routing = a parallel stable partition of the batch by owner, every access sequential.  Worker t takes the t-th contiguous chunk
-  // of the records: (1) it counts the owners in its chunk; the prefix sums give chunk t a place in every shard's staging behind the
+  // Routing = a parallel stable partition of the batch by owner, every access sequential.  Routing thread t (there are as many as
+  // the host offers, at most 16, at least G) takes the t-th contiguous chunk of the records: (1) it counts the owners in its chunk; the prefix sums give chunk t a place in every shard's staging behind the
   // chunks before it; (2) it streams its chunk once more and appends every record to its owner's staging (G write streams per
   // worker).  Inside a shard the records keep the caller's order (chunks are ordered, and so is each chunk), so the records of one
   // id stay in sequence.  (3) every shard runs its batched call on its own staging.  (A pass per shard over the whole batch, each
   // picking its own records out, gathered 56-byte records at a stride of G records: 300 ms for 33 M records on 8 shards.)
-  std::vector<size_t> count((size_t)G * G, 0);   // [chunk t][owner r]
-  auto chunk_lo = [&](unsigned t) { return (long long)((__int128)n * t / G); };
-  forEachShard([&](int t) {
-    size_t* c = &count[(size_t)t * G];
+  const unsigned T = (unsigned)routers_->size();   // routing threads (>= G)
+  std::vector<size_t> count((size_t)T * G, 0);     // [chunk t][owner r]
+  auto chunk_lo = [&](unsigned t) { return (long long)((__int128)n * t / T); };
+  const std::function<void(int)> count_pass = [&](int t) {
+    std::vector<size_t> c(G, 0);   // (local: neighbouring rows of `count` share cache lines)
     for (long long k = chunk_lo((unsigned)t), e = chunk_lo((unsigned)t + 1); k < e; ++k) ++c[owner_of(ids[k])];
-  });
-  std::vector<size_t> offset((size_t)G * G, 0), total(G, 0);
+    std::copy(c.begin(), c.end(), count.begin() + (long)t * G);
+  };
+  routers_->run(count_pass);
+  std::vector<size_t> offset((size_t)T * G, 0), total(G, 0);
   for (unsigned r = 0; r < G; ++r)
-    for (unsigned t = 0; t < G; ++t) {
+    for (unsigned t = 0; t < T; ++t) {
       offset[(size_t)t * G + r] = total[r];
       total[r] += count[(size_t)t * G + r];
     }
@@ -240,7 +248,7 @@ long long ShardedTargetManager::updateBatch(long long n, const unsigned* ids, do
     st.ids.resize(total[(size_t)r]);
     stageReserve(st.meas, st.action, st.cap, total[(size_t)r]);
   });
-  forEachShard([&](int t) {
+  const std::function<void(int)> scatter_pass = [&](int t) {
     std::vector<size_t> at(offset.begin() + (long)t * G, offset.begin() + (long)(t + 1) * G);
     for (long long k = chunk_lo((unsigned)t), e = chunk_lo((unsigned)t + 1); k < e; ++k) {
       const unsigned r = owner_of(ids[k]);
@@ -250,7 +258,8 @@ long long ShardedTargetManager::updateBatch(long long n, const unsigned* ids, do
       if (meas) std::memcpy(st.meas + 7 * j, meas + 7 * (size_t)k, 56);
       st.action[j] = action ? action[k] : (unsigned char)TE_ACT_UPDATE;
     }
-  });
+  };
+  routers_->run(scatter_pass);
   std::atomic<long long> applied{0};
   forEachShard([&](int r) {
     Stage& st = stage_[(size_t)r];
