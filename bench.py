@@ -38,7 +38,7 @@ METRIC = "kf_predict_update_target_steps_per_sec"
 UNIT = "target-steps/s"
 # dominant kernel per model with the default variant (te_pool.cu launch_step)
 KERNEL_NAME = {"uniform_velocity": "te::kf_step_kin_direct_kernel", "uniform_acceleration": "te::kf_step_kin_direct_kernel",
-               "angular_velocities": "te::kf_step_av_direct_kernel", "angular_rates": "te::kf_step_split_kernel"}
+               "angular_velocities": "te::kf_step_av_stream_kernel", "angular_rates": "te::kf_step_split_kernel"}
 MODEL_SHORT = {"uniform_velocity": "UV", "uniform_acceleration": "UA", "angular_velocities": "AV", "angular_rates": "AR"}
 MODEL_DIMS = {"uniform_velocity": (6, 3), "uniform_acceleration": (9, 3), "angular_velocities": (12, 6), "angular_rates": (18, 6)}   # (n, m)
 
@@ -413,26 +413,26 @@ def main():
     achieved_layout = layout_bytes / (ms / K * 1e-3) / 1e9
 
     # ---- e2e: host buffers through the C-ABI ---------------------------------------------------------
-    # Headline form: the pipelined host tick (te_pool_tick_host_async + te_pool_tick_host_wait(1): the copies of tick k + 1 run under
-    # the kernels and the read-back of tick k) with the measurement block the model reads -- [n][3] positions for the linear models
+    # Headline form: the pipelined host tick (te_pool_tick_host_async + te_pool_tick_host_wait(2): the copies of tick k + 1 run under
+    # the kernels of tick k and the read-back of tick k - 1) with the measurement block the model reads -- [n][3] positions for the linear models
     # (UV / UA use x y z of the pose only), [n][7] poses for the angular ones.  Every step moves its inputs from pinned host memory
     # and every target's estimated position back to pinned host memory inside the timed region.  The synchronous call and the
     # 56-byte pose form of the same tick are reported beside it.
     e2e = None
     if not args.no_e2e:
         h_act = [a.cpu().pin_memory() for a in act[:2]]
-        h_out = [torch.empty((n, 3), dtype=torch.float64).pin_memory() for _ in range(2)]
+        h_out = [torch.empty((n, 3), dtype=torch.float64).pin_memory() for _ in range(3)]
         Ke = max(5, min(K, 40))
 
         def run_e2e(h_in, st, pipelined):
             def one(k):
                 fn = te.lib.te_pool_tick_host_async if pipelined else te.lib.te_pool_tick_host
-                if fn(pool._h, DT, h_in[k % 2].data_ptr(), st, h_act[k % 2].data_ptr(), 2, h_out[k % 2].data_ptr()) < 0:
+                if fn(pool._h, DT, h_in[k % 2].data_ptr(), st, h_act[k % 2].data_ptr(), 2, h_out[k % 3].data_ptr()) < 0:
                     raise RuntimeError(te._lib.last_error())
-                if pipelined and te.lib.te_pool_tick_host_wait(pool._h, 1) < 0:      # results of tick k - 1 are in h_out[(k - 1) % 2] now
+                if pipelined and te.lib.te_pool_tick_host_wait(pool._h, 2) < 0:      # results of tick k - 2 are in h_out[(k - 2) % 3] now
                     raise RuntimeError(te._lib.last_error())
                 history.append(k % 2)
-            for k in range(3):
+            for k in range(4):
                 one(k)
             te.lib.te_pool_tick_host_wait(pool._h, 0)
             barrier()
@@ -454,13 +454,13 @@ def main():
         h3 = [m[:, :3].contiguous().cpu().pin_memory() for m in meas[:2]] if M == 3 else None
         if M == 3:
             e2e = run_e2e(h3, 3, True)
-            e2e["api"] = "te_pool_tick_host_async + te_pool_tick_host_wait(1): pinned host meas[n][3] (x y z: all the linear models read of a pose) + action[n] in, est. position [n][3] out, two ticks in flight"
+            e2e["api"] = "te_pool_tick_host_async + te_pool_tick_host_wait(2): pinned host meas[n][3] (x y z: all the linear models read of a pose) + action[n] in, est. position [n][3] out, three ticks in flight"
             e2e["pose7_pipelined"] = dict(run_e2e(h7, 7, True), api="the same with the reference's 56-byte pose measurements meas[n][7]")
             e2e["xyz_sync"] = dict(run_e2e(h3, 3, False), api="te_pool_tick_host (one tick at a time, returns when est_pos_out is complete), meas[n][3]")
             e2e["pose7_sync"] = dict(run_e2e(h7, 7, False), api="te_pool_tick_host, meas[n][7] (the round-1 headline form)")
         else:
             e2e = run_e2e(h7, 7, True)
-            e2e["api"] = "te_pool_tick_host_async + te_pool_tick_host_wait(1): pinned host meas[n][7] + action[n] in, est. position [n][3] out, two ticks in flight"
+            e2e["api"] = "te_pool_tick_host_async + te_pool_tick_host_wait(2): pinned host meas[n][7] + action[n] in, est. position [n][3] out, three ticks in flight"
             e2e["pose7_sync"] = dict(run_e2e(h7, 7, False), api="te_pool_tick_host (one tick at a time), meas[n][7]")
         h_meas = h7
 
@@ -495,16 +495,16 @@ def main():
                     tick_abi(k)
                 ta = (time.perf_counter() - t0) * 1e3
                 # the dense tick of the same library: records in target_manager_get_dense_ids order, no ids travel, every target's estimated
-                # position comes back (target_manager_update_dense_async / _wait: two ticks in flight, as the headline form)
+                # position comes back (target_manager_update_dense_async / _wait: three ticks in flight, as the headline form)
                 h_in_abi = h3 if M == 3 else h7
                 st_abi = 3 if M == 3 else 7
 
                 def tick_dense(k):
                     rc = clib.target_manager_update_dense_async(mg.h, DT, C.c_void_p(h_in_abi[k % 2].data_ptr()), st_abi, C.c_void_p(h_act[k % 2].data_ptr()),
-                                                                C.c_void_p(h_out[k % 2].data_ptr()))
-                    if rc != n or clib.target_manager_update_dense_wait(mg.h, 1) < 0:
+                                                                C.c_void_p(h_out[k % 3].data_ptr()))
+                    if rc != n or clib.target_manager_update_dense_wait(mg.h, 2) < 0:
                         raise RuntimeError("target_manager_update_dense_async: %s" % clib.target_manager_last_error().decode())
-                for k in range(3):
+                for k in range(4):
                     tick_dense(k)
                 clib.target_manager_update_dense_wait(mg.h, 0)
                 Kd = 20
@@ -516,7 +516,7 @@ def main():
                 e2e["reference_abi_dense"] = {"value": n * Kd / (td * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * (st_abi * 8 + 1), "d2h_bytes_per_step": n * 24,
                                               "ms_per_step": td / Kd, "n_gpus": 1,
                                               "api": "libtarget_c.so: target_manager_update_dense_async(dt, meas[n][%d], action[n], est_pos_out[n][3]) + "
-                                                     "target_manager_update_dense_wait(1), pinned host arrays in target_manager_get_dense_ids order" % st_abi}
+                                                     "target_manager_update_dense_wait(2), pinned host arrays in target_manager_get_dense_ids order" % st_abi}
                 e2e["reference_abi"] = {"value": n * Ka / (ta * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * (4 + 7 * 8 + 1), "d2h_bytes_per_step": 56,
                                         "ms_per_step": ta / Ka, "n_gpus": 1,
                                         "api": "libtarget_c.so: target_manager_update_batch(n, ids, dt, meas[n][7], action[n]) + target_manager_get_est_pose(id), "

@@ -54,8 +54,8 @@ long long target_manager_update_batch(const target_manager_c* self, long long n,
  * a sharded one: shard-major) -- no ids travel and nothing is looked up; meas [n][meas_stride] (7 = pose, 3 = x y z for the linear
  * models), action [n] or NULL = all 2, est_pos_out [n][3] or NULL = every target's estimated position after the tick.  The copies,
  * the step and the read-back are pipelined (te_pool_tick_host).  Needs a manager whose targets share one model type.  _async
- * enqueues the tick and returns (two ticks may be in flight, buffers stay valid until done); _wait(0) waits for all, (1) for all but
- * the newest.  Returns the number of targets, -1 on error. */
+ * enqueues the tick and returns (three ticks may be in flight, buffers stay valid until done); _wait(0) waits for all, (lag) for all
+ * but the newest `lag` (<= 2).  Returns the number of targets, -1 on error. */
 long long target_manager_update_dense(const target_manager_c* self, double dt, const double* meas, int meas_stride, const unsigned char* action,
                                       double* est_pos_out);
 long long target_manager_update_dense_async(const target_manager_c* self, double dt, const double* meas, int meas_stride,

@@ -114,11 +114,12 @@ int te_pool_step_dense_host(te_pool* p, double dt, const double* meas, int meas_
 int te_pool_tick_host(te_pool* p, double dt, const double* meas, int meas_stride, const uint8_t* action, int default_action,
                       double* est_pos_out);
 /* The same, pipelined ACROSS ticks (batched ingestion of a recorded or buffered stream at PCIe speed in both directions): the call
- * enqueues the tick and returns; up to two ticks are in flight, so the host->device copies of tick k + 1 run under the kernels and
- * the device->host read-back of tick k.  meas / action / est_pos_out of a tick must stay valid (and should be page-locked) until
- * that tick is done: te_pool_tick_host_wait(p, 0) waits for every tick issued, (p, 1) for all but the newest one -- the loop
- * "async(k); wait(1); consume est_pos_out of tick k - 1" keeps the link busy in both directions.  A third call waits for the tick
- * two back by itself.  Results are those of te_pool_tick_host tick by tick. */
+ * enqueues the tick and returns; up to three ticks are in flight, so the host->device copies of tick k + 1 run under the kernels of
+ * tick k and the device->host read-back of tick k - 1.  meas / action / est_pos_out of a tick must stay valid (and should be
+ * page-locked) until that tick is done: te_pool_tick_host_wait(p, 0) waits for every tick issued, (p, lag) for all but the newest
+ * `lag` ones (lag <= 2) -- the loop "async(k); wait(2); consume est_pos_out of tick k - 2" keeps the link busy in both directions
+ * (three buffers of each kind on the caller's side; wait(1) with two buffers leaves the copy-in engine idle a tenth of the time).  A
+ * fourth call waits for the tick three back by itself.  Results are those of te_pool_tick_host tick by tick. */
 int te_pool_tick_host_async(te_pool* p, double dt, const double* meas, int meas_stride, const uint8_t* action, int default_action,
                             double* est_pos_out);
 int te_pool_tick_host_wait(te_pool* p, int lag);

@@ -27,6 +27,214 @@ template <int N> struct SymP {
   }
 };
 
+// What the step needs of the previous posterior besides the covariance: the entries of the two Jacobians and the attitude
+// increment of f(x).  Depends on five state entries only (roll, pitch, body rates) -- the streaming kernel evaluates it
+// from a prefetched copy of those while the tile itself is still in flight (te_av_stream.cuh).
+struct AvFront {
+  double j10, j11, j12, j13, j14;          // J1 = [j10 j11 0; j12 1 0; j13 j14 1]   (EarBaseInvJacobianRpy, geometry.hpp:394-410)
+  double j20, j21, j22, j23, j24, j25;     // J2 = [dt j20 j21; 0 j22 j23; 0 j24 j25] (EarBaseInvJacobianOmega, :412-426)
+  double d3, d4, d5;                       // f(x)[3..5] - x[3..5] = dt * EarBaseInv(rpy) * w (geometry.hpp:359-374, angular_velocities.cpp:126-140)
+  double dt;
+  __device__ __forceinline__ void eval(double roll, double pitch, double wx, double wy, double wz, double dt_) {
+    dt = dt_;
+    double s_r, c_r, s_p, c_p;
+    sincos(roll, &s_r, &c_r);
+    sincos(pitch, &s_p, &c_p);
+    j10 = (dt * (wy * c_r * s_p - wz * s_p * s_r)) / c_p + 1;
+    j11 = (dt * (wz * c_r + wy * s_r)) / (c_p * c_p);
+    j12 = -dt * (wz * c_r + wy * s_r);
+    j13 = (dt * (wy * c_r - wz * s_r)) / c_p;
+    j14 = (dt * s_p * (wz * c_r + wy * s_r)) / (c_p * c_p);
+    j20 = (dt * s_p * s_r) / c_p;
+    j21 = (dt * c_r * s_p) / c_p;
+    j22 = dt * c_r;
+    j23 = -dt * s_r;
+    j24 = (dt * s_r) / c_p;
+    j25 = (dt * c_r) / c_p;
+    const double E01 = (s_p * s_r) / c_p, E02 = (c_r * s_p) / c_p, E11 = c_r, E12 = -s_r, E21 = s_r / c_p, E22 = c_r / c_p;
+    d3 = ((dt * 1.0) * wx + (dt * E01) * wy + (dt * E02) * wz);
+    d4 = ((dt * 0.0) * wx + (dt * E11) * wy + (dt * E12) * wz);
+    d5 = ((dt * 0.0) * wx + (dt * E21) * wy + (dt * E22) * wz);
+  }
+  // row i of J1 / J2 as compile-time-indexed values (structural 0 / 1 / dt entries fold away)
+  __device__ __forceinline__ double J1(int i, int k) const {
+    return i == 0 ? (k == 0 ? j10 : (k == 1 ? j11 : 0.0)) : (i == 1 ? (k == 0 ? j12 : (k == 1 ? 1.0 : 0.0)) : (k == 0 ? j13 : (k == 1 ? j14 : 1.0)));
+  }
+  __device__ __forceinline__ double J2(int i, int k) const {
+    return i == 0 ? (k == 0 ? dt : (k == 1 ? j20 : j21)) : (i == 1 ? (k == 0 ? 0.0 : (k == 1 ? j22 : j23)) : (k == 0 ? 0.0 : (k == 1 ? j24 : j25)));
+  }
+};
+
+// ---- covariance predict, blocks p = 0..2, r = 3..5, v = 6..8, w = 9..11.  T = A P, P' = T A^T + Q:
+//   P'pp = Tpp + dt Tpv          Tpp = Ppp + dt Pvp, Tpv = Ppv + dt Pvv
+//   P'pr = Tpr J1^T + Tpw J2^T   Tpr = Ppr + dt Pvr, Tpw = Ppw + dt Pvw
+//   P'pv = Tpv,  P'pw = Tpw
+//   P'rr = Trr J1^T + Trw J2^T   Trr = J1 Prr + J2 Pwr, Trw = J1 Prw + J2 Pww
+//   P'rv = J1 Prv + J2 Pwv,  P'rw = Trw,  vv / vw / ww unchanged.
+// In place, in an order in which every block reads only values that are still the old ones (or the T it needs), with at
+// most nine temporaries alive.  QV(idx) = entry idx of the class's row-major Q.
+template <class QV>
+__device__ __forceinline__ void av_predict_cov(SymP<12>& P, const AvFront& F, QV Qv) {
+  constexpr int N = 12;
+  const double dt = F.dt;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      if (i <= j) {
+        const double tpp = P(i, j) + dt * P(6 + i, j);
+        const double tpv = P(i, 6 + j) + dt * P(6 + i, 6 + j);
+        P(i, j) = (tpp + tpv * dt) + Qv(i * N + j);
+      }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) P(i, 9 + j) = P(i, 9 + j) + dt * P(6 + i, 9 + j);   // Ppw <- Tpw (Q added below)
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double tpr[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) tpr[k] = P(i, 3 + k) + dt * P(6 + i, 3 + k);       // Pvr(i,k) lives at P(3+k, 6+i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double s = tpr[0] * F.J1(j, 0) + tpr[1] * F.J1(j, 1) + tpr[2] * F.J1(j, 2) + P(i, 9) * F.J2(j, 0) + P(i, 10) * F.J2(j, 1) + P(i, 11) * F.J2(j, 2);
+      P(i, 3 + j) = s + Qv(i * N + 3 + j);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      P(i, 9 + j) = P(i, 9 + j) + Qv(i * N + 9 + j);
+      P(i, 6 + j) = (P(i, 6 + j) + dt * P(6 + i, 6 + j)) + Qv(i * N + 6 + j);
+    }
+  {
+    double trr[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) s += F.J1(i, k) * P(3 + k, 3 + j);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) s += F.J2(i, k) * P(9 + k, 3 + j);              // Pwr(k,j) lives at P(3+j, 9+k)
+        trr[i][j] = s;
+      }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {   // Prw <- Trw, one column at a time
+      double c[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) s += F.J1(i, k) * P(3 + k, 9 + j);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) s += F.J2(i, k) * P(9 + k, 9 + j);
+        c[i] = s;
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) P(3 + i, 9 + j) = c[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        if (i <= j) {
+          const double s = trr[i][0] * F.J1(j, 0) + trr[i][1] * F.J1(j, 1) + trr[i][2] * F.J1(j, 2) + P(3 + i, 9) * F.J2(j, 0) + P(3 + i, 10) * F.J2(j, 1) +
+                           P(3 + i, 11) * F.J2(j, 2);
+          P(3 + i, 3 + j) = s + Qv((3 + i) * N + 3 + j);
+        }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {     // Prv <- J1 Prv + J2 Pwv, one column at a time; Prw += Q
+    double c[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) s += F.J1(i, k) * P(3 + k, 6 + j);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) s += F.J2(i, k) * P(9 + k, 6 + j);                // Pwv(k,j) lives at P(6+j, 9+k)
+      c[i] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      P(3 + i, 6 + j) = c[i] + Qv((3 + i) * N + 6 + j);
+      P(3 + i, 9 + j) = P(3 + i, 9 + j) + Qv((3 + i) * N + 9 + j);
+    }
+  }
+#pragma unroll
+  for (int i = 6; i < N; ++i)
+#pragma unroll
+    for (int j = 6; j < N; ++j)
+      if (i <= j) P(i, j) = P(i, j) + Qv(i * N + j);
+}
+
+// ---- update (src/kalman.cpp:135-140 with C = [I6 0]) ----
+// xs  : the lane's column holding x' (entry j at xs[j * TILE]); updated in place
+// zs  : the lane's column of a 72-field scratch: Z[k][j] at zs[(k * N + j) * TILE]
+// ypos: measured position (3 values, registers); yang: the lane's column of the unwrapped measured angles (stride TILE)
+// (the empty asm statements are scheduling fences for the front end: without them it hoists the shared-memory loads of
+//  all six Z rows / interleaves all twelve column solves, and ptxas has to spill ~80 doubles)
+template <int ZF, class RV>
+__device__ __forceinline__ void av_update(SymP<12>& P, double* xs, double* zs, const double* ypos, const double* yang, RV Rv) {
+  constexpr int N = 12, M = 6;
+  {
+    Chol<M> ch;
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+        if (j <= i) ch.at(i, j) = P(j, i) + Rv(i * M + j);
+    ch.factor();
+    double u[M];   // L^-1 (y - x'[0:6])
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+      const double yk = k < 3 ? ypos[k < 3 ? k : 0] : yang[(k < 3 ? 0 : k - 3) * TILE];
+      double s = yk - xs[k * TILE];
+#pragma unroll
+      for (int m = 0; m < M; ++m)
+        if (m < k) s -= ch.L[k][m] * u[m];
+      u[k] = s * ch.L[k][k];
+    }
+    // Z = L^-1 P'[0:6,:] column by column (forward substitution; the diagonal of ch holds 1 / L_kk), and with column j
+    // the state update x_j += Z[:,j] . u
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double z[M];
+#pragma unroll
+      for (int k = 0; k < M; ++k) {
+        double s = P(k, j);
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+          if (m < k) s -= ch.L[k][m] * z[m];
+        z[k] = s * ch.L[k][k];
+      }
+      double xj = xs[j * TILE];
+#pragma unroll
+      for (int k = 0; k < M; ++k) {
+        zs[(k * N + j) * TILE] = z[k];
+        xj += z[k] * u[k];
+      }
+      xs[j * TILE] = xj;
+      if (j % ZF == ZF - 1) asm volatile("" ::: "memory");
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < M; ++k) {
+    double zr[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) zr[j] = zs[(k * N + j) * TILE];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+        if (i <= j) P(i, j) -= zr[i] * zr[j];
+    asm volatile("" ::: "memory");
+  }
+}
+
 // in  : the lane's column of the source tile   (field f at in[f * TILE]); staged tile in shared memory or the tile in HBM
 // out : the lane's column of the destination tile (may alias in)
 // sc  : the lane's column of a shared-memory scratch with the tile's field numbering for x (F_X..) and for the first 72
@@ -37,7 +245,7 @@ template <int PREV_S, bool DIRECT, int ZF = 2>
 __device__ __forceinline__ void step_lane_av_sym(const double* in, double* out, double* sc, int action, double dt, const double* meas,
                                                  const double* __restrict__ Q, const double* __restrict__ R, bool packed = false) {
   using LY = Layout<ANGULAR_VELOCITIES>;
-  constexpr int N = 12, M = 6;
+  constexpr int N = 12;
   // Register budget: the 78 covariance entries stay in registers from the load to the store; everything else is kept
   // short-lived (state, innovation and Z rows are parked in the scratch column between uses).
 
@@ -72,202 +280,20 @@ __device__ __forceinline__ void step_lane_av_sym(const double* in, double* out, 
   for (int k = 0; k < 3; ++k) out[(LY::F_PREV + k) * TILE] = prev[k];
 
   // ---- state predict x' = f(x) and the Jacobians at the previous posterior ----
-  double j10, j11, j12, j13, j14;          // J1 = [j10 j11 0; j12 1 0; j13 j14 1]   (EarBaseInvJacobianRpy, geometry.hpp:394-410)
-  double j20, j21, j22, j23, j24, j25;     // J2 = [dt j20 j21; 0 j22 j23; 0 j24 j25] (EarBaseInvJacobianOmega, :412-426)
-  {
-    double s_r, c_r, s_p, c_p;
-    sincos(x[3], &s_r, &c_r);
-    sincos(x[4], &s_p, &c_p);
-    const double wx = x[9], wy = x[10], wz = x[11];
-    j10 = (dt * (wy * c_r * s_p - wz * s_p * s_r)) / c_p + 1;
-    j11 = (dt * (wz * c_r + wy * s_r)) / (c_p * c_p);
-    j12 = -dt * (wz * c_r + wy * s_r);
-    j13 = (dt * (wy * c_r - wz * s_r)) / c_p;
-    j14 = (dt * s_p * (wz * c_r + wy * s_r)) / (c_p * c_p);
-    j20 = (dt * s_p * s_r) / c_p;
-    j21 = (dt * c_r * s_p) / c_p;
-    j22 = dt * c_r;
-    j23 = -dt * s_r;
-    j24 = (dt * s_r) / c_p;
-    j25 = (dt * c_r) / c_p;
-    // f(x): p += dt v ; rpy += dt * EarBaseInv(rpy) * w (geometry.hpp:359-374, angular_velocities.cpp:126-140)
-    const double E01 = (s_p * s_r) / c_p, E02 = (c_r * s_p) / c_p, E11 = c_r, E12 = -s_r, E21 = s_r / c_p, E22 = c_r / c_p;
+  AvFront F;
+  F.eval(x[3], x[4], x[9], x[10], x[11], dt);
+  // f(x): p += dt v ; rpy += dt * EarBaseInv(rpy) * w
 #pragma unroll
-    for (int i = 0; i < 3; ++i) sc[(LY::F_X + i) * TILE] = x[i] + dt * x[6 + i];
-    sc[(LY::F_X + 3) * TILE] = x[3] + ((dt * 1.0) * wx + (dt * E01) * wy + (dt * E02) * wz);
-    sc[(LY::F_X + 4) * TILE] = x[4] + ((dt * 0.0) * wx + (dt * E11) * wy + (dt * E12) * wz);
-    sc[(LY::F_X + 5) * TILE] = x[5] + ((dt * 0.0) * wx + (dt * E21) * wy + (dt * E22) * wz);
+  for (int i = 0; i < 3; ++i) sc[(LY::F_X + i) * TILE] = x[i] + dt * x[6 + i];
+  sc[(LY::F_X + 3) * TILE] = x[3] + F.d3;
+  sc[(LY::F_X + 4) * TILE] = x[4] + F.d4;
+  sc[(LY::F_X + 5) * TILE] = x[5] + F.d5;
 #pragma unroll
-    for (int i = 6; i < N; ++i) sc[(LY::F_X + i) * TILE] = x[i];
-  }
-  // row i of J1 / J2 as compile-time-indexed values (structural 0 / 1 / dt entries fold away)
-  auto J1 = [&](int i, int k) -> double {
-    return i == 0 ? (k == 0 ? j10 : (k == 1 ? j11 : 0.0)) : (i == 1 ? (k == 0 ? j12 : (k == 1 ? 1.0 : 0.0)) : (k == 0 ? j13 : (k == 1 ? j14 : 1.0)));
-  };
-  auto J2 = [&](int i, int k) -> double {
-    return i == 0 ? (k == 0 ? dt : (k == 1 ? j20 : j21)) : (i == 1 ? (k == 0 ? 0.0 : (k == 1 ? j22 : j23)) : (k == 0 ? 0.0 : (k == 1 ? j24 : j25)));
-  };
+  for (int i = 6; i < N; ++i) sc[(LY::F_X + i) * TILE] = x[i];
 
-  // ---- covariance predict, blocks p = 0..2, r = 3..5, v = 6..8, w = 9..11.  T = A P, P' = T A^T + Q:
-  //   P'pp = Tpp + dt Tpv          Tpp = Ppp + dt Pvp, Tpv = Ppv + dt Pvv
-  //   P'pr = Tpr J1^T + Tpw J2^T   Tpr = Ppr + dt Pvr, Tpw = Ppw + dt Pvw
-  //   P'pv = Tpv,  P'pw = Tpw
-  //   P'rr = Trr J1^T + Trw J2^T   Trr = J1 Prr + J2 Pwr, Trw = J1 Prw + J2 Pww
-  //   P'rv = J1 Prv + J2 Pwv,  P'rw = Trw,  vv / vw / ww unchanged.
-  // In place, in an order in which every block reads only values that are still the old ones (or the T it needs), with at
-  // most nine temporaries alive.
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-      if (i <= j) {
-        const double tpp = P(i, j) + dt * P(6 + i, j);
-        const double tpv = P(i, 6 + j) + dt * P(6 + i, 6 + j);
-        P(i, j) = (tpp + tpv * dt) + __ldg(&Q[i * N + j]);
-      }
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) P(i, 9 + j) = P(i, 9 + j) + dt * P(6 + i, 9 + j);   // Ppw <- Tpw (Q added below)
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    double tpr[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) tpr[k] = P(i, 3 + k) + dt * P(6 + i, 3 + k);       // Pvr(i,k) lives at P(3+k, 6+i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const double s = tpr[0] * J1(j, 0) + tpr[1] * J1(j, 1) + tpr[2] * J1(j, 2) + P(i, 9) * J2(j, 0) + P(i, 10) * J2(j, 1) + P(i, 11) * J2(j, 2);
-      P(i, 3 + j) = s + __ldg(&Q[i * N + 3 + j]);
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      P(i, 9 + j) = P(i, 9 + j) + __ldg(&Q[i * N + 9 + j]);
-      P(i, 6 + j) = (P(i, 6 + j) + dt * P(6 + i, 6 + j)) + __ldg(&Q[i * N + 6 + j]);
-    }
-  {
-    double trr[3][3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) s += J1(i, k) * P(3 + k, 3 + j);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) s += J2(i, k) * P(9 + k, 3 + j);              // Pwr(k,j) lives at P(3+j, 9+k)
-        trr[i][j] = s;
-      }
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {   // Prw <- Trw, one column at a time
-      double c[3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) s += J1(i, k) * P(3 + k, 9 + j);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) s += J2(i, k) * P(9 + k, 9 + j);
-        c[i] = s;
-      }
-#pragma unroll
-      for (int i = 0; i < 3; ++i) P(3 + i, 9 + j) = c[i];
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j)
-        if (i <= j) {
-          const double s = trr[i][0] * J1(j, 0) + trr[i][1] * J1(j, 1) + trr[i][2] * J1(j, 2) + P(3 + i, 9) * J2(j, 0) + P(3 + i, 10) * J2(j, 1) +
-                           P(3 + i, 11) * J2(j, 2);
-          P(3 + i, 3 + j) = s + __ldg(&Q[(3 + i) * N + 3 + j]);
-        }
-  }
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {     // Prv <- J1 Prv + J2 Pwv, one column at a time; Prw += Q
-    double c[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      double s = 0.0;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) s += J1(i, k) * P(3 + k, 6 + j);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) s += J2(i, k) * P(9 + k, 6 + j);                // Pwv(k,j) lives at P(6+j, 9+k)
-      c[i] = s;
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      P(3 + i, 6 + j) = c[i] + __ldg(&Q[(3 + i) * N + 6 + j]);
-      P(3 + i, 9 + j) = P(3 + i, 9 + j) + __ldg(&Q[(3 + i) * N + 9 + j]);
-    }
-  }
-#pragma unroll
-  for (int i = 6; i < N; ++i)
-#pragma unroll
-    for (int j = 6; j < N; ++j)
-      if (i <= j) P(i, j) = P(i, j) + __ldg(&Q[i * N + j]);
-
-  // ---- update ----
-  // (the empty asm statements are scheduling fences for the front end: without them it hoists the shared-memory loads of
-  //  all six Z rows / interleaves all twelve column solves, and ptxas has to spill ~80 doubles)
-  if (action == ACT_UPDATE) {
-    double* zs = sc + LY::F_P * TILE;   // Z[k][j] at zs[(k * N + j) * TILE]
-    {
-      Chol<M> ch;
-#pragma unroll
-      for (int i = 0; i < M; ++i)
-#pragma unroll
-        for (int j = 0; j < M; ++j)
-          if (j <= i) ch.at(i, j) = P(j, i) + __ldg(&R[i * M + j]);
-      ch.factor();
-      double u[M];   // L^-1 (y - x'[0:6])
-#pragma unroll
-      for (int k = 0; k < M; ++k) {
-        const double yk = k < 3 ? meas[k] : sc[(PREV_S + (k - 3)) * TILE];
-        double s = yk - sc[(LY::F_X + k) * TILE];
-#pragma unroll
-        for (int m = 0; m < M; ++m)
-          if (m < k) s -= ch.L[k][m] * u[m];
-        u[k] = s * ch.L[k][k];
-      }
-      // Z = L^-1 P'[0:6,:] column by column (forward substitution; the diagonal of ch holds 1 / L_kk), and with column j
-      // the state update x_j += Z[:,j] . u
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        double z[M];
-#pragma unroll
-        for (int k = 0; k < M; ++k) {
-          double s = P(k, j);
-#pragma unroll
-          for (int m = 0; m < M; ++m)
-            if (m < k) s -= ch.L[k][m] * z[m];
-          z[k] = s * ch.L[k][k];
-        }
-        double xs = sc[(LY::F_X + j) * TILE];
-#pragma unroll
-        for (int k = 0; k < M; ++k) {
-          zs[(k * N + j) * TILE] = z[k];
-          xs += z[k] * u[k];
-        }
-        sc[(LY::F_X + j) * TILE] = xs;
-        if (j % ZF == ZF - 1) asm volatile("" ::: "memory");
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < M; ++k) {
-      double zr[N];
-#pragma unroll
-      for (int j = 0; j < N; ++j) zr[j] = zs[(k * N + j) * TILE];
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-#pragma unroll
-        for (int j = 0; j < N; ++j)
-          if (i <= j) P(i, j) -= zr[i] * zr[j];
-      asm volatile("" ::: "memory");
-    }
-  }
+  av_predict_cov(P, F, [&](int idx) -> double { return __ldg(&Q[idx]); });
+  if (action == ACT_UPDATE)
+    av_update<ZF>(P, sc + LY::F_X * TILE, sc + LY::F_P * TILE, meas, sc + PREV_S * TILE, [&](int idx) -> double { return __ldg(&R[idx]); });
 
 #pragma unroll
   for (int i = 0; i < N; ++i)

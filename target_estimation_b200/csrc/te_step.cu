@@ -5,6 +5,7 @@
 #include "te_pool_internal.cuh"
 #include "te_split.cuh"
 #include "te_direct.cuh"
+#include "te_av_stream.cuh"
 
 namespace tehost {
 
@@ -79,6 +80,29 @@ void launch_av_direct(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   CK(cudaGetLastError());
 }
 
+// dense in-place packed tick of an AV pool: the TMA-streamed kernel (te_av_stream.cuh)
+bool av_stream_serves(const te_pool* p, const te::StepArgs& a) {
+  if (p->variant != 0 || !a.packed) return false;   // 13 = the direct kernel for every launch
+  if (a.tile_list || a.d_nwork || a.dt_slot || a.dst_tiles || a.clear_action || a.n_ticks != 1 || a.tick_gate) return false;
+  if (a.meas && (a.meas_stride != 7 || (reinterpret_cast<uintptr_t>(a.meas) & 15) != 0)) return false;
+  if (!a.meas && (a.action || a.default_action == te::ACT_UPDATE)) return false;
+  return true;
+}
+template <bool QC>
+void launch_av_stream(te_pool* p, const te::StepArgs& a, int n_work_hint) {
+  constexpr int WARPS = 8;
+  auto kern = te::kf_step_av_stream_kernel<WARPS, QC>;
+  const size_t smem = te::av_stream_smem_bytes(WARPS);
+  static bool configured[64] = {false};
+  if (!configured[p->device & 63]) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[p->device & 63] = true;
+  }
+  int grid = capped(p, std::min(p->n_sm, std::max(1, cdiv(n_work_hint, WARPS))));
+  kern<<<grid, WARPS * 32, smem, p->stream>>>(a);
+  CK(cudaGetLastError());
+}
+
 template <int TYPE, int WARPS, int CTAS>
 void launch_kin_direct_k(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   auto kern = te::kf_step_kin_direct_kernel<TYPE, WARPS, CTAS>;
@@ -114,7 +138,7 @@ bool uses_direct(const te_pool* p) {
   // variant 0 = the defaults; 12 = the direct kernels writing both halves of the covariance (unpacked); 1 / 10 / 11 = staged forms
   const int v = p->variant;
   if (p->model == te::ANGULAR_RATES) return false;
-  return (v == 0 && p->all_sym) || v == 12;
+  return ((v == 0 || v == 13) && p->all_sym) || v == 12;
 }
 // full-matrix kernels (and anything else that reads both halves) first get the lower triangles back
 void ensure_full(te_pool* p) {
@@ -148,7 +172,7 @@ void launch_step(te_pool* p, const te::StepArgs& a_in, int n_work_hint) {
   const int v = p->variant;
   te::StepArgs a = a_in;
   if (uses_direct(p)) {
-    a.packed = (p->all_sym && v != 12) ? 1 : 0;
+    a.packed = (p->all_sym && v != 12) ? 1 : 0;   // (0 / 13)
     if (a.packed) p->lower_stale = true;
     switch (p->model) {
       case te::UNIFORM_VELOCITY:
@@ -159,7 +183,12 @@ void launch_step(te_pool* p, const te::StepArgs& a_in, int n_work_hint) {
         launch_kin_direct<te::UNIFORM_ACCELERATION, 8, 1>(p, a, n_work_hint);
         return;
       default:
-        launch_av_direct<8>(p, a, n_work_hint);
+        if (av_stream_serves(p, a)) {
+          if (p->hQ.size() == 1 && a.cls_c == 0) launch_av_stream<true>(p, a, n_work_hint);
+          else launch_av_stream<false>(p, a, n_work_hint);
+        } else {
+          launch_av_direct<8>(p, a, n_work_hint);
+        }
         return;
     }
   }
@@ -481,8 +510,8 @@ void tick_host_enqueue(te_pool* p, double dt, const double* meas, int meas_strid
   const int chunk_env = chunk_str ? std::atoi(chunk_str) : 0;
   const int chunk_tiles = std::max(256, std::min(n_tiles, chunk_env > 0 ? chunk_env : (pipelined ? 131072 : 32768)));
   const int n_chunks = cdiv(n_tiles, chunk_tiles);
-  te_pool::TickSet& ts = p->tick_set[p->ticks_issued & 1];
-  if (ts.busy) {   // the tick that used this set two ticks ago must have left it (its results are in the caller's buffer by then)
+  te_pool::TickSet& ts = p->tick_set[p->ticks_issued % te_pool::TICK_SETS];
+  if (ts.busy) {   // the tick that used this set three ticks ago must have left it (its results are in the caller's buffer by then)
     CK(cudaEventSynchronize(ts.d2h_done));
     ts.busy = false;
   }
@@ -495,7 +524,7 @@ void tick_host_enqueue(te_pool* p, double dt, const double* meas, int meas_strid
   double* d_meas = meas ? ts.meas : nullptr;
   uint8_t* d_act = action ? ts.act : nullptr;
   double* d_pos = est_pos_out ? ts.pos : nullptr;
-  // the copies of this tick may start as soon as the kernels that last read this set's staging are done (two ticks ago: already
+  // the copies of this tick may start as soon as the kernels that last read this set's staging are done (three ticks ago: already
   // waited for above through d2h_done, which follows them) and whatever the caller queued on the pool's stream before this call
   // that could touch the pool -- nothing reads the staging but the step kernels, so the copy stream needs no further wait
   te::StepArgs a = base_args(p);
@@ -537,12 +566,12 @@ void tick_host_enqueue(te_pool* p, double dt, const double* meas, int meas_strid
 }
 
 void tick_host_wait(te_pool* p, int lag) {
-  // ticks are numbered by issue; tick i used set i & 1.  lag 0: everything done; lag 1: all but the newest tick done
-  for (int back = 1; back >= 0; --back) {
+  // ticks are numbered by issue; tick i used set i % TICK_SETS.  lag 0: everything done; lag k: all but the newest k ticks done
+  for (int back = te_pool::TICK_SETS - 1; back >= 0; --back) {
     if (back < lag) continue;
     const long long i = p->ticks_issued - 1 - back;
     if (i < 0) continue;
-    te_pool::TickSet& ts = p->tick_set[i & 1];
+    te_pool::TickSet& ts = p->tick_set[i % te_pool::TICK_SETS];
     if (ts.busy) {
       CK(cudaEventSynchronize(ts.d2h_done));
       ts.busy = false;
@@ -573,7 +602,7 @@ int te_pool_tick_host_async(te_pool* p, double dt, const double* meas, int meas_
 
 int te_pool_tick_host_wait(te_pool* p, int lag) {
   return guarded(p, [&] {
-    if (lag < 0 || lag > 1) throw std::invalid_argument("lag must be 0 or 1");
+    if (lag < 0 || lag >= te_pool::TICK_SETS) throw std::invalid_argument("lag must be 0, 1 or 2");
     tick_host_wait(p, lag);
     return 0;
   });

@@ -81,9 +81,10 @@ def test_step_parity_ar_kernels(variant):
     assert w["x"] <= 1.0 and w["P"] <= 1.0, w
 
 
-@pytest.mark.parametrize("variant", [12])
+@pytest.mark.parametrize("variant", [12, 13])
 def test_step_parity_av_kernels(variant):
-    """AV: the direct symmetric-covariance kernel writing both halves (12; 0 = default, packed; 1 / 10: test_step_parity_variants)"""
+    """AV: the direct symmetric-covariance kernel writing both halves (12) and packed (13: what sparse and compacting ticks run);
+    0 = default, dense ticks on the TMA-streamed kernel; 1 / 10: test_step_parity_variants"""
     w = _run("angular_velocities", 200, 60, variant=variant, check_every=20)
     assert w["x"] <= 1.0 and w["P"] <= 1.0, w
 
@@ -198,3 +199,43 @@ def test_replay_launch_is_bit_identical_to_sequential_ticks(model, variant):
     assert synth.compare_h2(a["x"], ref["x"]) <= 1.0 and synth.compare_h2(a["P"], ref["P"]) <= 1.0
     for p in pools:
         p.close()
+
+
+def test_av_streamed_kernel_matches_direct_kernel_and_serves_several_classes():
+    """The TMA-streamed dense tick of the angular-velocities pool (te_av_stream.cuh) shares its arithmetic with the direct kernel
+    (variant 13).  Two model classes (Q / R from the device tables instead of the constant bank) against the oracle,
+    on a ragged pool (last tile partial: its measurement block is read per lane) under a grid cap (each warp walks many tiles)."""
+    import target_estimation_b200 as te
+    mtype, freq, Q, R, P0 = te.load_model("angular_velocities")
+    n, ticks = 2000 + 13, 40
+    meas, action, scale = synth.make_streams(n, ticks, DT, accel=False, angular=True, seed=77)
+    ids = np.arange(n, dtype=np.uint32) * 2 + 1
+    for n_cls in (1, 2):
+        cls = (np.arange(n) % n_cls).astype(np.uint16)
+        Qs = [Q, 1.7 * Q]; Rs = [R, 0.6 * R]
+        pools = []
+        for variant in (0, 13):
+            p = te.TargetPool(mtype); p.set_variant(variant); p.set_grid_cap(2)
+            for c in range(n_cls):
+                assert p.register_class(Qs[c], Rs[c], P0) == c
+            assert p.add(ids, meas[0], cls=cls, p0_scale=scale) == n
+            pools.append(p)
+        mgr = orc.Manager()
+        for k, i in enumerate(ids):
+            mgr.init_full(mtype, int(i), DT, 0.0, Qs[cls[k]], Rs[cls[k]], scale[k] * P0, meas[0, k])
+        for k in range(ticks):
+            mgr.step_batch(ids, DT, meas[k], action[k])
+            for p in pools:
+                p.step_dense_host(DT, meas[k], action[k])
+        ref = mgr.states(ids, 12)
+        got = [p.read_state() for p in pools]
+        for f in ("t", "n_meas"):
+            assert np.array_equal(got[0][f], got[1][f]), (n_cls, f)
+        # (two kernels: ptxas contracts multiply-adds per kernel, so the last bits may differ -- far inside the bar)
+        for f in ("x", "P", "prev_rpy"):
+            assert synth.compare_h2(got[0][f], got[1][f]) <= 0.5, (n_cls, f, synth.compare_h2(got[0][f], got[1][f]))
+        assert synth.compare_h2(got[0]["x"], ref["x"]) <= 1.0 and synth.compare_h2(got[0]["P"], ref["P"]) <= 1.0
+        assert np.array_equal(got[0]["n_meas"], ref["n_meas"]) and np.array_equal(got[0]["t"], ref["t"])
+        assert synth.compare_h2(got[0]["prev_rpy"], ref["prev_rpy"]) <= 1.0
+        for p in pools:
+            p.close()

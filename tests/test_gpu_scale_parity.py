@@ -88,7 +88,7 @@ def test_bench_scale_dense(model, cap):
 # 2. a handful of CTAs over ~100 tiles: every stage of every ring is reused tens of times; dense, sparse, packed, staged
 # ---------------------------------------------------------------------------------------------------------------------
 CASES = [("uniform_velocity", 0), ("uniform_velocity", 10), ("uniform_acceleration", 0), ("uniform_acceleration", 10), ("uniform_acceleration", 1),
-         ("angular_velocities", 0), ("angular_velocities", 10), ("angular_velocities", 1), ("angular_rates", 0), ("angular_rates", 11)]
+         ("angular_velocities", 0), ("angular_velocities", 13), ("angular_velocities", 10), ("angular_velocities", 1), ("angular_rates", 0), ("angular_rates", 11)]
 
 
 @pytest.mark.parametrize("cap", [1, 4])
@@ -272,13 +272,13 @@ def test_av_pitch_range(pitch_max):
 # ---------------------------------------------------------------------------------------------------------------------
 # 6. the host-buffer tick the bench's e2e figure times (te_pool_tick_host: chunked H2D / step / D2H pipeline over three streams)
 # ---------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("pipelined", [False, True], ids=["sync", "two_in_flight"])
+@pytest.mark.parametrize("pipelined", [0, 1, 2], ids=["sync", "two_in_flight", "three_in_flight"])
 @pytest.mark.parametrize("stride", [7, 3])
 def test_tick_host_pipeline(stride, pipelined, monkeypatch):
     """300 000 uniform-acceleration targets in pipeline chunks of 2048 tiles (65 536 targets: four chunks + a ragged tail); pose [n][7] and
-    xyz-only [n][3] measurements; state, covariance and the returned positions against the oracle.  two_in_flight: the same ticks
-    through te_pool_tick_host_async / te_pool_tick_host_wait(1) (the copies of tick k + 1 under the kernels and read-back of tick
-    k), every tick's returned positions checked against the synchronous run's."""
+    xyz-only [n][3] measurements; state, covariance and the returned positions against the oracle.  two / three_in_flight: the same
+    ticks through te_pool_tick_host_async / te_pool_tick_host_wait(lag = 1 / 2) (the copies of tick k + 1 under the kernels of tick k
+    and the read-back of tick k - 1), every tick's returned positions checked against the oracle's."""
     import ctypes as C
     monkeypatch.setenv("TE_TICK_CHUNK_TILES", "2048")     # (the default chunk is the whole pool at this size)
     n, ticks = 300000 + 5, 6
@@ -292,9 +292,9 @@ def test_tick_host_pipeline(stride, pipelined, monkeypatch):
         rc = fn(pool._h, DT, ms[k].ctypes.data_as(C.c_void_p), stride, acts[k].ctypes.data_as(C.c_void_p), 2, outs[k].ctypes.data_as(C.c_void_p))
         assert rc == 0, te._lib.last_error()
         if pipelined:
-            assert te.lib.te_pool_tick_host_wait(pool._h, 1) == 0
-            if k > 0:
-                assert np.abs(outs[k - 1]).max() > 0          # tick k - 1 has landed while tick k is in flight
+            assert te.lib.te_pool_tick_host_wait(pool._h, pipelined) == 0
+            if k >= pipelined:
+                assert np.abs(outs[k - pipelined]).max() > 0  # tick k - lag has landed while the newer ones are in flight
     assert te.lib.te_pool_tick_host_wait(pool._h, 0) == 0
     # the oracle tick by tick: the returned positions of EVERY tick are that tick's estimated positions
     for k in range(ticks):

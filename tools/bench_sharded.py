@@ -3,7 +3,7 @@
 
     python tools/bench_sharded.py [--gpus 1,2,4,8] [--targets-per-gpu 4194304] [--steps 20]
 
-per G: (a) the dense host tick target_manager_update_dense_async / _wait(1) -- shard-major pinned host arrays in, every target's
+per G: (a) the dense host tick target_manager_update_dense_async / _wait(2) -- shard-major pinned host arrays in, every target's
 estimated position out, every shard's slice copied / stepped / read back on its own device, two ticks in flight; (b) the routed
 batch call target_manager_update_batch (ids in arbitrary order, routed to the owners on the host by the shard worker threads);
 (c) the all-gather of [pose7 | twist6] records between the devices, issued from C++ over NCCL (target_manager_gather_estimates with
@@ -52,13 +52,13 @@ def main():
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         h_in = [pin(rng.uniform(-5, 5, (n, stride))) for _ in range(2)]
         h_act = [pin(np.where(rng.random(n) < 0.05, 1, 2).astype(np.uint8)) for _ in range(2)]
-        h_out = [pin(np.zeros((n, 3))) for _ in range(2)]
+        h_out = [pin(np.zeros((n, 3))) for _ in range(3)]
         K = args.steps
 
         def one(k):
-            assert mgr.update_dense(DT, h_in[k % 2].numpy(), h_act[k % 2].numpy(), h_out[k % 2].numpy(), pipelined=True) == n
-            mgr.update_dense_wait(1)
-        for k in range(3):
+            assert mgr.update_dense(DT, h_in[k % 2].numpy(), h_act[k % 2].numpy(), h_out[k % 3].numpy(), pipelined=True) == n
+            mgr.update_dense_wait(2)
+        for k in range(4):
             one(k)
         mgr.update_dense_wait(0)
         t0 = time.perf_counter()
@@ -88,7 +88,7 @@ def main():
         out = {"tool": "bench_sharded", "n_gpus": G, "model": args.model, "targets_per_gpu": args.targets_per_gpu, "targets_total": n,
                "init_s": t_init,
                "dense_tick": {"ms_per_step": 1e3 * t_dense, "target_steps_per_s": n / t_dense, "h2d_bytes_per_step": n * (stride * 8 + 1), "d2h_bytes_per_step": n * 24,
-                              "api": "target_manager_update_dense_async + _wait(1), shard-major pinned arrays, one process"},
+                              "api": "target_manager_update_dense_async + _wait(2), shard-major pinned arrays, one process"},
                "routed_batch": {"ms_per_step": 1e3 * t_batch, "target_steps_per_s": n / t_batch,
                                 "api": "target_manager_update_batch(ids in arbitrary order, meas[n][7]): host routing by id mod G on the shard worker threads"},
                "allgather": {"ms": ag, "uses_nccl": mgr.gather_uses_nccl(), "bytes_per_rank": args.targets_per_gpu * 104,

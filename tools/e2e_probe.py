@@ -27,19 +27,20 @@ def child():
         pool.add(np.arange(s, s + (1 << 20), dtype=np.uint32), p0)
     h3 = [torch.from_numpy(rng.uniform(-5, 5, (n, 3))).pin_memory() for _ in range(2)]
     act = [torch.full((n,), 2, dtype=torch.uint8).pin_memory() for _ in range(2)]
-    out = [torch.empty((n, 3), dtype=torch.float64).pin_memory() for _ in range(2)]
+    out = [torch.empty((n, 3), dtype=torch.float64).pin_memory() for _ in range(3)]
+    lag = int(os.environ.get("TE_PROBE_LAG", "2"))   # ticks left in flight by the loop (the pool stages three)
     L = te.lib
-    res = {"chunk_tiles": os.environ.get("TE_TICK_CHUNK_TILES", "default")}
+    res = {"chunk_tiles": os.environ.get("TE_TICK_CHUNK_TILES", "default"), "lag": lag}
 
     def run(name, pipelined, with_in, with_out, K=20):
         def one(k):
             fn = L.te_pool_tick_host_async if pipelined else L.te_pool_tick_host
             rc = fn(pool._h, 0.004, h3[k % 2].data_ptr() if with_in else None, 3, act[k % 2].data_ptr() if with_in else None, 2 if with_in else 1,
-                    out[k % 2].data_ptr() if with_out else None)
+                    out[k % 3].data_ptr() if with_out else None)
             assert rc == 0, te._lib.last_error()
             if pipelined:
-                L.te_pool_tick_host_wait(pool._h, 1)
-        for k in range(3):
+                L.te_pool_tick_host_wait(pool._h, lag)
+        for k in range(4):
             one(k)
         L.te_pool_tick_host_wait(pool._h, 0)
         t0 = time.perf_counter()
@@ -61,7 +62,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
     else:
-        for c in ("2048", "8192", "32768", "131072"):
-            env = dict(os.environ, TE_TICK_CHUNK_TILES=c)
+        for c, lag in (("8192", "2"), ("32768", "1"), ("32768", "2"), ("131072", "1"), ("131072", "2")):
+            env = dict(os.environ, TE_TICK_CHUNK_TILES=c, TE_PROBE_LAG=lag)
             pr = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, capture_output=True, text=True)
             print(pr.stdout.strip().splitlines()[-1] if pr.stdout.strip() else pr.stderr[-500:], flush=True)
