@@ -21,6 +21,11 @@ int mailbox_ingest_impl(te_pool* p, long long n, const uint32_t* ids, const uint
   const bool host_src = ids != nullptr;
   enable_mail(p);
   const int nr = (int)n;
+  static const bool dbg = std::getenv("TE_MB_DEBUG") != nullptr;   // phase times of the call on stderr (each mark synchronises: debugging only)
+  auto wall = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double tw[5] = {0, 0, 0, 0, 0};
+  auto mark = [&](int i, bool sync) { if (dbg) { if (sync) cudaStreamSynchronize(p->stream); tw[i] = wall(); } };
+  mark(0, true);
   auto queue = [&](uint32_t id, uint32_t s, uint32_t ns, const double* pose) {   // unknown id: queued in arrival order for the next tick
     PendingRec r;
     r.id = id;
@@ -58,19 +63,25 @@ int mailbox_ingest_impl(te_pool* p, long long n, const uint32_t* ids, const uint
     CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_in, key_out, rec_in, rec_out, nr, 0, bits, p->stream));
     void* tmp = p->arena.get(tmp_bytes);
     CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key_in, key_out, rec_in, rec_out, nr, 0, bits, p->stream));
+    mark(1, true);
     if (payload_ready) CK(cudaStreamWaitEvent(p->stream, payload_ready, 0));   // lookup and sort ran under the tail of the copy
+    mark(2, true);
     te::mb_apply_kernel<<<cdiv(n, 256), 256, 0, p->stream>>>(nr, (int)p->n, key_out, rec_out, d_sec, d_nsec, d_pose, p->mb[p->mb_cur].a, b.cold.last_meas);
     CK(cudaGetLastError());
   }
   int n_unknown = 0;
   CK(cudaMemcpyAsync(&n_unknown, counter, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
   CK(cudaStreamSynchronize(p->stream));   // also: a host caller's record arrays are free again
+  mark(3, false);
   if (n_unknown == 0) return 0;
   if (host_src) {
     std::vector<int> list((size_t)n_unknown);
     CK(cudaMemcpy(list.data(), unknown, (size_t)n_unknown * sizeof(int), cudaMemcpyDeviceToHost));
     std::sort(list.begin(), list.end());   // arrival order
     for (int k : list) queue(ids[k], sec[k], nsec[k], poses + 7 * (size_t)k);
+    mark(4, false);
+    if (dbg) std::fprintf(stderr, "[te mailbox ingest] lookup + sort %.3f ms, wait for the payload %.3f ms, apply %.3f ms, unknown ids to the host queue %.3f ms (%d)\n",
+                          tw[1] - tw[0], tw[2] - tw[1], tw[3] - tw[2], tw[4] - tw[3], n_unknown);
     return 0;
   }
   // device source: pack the unknown records (device order) into one block [pose 7 | index | id | sec | nsec] x n_unknown, read it
