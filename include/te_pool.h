@@ -92,7 +92,9 @@ int te_pool_step_dense_ticks(te_pool* p, int n_ticks, double dt, const double* d
  * target's estimated position to dev_pos[k][size][3] (NULL = none).  Results are bit-identical to max_ticks calls of
  * te_pool_step_dense.  te_pool_live_push copies one tick's host arrays into the rings and releases it (in order, on the pool's copy
  * stream); te_pool_live_release(upto) releases ticks whose blocks the caller has written itself.  te_pool_live_wait(ticks) spins until
- * `ticks` ticks have been applied (the last warp of a tick writes a page-locked flag) and returns the number applied;
+ * `ticks` ticks have been applied (the last warp of a tick writes a page-locked flag) and returns the number applied -- of ticks
+ * released in one burst only the last is announced (every warp applies its ticks in order, so it stands for all of them): waiting
+ * for a tick inside a burst returns when the burst is done;
  * te_pool_live_end stops the launch (unreleased ticks are skipped), waits for it and returns the ticks applied.  While the launch
  * runs the pool accepts no other call, and the process must not issue anything that waits for the whole device (cudaFree,
  * cudaDeviceSynchronize, cudaStreamCreate -- measured --, a legacy-default-stream operation): it would wait for the resident

@@ -140,58 +140,81 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) kf_step_kin_direct_kerne
           }
           pending = 0;
         };
+        auto count_done = [&](int tk) {   // lane `first`
+          resolve();            // (one count in flight at a time: `before` is its return value)
+          asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(before) : "l"(a.tick_done + tk) : "memory");
+          pending = tk + 1;
+        };
+        int at_n = ACT_NONE;                      // inputs of the next tick, requested a tick ahead when it is already released
+        double meas_n[3] = {0.0, 0.0, 0.0};
+        bool have_n = false;
         for (int tick = 0; tick < a.n_ticks; ++tick) {
           int at = ACT_NONE;
           double meas[3] = {0.0, 0.0, 0.0};
-          auto fetch = [&]() {   // the tick's inputs (written while this kernel runs: not through the read-only path)
-            at = a.action ? (int)__ldcg(a.action + (size_t)tick * a.action_tick_stride + slot) : a.default_action;
-            if (at == ACT_UPDATE) {
-              const double* mp = a.meas + (size_t)tick * a.meas_tick_stride + (size_t)slot * a.meas_stride;
+          auto fetch = [&](int tk, int& at_o, double* meas_o) {   // a tick's inputs (written while this kernel runs: not through the read-only path)
+            // (the measurement is requested whatever the action byte says: behind a branch on the byte the two L2 round trips would
+            //  run one after the other)
+            at_o = a.action ? (int)__ldcg(a.action + (size_t)tk * a.action_tick_stride + slot) : a.default_action;
+            if (a.meas) {
+              const double* mp = a.meas + (size_t)tk * a.meas_tick_stride + (size_t)slot * a.meas_stride;
 #pragma unroll
-              for (int k = 0; k < 3; ++k) meas[k] = __ldcg(mp + k);
+              for (int k = 0; k < 3; ++k) meas_o[k] = __ldcg(mp + k);
             }
           };
-          // a tick already known to be released: its inputs are requested before the previous tick's count is waited for, so the
-          // two L2 round trips overlap
-          const int ahead = __shfl_sync(m, known > tick ? 1 : 0, first);
-          if (ahead) fetch();
-          if (lane == first) resolve();
-          if (!ahead) {
-            int go = 1;
-            if (lane == first) {
-              // Two sources open the gate: the copy engine (a pushed tick: its block and then the count travel in order on the copy
-              // stream) and the host itself (a released tick: one store to a page-locked word, no CUDA call).  The warp of tile 0
-              // reads both -- the host word across PCIe -- and republishes their maximum in device memory for everybody else.
-              for (;;) {
-                int released, stop;
-                if (gw == 0) {
-                  int hr, hs, dr, ds;
-                  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(hr) : "l"(a.tick_gate_host) : "memory");
-                  asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(hs) : "l"(a.tick_gate_host + 1) : "memory");
-                  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(dr) : "l"(a.tick_gate) : "memory");
-                  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(ds) : "l"(a.tick_gate + 1) : "memory");
-                  released = hr > dr ? hr : dr;
-                  stop = hs | ds;
-                  if (released > pub_released || stop != pub_stop) {
-                    if (stop != pub_stop) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(a.tick_gate_eff + 1), "r"(stop) : "memory");
-                    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.tick_gate_eff), "r"(released) : "memory");
-                    pub_released = released;
-                    pub_stop = stop;
+          if (have_n) {
+            // requested under the previous tick's arithmetic: a burst of released ticks costs no L2 round trip per tick
+            at = at_n;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) meas[k] = meas_n[k];
+            // (no resolve() here: the count in flight was issued a moment ago, reading its return value now would wait for the whole
+            //  L2 round trip; it is resolved in front of the next count, a tick of arithmetic later)
+          } else {
+            // a tick already known to be released: its inputs are requested before the previous tick's count is waited for, so the
+            // two L2 round trips overlap
+            const int ahead = __shfl_sync(m, known > tick ? 1 : 0, first);
+            if (ahead) fetch(tick, at, meas);
+            if (lane == first) resolve();
+            if (!ahead) {
+              int go = 1;
+              if (lane == first) {
+                // Two sources open the gate: the copy engine (a pushed tick: its block and then the count travel in order on the copy
+                // stream) and the host itself (a released tick: one store to a page-locked word, no CUDA call).  The warp of tile 0
+                // reads both -- the host word across PCIe -- and republishes their maximum in device memory for everybody else.
+                for (;;) {
+                  int released, stop;
+                  if (gw == 0) {
+                    int hr, hs, dr, ds;
+                    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(hr) : "l"(a.tick_gate_host) : "memory");
+                    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(hs) : "l"(a.tick_gate_host + 1) : "memory");
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(dr) : "l"(a.tick_gate) : "memory");
+                    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(ds) : "l"(a.tick_gate + 1) : "memory");
+                    released = hr > dr ? hr : dr;
+                    stop = hs | ds;
+                    if (released > pub_released || stop != pub_stop) {
+                      if (stop != pub_stop) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(a.tick_gate_eff + 1), "r"(stop) : "memory");
+                      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.tick_gate_eff), "r"(released) : "memory");
+                      pub_released = released;
+                      pub_stop = stop;
+                    }
+                  } else {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(released) : "l"(a.tick_gate_eff) : "memory");
+                    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(stop) : "l"(a.tick_gate_eff + 1) : "memory");
                   }
-                } else {
-                  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(released) : "l"(a.tick_gate_eff) : "memory");
-                  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(stop) : "l"(a.tick_gate_eff + 1) : "memory");
+                  known = released;
+                  if (released > tick) break;
+                  if (stop) { go = 0; break; }
+                  __nanosleep(20);
                 }
-                known = released;
-                if (released > tick) break;
-                if (stop) { go = 0; break; }
-                __nanosleep(20);
               }
+              go = __shfl_sync(m, go, first);
+              if (!go) break;
+              fetch(tick, at, meas);
             }
-            go = __shfl_sync(m, go, first);
-            if (!go) break;
-            fetch();
           }
+          // the next tick, if the gate read above has already shown it released: its inputs travel under this tick's arithmetic
+          // (the acquire that showed the count orders them; the warp of tile 0 keeps republishing through its own reads)
+          have_n = tick + 1 < a.n_ticks && __shfl_sync(m, known > tick + 1 ? 1 : 0, first) != 0;
+          if (have_n) fetch(tick + 1, at_n, meas_n);
           if (at != ACT_NONE) ks.tick(at, dt, meas, Q, R);
           if (a.pos_out && a.pos_tick_stride > 0) {
 #pragma unroll
@@ -199,12 +222,11 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) kf_step_kin_direct_kerne
           }
           // completion count: the warp barrier orders every lane's position stores before lane `first`'s acq_rel increment
           // (release patterns are cumulative), so whoever sees the full count -- the last warp -- has every warp's stores behind it.
-          // The count comes back under the next tick's input loads (resolve above).
+          // A tick whose successor is already here (a burst) is NOT counted: a warp applies its ticks in order, so the count of the
+          // burst's last tick announces all of them, and the release fence in front of every count -- an L2 round trip with the whole
+          // warp waiting behind lane `first` -- is paid once per burst.  A tick released alone is counted at once, as before.
           __syncwarp(m);
-          if (lane == first) {
-            asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(before) : "l"(a.tick_done + tick) : "memory");
-            pending = tick + 1;
-          }
+          if (lane == first && !have_n) count_done(tick);
         }
         if (lane == first) resolve();
         ks.store(out, a.packed != 0);
@@ -214,15 +236,24 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) kf_step_kin_direct_kerne
         }
         continue;
       }
-      for (int tick = 0; tick < a.n_ticks; ++tick) {
-        const int at = a.action ? (int)a.action[(size_t)tick * a.action_tick_stride + slot] : a.default_action;
-        if (at == ACT_NONE) continue;
-        double meas[3] = {0.0, 0.0, 0.0};
-        if (at == ACT_UPDATE) {
-          const double* mp = a.meas + (size_t)tick * a.meas_tick_stride + (size_t)slot * a.meas_stride;
+      // replay: the inputs of tick k + 1 are requested before tick k is applied (and the measurement whatever the action byte says),
+      // so no tick waits for an L2 round trip
+      auto fetch_replay = [&](int tk, int& at_o, double* meas_o) {
+        at_o = a.action ? (int)a.action[(size_t)tk * a.action_tick_stride + slot] : a.default_action;
+        if (a.meas) {
+          const double* mp = a.meas + (size_t)tk * a.meas_tick_stride + (size_t)slot * a.meas_stride;
 #pragma unroll
-          for (int k = 0; k < 3; ++k) meas[k] = __ldg(mp + k);
+          for (int k = 0; k < 3; ++k) meas_o[k] = __ldg(mp + k);
         }
+      };
+      int at_n = ACT_NONE;
+      double meas_n[3] = {0.0, 0.0, 0.0};
+      fetch_replay(0, at_n, meas_n);
+      for (int tick = 0; tick < a.n_ticks; ++tick) {
+        const int at = at_n;
+        const double meas[3] = {meas_n[0], meas_n[1], meas_n[2]};
+        if (tick + 1 < a.n_ticks) fetch_replay(tick + 1, at_n, meas_n);
+        if (at == ACT_NONE) continue;
         ks.tick(at, dt, meas, Q, R);
       }
       ks.store(out, a.packed != 0);
