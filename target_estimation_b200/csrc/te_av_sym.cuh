@@ -235,6 +235,52 @@ __device__ __forceinline__ void av_update(SymP<12>& P, double* xs, double* zs, c
   }
 }
 
+// ---- the same update as M scalar updates, everything in registers ----
+// With R = L L^T and T = L^-1 (per class, from the host: StepArgs::Tc / Ttab) the whitened measurement T y = (T C) x + e has unit,
+// uncorrelated noise, so its six components may be applied one after the other -- in exact arithmetic the posterior of the joint
+// update (x + K (y - C x), (I - K C) P; src/kalman.cpp:135-140).  Row i of T C has the entries T[i][0..i] at the state indices
+// 0..i, so scalar update i is   g = P[:, 0..i] T[i][0..i]^T,  s = T[i][0..i] g[0..i] + 1,  r = T[i][0..i] (y - x)[0..i],
+// x += g r / s,  P -= g g^T / s.   No 6 x 12 intermediate (the joint form parks Z = L_S^-1 P'[0:6,:] in shared memory): the
+// streaming kernel needs its shared memory for the NEXT tile.  Against the joint form on the SURVEY.md 8(d) streams (numpy, 24
+// targets x 2000 ticks): <= 1.4e-11 relative on state and covariance.
+// y: the measurement (position, unwrapped angles), entry k at y[k * YS] (registers: YS = 1; the lane's column of a parking area
+// in shared memory: YS = TILE).  The empty asm statements keep the front end from interleaving two scalar updates (each needs the
+// covariance the previous one left; hoisted loads only cost registers).
+template <int YS, class TV>
+__device__ __forceinline__ void av_update_seq(SymP<12>& P, double* x, const double* y, TV Tv) {
+  constexpr int N = 12, M = 6;
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    double g[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double s = P(j, 0) * Tv(i * M + 0);
+#pragma unroll
+      for (int k = 1; k < M; ++k)
+        if (k <= i) s += P(j, k) * Tv(i * M + k);
+      g[j] = s;
+    }
+    double s = 1.0, r = 0.0;
+#pragma unroll
+    for (int k = 0; k < M; ++k)
+      if (k <= i) {
+        s += Tv(i * M + k) * g[k];
+        r += Tv(i * M + k) * (y[k * YS] - x[k]);
+      }
+    const double inv = 1.0 / s;
+    const double ri = r * inv;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      x[j] += g[j] * ri;
+      const double gj = g[j] * inv;
+#pragma unroll
+      for (int l = 0; l < N; ++l)
+        if (j <= l) P(j, l) -= gj * g[l];
+    }
+    if (i + 1 < M) asm volatile("" ::: "memory");   // (none after the last one: the caller's stores may start under its downdates)
+  }
+}
+
 // in  : the lane's column of the source tile   (field f at in[f * TILE]); staged tile in shared memory or the tile in HBM
 // out : the lane's column of the destination tile (may alias in)
 // sc  : the lane's column of a shared-memory scratch with the tile's field numbering for x (F_X..) and for the first 72

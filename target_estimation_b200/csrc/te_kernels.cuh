@@ -66,6 +66,8 @@ struct StepArgs {
   int cls_c;                // class held in Qc / Rc, -1 = none
   double Rc[36];
   double Qc[324];
+  const double* Ttab;       // [n_classes][M*M] row-major lower triangular: T = L^-1, R = L L^T (te_av_sym.cuh av_update_seq)
+  double Tc[36];            // the same for class cls_c
 };
 
 constexpr int MEAS_DOUBLES = 7 * TILE;   // measurement block of a stage (max stride 7)

@@ -10,6 +10,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <cmath>
+
 #include "te_pool_internal.cuh"
 
 namespace tehost {
@@ -180,22 +182,25 @@ void upload_classes(te_pool* p) {
   const int nc = (int)p->hQ.size();
   if (nc > p->cls_cap) {
     CK(cudaStreamSynchronize(p->stream));
-    cudaFree(p->dQ); cudaFree(p->dR); cudaFree(p->dP0);
+    cudaFree(p->dQ); cudaFree(p->dR); cudaFree(p->dP0); cudaFree(p->dT);
     int cap = std::max(nc, std::max(4, p->cls_cap * 2));
     CK(cudaMalloc(&p->dQ, (size_t)cap * p->N * p->N * sizeof(double)));
     CK(cudaMalloc(&p->dR, (size_t)cap * p->M * p->M * sizeof(double)));
     CK(cudaMalloc(&p->dP0, (size_t)cap * p->N * p->N * sizeof(double)));
+    CK(cudaMalloc(&p->dT, (size_t)cap * p->M * p->M * sizeof(double)));
     p->cls_cap = cap;
     for (int c = 0; c < nc; ++c) {
       CK(cudaMemcpyAsync(p->dQ + (size_t)c * p->N * p->N, p->hQ[c].data(), p->N * p->N * sizeof(double), cudaMemcpyHostToDevice, p->stream));
       CK(cudaMemcpyAsync(p->dR + (size_t)c * p->M * p->M, p->hR[c].data(), p->M * p->M * sizeof(double), cudaMemcpyHostToDevice, p->stream));
       CK(cudaMemcpyAsync(p->dP0 + (size_t)c * p->N * p->N, p->hP0[c].data(), p->N * p->N * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+      CK(cudaMemcpyAsync(p->dT + (size_t)c * p->M * p->M, p->hT[c].data(), p->M * p->M * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     }
   } else {
     const int c = nc - 1;
     CK(cudaMemcpyAsync(p->dQ + (size_t)c * p->N * p->N, p->hQ[c].data(), p->N * p->N * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     CK(cudaMemcpyAsync(p->dR + (size_t)c * p->M * p->M, p->hR[c].data(), p->M * p->M * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     CK(cudaMemcpyAsync(p->dP0 + (size_t)c * p->N * p->N, p->hP0[c].data(), p->N * p->N * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(p->dT + (size_t)c * p->M * p->M, p->hT[c].data(), p->M * p->M * sizeof(double), cudaMemcpyHostToDevice, p->stream));
   }
   CK(cudaStreamSynchronize(p->stream));
 }
@@ -484,7 +489,7 @@ void te_pool_destroy(te_pool* p) {
   if (p->h_stage) cudaFreeHost(p->h_stage);
   cudaFree(p->action); cudaFree(p->dt_slot); cudaFree(p->tile_flag); cudaFree(p->tile_list);
   cudaFree(p->alive); cudaFree(p->pos); cudaFree(p->srcmap); cudaFree(p->d_counters); cudaFree(p->cub_tmp);
-  cudaFree(p->dQ); cudaFree(p->dR); cudaFree(p->dP0);
+  cudaFree(p->dQ); cudaFree(p->dR); cudaFree(p->dP0); cudaFree(p->dT);
   p->arena.destroy();
   cudaFree(p->live.d_gate);
   if (p->live.h_ring) cudaFreeHost(p->live.h_ring);
@@ -588,6 +593,35 @@ int te_pool_register_class(te_pool* p, const double* Q, const double* R, const d
       return true;
     };
     if (!sym(Q, p->N) || !sym(R, p->M) || !sym(P0, p->N)) p->all_sym = false;
+    {
+      // T = L^-1, R = L L^T (plain FP64 Cholesky, then forward substitution against the identity); zeros if R has no factor
+      const int m = p->M;
+      std::vector<double> L((size_t)m * m, 0.0), T((size_t)m * m, 0.0);
+      bool ok = true;
+      for (int j = 0; j < m && ok; ++j) {
+        double d = R[j * m + j];
+        for (int k = 0; k < j; ++k) d -= L[j * m + k] * L[j * m + k];
+        if (!(d > 0.0) || !std::isfinite(d)) { ok = false; break; }
+        L[j * m + j] = std::sqrt(d);
+        for (int i = j + 1; i < m; ++i) {
+          double s2 = R[i * m + j];
+          for (int k = 0; k < j; ++k) s2 -= L[i * m + k] * L[j * m + k];
+          L[i * m + j] = s2 / L[j * m + j];
+        }
+      }
+      if (ok) {
+        for (int c = 0; c < m; ++c)
+          for (int i = c; i < m; ++i) {
+            double s2 = (i == c) ? 1.0 : 0.0;
+            for (int k = c; k < i; ++k) s2 -= L[i * m + k] * T[k * m + c];
+            T[i * m + c] = s2 / L[i * m + i];
+          }
+      } else {
+        std::fill(T.begin(), T.end(), 0.0);
+        p->whiten_ok = false;
+      }
+      p->hT.push_back(T);
+    }
     upload_classes(p);
     return (int)p->hQ.size() - 1;
   });

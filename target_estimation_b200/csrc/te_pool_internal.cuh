@@ -153,6 +153,11 @@ struct te_pool {
   // model classes
   std::vector<std::vector<double>> hQ, hR, hP0;
   double *dQ = nullptr, *dR = nullptr, *dP0 = nullptr;
+  // per class: T = L^-1 with R = L L^T (lower triangular, row-major M x M): the whitening of the measurement that lets a kernel apply
+  // an update as M scalar updates (te_av_sym.cuh av_update_seq).  whiten_ok = every class's R has a Cholesky factor.
+  double* dT = nullptr;
+  std::vector<std::vector<double>> hT;
+  bool whiten_ok = true;
   int cls_cap = 0;
   // host mirror of the sorted ids (lazy)
   std::vector<uint32_t> h_ids;

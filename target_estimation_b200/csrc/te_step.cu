@@ -82,7 +82,7 @@ void launch_av_direct(te_pool* p, const te::StepArgs& a, int n_work_hint) {
 
 // dense in-place packed tick of an AV pool: the TMA-streamed kernel (te_av_stream.cuh)
 bool av_stream_serves(const te_pool* p, const te::StepArgs& a) {
-  if (p->variant != 0 || !a.packed) return false;   // 13 = the direct kernel for every launch
+  if (p->variant != 0 || !a.packed || !p->whiten_ok) return false;   // 13 = the direct kernel for every launch
   if (a.tile_list || a.d_nwork || a.dt_slot || a.dst_tiles || a.clear_action || a.n_ticks != 1 || a.tick_gate) return false;
   if (a.meas && (a.meas_stride != 7 || (reinterpret_cast<uintptr_t>(a.meas) & 15) != 0)) return false;
   if (!a.meas && (a.action || a.default_action == te::ACT_UPDATE)) return false;
@@ -224,12 +224,14 @@ te::StepArgs base_args(te_pool* p) {
   a.cls = b.cold.cls;
   a.Qtab = p->dQ;
   a.Rtab = p->dR;
+  a.Ttab = p->dT;
   a.n_ticks = 1;
   a.cls_c = -1;
   if (!p->hQ.empty()) {   // class 0 rides in the parameter constant bank
     a.cls_c = 0;
     std::memcpy(a.Qc, p->hQ[0].data(), sizeof(double) * p->N * p->N);
     std::memcpy(a.Rc, p->hR[0].data(), sizeof(double) * p->M * p->M);
+    std::memcpy(a.Tc, p->hT[0].data(), sizeof(double) * p->M * p->M);
   }
   return a;
 }
