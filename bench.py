@@ -740,7 +740,7 @@ def main():
                 pr = subprocess.run([sys.executable, tool, "benchline", model], capture_output=True, text=True, timeout=420, env=env)
                 r = json.loads(pr.stdout.strip().splitlines()[-1])
                 keep = ("model", "targets", "ticks", "erased", "added", "records_per_tick", "h2d_bytes_per_tick", "records_in", "ms_per_tick", "target_steps_per_s",
-                        "ms_per_tick_parts", "note", "error")
+                        "ms_per_tick_median", "ms_per_tick_worst", "ms_per_tick_parts", "note", "error")
                 for key in ("c3", "node_loop", "c3_sync", "node_loop_sync"):
                     if key in r:
                         out[key] = {k_: r[key][k_] for k_ in keep if k_ in r[key]}
