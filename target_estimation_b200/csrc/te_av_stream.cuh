@@ -21,9 +21,10 @@
 // warp's critical path.  This form: 0.315 ms.
 //
 // Predict and Jacobians are the direct kernel's (the shared pieces of te_av_sym.cuh).  Serves dense in-place packed ticks of one tick
-// (no tile list, no per-slot dt, no compaction, 16-byte aligned measurements of stride 7) of pools whose classes all have a
-// Cholesky factor of R; everything else stays on the direct kernel.  Lanes that are not stepped (ACT_NONE, slots beyond the pool)
-// write nothing.
+// (no tile list, no per-slot dt, 16-byte aligned measurements of stride 7) of pools whose classes all have a
+// Cholesky factor of R, in place or compacting (StepArgs::dst_*: every survivor's column goes to its compacted slot -- the results
+// leave from registers by per-lane stores anyway); everything else stays on the direct kernel.  In place, lanes that are not stepped
+// (ACT_NONE, slots beyond the pool) write nothing.
 #pragma once
 #include "te_av_sym.cuh"
 #include "te_kernels.cuh"
@@ -31,14 +32,16 @@
 namespace te {
 
 constexpr int AVS_X = 0, AVS_P = 12, AVS_T = 90, AVS_NM = 91, AVS_PREV = 92, AVS_FIELDS = 95;   // field numbering of the zone
-constexpr int AVS_TAIL_BYTES = 128;   // per warp, behind the zones: the mbarrier (16 B) | the tile's action bytes (32 B) | its class ids (64 B)
+constexpr int AVS_TAIL_BYTES = 384;   // per warp, behind the zones: the mbarrier (16 B) | the tile's action bytes (32 B) | its class ids (64 B) |
+                                      // 16 B unused | compacting tick: the tile's survivor flags (128 B) | their destination slots (128 B)
 constexpr int AVL_PARK_FIELDS = 6;                                              // the measurement y of the tile being stepped
 constexpr int AVL_WARP_BYTES = (AVS_FIELDS + 7 + AVL_PARK_FIELDS) * TILE * 8;   // landed fields + measurement block [32][7] + parking area
 __host__ __device__ constexpr size_t av_stream_smem_bytes(int warps) { return (size_t)warps * (AVL_WARP_BYTES + AVS_TAIL_BYTES); }
 
 // QC: the pool has one class and its Q / T ride in the kernel-parameter constant bank (StepArgs::Qc / Tc): the table reads
-// become constant operands
-template <int WARPS, bool QC>
+// become constant operands.  COMPACT: the compacting tick, an instantiation of its own (its extra registers cost the in-place
+// tick 2 %).
+template <int WARPS, bool QC, bool COMPACT>
 __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_av_stream_kernel(const __grid_constant__ StepArgs a) {
   using LY = Layout<ANGULAR_VELOCITIES>;
   constexpr int N = 12, M = 6;
@@ -55,6 +58,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_av_stream_kernel(const 
   uint64_t* const bar = reinterpret_cast<uint64_t*>(tail);
   const uint8_t* const Az = tail + 16;
   const uint16_t* const Cz = reinterpret_cast<const uint16_t*>(tail + 48);
+  const int* const Dalive = reinterpret_cast<const int*>(tail + 128);
+  const int* const Dpos = reinterpret_cast<const int*>(tail + 256);
+  constexpr bool compacting = COMPACT;   // te_pool_step_dense_expire / the fused mailbox tick: survivors go to their compacted slots (StepArgs::dst_*)
   if (lane == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
@@ -72,7 +78,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_av_stream_kernel(const 
     const double* tb = a.tiles + (size_t)tile * LY::TILE_DOUBLES;
     const bool full = full_tile(tile);
     const bool mt = full && a.meas != nullptr, at = full && act_tma, ct = full && !QC;
-    mbar_expect_tx(bar, AVS_FIELDS * TILE * 8 + (mt ? 7 * TILE * 8 : 0) + (at ? TILE : 0) + (ct ? 2 * TILE : 0));
+    const bool dt_ = full && compacting;
+    mbar_expect_tx(bar, AVS_FIELDS * TILE * 8 + (mt ? 7 * TILE * 8 : 0) + (at ? TILE : 0) + (ct ? 2 * TILE : 0) + (dt_ ? 8 * TILE : 0));
     bulk_g2s(Sw + AVS_X * TILE, tb + LY::F_X * TILE, N * TILE * 8, bar);
     int pk = 0;
 #pragma unroll
@@ -84,6 +91,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_av_stream_kernel(const 
     if (mt) bulk_g2s(Sw + AVS_FIELDS * TILE, a.meas + (size_t)tile * TILE * 7, 7 * TILE * 8, bar);
     if (at) bulk_g2s(tail + 16, a.action + (size_t)tile * TILE, TILE, bar);
     if (ct) bulk_g2s(tail + 48, a.cls + (size_t)tile * TILE, 2 * TILE, bar);
+    if (dt_) {
+      bulk_g2s(tail + 128, a.dst_alive + (size_t)tile * TILE, 4 * TILE, bar);
+      bulk_g2s(tail + 256, a.dst_pos + (size_t)tile * TILE, 4 * TILE, bar);
+    }
   };
   if (w < n_work && lane == 0) issue(a.tile_begin + w);
   const double dt = a.dt;
@@ -93,10 +104,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_av_stream_kernel(const 
     const bool valid = slot < a.n_slots;
     const bool full = full_tile(tile);
     mbar_wait(bar, it & 1);
-    int act = ACT_NONE, cls = 0;
+    int act = ACT_NONE, cls = 0, dst = -1;   // dst: compacting tick, destination slot of the lane's target (-1 = erased at the end of this tick)
     if (valid) {
       act = a.action ? (int)((full && act_tma) ? Az[lane] : a.action[slot]) : a.default_action;
       if (!QC) cls = (int)(full ? Cz[lane] : a.cls[slot]);
+      if (compacting) {
+        const int alive = full ? Dalive[lane] : a.dst_alive[slot];
+        if (alive) dst = full ? Dpos[lane] : a.dst_pos[slot];
+        else act = ACT_NONE;   // its step is unobservable
+      }
     }
     // ---- front end while few registers are live: measurement conversion (angular_velocities.cpp:87-96), Jacobians ----
     double prev[3];
@@ -136,7 +152,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_av_stream_kernel(const 
     const int wn = w + GW;
     if (lane == 0 && wn < n_work) issue(a.tile_begin + wn);
 
-    double* const out = a.tiles + (size_t)tile * LY::TILE_DOUBLES + lane;
+    double* const out = compacting ? a.dst_tiles + (size_t)((dst < 0 ? 0 : dst) / TILE) * LY::TILE_DOUBLES + ((dst < 0 ? 0 : dst) % TILE)
+                                   : a.tiles + (size_t)tile * LY::TILE_DOUBLES + lane;
+    if (compacting && dst >= 0 && act != ACT_UPDATE) {
+      // the fields a stepped lane does not rewrite travel with the target: everything for an untouched survivor, the measurement
+      // count and the previous angles for a predicted one
+      if (act == ACT_NONE) out[LY::F_T * TILE] = t_in;
+      reinterpret_cast<long long*>(out)[LY::F_NMEAS * TILE] = nm_in;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) out[(LY::F_PREV + k) * TILE] = prev[k];
+    }
     if (act != ACT_NONE) {
       // bookkeeping first (its values are final, its registers are wanted): updateTime (src/target_interface.cpp:148-152),
       // updateMeasurement (:142-146), meas_rpy_internal_
@@ -156,6 +181,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_av_stream_kernel(const 
       const double* __restrict__ T = a.Ttab + (size_t)cls * M * M;
       av_predict_cov(P, F, [&](int idx) -> double { return QC ? a.Qc[idx] : __ldg(&Q[idx]); });
       if (act == ACT_UPDATE) av_update_seq<TILE>(P, x, Yp, [&](int idx) -> double { return QC ? a.Tc[idx] : __ldg(&T[idx]); });
+    }
+    if (act != ACT_NONE || (compacting && dst >= 0)) {   // (compacting: an untouched survivor moves as it was loaded)
 #pragma unroll
       for (int i = 0; i < N; ++i) out[(LY::F_X + i) * TILE] = x[i];
 #pragma unroll

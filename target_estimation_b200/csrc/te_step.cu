@@ -83,15 +83,15 @@ void launch_av_direct(te_pool* p, const te::StepArgs& a, int n_work_hint) {
 // dense in-place packed tick of an AV pool: the TMA-streamed kernel (te_av_stream.cuh)
 bool av_stream_serves(const te_pool* p, const te::StepArgs& a) {
   if (p->variant != 0 || !a.packed || !p->whiten_ok) return false;   // 13 = the direct kernel for every launch
-  if (a.tile_list || a.d_nwork || a.dt_slot || a.dst_tiles || a.clear_action || a.n_ticks != 1 || a.tick_gate) return false;
+  if (a.tile_list || a.d_nwork || a.dt_slot || a.clear_action || a.n_ticks != 1 || a.tick_gate) return false;
   if (a.meas && (a.meas_stride != 7 || (reinterpret_cast<uintptr_t>(a.meas) & 15) != 0)) return false;
   if (!a.meas && (a.action || a.default_action == te::ACT_UPDATE)) return false;
   return true;
 }
-template <bool QC>
-void launch_av_stream(te_pool* p, const te::StepArgs& a, int n_work_hint) {
+template <bool QC, bool COMPACT>
+void launch_av_stream_k(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   constexpr int WARPS = 8;
-  auto kern = te::kf_step_av_stream_kernel<WARPS, QC>;
+  auto kern = te::kf_step_av_stream_kernel<WARPS, QC, COMPACT>;
   const size_t smem = te::av_stream_smem_bytes(WARPS);
   static bool configured[64] = {false};
   if (!configured[p->device & 63]) {
@@ -101,6 +101,11 @@ void launch_av_stream(te_pool* p, const te::StepArgs& a, int n_work_hint) {
   int grid = capped(p, std::min(p->n_sm, std::max(1, cdiv(n_work_hint, WARPS))));
   kern<<<grid, WARPS * 32, smem, p->stream>>>(a);
   CK(cudaGetLastError());
+}
+template <bool QC>
+void launch_av_stream(te_pool* p, const te::StepArgs& a, int n_work_hint) {
+  if (a.dst_tiles) launch_av_stream_k<QC, true>(p, a, n_work_hint);
+  else launch_av_stream_k<QC, false>(p, a, n_work_hint);
 }
 
 template <int TYPE, int WARPS, int CTAS>

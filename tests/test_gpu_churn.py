@@ -136,7 +136,7 @@ def test_expiry_bit_exact(n0, ticks):
 
 
 @pytest.mark.parametrize("name,variant", [("uniform_velocity", 0), ("uniform_acceleration", 0), ("angular_velocities", 0), ("angular_rates", 0),
-                                          ("uniform_acceleration", 10), ("angular_velocities", 10), ("angular_rates", 11)])
+                                          ("uniform_acceleration", 10), ("angular_velocities", 10), ("angular_velocities", 13), ("angular_rates", 11)])
 def test_fused_step_expire_is_bit_identical(name, variant):
     """te_pool_step_dense_expire (compaction fused into the step kernel: survivors' columns go straight to their compacted
     slots in the second buffer) == te_pool_step_dense + te_pool_stamp_dense + te_pool_expire, bit for bit: erased ids,
@@ -152,10 +152,9 @@ def test_fused_step_expire_is_bit_identical(name, variant):
     pools = []
     for _ in range(2):
         p = te.TargetPool(mtype); p.register_class(Q, R, P0)
-        # 0: the default kernels; 10: the full-matrix kernels; 11: AR row-split kernel, packed.  Angular velocities: the default in-place
-        # tick is the TMA-streamed kernel, the compacting one the direct kernel -- same source arithmetic, but ptxas contracts
-        # multiply-adds per kernel, so bits are compared between the two forms of one kernel (13 = the direct kernel everywhere)
-        p.set_variant(13 if (name == "angular_velocities" and variant == 0) else variant)
+        # 0: the default kernels (angular velocities: the TMA-streamed kernel in both forms); 10: the full-matrix kernels; 11: AR
+        # row-split kernel, packed; 13: AV direct kernel in both forms
+        p.set_variant(variant)
         p.add(np.arange(n0, dtype=np.uint32), meas_all[0, :n0], p0_scale=scale[:n0])
         pools.append(p)
     rng = np.random.default_rng(23)
