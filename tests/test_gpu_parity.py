@@ -273,3 +273,41 @@ def test_av_semidefinite_R_stays_on_the_joint_update():
     assert np.array_equal(got[0]["n_meas"], ref["n_meas"]) and np.array_equal(got[0]["t"], ref["t"])
     for p in pools:
         p.close()
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 64, 95])
+def test_av_streamed_kernel_small_and_ragged_pools(n):
+    """pools of less than a tile, exactly one / two tiles and ragged ones through the streamed angular-velocities kernel: device
+    measurements at a 16-byte aligned and at an odd address (the unaligned tick runs the direct kernel), an action array at an odd
+    address (flags read per lane), predict-only ticks without measurements (update(dt)); against the oracle"""
+    import torch
+    import target_estimation_b200 as te
+    mtype, freq, Q, R, P0 = te.load_model("angular_velocities")
+    ticks = 24
+    meas, action, scale = synth.make_streams(n, ticks, DT, accel=False, angular=True, seed=100 + n)
+    ids = np.arange(n, dtype=np.uint32) * 5 + 2
+    pool = te.TargetPool(mtype)
+    assert pool.register_class(Q, R, P0) == 0
+    assert pool.add(ids, meas[0], p0_scale=scale) == n
+    mgr = orc.Manager()
+    for k, i in enumerate(ids):
+        mgr.init_full(mtype, int(i), DT, 0.0, Q, R, scale[k] * P0, meas[0, k])
+    # one flat device buffer per kind, ticks at offsets that are not all 16-byte aligned
+    d_meas = torch.zeros(ticks * n * 7 + 1, dtype=torch.float64, device="cuda")
+    d_act = torch.zeros(ticks * n + 3, dtype=torch.uint8, device="cuda")
+    for k in range(ticks):
+        mo = k * n * 7 + (1 if k % 3 == 2 else 0)        # every third tick: measurements 8 bytes off a 16-byte boundary
+        ao = k * n + (3 if k % 2 else 0)
+        if k % 6 == 5:
+            mgr.update_all(DT)
+            pool.predict_all(DT)
+            continue
+        d_meas[mo:mo + n * 7] = torch.from_numpy(meas[k].reshape(-1)).cuda()
+        d_act[ao:ao + n] = torch.from_numpy(action[k]).cuda()
+        mgr.step_batch(ids, DT, meas[k], action[k])
+        pool.step_dense(DT, d_meas[mo:mo + n * 7], 7, d_act[ao:ao + n])
+    ref, got = mgr.states(ids, 12), pool.read_state()
+    assert synth.compare_h2(got["x"], ref["x"]) <= 1.0 and synth.compare_h2(got["P"], ref["P"]) <= 1.0
+    assert np.array_equal(got["n_meas"], ref["n_meas"]) and np.array_equal(got["t"], ref["t"])
+    assert synth.compare_h2(got["prev_rpy"], ref["prev_rpy"]) <= 1.0
+    pool.close()
