@@ -78,7 +78,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) kf_step_av_direct_kernel(const 
 
 // The same for the linear models (UV / UA): no shared memory at all, everything lives in registers.  n_ticks > 1 = replay
 // launch (te_pool_step_dense_ticks): the target stays in registers for all its ticks.
-template <int TYPE, int WARPS, int MIN_CTAS>
+// MULTI: the replay / live instantiation (n_ticks > 1 or a tick gate); the single-tick instantiation carries none of its code (its
+// registers cost the dense tick a spill).
+template <int TYPE, int WARPS, int MIN_CTAS, bool MULTI = false>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) kf_step_kin_direct_kernel(const StepArgs a) {
   using MT = Model<TYPE>;
   using LY = Layout<TYPE>;
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) kf_step_kin_direct_kerne
                               : a.tiles + (size_t)tile * LY::TILE_DOUBLES + lane;
     const double* __restrict__ Q = a.Qtab + (size_t)cls * N * N;
     const double* __restrict__ R = a.Rtab + (size_t)cls * M * M;
-    if (a.n_ticks > 1 || a.tick_gate) {
+    if (MULTI) {
       if (!valid) continue;
       // a lane whose actions are all ACT_NONE still goes through load / store: cheaper than a second pass to find out
       KinSym<TYPE> ks;

@@ -110,7 +110,8 @@ void launch_av_stream(te_pool* p, const te::StepArgs& a, int n_work_hint) {
 
 template <int TYPE, int WARPS, int CTAS>
 void launch_kin_direct_k(te_pool* p, const te::StepArgs& a, int n_work_hint) {
-  auto kern = te::kf_step_kin_direct_kernel<TYPE, WARPS, CTAS>;
+  const bool multi = a.n_ticks > 1 || a.tick_gate != nullptr;   // replay / live launches: an instantiation of their own
+  auto kern = multi ? te::kf_step_kin_direct_kernel<TYPE, WARPS, CTAS, true> : te::kf_step_kin_direct_kernel<TYPE, WARPS, CTAS, false>;
   int grid = capped(p, std::min(p->n_sm * CTAS, std::max(1, cdiv(n_work_hint, WARPS))));
   // programmatic stream serialization: see the kernel's griddepcontrol.wait
   cudaLaunchConfig_t cfg{};
