@@ -161,17 +161,17 @@ void ensure_full(te_pool* p) {
   p->lower_stale = false;
 }
 
-// variant -> kernel.  0 = default: the direct symmetric-covariance kernels for UV / UA / AV when every class is symmetric
-// (packed: upper triangle only), else the full-matrix kernels; 10 = force the full-matrix kernel (TMA-staged / row-split);
-// 12 = direct kernel writing both halves; the others are launch shapes kept for experiments (tests cover all of them).
 // Stage bytes of the staged kernel: UV 13056, UA 25344, AV 43008, AR 90624.
 // Kernel per model and variant.  Variants are what the tests switch between, not tuning shapes:
-//   0   default: UV / UA / AV direct symmetric-covariance kernels (packed; te_direct.cuh) while every class is bitwise symmetric,
-//       AR the warp-specialised row-split kernel on the full matrix (te_split.cuh)
+//   0   default, while every class is bitwise symmetric (packed: upper triangle only): UV / UA direct symmetric-covariance kernels
+//       (te_direct.cuh); AV dense ticks (in place and compacting) the TMA-streamed kernel (te_av_stream.cuh), AV sparse ticks and pools
+//       with a class whose R has no Cholesky factor the direct kernel; AR the warp-specialised row-split kernel on the full matrix
+//       (te_split.cuh).  A pool with an asymmetric class runs the full-matrix kernels (10).
 //   1   the TMA-staged one-warp-per-tile kernel on the full matrix (te_kernels.cuh; also what replay launches of AV / AR run)
 //   10  forced full-matrix kernels (UV / UA staged, AV row-split): what a pool with an asymmetric class runs
 //   11  AR row-split kernel moving the upper triangle only (44 % fewer bytes, not faster: DESIGN.md section 7)
 //   12  UV / UA / AV direct kernels writing both halves of the covariance
+//   13  as 0, but AV dense ticks on the direct kernel too
 // Shape experiments of round 1 (warps x stages sweeps, the AR / AV two-lanes-per-target kernels, thread-per-target AR) were
 // measured, lost, and are gone from the tree: DESIGN.md section 7 keeps their numbers.
 void launch_step(te_pool* p, const te::StepArgs& a_in, int n_work_hint) {
